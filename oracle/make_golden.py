@@ -1,0 +1,161 @@
+"""Freeze outputs of the REFERENCE's own functions as golden vectors (authoring container only).
+
+    python -m oracle.make_golden            # writes tests/golden/*.npz
+
+The reference has no tests or fixtures for this path, so parity is pinned by
+running its functions here on the deterministic synthetic inputs of skiing_analysis_pytorch_b200/
+synth.py and committing inputs + outputs.  /root/reference does not exist on the GPU box; the
+tests only ever read the .npz files.  Golden sets:
+  G1  triangulation.triangulate.triangulate_joints, triangulation.reproject.reproject_points /
+      reproject_and_visualize statistics on the config-1 rig (FIXED pose, two_view.py:209-221)
+  G2  vggt.triangulate.make_P / triangulate_point / triangulate_one_frame and
+      bundle_adjustment.reproject.reproject_points mode A on two non-identity cameras (quirk Q3)
+  G3  bundle_adjustment.loss.project_points / reprojection_loss for every accepted shape, f32+f64
+  G4  camera_smooth / baseline_reg / bone_length / pose_temporal scalars
+"""
+from __future__ import annotations
+
+import logging
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import ref_import  # noqa: E402
+from skiing_analysis_pytorch_b200 import synth  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+
+
+def g1():
+    tri = ref_import.load("triangulation.triangulate")
+    rep = ref_import.load("triangulation.reproject")
+    clip = synth.make_clip("2a", T=48, J=17, seed=0)
+    K = clip.K[0]
+    R, t = clip.R[1], clip.t[1]  # cam2 w.r.t. cam1 (cam1 = identity on this rig)
+    assert np.allclose(clip.R[0], np.eye(3)) and np.allclose(clip.t[0], 0)
+    assert np.array_equal(tri.K_dist, synth.DIST_CALIB)
+    kL, kR = clip.x_vm[0], clip.x_vm[1]
+    X32 = np.stack([tri.triangulate_joints(kL[i], kR[i], K, R, t) for i in range(len(kL))])
+    X64 = np.stack([tri.triangulate_joints(kL[i].astype(np.float64), kR[i].astype(np.float64), K, R, t.reshape(3, 1)) for i in range(len(kL))])
+    assert X32.dtype == np.float32 and X64.dtype == np.float64
+    projL_d, projR_d, projL_p, projR_p = [], [], [], []
+    for i in range(len(kL)):
+        pd = rep.reproject_points(X32[i], K, tri.K_dist, K, tri.K_dist, R, t)
+        pp = rep.reproject_points(X32[i], K, None, K, None, R, t)
+        projL_d.append(pd["proj_L"]); projR_d.append(pd["proj_R"])
+        projL_p.append(pp["proj_L"]); projR_p.append(pp["proj_R"])
+    img = np.zeros((108, 192, 3), np.uint8)
+    stats = []
+    keys = ["rmse_L", "rmse_R", "mean_err_L", "mean_err_R", "median_err_L", "median_err_R", "max_err_L", "max_err_R"]
+    errL, errR = [], []
+    with tempfile.TemporaryDirectory() as td:
+        for i in range(8):
+            res = rep.reproject_and_visualize(img, img, X32[i], kL[i], kR[i], K, tri.K_dist, K, tri.K_dist, R, t,
+                                              out_path=str(Path(td) / "p.jpg"))
+            stats.append([res[k] for k in keys])
+            errL.append(res["err_L"]); errR.append(res["err_R"])
+    np.savez_compressed(
+        OUT / "g1_two_view_fixed_rig.npz", K=K, R=R, t=t, dist=tri.K_dist, kptL=kL, kptR=kR, X_f32=X32, X_f64=X64,
+        projL_dist=np.stack(projL_d), projR_dist=np.stack(projR_d), projL_pin=np.stack(projL_p), projR_pin=np.stack(projR_p),
+        stats=np.array(stats), stats_keys=np.array(keys), errL=np.stack(errL), errR=np.stack(errR),
+    )
+
+
+def g2():
+    vt = ref_import.load("vggt.triangulate")
+    brp = ref_import.load("bundle_adjustment.reproject")
+    vrp = ref_import.load("vggt.reproject")
+    rng = np.random.default_rng(7)
+    clip = synth.make_clip("2b", T=16, J=17, seed=3)
+    # move the world frame so that NEITHER camera is the identity (quirk Q3 needs this)
+    Rw = synth.so3_exp(np.array([0.1, -0.3, 0.05]))
+    tw = np.array([0.4, -0.2, 1.5])
+    R = np.stack([clip.R[c] @ Rw for c in range(2)])
+    t = np.stack([clip.R[c] @ tw + clip.t[c] for c in range(2)])
+    K = np.stack([clip.K[0], clip.K[1] * np.array([[1.02, 1, 0.99], [1, 0.98, 1.01], [1, 1, 1]])])
+    P = np.stack([vt.make_P(K[c], R[c], t[c]) for c in range(2)])
+    kL, kR = clip.x_vm[0], clip.x_vm[1]
+    Xpt = np.array([[vt.triangulate_point(P[0], P[1], kL[i, j], kR[i, j]) for j in range(17)] for i in range(len(kL))])
+    img = np.zeros((108, 192, 3), np.uint8)
+    X_frame, means = [], []
+    logging.disable(logging.CRITICAL)
+    with tempfile.TemporaryDirectory() as td:
+        for i in range(4):
+            X3d, res = vt.triangulate_one_frame(K, R, t, kL[i], kR[i], img, img, save_dir=Path(td), dist=None)
+            X_frame.append(X3d); means.append([res["mean_err_L"], res["mean_err_R"]])
+    pa = [brp.reproject_points(Xpt[i], K[0], None, K[1], None, R, t) for i in range(len(kL))]
+    pa_d = [vrp.reproject_points(Xpt[i], K[0], synth.DIST_CALIB, K[1], synth.DIST_CALIB, list(R), list(t)) for i in range(len(kL))]
+    R_rel = R[1] @ R[0].T
+    t_rel = t[1] - R_rel @ t[0]
+    pb = [brp.reproject_points(Xpt[i], K[0], None, K[1], None, R_rel, t_rel.reshape(3, 1)) for i in range(len(kL))]
+    np.savez_compressed(
+        OUT / "g2_vggt_two_cameras.npz", K=K, R=R, t=t, P=P, kptL=kL, kptR=kR, X_point=Xpt, X_frame=np.stack(X_frame),
+        frame_mean_err=np.array(means), modeA_L=np.stack([p["proj_L"] for p in pa]), modeA_R=np.stack([p["proj_R"] for p in pa]),
+        modeA_dist_L=np.stack([p["proj_L"] for p in pa_d]), modeA_dist_R=np.stack([p["proj_R"] for p in pa_d]),
+        modeB_L=np.stack([p["proj_L"] for p in pb]), modeB_R=np.stack([p["proj_R"] for p in pb]), dist=synth.DIST_CALIB,
+    )
+    del rng
+
+
+def g3_g4():
+    import torch
+
+    loss = ref_import.load("bundle_adjustment.loss")
+    clip = synth.make_clip("4", T=12, J=17, seed=5)
+    T, C, J = 12, 4, 17
+    rng = np.random.default_rng(11)
+    X = clip.X + rng.normal(0, 0.01, clip.X.shape)
+    Kc = clip.K.copy()
+    Kc[:, 0, 1] = [0.0, 0.7, -0.4, 0.2]  # skew is honoured by loss.py:74-82
+    Rt = np.stack([np.stack([synth.so3_exp(rng.normal(0, 0.01, 3)) @ clip.R[c] for c in range(C)]) for _ in range(T)])
+    tt = clip.t[None] + rng.normal(0, 0.02, (T, C, 3))
+    Kt = Kc[None] * (1 + rng.normal(0, 1e-3, (T, C, 1, 1)))
+    Kt[..., 2, :] = [0, 0, 1]
+    x2d, conf = clip.x_fm, clip.conf_fm
+    out = dict(X=X, K_c=Kc, R_c=clip.R, t_c=clip.t, R_t=Rt, t_t=tt, K_t=Kt, x2d=x2d, conf=conf)
+    tt_ = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt)
+    for name, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        Xt = tt_(X, dt)
+        out[f"proj_static_{name}"] = loss.project_points(Xt, tt_(clip.R, dt), tt_(clip.t, dt), tt_(Kc, dt)).numpy()
+        out[f"proj_perframe_{name}"] = loss.project_points(Xt, tt_(Rt, dt), tt_(tt, dt), tt_(Kt, dt)).numpy()
+        out[f"proj_perframeR_statict_{name}"] = loss.project_points(Xt, tt_(Rt, dt), tt_(clip.t, dt), tt_(Kc, dt)).numpy()
+        out[f"proj_single_{name}"] = loss.project_points(Xt[0], tt_(clip.R, dt), tt_(clip.t, dt), tt_(Kc, dt)).numpy()
+        out[f"loss_static_{name}"] = loss.reprojection_loss(Xt, tt_(clip.R, dt), tt_(clip.t, dt), tt_(Kc, dt), tt_(x2d, dt), tt_(conf, dt)).item()
+        out[f"loss_perframe_w_{name}"] = loss.reprojection_loss(Xt, tt_(Rt, dt), tt_(tt, dt), tt_(Kt, dt), tt_(x2d, dt), tt_(conf, dt), w=0.5).item()
+        # a point behind a camera exercises Z.clamp(min=1e-6) (loss.py:67)
+        Xb = Xt.clone()
+        Xb[0, 0] = torch.tensor([0.0, 0.0, -5.0], dtype=dt)
+        out[f"proj_clamped_{name}"] = loss.project_points(Xb, tt_(clip.R, dt), tt_(clip.t, dt), tt_(Kc, dt)).numpy()
+    d = torch.float64
+    out["camera_center"] = loss.camera_center_from_Rt(tt_(Rt, d), tt_(tt, d)).numpy()
+    out["camera_smooth"] = loss.camera_smooth_loss(tt_(Rt, d), tt_(tt, d), w=0.1).item()
+    out["baseline_reg"] = loss.baseline_reg_loss(tt_(Rt, d), tt_(tt, d), w=0.01).item()
+    out["bone_length"] = loss.bone_length_loss(tt_(X, d), w=0.1).item()
+    ref_len = np.linspace(0.2, 0.6, len(loss.BONES))
+    out["bone_length_ref"] = loss.bone_length_loss(tt_(X, d), ref_bone_len=tt_(ref_len, d), w=0.1).item()
+    out["ref_len"] = ref_len
+    out["pose_temporal"] = loss.pose_temporal_loss(tt_(X, d), w=0.1).item()
+    out["bones"] = np.array(loss.BONES)
+    # J=70 (MHR skeleton): indices are applied blindly
+    X70 = synth.make_clip("2b", T=6, J=70, seed=9).X
+    out["X70"] = X70
+    out["bone_length_70"] = loss.bone_length_loss(tt_(X70, d), w=0.1).item()
+    np.savez_compressed(OUT / "g3_g4_loss.npz", **out)
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    g1()
+    g2()
+    g3_g4()
+    for f in sorted(OUT.glob("*.npz")):
+        print(f.name, f.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()

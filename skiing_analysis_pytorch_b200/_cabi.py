@@ -1,0 +1,66 @@
+"""ctypes mirror of include/ska.h (structs, constants) - no compute here."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+ABI_VERSION = 1
+MAX_VIEWS = 16
+
+LAYOUT_VIEW_MAJOR = 0
+LAYOUT_FRAME_MAJOR = 1
+
+SOLVER_SECULAR = 0
+SOLVER_JACOBI64 = 1
+SOLVER_JACOBI32 = 2
+WEIGHT_SQRT = 4
+PINHOLE_REPROJ = 8
+
+SOLVERS = {"secular": SOLVER_SECULAR, "jacobi64": SOLVER_JACOBI64, "jacobi32": SOLVER_JACOBI32}
+
+CTRL_LAMBDA, CTRL_NU, CTRL_COST, CTRL_SUMCONF, CTRL_ACCEPTED, CTRL_ITER = range(6)
+CTRL_SIZE = 8
+HIST_SIZE = 8
+
+ERRORS = {-1: "SKA_EINVAL", -2: "SKA_EUNSUPPORTED", -3: "SKA_EALIGN", -4: "SKA_EWORKSPACE"}
+
+
+class SkaCamera(C.Structure):
+    _fields_ = [
+        ("K", C.c_double * 9),
+        ("R", C.c_double * 9),
+        ("t", C.c_double * 3),
+        ("dist", C.c_double * 14),
+    ]
+
+
+def make_cameras(K, R, t, dist=None):
+    """Pack V cameras into a ctypes SkaCamera array.
+
+    K (3,3)|(V,3,3); R (V,3,3); t (V,3); dist None | (n,) shared | list of per-view (n,)|None.
+    """
+    R = np.asarray(R, np.float64)
+    V = R.shape[0]
+    t = np.asarray(t, np.float64).reshape(V, 3)
+    K = np.asarray(K, np.float64)
+    K = np.broadcast_to(K, (V, 3, 3)) if K.ndim == 2 else K.reshape(V, 3, 3)
+    if dist is None or (not isinstance(dist, (list, tuple)) and np.ndim(dist) >= 1 and not isinstance(dist, list)):
+        dists = [dist] * V
+    else:
+        dists = list(dist)
+        if len(dists) != V:
+            raise ValueError(f"need {V} distortion vectors, got {len(dists)}")
+    cams = (SkaCamera * V)()
+    for v in range(V):
+        cams[v].K[:] = K[v].reshape(-1).tolist()
+        cams[v].R[:] = R[v].reshape(-1).tolist()
+        cams[v].t[:] = t[v].tolist()
+        d = np.zeros(14)
+        if dists[v] is not None:
+            dv = np.asarray(dists[v], np.float64).reshape(-1)
+            if dv.size not in (4, 5, 8, 12, 14):
+                raise ValueError(f"distortion vector must have 4, 5, 8, 12 or 14 entries, got {dv.size}")
+            d[: dv.size] = dv
+        cams[v].dist[:] = d.tolist()
+    return cams

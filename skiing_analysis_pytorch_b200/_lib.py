@@ -1,0 +1,72 @@
+"""ctypes loader for lib/libska.so.  There is NO fallback: if the CUDA library is missing or a
+call fails, the caller gets an exception (SkaError / RuntimeError), never a CPU path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from pathlib import Path
+
+from . import _cabi
+
+_LOCK = threading.Lock()
+_LIB = None
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libska.so"
+
+
+class SkaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        self.code = code
+        name = _cabi.ERRORS.get(code, f"cudaError {code}" if code > 0 else f"error {code}")
+        super().__init__(f"libska: {name}: {msg}")
+
+
+_vp = C.c_void_p
+_SIGS = {
+    "ska_abi_version": (C.c_int, []),
+    "ska_last_error": (C.c_char_p, []),
+    "ska_build_arch": (C.c_char_p, []),
+    "ska_triangulate_reproject_f32": (
+        C.c_int,
+        [C.POINTER(_cabi.SkaCamera), C.c_int32, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint32,
+         _vp, _vp, _vp, _vp, _vp],
+    ),
+}
+
+
+def exported_symbols():
+    """Every symbol include/ska.h declares (used by the CPU-side ABI test)."""
+    return sorted(_SIGS)
+
+
+def load():
+    """Load libska.so once; build it first if the sources are newer (needs nvcc).  Raises if it
+    cannot be had - the product has no CPU path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    with _LOCK:
+        if _LIB is not None:
+            return _LIB
+        if not LIB_PATH.exists() or os.environ.get("SKA_REBUILD") == "1":
+            from . import build as _build
+
+            _build.build(force=os.environ.get("SKA_REBUILD") == "1")
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing and could not be built; there is no CPU fallback")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)  # AttributeError here = header / library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        if lib.ska_abi_version() != _cabi.ABI_VERSION:
+            raise RuntimeError(f"libska ABI {lib.ska_abi_version()} != expected {_cabi.ABI_VERSION}")
+        _LIB = lib
+    return _LIB
+
+
+def check(code: int):
+    if code != 0:
+        msg = load().ska_last_error()
+        raise SkaError(code, msg.decode() if msg else "")

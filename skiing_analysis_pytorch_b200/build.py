@@ -1,0 +1,84 @@
+"""Build libska.so (hand-written sm_100a CUDA behind the C ABI of include/ska.h) in-tree.
+
+nvcc cross-compiles without a GPU; the resulting lib/libska.so travels with the repo snapshot to
+the GPU box (it is git-ignored, not gpurun-ignored).  No torch linkage: the boundary is plain C,
+loaded with ctypes (see _lib.py).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+OBJ = CSRC / "_obj"
+LIB = PKG / "lib" / "libska.so"
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: libska.so cannot be built (no CPU fallback exists)")
+
+
+def sources():
+    return sorted(CSRC.glob("*.cu"))
+
+
+def _deps_mtime() -> float:
+    files = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "ska.h"]
+    return max(f.stat().st_mtime for f in files)
+
+
+def needs_build() -> bool:
+    return not LIB.exists() or LIB.stat().st_mtime < _deps_mtime()
+
+
+def build(force: bool = False, verbose: bool = False, extra_flags=()) -> Path:
+    if not force and not needs_build():
+        return LIB
+    nvcc = _nvcc()
+    OBJ.mkdir(parents=True, exist_ok=True)
+    LIB.parent.mkdir(parents=True, exist_ok=True)
+    dep_m = _deps_mtime()
+    hdr_m = max(
+        f.stat().st_mtime for f in list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "ska.h"]
+    )
+
+    def compile_one(src: Path) -> Path:
+        obj = OBJ / (src.stem + ".o")
+        if not force and obj.exists() and obj.stat().st_mtime >= max(src.stat().st_mtime, hdr_m):
+            return obj
+        cmd = [nvcc, *ARCH_FLAGS, *NVCC_FLAGS, *extra_flags, "-I", str(ROOT / "include"), "-c", str(src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose:
+            sys.stderr.write(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src.name}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    tmp = LIB.with_suffix(".so.tmp")
+    cmd = [nvcc, *ARCH_FLAGS, "-shared", "-o", str(tmp), *map(str, objs), "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
+    del dep_m
+    return LIB
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

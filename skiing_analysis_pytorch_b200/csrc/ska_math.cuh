@@ -1,0 +1,260 @@
+// ska_math.cuh - per-point arithmetic shared by the sm_100a kernels and the host-emulation test
+// harness (tests/hostemu).  Everything here is __host__ __device__ so the exact instruction
+// sequence the GPU runs (fmaf chains, hi/lo splits, secular iteration) can be exercised on the
+// CPU-only authoring box; the product only ever calls it from device code.
+//
+// Math restated from SURVEY.md appendix A:
+//   A.1 weighted DLT rows w(u P2 - P0), w(v P2 - P1)   (vggt/triangulate.py:23-31, cv2.triangulatePoints)
+//   A.2 rational/tangential/thin-prism distortion      (cv2.projectPoints; triangulation/reproject.py:77-78)
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SKA_HD __host__ __device__ __forceinline__
+#define SKA_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define SKA_HD inline
+#define SKA_HD_NOINLINE inline
+#endif
+
+namespace ska {
+
+// ---------------------------------------------------------------------------------------------
+// Kernel-side camera, fp32, prepared on the host in fp64 (prep_camera in ska_capi.cu).
+// All quantities are expressed in CENTRED coordinates Y = X - c: P' = K [R | R c + t].
+// Centring is numerical conditioning only; the eigenproblem solved is the reference's
+// (un-centred, ||X~|| = 1) one - see secular_solve below.
+struct CamDev {
+  float Ph[12];   // P' hi part, row-major 3x4, scaled so that P'[2] = [r3 | t'_z] (K[2][2] == 1)
+  float Pl[12];   // P' lo part (P' - (double)Ph)
+  float Rxy[6];   // rows 0 and 1 of R           (normalised coordinates for the distortion model)
+  float txy[2];   // (R c + t).x, .y
+  float fx, fy, skew;
+  float dk[3];    // k1-k4, k2-k5, k3-k6  (numerator minus denominator of the rational term)
+  float kd[3];    // k4, k5, k6
+  float p1, p2;
+  float s[4];     // s1..s4
+};
+
+// fp64 camera for the Jacobi fallback / exact mode: un-centred P = K [R|t], plus cv2 intrinsics.
+struct CamDev64 {
+  double P[12];
+  double R[9];
+  double t[3];
+  double fx, fy, cx, cy;
+  double dist[12];
+};
+
+SKA_HD float rcp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(1.0f, x);
+#else
+  return 1.0f / x;
+#endif
+}
+SKA_HD float sqrt_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
+
+// One DLT row pair for one view: a = u*P2 - P0, b = v*P2 - P1 (4 entries each).  The products are
+// fused (single rounding of the exact u*P2h - P0h, so the cancellation between u*r3 and cx*r3
+// costs nothing) and the lo parts of P' restore the bits fp32 P' lost.
+template <bool USE_LO>
+SKA_HD void dlt_rows(const CamDev& c, float u, float v, float a[4], float b[4]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    float ah = fmaf(u, c.Ph[8 + m], -c.Ph[m]);
+    float bh = fmaf(v, c.Ph[8 + m], -c.Ph[4 + m]);
+    if (USE_LO) {
+      ah += fmaf(u, c.Pl[8 + m], -c.Pl[m]);
+      bh += fmaf(v, c.Pl[8 + m], -c.Pl[4 + m]);
+    }
+    a[m] = ah;
+    b[m] = bh;
+  }
+}
+
+// Symmetric 4x4 accumulator, upper triangle: 00 01 02 03 11 12 13 22 23 33.
+struct Sym4 {
+  float m00, m01, m02, m03, m11, m12, m13, m22, m23, m33;
+};
+SKA_HD void sym4_zero(Sym4& M) { M.m00 = M.m01 = M.m02 = M.m03 = M.m11 = M.m12 = M.m13 = M.m22 = M.m23 = M.m33 = 0.f; }
+SKA_HD void sym4_rank1(Sym4& M, const float r[4], float w2) {
+  const float s0 = r[0] * w2, s1 = r[1] * w2, s2 = r[2] * w2, s3 = r[3] * w2;
+  M.m00 = fmaf(s0, r[0], M.m00);
+  M.m01 = fmaf(s0, r[1], M.m01);
+  M.m02 = fmaf(s0, r[2], M.m02);
+  M.m03 = fmaf(s0, r[3], M.m03);
+  M.m11 = fmaf(s1, r[1], M.m11);
+  M.m12 = fmaf(s1, r[2], M.m12);
+  M.m13 = fmaf(s1, r[3], M.m13);
+  M.m22 = fmaf(s2, r[2], M.m22);
+  M.m23 = fmaf(s2, r[3], M.m23);
+  M.m33 = fmaf(s3, r[3], M.m33);
+}
+SKA_HD void sym4_rank1_unit(Sym4& M, const float r[4]) {
+  M.m00 = fmaf(r[0], r[0], M.m00);
+  M.m01 = fmaf(r[0], r[1], M.m01);
+  M.m02 = fmaf(r[0], r[2], M.m02);
+  M.m03 = fmaf(r[0], r[3], M.m03);
+  M.m11 = fmaf(r[1], r[1], M.m11);
+  M.m12 = fmaf(r[1], r[2], M.m12);
+  M.m13 = fmaf(r[1], r[3], M.m13);
+  M.m22 = fmaf(r[2], r[2], M.m22);
+  M.m23 = fmaf(r[2], r[3], M.m23);
+  M.m33 = fmaf(r[3], r[3], M.m33);
+}
+
+// LDL^T of a symmetric 3x3 (a00 a01 a02 a11 a12 a22), reciprocal pivots kept.
+struct Ldl3 {
+  float l10, l20, l21, r0, r1, r2;
+  bool pos;  // all pivots > 0  <=>  matrix positive definite
+};
+SKA_HD Ldl3 ldl3(float a00, float a01, float a02, float a11, float a12, float a22) {
+  Ldl3 f;
+  f.r0 = rcp_fast(a00);
+  f.l10 = a01 * f.r0;
+  f.l20 = a02 * f.r0;
+  const float d1 = fmaf(-f.l10, a01, a11);
+  f.r1 = rcp_fast(d1);
+  const float t21 = fmaf(-f.l20, a01, a12);
+  f.l21 = t21 * f.r1;
+  const float d2 = fmaf(-f.l21, t21, fmaf(-f.l20, a02, a22));
+  f.r2 = rcp_fast(d2);
+  f.pos = (a00 > 0.f) & (d1 > 0.f) & (d2 > 0.f);
+  return f;
+}
+SKA_HD void ldl3_solve(const Ldl3& f, float b0, float b1, float b2, float& x0, float& x1, float& x2) {
+  const float y1 = fmaf(-f.l10, b0, b1);
+  const float y2 = fmaf(-f.l21, y1, fmaf(-f.l20, b0, b2));
+  x2 = y2 * f.r2;
+  x1 = fmaf(-f.l21, x2, y1 * f.r1);
+  x0 = fmaf(-f.l20, x2, fmaf(-f.l10, x1, b0 * f.r0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Smallest eigenpair of the un-centred DLT normal matrix M = A^T A, computed in centred
+// coordinates.  With X~ = [c + Y; 1] the eigen-equations (M - lam I) X~ = 0 read
+//     (M'33 - lam I) Y = -m'34 + lam c            (rows 1..3, M' = T^T M T, T = [I c; 0 1])
+//     lam = |A' [Y;1]|^2 / (|c + Y|^2 + 1)        (Rayleigh quotient, evaluated from the rows so
+//                                                  the 1e8 -> 1 cancellation never happens in M)
+// Fixed-point iteration on lam starting from lam = 0 (the inhomogeneous least-squares point);
+// quadratically convergent because the Rayleigh quotient is stationary at eigenvectors.
+// Certificate: if LDL^T of (M'33 - lam I) has all pivots > 0 then lam < lambda_min(M33) and by
+// Cauchy interlacing M has exactly ONE eigenvalue below lambda_min(M33) - the converged pair is
+// the smallest one, i.e. the vector np.linalg.svd / cv2.triangulatePoints return.
+// Callers fall back to the fp64 Jacobi solver when `ok` comes back false.
+struct SecularState {
+  float y0, y1, y2;  // centred solution
+  float lam;
+  bool ok;
+};
+
+constexpr int kSecularMaxIter = 4;
+constexpr float kSecularTol2 = 1e-8f;  // (relative step)^2 below which the NEXT iterate is exact to fp32
+
+SKA_HD bool secular_step(const Sym4& M, const float cx, const float cy, const float cz, float lam, SecularState& s) {
+  // one update for a given Rayleigh quotient; returns the converged flag
+  const Ldl3 f = ldl3(M.m00 - lam, M.m01, M.m02, M.m11 - lam, M.m12, M.m22 - lam);
+  float n0, n1, n2;
+  ldl3_solve(f, fmaf(lam, cx, -M.m03), fmaf(lam, cy, -M.m13), fmaf(lam, cz, -M.m23), n0, n1, n2);
+  const float d0 = n0 - s.y0, d1 = n1 - s.y1, d2 = n2 - s.y2;
+  const float step2 = fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
+  const float X0 = n0 + cx, X1 = n1 + cy, X2 = n2 + cz;
+  const float nrm2 = fmaf(X0, X0, fmaf(X1, X1, fmaf(X2, X2, 1.0f)));
+  s.y0 = n0;
+  s.y1 = n1;
+  s.y2 = n2;
+  s.lam = lam;
+  s.ok = f.pos;
+  return f.pos && (step2 <= kSecularTol2 * nrm2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cyclic Jacobi on a symmetric 4x4, register resident; returns the eigenvector of the smallest
+// eigenvalue.  T = float (north-star design point) or double (exact mode / fallback).
+template <typename T>
+SKA_HD void jacobi4_smallest(T a[4][4], T vec[4], int sweeps) {
+  T v[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? T(1) : T(0);
+  for (int sw = 0; sw < sweeps; ++sw) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+#pragma unroll
+      for (int q = p + 1; q < 4; ++q) {
+        const T apq = a[p][q];
+        if (apq != T(0)) {
+          const T theta = (a[q][q] - a[p][p]) / (T(2) * apq);
+          const T tt = (theta >= T(0) ? T(1) : T(-1)) / (fabs(theta) + sqrt(theta * theta + T(1)));
+          const T c = T(1) / sqrt(tt * tt + T(1));
+          const T s = tt * c;
+          if (isfinite(c) && isfinite(s)) {
+            a[p][p] -= tt * apq;
+            a[q][q] += tt * apq;
+            a[p][q] = a[q][p] = T(0);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              if (r != p && r != q) {
+                const T arp = a[r][p], arq = a[r][q];
+                a[r][p] = a[p][r] = c * arp - s * arq;
+                a[r][q] = a[q][r] = s * arp + c * arq;
+              }
+              const T vrp = v[r][p], vrq = v[r][q];
+              v[r][p] = c * vrp - s * vrq;
+              v[r][q] = s * vrp + c * vrq;
+            }
+          }
+        }
+      }
+    }
+  }
+  int best = 0;
+  T lo = a[0][0];
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (a[i][i] < lo) {
+      lo = a[i][i];
+      best = i;
+    }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    T x = v[i][0];
+    if (best == 1) x = v[i][1];
+    if (best == 2) x = v[i][2];
+    if (best == 3) x = v[i][3];
+    vec[i] = x;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cv2.projectPoints distortion increment on normalised coordinates: returns (x'' - x, y'' - y).
+// rad - 1 is formed as ((k1-k4) r2 + (k2-k5) r4 + (k3-k6) r6) / den so no bits are lost to 1 + ...
+SKA_HD void distort_delta(const CamDev& c, float x, float y, float& dx, float& dy) {
+  const float xx = x * x, yy = y * y, xy = x * y;
+  const float r2 = xx + yy;
+  const float num = r2 * fmaf(r2, fmaf(r2, c.dk[2], c.dk[1]), c.dk[0]);
+  const float den = fmaf(r2, fmaf(r2, fmaf(r2, c.kd[2], c.kd[1]), c.kd[0]), 1.0f);
+  const float radm1 = num * rcp_fast(den);
+  const float r4 = r2 * r2;
+  dx = fmaf(x, radm1, fmaf(2.0f * c.p1, xy, fmaf(c.p2, fmaf(2.0f, xx, r2), fmaf(c.s[0], r2, c.s[1] * r4))));
+  dy = fmaf(y, radm1, fmaf(2.0f * c.p2, xy, fmaf(c.p1, fmaf(2.0f, yy, r2), fmaf(c.s[2], r2, c.s[3] * r4))));
+}
+
+SKA_HD void distort64(const double* d /*12*/, double x, double y, double& xd, double& yd) {
+  const double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+  const double rad = (1.0 + d[0] * r2 + d[1] * r4 + d[4] * r6) / (1.0 + d[5] * r2 + d[6] * r4 + d[7] * r6);
+  xd = x * rad + 2.0 * d[2] * x * y + d[3] * (r2 + 2.0 * x * x) + d[8] * r2 + d[9] * r4;
+  yd = y * rad + d[2] * (r2 + 2.0 * y * y) + 2.0 * d[3] * x * y + d[10] * r2 + d[11] * r4;
+}
+
+}  // namespace ska

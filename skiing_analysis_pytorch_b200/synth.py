@@ -1,0 +1,138 @@
+"""Deterministic synthetic rigs, skeleton clips and observations.
+
+There is no dataset in the reference (and no network): every test and benchmark runs on these.
+Conventions: world->camera ``x_c = R x_w + t``; ``R_y(theta) = [[c,0,s],[0,1,0],[-s,0,c]]``
+(two_view.py:209-211); look-at placement ``C_v = centre - d * R_v^T e_z``, ``t_v = -R_v C_v``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+# camera_calibration/calibration_parameters.npz (camera_matrix / dist_coeffs), also hard-coded at
+# triangulation/main.py:51-63 and triangulation/triangulate.py:39-56 of the reference.
+K_CALIB = np.array(
+    [
+        [1116.9289548941917, 0.0, 955.77175993563799],
+        [0.0, 1117.3341496962166, 538.91061167202145],
+        [0.0, 0.0, 1.0],
+    ]
+)
+DIST_CALIB = np.array(
+    [
+        -1.1940477842823853,
+        -15.440461757486913,
+        0.00013163161053023783,
+        0.00019082529328353381,
+        98.843073622415901,
+        -1.3588290520381034,
+        -14.555841222727574,
+        96.219667412855202,
+        0.0,
+        0.0,
+        0.0,
+        0.0,
+        0.0,
+        0.0,
+    ]
+)
+IMAGE_SIZE = (1920, 1080)
+CENTRE = np.array([0.0, 0.0, 10.0])
+
+
+def rot_y(theta: float) -> np.ndarray:
+    c, s = np.cos(theta), np.sin(theta)
+    return np.array([[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]])
+
+
+def look_at_rig(thetas, centre=CENTRE, d: float = 10.0):
+    """Cameras on a circle of radius d around ``centre``, all looking at it. -> R (V,3,3), t (V,3)."""
+    Rs, ts = [], []
+    for th in thetas:
+        R = rot_y(float(th))
+        C = np.asarray(centre, float) - d * R.T @ np.array([0.0, 0.0, 1.0])
+        Rs.append(R)
+        ts.append(-R @ C)
+    return np.stack(Rs), np.stack(ts)
+
+
+def rig(name: str):
+    """'2a' = the reference's FIXED pose (cam1 yaw 180 deg at z=20 m, two_view.py:209-221; near
+    degenerate, triangulation parity only); '2b' = front/side (cam1 yaw +90 deg); '8' = 8-view ring."""
+    if name == "2a":
+        return look_at_rig([0.0, np.pi])
+    if name == "2b":
+        return look_at_rig([0.0, np.pi / 2])
+    if name == "8":
+        return look_at_rig([2 * np.pi * v / 8 for v in range(8)])
+    if name.isdigit():
+        n = int(name)
+        return look_at_rig([2 * np.pi * v / n for v in range(n)])
+    raise ValueError(f"unknown rig {name!r}")
+
+
+@dataclass
+class Clip:
+    X: np.ndarray  # (T,J,3) f64 ground truth
+    R: np.ndarray  # (V,3,3)
+    t: np.ndarray  # (V,3)
+    K: np.ndarray  # (V,3,3)
+    x_vm: np.ndarray  # (V,T,J,2) f32 observations, view-major
+    conf_vm: np.ndarray  # (V,T,J) f32 confidences in U(0.2,1)
+
+    @property
+    def x_fm(self) -> np.ndarray:  # (T,V,J,2) frame-major (loss.py layout)
+        return np.ascontiguousarray(self.x_vm.transpose(1, 0, 2, 3))
+
+    @property
+    def conf_fm(self) -> np.ndarray:
+        return np.ascontiguousarray(self.conf_vm.transpose(1, 0, 2))
+
+
+def skeleton_clip(T: int, J: int, rng) -> np.ndarray:
+    """template ~ N(0,0.4^2) fixed over time, Lissajous root motion, 2 cm per-joint jitter."""
+    template = rng.normal(0.0, 0.4, (J, 3))
+    tt = np.arange(T, dtype=float)
+    root = CENTRE + np.stack(
+        [1.5 * np.sin(2 * np.pi * tt / 300), 0.3 * np.sin(2 * np.pi * tt / 90), 1.0 * np.cos(2 * np.pi * tt / 240)], -1
+    )
+    return root[:, None, :] + template[None] + rng.normal(0.0, 0.02, (T, J, 3))
+
+
+def pinhole(X, R, t, K):
+    Xc = X @ R.T + t
+    xy = Xc[..., :2] / Xc[..., 2:3]
+    return np.stack([K[0, 0] * xy[..., 0] + K[0, 1] * xy[..., 1] + K[0, 2], K[1, 1] * xy[..., 1] + K[1, 2]], -1)
+
+
+def make_clip(rig_name: str, T: int, J: int, seed: int = 0, noise_px: float = 1.0, K=None) -> Clip:
+    rng = np.random.default_rng(seed)
+    R, t = rig(rig_name)
+    V = len(R)
+    K = np.broadcast_to(K_CALIB if K is None else np.asarray(K, float), (V, 3, 3)).copy()
+    X = skeleton_clip(T, J, rng)
+    x = np.stack([pinhole(X, R[v], t[v], K[v]) for v in range(V)])
+    x = (x + rng.normal(0.0, noise_px, x.shape)).astype(np.float32)
+    conf = rng.uniform(0.2, 1.0, (V, T, J)).astype(np.float32)
+    return Clip(X=X, R=R, t=t, K=K, x_vm=x, conf_vm=conf)
+
+
+def so3_exp(w):
+    w = np.asarray(w, float)
+    th = np.linalg.norm(w)
+    W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-8:
+        return np.eye(3) + W
+    return np.eye(3) + np.sin(th) / th * W + (1 - np.cos(th)) / th**2 * (W @ W)
+
+
+def perturb_cameras(R, t, seed: int = 1, rot_sigma: float = 0.01, trans_sigma: float = 0.05):
+    """BA initialisation: left-multiply exp(N(0,rot_sigma^2)) and add N(0,trans_sigma^2) to every
+    camera except camera 0 (the gauge)."""
+    rng = np.random.default_rng(seed)
+    R2, t2 = R.copy(), t.copy()
+    for c in range(1, len(R)):
+        R2[c] = so3_exp(rng.normal(0.0, rot_sigma, 3)) @ R[c]
+        t2[c] = t[c] + rng.normal(0.0, trans_sigma, 3)
+    return R2, t2

@@ -1,0 +1,79 @@
+// Host emulation of the per-point device arithmetic (TEST INFRASTRUCTURE, CPU-only box).
+// Compiles ska_tri_point.cuh with g++ so the fp32 secular solver / differential reprojection can
+// be checked against the fp64 oracle without a GPU.  Never linked into libska.so, never imported
+// by the package: the product path is CUDA only.
+#include <stdint.h>
+#include <vector>
+
+#include "../../skiing_analysis_pytorch_b200/csrc/ska_prep.h"
+#include "../../skiing_analysis_pytorch_b200/csrc/ska_tri_point.cuh"
+
+using namespace ska;
+
+template <int V>
+static int run(const SkaCamera* cams, const double* centre, const float* kpts, const float* conf, int64_t N,
+               uint32_t flags, float* X, float* err, uint8_t* status) {
+  double c[3];
+  if (centre) {
+    for (int k = 0; k < 3; ++k) c[k] = (double)(float)centre[k];
+  } else {
+    default_centre(cams, V, c);
+  }
+  CamDev cam[V];
+  double P64[V][12];
+  bool dist = false;
+  for (int v = 0; v < V; ++v) {
+    bool d;
+    const char* why = "";
+    int rc = prep_camera(cams[v], c, (flags & SKA_PINHOLE_REPROJ) != 0, cam[v], P64[v], d, &why);
+    if (rc) return rc;
+    dist = dist || d;
+  }
+  const uint32_t solver = flags & SKA_SOLVER_MASK;
+  for (int64_t i = 0; i < N; ++i) {
+    float u[V], vv[V], w2[V], du[V], dv[V], Xp[3];
+    for (int v = 0; v < V; ++v) {
+      u[v] = kpts[(v * N + i) * 2];
+      vv[v] = kpts[(v * N + i) * 2 + 1];
+      const float cf = conf ? conf[v * N + i] : 1.0f;
+      w2[v] = (flags & SKA_WEIGHT_SQRT) ? cf : cf * cf;
+    }
+    uint8_t st;
+    const float cx = (float)c[0], cy = (float)c[1], cz = (float)c[2];
+    const float(*U)[V] = (const float(*)[V])u;
+    const float(*VV)[V] = (const float(*)[V])vv;
+    const float(*W)[V] = (const float(*)[V])w2;
+    float(*XO)[3] = (float(*)[3])Xp;
+    float(*DU)[V] = (float(*)[V])du;
+    float(*DV)[V] = (float(*)[V])dv;
+#define GO(CONF, DIST)                                                                                         \
+  do {                                                                                                         \
+    if (solver == kSolverSecular) tri_points<V, 1, CONF, DIST, kSolverSecular>(cam, P64, cx, cy, cz, U, VV, W, XO, DU, DV, &st); \
+    else if (solver == kSolverJacobi64) tri_points<V, 1, CONF, DIST, kSolverJacobi64>(cam, P64, cx, cy, cz, U, VV, W, XO, DU, DV, &st); \
+    else tri_points<V, 1, CONF, DIST, kSolverJacobi32>(cam, P64, cx, cy, cz, U, VV, W, XO, DU, DV, &st);      \
+  } while (0)
+    if (conf) {
+      if (dist) GO(true, 1); else GO(true, 0);
+    } else {
+      if (dist) GO(false, 1); else GO(false, 0);
+    }
+#undef GO
+    for (int k = 0; k < 3; ++k) X[3 * i + k] = Xp[k];
+    if (err)
+      for (int v = 0; v < V; ++v) err[v * N + i] = sqrtf(du[v] * du[v] + dv[v] * dv[v]);
+    if (status) status[i] = st;
+  }
+  return 0;
+}
+
+extern "C" int hostemu_triangulate(const SkaCamera* cams, int32_t V, const double* centre, const float* kpts,
+                                   const float* conf, int64_t N, uint32_t flags, float* X, float* err,
+                                   uint8_t* status) {
+  switch (V) {
+    case 2: return run<2>(cams, centre, kpts, conf, N, flags, X, err, status);
+    case 3: return run<3>(cams, centre, kpts, conf, N, flags, X, err, status);
+    case 4: return run<4>(cams, centre, kpts, conf, N, flags, X, err, status);
+    case 8: return run<8>(cams, centre, kpts, conf, N, flags, X, err, status);
+    default: return SKA_EUNSUPPORTED;
+  }
+}
