@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the multi-view reconstruction hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the fused triangulate+reproject kernel over one clip of synthetic
+observations (BASELINE config 2: 2-view front/side rig, 1M frames x 17 COCO joints, K / distortion
+from camera_calibration/calibration_parameters.npz).  With N>1 (torchrun, one rank per GPU) every
+rank processes its own 1M-frame clip - frames shard with no data-path collective - so scaling is
+"weak" and `value` is the whole-job joints/s = N*T*J / max-over-ranks time.
+
+Prints ONE JSON line (see the task contract): value = kernel throughput with inputs resident in
+HBM, e2e = the same metric through the host-buffer API (pinned H2D + kernel + D2H every step),
+roofline = algorithmic bytes / CUDA-event time against the measured HBM peak, cpu_baseline = the
+reference's per-frame CPU path (oracle port: cv2.triangulatePoints + cv2.projectPoints loop) timed
+on this box's host cores on a bounded sample.  `--impl reference` times that CPU path alone with
+all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "triangulated_joints_per_sec"
+UNIT = "joints/s"
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1_000_000)
+    ap.add_argument("--joints", type=int, default=17)
+    ap.add_argument("--rig", default="2b")
+    ap.add_argument("--conf", action="store_true", help="confidence-weighted DLT (default: unit weights, the reference's behaviour)")
+    ap.add_argument("--pinhole", action="store_true", help="score without the distortion model")
+    ap.add_argument("--solver", default="secular")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ba", action="store_true")
+    ap.add_argument("--cpu-sample-frames", type=int, default=20000)
+    return ap.parse_args()
+
+
+def workload_config(a, V):
+    return {
+        "workload": f"config2: {V}-view rig '{a.rig}' DLT triangulation + fused reprojection scoring, "
+        f"T={a.frames} frames x J={a.joints} joints per GPU",
+        "frames_per_gpu": a.frames,
+        "joints": a.joints,
+        "views": V,
+        "confidence_weighted": bool(a.conf),
+        "distortion_scoring": (not a.pinhole),
+        "layout": "view-major (V,T,J,2)",
+        "solver": a.solver,
+        "parallelism": f"frame-sharded x{a.gpus}, no data-path collective",
+        "l2_policy": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
+    }
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    kL, kR, K, R, t, dist = args
+    from oracle import reference_path as RP
+
+    n = len(kL)
+    RP.clip_two_view(kL, kR, K, [R] * n, [t] * n, dist=dist)
+    return n
+
+
+def cpu_reference_rate(clip, dist, frames, procs):
+    """joints/s of the reference's per-frame CPU path (oracle port) on `frames` frames with `procs`
+    worker processes (1 = how the reference itself runs: a single Python loop)."""
+    kL, kR = clip.x_vm[0][:frames], clip.x_vm[1][:frames]
+    K, R, t = clip.K[0], clip.R[1], clip.t[1]
+    J = kL.shape[1]
+    if procs <= 1:
+        t0 = time.perf_counter()
+        _cpu_worker((kL, kR, K, R, t, dist))
+        dt = time.perf_counter() - t0
+    else:
+        import multiprocessing as mp
+
+        chunks = np.array_split(np.arange(frames), procs)
+        jobs = [(kL[c], kR[c], K, R, t, dist) for c in chunks if len(c)]
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_cpu_worker, [(kL[:8], kR[:8], K, R, t, dist)] * procs)  # spin the workers up
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, jobs)
+            dt = time.perf_counter() - t0
+    return frames * J / dt, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from skiing_analysis_pytorch_b200 import synth
+
+    if a.rig not in ("2a", "2b", "2"):
+        print(json.dumps({"impl": "reference", "unavailable": "the reference's CPU path is two-view only (triangulate.py:65-67)"}))
+        return 0
+    cores = os.cpu_count() or 1
+    per_step = max(cores * 500, min(a.cpu_sample_frames, 4000 * cores))
+    clip = synth.make_clip(a.rig, per_step, a.joints, seed=0)
+    dist = None if a.pinhole else synth.DIST_CALIB
+    for _ in range(a.warmup):
+        cpu_reference_rate(clip, dist, min(per_step, cores * 64), cores)
+    times = []
+    for _ in range(a.steps):
+        _, dt = cpu_reference_rate(clip, dist, per_step, cores)
+        times.append(dt)
+    total = float(np.sum(times))
+    value = a.steps * per_step * a.joints / total
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": a.gpus,
+        "steps": a.steps,
+        "warmup": a.warmup,
+        "ms_per_step": 1e3 * total / a.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(a, 2),
+        "cpu_baseline": {
+            "value": value,
+            "unit": UNIT,
+            "cores": cores,
+            "kind": "port",
+            "sample": f"{per_step} frames x {a.joints} joints per step, per-frame cv2.triangulatePoints + cv2.projectPoints "
+            f"loop (oracle/reference_path.py) split over {cores} processes",
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    REASONS = {
+        0x8: "hw_slowdown",
+        0x40: "hw_thermal_slowdown",
+        0x20: "sw_thermal_slowdown",
+        0x4: "sw_power_cap",
+        0x80: "hw_power_brake_slowdown",
+    }
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
+
+    def __enter__(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        except Exception:
+            self._nvml = None
+        return self
+
+    def _run(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for b, name in self.REASONS.items():
+                    if bits & b:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {
+            "sm_mhz": float(np.median(self.samples)),
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(key: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(key)
+        except Exception:
+            return None
+    return None
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from skiing_analysis_pytorch_b200 import api, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    T, J = a.frames, a.joints
+    clip = synth.make_clip(a.rig, T, J, seed=rank)
+    V = len(clip.R)
+    dist_coeffs = None if a.pinhole else synth.DIST_CALIB
+    # host side: pinned buffers (the e2e arm copies from / to these every step)
+    h_k = torch.from_numpy(clip.x_vm).pin_memory()
+    h_c = torch.from_numpy(clip.conf_vm).pin_memory() if a.conf else None
+    d_k = h_k.to(dev, non_blocking=True)
+    d_c = h_c.to(dev, non_blocking=True) if a.conf else None
+    outs = {
+        "X": torch.empty((T, J, 3), dtype=torch.float32, device=dev),
+        "err": torch.empty((V, T, J), dtype=torch.float32, device=dev),
+    }
+    kw = dict(K=clip.K, R=clip.R, t=clip.t, dist=dist_coeffs, solver=a.solver, want=("X", "err"))
+
+    def step():
+        api.triangulate_reproject(d_k, conf=d_c, out=outs, **kw)
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(a.steps):
+            step()
+        ev1.record()
+        barrier()
+        kernel_ms = ev0.elapsed_time(ev1)
+
+        # ---- end to end through the host-buffer API: pinned H2D + kernel + D2H, every step
+        h_X = torch.empty((T, J, 3), dtype=torch.float32).pin_memory()
+        h_err = torch.empty((V, T, J), dtype=torch.float32).pin_memory()
+        host_out = {"X": h_X, "err": h_err}
+        e2e_steps = max(3, min(a.steps, 10))
+        for _ in range(2):
+            api.triangulate_reproject_host(h_k, conf=h_c, out=host_out, **kw)
+        barrier()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        for _ in range(e2e_steps):
+            api.triangulate_reproject_host(h_k, conf=h_c, out=host_out, **kw)
+        ev3.record()
+        barrier()
+        e2e_ms = ev2.elapsed_time(ev3)
+
+    t_k = torch.tensor([kernel_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_k, op=dist.ReduceOp.MAX)
+    kernel_ms, e2e_ms = (float(x) for x in t_k.cpu())
+
+    pts = T * J
+    value = n_gpus * pts * a.steps / (kernel_ms * 1e-3)
+    e2e_value = n_gpus * pts * e2e_steps / (e2e_ms * 1e-3)
+    bytes_per_pt = 8 * V + (4 * V if a.conf else 0) + 12 + 4 * V
+    peak, peak_src = hbm_peak()
+    achieved = bytes_per_pt * pts / (kernel_ms * 1e-3 / a.steps) / 1e9
+    h2d = h_k.numel() * 4 + (h_c.numel() * 4 if a.conf else 0)
+    d2h = h_X.numel() * 4 + h_err.numel() * 4
+
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": n_gpus,
+        "steps": a.steps,
+        "warmup": max(a.warmup, 3),
+        "ms_per_step": kernel_ms / a.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(a, V),
+        "clocks": clocks.summary(),
+        "e2e": {
+            "value": e2e_value,
+            "unit": UNIT,
+            "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h,
+            "steps": e2e_steps,
+            "ms_per_step": e2e_ms / e2e_steps,
+        },
+        "gpu_launches": a.steps,
+        "roofline": {
+            "bound": "hbm",
+            "kernel": "ska::tri_kernel",
+            "achieved": achieved,
+            "peak": peak,
+            "peak_source": peak_src,
+            "unit": "GB/s",
+            "frac": achieved / peak,
+            "bytes_per_joint": bytes_per_pt,
+            "traffic": recorded_traffic("tri_kernel_config2"),
+        },
+    }
+
+    if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline and V == 2:
+        frames = min(T, a.cpu_sample_frames)
+        rate, dt = cpu_reference_rate(clip, dist_coeffs, frames, 1)
+        line["cpu_baseline"] = {
+            "value": rate,
+            "unit": UNIT,
+            "cores": 1,
+            "kind": "port",
+            "seconds": dt,
+            "sample": f"first {frames} frames x {J} joints of the same clip, single-process per-frame "
+            "cv2.triangulatePoints + cv2.projectPoints loop (oracle/reference_path.py), as the reference runs it",
+        }
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    return run_ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -45,12 +45,21 @@ def make_cameras(K, R, t, dist=None):
     t = np.asarray(t, np.float64).reshape(V, 3)
     K = np.asarray(K, np.float64)
     K = np.broadcast_to(K, (V, 3, 3)) if K.ndim == 2 else K.reshape(V, 3, 3)
-    if dist is None or (not isinstance(dist, (list, tuple)) and np.ndim(dist) >= 1 and not isinstance(dist, list)):
-        dists = [dist] * V
+    if dist is None:
+        dists = [None] * V
     else:
-        dists = list(dist)
-        if len(dists) != V:
-            raise ValueError(f"need {V} distortion vectors, got {len(dists)}")
+        try:
+            arr = np.asarray(dist, np.float64)
+        except (TypeError, ValueError):  # ragged / contains None: one entry per view
+            arr = None
+        if arr is not None and arr.ndim <= 1:
+            dists = [arr.reshape(-1)] * V
+        elif arr is not None and arr.ndim == 2 and arr.shape[0] != V and 1 in arr.shape:
+            dists = [arr.reshape(-1)] * V  # (1,n) / (n,1) as OpenCV returns it
+        else:
+            dists = list(dist)
+            if len(dists) != V:
+                raise ValueError(f"need {V} distortion vectors, got {len(dists)}")
     cams = (SkaCamera * V)()
     for v in range(V):
         cams[v].K[:] = K[v].reshape(-1).tolist()

@@ -121,6 +121,8 @@ def triangulate_reproject(
         carr = (C.c_double * 3)(*[float(x) for x in centre])
         cptr = C.cast(carr, C.c_void_p)
     lib = _lib.load()
+    if T == 0:  # empty clip: nothing to launch (an empty tensor has a NULL data pointer)
+        return TriangulationResult(X=X, err=err, proj=proj, status=status)
     with torch.cuda.device(dev):
         rc = lib.ska_triangulate_reproject_f32(
             cams, V, cptr, None, _ptr(kpts), _ptr(conf), T, J, lay, flags, _ptr(X), _ptr(err), _ptr(proj),
@@ -128,3 +130,91 @@ def triangulate_reproject(
         )
     _lib.check(rc)
     return TriangulationResult(X=X, err=err, proj=proj, status=status)
+
+
+_HOST_PIPE_CACHE: dict = {}
+
+
+def triangulate_reproject_host(
+    kpts: torch.Tensor,
+    K,
+    R,
+    t,
+    conf: Optional[torch.Tensor] = None,
+    dist=None,
+    *,
+    device=None,
+    chunk_frames: int = 65536,
+    n_streams: int = 3,
+    out: Optional[dict] = None,
+    **kw,
+) -> TriangulationResult:
+    """Host-buffer entry point (what a reference pipeline holding numpy clips calls): view-major
+    (V,T,J,2) float32 HOST tensors in, HOST tensors out.  The clip is cut into frame chunks that
+    flow H2D -> fused kernel -> D2H on `n_streams` CUDA streams so the two PCIe directions and the
+    kernel overlap.  Pinned inputs/outputs make the copies asynchronous; pageable ones still work.
+    Returns after the last chunk has landed on the host."""
+    if kpts.is_cuda:
+        raise ValueError("triangulate_reproject_host takes host tensors; use triangulate_reproject for CUDA tensors")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: this package has no CPU path")
+    if kw.get("layout", "VTJ2") != "VTJ2":
+        raise ValueError("the host pipeline takes view-major (V,T,J,2) clips")
+    kw.pop("layout", None)
+    want = tuple(kw.pop("want", ("X", "err")))
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    V, T, J, _ = kpts.shape
+    out = out or {}
+    hX = out.get("X")
+    if hX is None:
+        hX = torch.empty((T, J, 3), dtype=torch.float32).pin_memory()
+    hE = out.get("err") if "err" in want else None
+    if "err" in want and hE is None:
+        hE = torch.empty((V, T, J), dtype=torch.float32).pin_memory()
+    Tc = max(1, min(chunk_frames, T))
+    key = (dev.index, V, Tc, J, conf is not None, n_streams)
+    slots = _HOST_PIPE_CACHE.get(key)
+    if slots is None:
+        slots = []
+        for _ in range(n_streams):
+            slots.append(
+                {
+                    "stream": torch.cuda.Stream(dev),
+                    "k": torch.empty((V, Tc, J, 2), dtype=torch.float32, device=dev),
+                    "c": torch.empty((V, Tc, J), dtype=torch.float32, device=dev) if conf is not None else None,
+                    "X": torch.empty((Tc, J, 3), dtype=torch.float32, device=dev),
+                    "err": torch.empty((V, Tc, J), dtype=torch.float32, device=dev),
+                }
+            )
+        _HOST_PIPE_CACHE.clear()
+        _HOST_PIPE_CACHE[key] = slots
+    cur = torch.cuda.current_stream(dev)
+    start = torch.cuda.Event()
+    start.record(cur)
+    i = 0
+    for a in range(0, T, Tc):
+        b = min(a + Tc, T)
+        n = b - a
+        s = slots[i % n_streams]
+        i += 1
+        with torch.cuda.stream(s["stream"]):
+            s["stream"].wait_event(start)
+            dk = s["k"] if n == Tc else s["k"].flatten()[: V * n * J * 2].view(V, n, J, 2)
+            dc = None
+            if conf is not None:
+                dc = s["c"] if n == Tc else s["c"].flatten()[: V * n * J].view(V, n, J)
+            dX = s["X"][:n]
+            dE = s["err"] if n == Tc else s["err"].flatten()[: V * n * J].view(V, n, J)
+            for v in range(V):
+                dk[v].copy_(kpts[v, a:b], non_blocking=True)
+                if dc is not None:
+                    dc[v].copy_(conf[v, a:b], non_blocking=True)
+            triangulate_reproject(dk, K, R, t, conf=dc, dist=dist, want=want, out={"X": dX, "err": dE}, **kw)
+            hX[a:b].copy_(dX, non_blocking=True)
+            if hE is not None:
+                for v in range(V):
+                    hE[v, a:b].copy_(dE[v], non_blocking=True)
+    for s in slots:
+        cur.wait_stream(s["stream"])
+    cur.synchronize()
+    return TriangulationResult(X=hX, err=hE, proj=None, status=None)

@@ -1,0 +1,77 @@
+"""CPU-side boundary checks: the C-ABI library builds for sm_100a, loads, and exports every symbol
+include/ska.h declares.  No compute calls (there is no GPU on the authoring box)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _header_symbols():
+    txt = (ROOT / "include" / "ska.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ska_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    from skiing_analysis_pytorch_b200 import _lib, build
+
+    build.build()
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert "ska_triangulate_reproject_f32" in syms
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ska.h but not exported by libska.so"
+    assert sorted(_lib.exported_symbols()) == syms, "ctypes signature table and header disagree"
+    assert lib.ska_abi_version() == 1
+    assert lib.ska_build_arch() == b"sm_100a"
+
+
+def test_library_contains_sm100a_sass():
+    import shutil
+    import subprocess
+
+    from skiing_analysis_pytorch_b200 import _lib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_argument_errors_without_gpu():
+    """Validation happens before any CUDA call, so it is testable on the CPU box."""
+    from skiing_analysis_pytorch_b200 import _cabi, _lib, synth
+
+    lib = _lib.load()
+    R, t = synth.rig("2b")
+    cams = _cabi.make_cameras(synth.K_CALIB, R, t)
+    fake = C.c_void_p(256)
+    args = lambda **kw: [kw.get("cams", cams), kw.get("V", 2), None, None, kw.get("kpts", fake), None, kw.get("T", 1),
+                         kw.get("J", 17), kw.get("layout", 0), kw.get("flags", 0), kw.get("X", fake), None, None, None, None]
+    assert lib.ska_triangulate_reproject_f32(*args(V=1)) == -1
+    assert lib.ska_triangulate_reproject_f32(*args(V=9)) == -1
+    assert lib.ska_triangulate_reproject_f32(*args(kpts=None)) == -1
+    assert lib.ska_triangulate_reproject_f32(*args(layout=7)) == -1
+    assert lib.ska_triangulate_reproject_f32(*args(flags=3)) == -1
+    assert lib.ska_triangulate_reproject_f32(*args(kpts=C.c_void_p(260))) == -3
+    assert lib.ska_triangulate_reproject_f32(*args(T=2**31, J=1)) == -1
+    assert b"2^31" in lib.ska_last_error()
+    assert lib.ska_triangulate_reproject_f32(*args(T=0)) == 0  # empty clip is a no-op
+    tilted = _cabi.make_cameras(synth.K_CALIB, R, t, [0.1] * 14)
+    assert lib.ska_triangulate_reproject_f32(*args(cams=tilted)) == -2
+    with pytest.raises(ValueError):
+        _cabi.make_cameras(synth.K_CALIB, R, t, [0.1] * 6)
+
+
+def test_api_refuses_cpu_tensors():
+    import torch
+
+    from skiing_analysis_pytorch_b200 import api, synth
+
+    R, t = synth.rig("2b")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        api.triangulate_reproject(torch.zeros(2, 1, 17, 2), synth.K_CALIB, R, t)

@@ -1,0 +1,210 @@
+"""GPU parity: the CUDA path (through the C ABI) against the fp64 oracle and the reference goldens.
+Tolerances are the north-star ones and are written where they are used."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as G
+from skiing_analysis_pytorch_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+X_REL_TOL = 1e-4    # north star: 3D joints within 1e-4 relative of the fp64 SVD
+X_REL_HELD = 2e-6   # regression guard: what the fp32 secular solver holds on these rigs
+RMSE_TOL = 1e-5     # px, north star (aggregate RMSE)
+POINT_TOL = 2e-4    # px per point: the reference's own f32 noise floor
+
+
+def _oracle(clip, conf, dist):
+    V, T, J, _ = clip.x_vm.shape
+    P = np.stack([G.make_P(clip.K[v], clip.R[v], clip.t[v]) for v in range(V)])
+    x = clip.x_vm.reshape(V, -1, 2)
+    w = None if conf is None else conf.reshape(V, -1)
+    X = G.dlt_triangulate(P, x, w)
+    proj = np.stack([G.project_cv(X, clip.R[v], clip.t[v], clip.K[v], dist) for v in range(V)])
+    err = np.linalg.norm(proj - x, axis=-1)
+    return X.reshape(T, J, 3), err.reshape(V, T, J), proj.reshape(V, T, J, 2)
+
+
+def _rmse(e):
+    return float(np.sqrt(np.mean(np.asarray(e, np.float64) ** 2)))
+
+
+CASES = [
+    ("2a", 300, 17, False, None),                     # BASELINE config 1 (pinhole scoring)
+    ("2a", 300, 17, False, synth.DIST_CALIB),         # BASELINE config 1 as process_triangulate runs it (Q1)
+    ("2b", 301, 17, False, synth.DIST_CALIB),         # odd point count -> 64-bit path
+    ("2b", 128, 17, True, None),
+    ("3", 64, 17, True, synth.DIST_CALIB),
+    ("4", 64, 17, True, synth.DIST_CALIB[:5]),
+    ("5", 16, 17, False, None),
+    ("6", 16, 70, True, synth.DIST_CALIB),
+    ("7", 16, 17, True, None),
+    ("8", 32, 70, True, synth.DIST_CALIB),            # BASELINE config 4 shape (SAM-3D-Body 70 joints)
+]
+
+
+@pytest.mark.parametrize("rig,T,J,use_conf,dist", CASES)
+@pytest.mark.parametrize("layout", ["VTJ2", "TVJ2"])
+def test_parity_with_oracle(cuda, rig, T, J, use_conf, dist, layout):
+    clip = synth.make_clip(rig, T, J, seed=0)
+    conf = clip.conf_vm if use_conf else None
+    Xo, eo, po = _oracle(clip, conf, dist)
+    if layout == "VTJ2":
+        k, c = clip.x_vm, conf
+    else:
+        k, c = clip.x_fm, (None if conf is None else clip.conf_fm)
+    kt = torch.from_numpy(k).to(cuda)
+    ct = None if c is None else torch.from_numpy(c).to(cuda)
+    res = api.triangulate_reproject(kt, clip.K, clip.R, clip.t, conf=ct, dist=dist, layout=layout,
+                                    want=("X", "err", "proj", "status"))
+    torch.cuda.synchronize()
+    X = res.X.cpu().numpy()
+    err = res.err.cpu().numpy()
+    proj = res.proj.cpu().numpy()
+    if layout == "TVJ2":
+        err = err.transpose(1, 0, 2)
+        proj = proj.transpose(1, 0, 2, 3)
+    rel = np.linalg.norm(X - Xo, axis=-1) / np.linalg.norm(Xo, axis=-1)
+    assert rel.max() < X_REL_HELD < X_REL_TOL
+    assert np.abs(err - eo).max() < POINT_TOL
+    assert abs(_rmse(err) - _rmse(eo)) < RMSE_TOL
+    assert np.abs(proj - po).max() < 5e-4  # f32 storage of ~1e3 px values (ulp 6e-5) + POINT_TOL
+    assert (res.status.cpu().numpy() == 0).all()
+
+
+@pytest.mark.parametrize("solver", ["jacobi64", "jacobi32"])
+def test_other_solvers(cuda, solver):
+    clip = synth.make_clip("2b", 100, 17, seed=1)
+    Xo, eo, _ = _oracle(clip, clip.conf_vm, synth.DIST_CALIB)
+    res = api.triangulate_reproject(torch.from_numpy(clip.x_vm).to(cuda), clip.K, clip.R, clip.t,
+                                    conf=torch.from_numpy(clip.conf_vm).to(cuda), dist=synth.DIST_CALIB, solver=solver)
+    rel = np.linalg.norm(res.X.cpu().numpy() - Xo, axis=-1) / np.linalg.norm(Xo, axis=-1)
+    # fp32 Jacobi on the un-centred normal matrix is the north-star design point: it meets the
+    # 1e-4 tolerance but with 50x less margin than the default solver
+    assert rel.max() < (2e-7 if solver == "jacobi64" else X_REL_TOL)
+    assert np.abs(res.err.cpu().numpy() - eo).max() < (POINT_TOL if solver == "jacobi64" else 5e-3)
+
+
+def test_weight_power_and_pinhole_flags(cuda):
+    clip = synth.make_clip("4", 32, 17, seed=2)
+    V = 4
+    P = np.stack([G.make_P(clip.K[v], clip.R[v], clip.t[v]) for v in range(V)])
+    x = clip.x_vm.reshape(V, -1, 2)
+    Xo = G.dlt_triangulate(P, x, clip.conf_vm.reshape(V, -1), weight_power=0.5).reshape(32, 17, 3)
+    kt, ct = torch.from_numpy(clip.x_vm).to(cuda), torch.from_numpy(clip.conf_vm).to(cuda)
+    res = api.triangulate_reproject(kt, clip.K, clip.R, clip.t, conf=ct, dist=synth.DIST_CALIB, weight_power=0.5,
+                                    pinhole_reproj=True)
+    rel = np.linalg.norm(res.X.cpu().numpy() - Xo, axis=-1) / np.linalg.norm(Xo, axis=-1)
+    assert rel.max() < X_REL_HELD
+    eo = np.stack([np.linalg.norm(G.project_cv(Xo.reshape(-1, 3), clip.R[v], clip.t[v], clip.K[v], None) - x[v], axis=1) for v in range(V)])
+    assert np.abs(res.err.cpu().numpy().reshape(V, -1) - eo).max() < POINT_TOL
+
+
+def test_golden_g1_reference_outputs(cuda, golden):
+    """BASELINE config 1 against what the reference's own functions returned (cv2 path)."""
+    g = golden("g1_two_view_fixed_rig.npz")
+    K, R, t, dist = g["K"], g["R"], g["t"], g["dist"]
+    k = torch.from_numpy(np.stack([g["kptL"], g["kptR"]])).to(cuda)
+    Rs, ts = np.stack([np.eye(3), R]), np.stack([np.zeros(3), t])
+    res = api.triangulate_reproject(k, K, Rs, ts, dist=dist, want=("X", "err", "proj"))
+    X = res.X.cpu().numpy()
+    rel = np.linalg.norm(X - g["X_f64"], axis=-1) / np.linalg.norm(g["X_f64"], axis=-1)
+    assert rel.max() < X_REL_HELD
+    proj = res.proj.cpu().numpy()
+    # the reference reprojects ITS f32-rounded X through an f32 Rodrigues round trip: 2e-4 px floor
+    # plus the sensitivity of the projection to the last-ulp differences between the two X
+    assert np.abs(proj[0] - g["projL_dist"]).max() < 1e-3
+    assert np.abs(proj[1] - g["projR_dist"]).max() < 1e-3
+    err = res.err.cpu().numpy()
+    n = g["errL"].shape[0]
+    assert np.abs(err[0, :n] - g["errL"]).max() < 1e-3
+    keys = [str(s) for s in g["stats_keys"]]
+    for i in range(n):
+        ref = dict(zip(keys, g["stats"][i]))
+        for side, v in (("L", 0), ("R", 1)):
+            e = err[v, i].astype(np.float64)
+            assert abs(np.sqrt(np.mean(e**2)) - ref[f"rmse_{side}"]) < 2e-4
+            assert abs(e.mean() - ref[f"mean_err_{side}"]) < 2e-4
+            assert abs(np.median(e) - ref[f"median_err_{side}"]) < 1e-3
+            assert abs(e.max() - ref[f"max_err_{side}"]) < 1e-3
+    # clip-level RMSE (the north-star 1e-5 px statement)
+    eo = np.concatenate([g["errL"].ravel(), g["errR"].ravel()])
+    assert abs(_rmse(np.concatenate([err[0, :n].ravel(), err[1, :n].ravel()])) - _rmse(eo)) < 1e-4
+
+
+def test_golden_g2_vggt(cuda, golden):
+    g = golden("g2_vggt_two_cameras.npz")
+    k = torch.from_numpy(np.stack([g["kptL"], g["kptR"]])).to(cuda)
+    res = api.triangulate_reproject(k, g["K"], g["R"], g["t"])
+    X = res.X.cpu().numpy()
+    rel = np.linalg.norm(X - g["X_point"], axis=-1) / np.linalg.norm(g["X_point"], axis=-1)
+    assert rel.max() < X_REL_HELD
+
+
+def test_fallback_and_nan(cuda):
+    clip = synth.make_clip("2a", 300, 17, seed=0, noise_px=20.0)
+    x = clip.x_vm.copy()
+    x[1, 7, 3, 0] = np.nan
+    kt = torch.from_numpy(x).to(cuda)
+    res = api.triangulate_reproject(kt, clip.K, clip.R, clip.t, want=("X", "err", "status"))
+    exact = api.triangulate_reproject(kt, clip.K, clip.R, clip.t, solver="jacobi64", want=("X", "err"))
+    st = res.status.cpu().numpy()
+    X, Xe = res.X.cpu().numpy(), exact.X.cpu().numpy()
+    assert st[7, 3] == 2 and np.isnan(X[7, 3]).all()
+    fb = st == 1
+    assert fb.sum() > 0
+    np.testing.assert_array_equal(X[fb], Xe[fb])
+    ok = st == 0
+    rel = np.linalg.norm(X[ok] - Xe[ok], axis=-1) / np.linalg.norm(Xe[ok], axis=-1)
+    assert rel.max() < X_REL_TOL
+
+
+def test_empty_and_tiny(cuda):
+    R, t = synth.rig("2b")
+    res = api.triangulate_reproject(torch.zeros(2, 0, 17, 2, device=cuda), synth.K_CALIB, R, t)
+    assert res.X.shape == (0, 17, 3)
+    clip = synth.make_clip("2b", 1, 1, seed=0)
+    Xo, eo, _ = _oracle(clip, None, None)
+    res = api.triangulate_reproject(torch.from_numpy(clip.x_vm).to(cuda), clip.K, clip.R, clip.t)
+    assert np.linalg.norm(res.X.cpu().numpy() - Xo) / np.linalg.norm(Xo) < X_REL_HELD
+
+
+def test_full_size_properties_config2(cuda):
+    """BASELINE config 2 (1M frames x 17 joints x 2 views) through size-independent properties:
+    (1) every contiguous shard of the clip gives bit-identical results (no cross-point coupling);
+    (2) a seeded random sample of points matches the fp64 oracle;
+    (3) noise-free observations reproduce the ground truth and score ~0 px."""
+    T, J = 1_000_000, 17
+    R, t = synth.rig("2b")
+    gen = torch.Generator(device=cuda).manual_seed(0)
+    Xgt = torch.tensor(synth.CENTRE, device=cuda, dtype=torch.float64) + torch.randn(T, J, 3, device=cuda, dtype=torch.float64, generator=gen) * 0.6
+    clean = torch.empty(2, T, J, 2, device=cuda, dtype=torch.float64)
+    K = torch.tensor(synth.K_CALIB, device=cuda)
+    for v in range(2):
+        Xc = Xgt @ torch.tensor(R[v], device=cuda).T + torch.tensor(t[v], device=cuda)
+        clean[v, ..., 0] = K[0, 0] * Xc[..., 0] / Xc[..., 2] + K[0, 2]
+        clean[v, ..., 1] = K[1, 1] * Xc[..., 1] / Xc[..., 2] + K[1, 2]
+    noisy = (clean + torch.randn(clean.shape, device=cuda, dtype=torch.float64, generator=gen)).float()
+    full = api.triangulate_reproject(noisy, synth.K_CALIB, R, t, dist=synth.DIST_CALIB)
+    # (1) shards
+    for a, b in ((0, 1000), (333_333, 666_667), (999_001, 1_000_000)):
+        part = api.triangulate_reproject(noisy[:, a:b].contiguous(), synth.K_CALIB, R, t, dist=synth.DIST_CALIB)
+        assert torch.equal(part.X, full.X[a:b])
+        assert torch.equal(part.err, full.err[:, a:b])
+    # (2) oracle on a sample
+    idx = torch.randint(0, T * J, (20000,), device=cuda, generator=gen)
+    xs = noisy.reshape(2, -1, 2)[:, idx].cpu().numpy()
+    P = np.stack([G.make_P(synth.K_CALIB, R[v], t[v]) for v in range(2)])
+    Xo = G.dlt_triangulate(P, xs)
+    Xs = full.X.reshape(-1, 3)[idx].cpu().numpy()
+    assert (np.linalg.norm(Xs - Xo, axis=1) / np.linalg.norm(Xo, axis=1)).max() < X_REL_HELD
+    eo = np.stack([np.linalg.norm(G.project_cv(Xo, R[v], t[v], synth.K_CALIB, synth.DIST_CALIB) - xs[v], axis=1) for v in range(2)])
+    es = full.err.reshape(2, -1)[:, idx].cpu().numpy()
+    assert np.abs(es - eo).max() < POINT_TOL
+    assert abs(_rmse(es) - _rmse(eo)) < RMSE_TOL
+    # (3) noise-free (f32 rounding of the pixels is the only noise: 6e-5 px)
+    ex = api.triangulate_reproject(clean.float(), synth.K_CALIB, R, t)
+    rel = (ex.X.double() - Xgt).norm(dim=-1) / Xgt.norm(dim=-1)
+    assert rel.max().item() < 1e-6
+    assert ex.err.max().item() < 1e-3
