@@ -12,7 +12,8 @@ from . import _cabi
 _LOCK = threading.Lock()
 _LIB = None
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libska.so"
+# SKA_LIB_PATH selects an experimental build of the SAME CUDA library (tools/variants.py); never a CPU path
+LIB_PATH = Path(os.environ.get("SKA_LIB_PATH") or (Path(__file__).resolve().parent / "lib" / "libska.so"))
 
 
 class SkaError(RuntimeError):

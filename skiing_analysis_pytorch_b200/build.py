@@ -42,7 +42,16 @@ def needs_build() -> bool:
     return not LIB.exists() or LIB.stat().st_mtime < _deps_mtime()
 
 
-def build(force: bool = False, verbose: bool = False, extra_flags=()) -> Path:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: Path | None = None) -> Path:
+    """out/extra_flags: build an experimental variant next to the product library (tools/variants.py)."""
+    global LIB, OBJ
+    if out is not None:
+        saved = (LIB, OBJ)
+        LIB, OBJ = Path(out), CSRC / ("_obj_" + Path(out).stem)
+        try:
+            return build(force=True, verbose=verbose, extra_flags=extra_flags)
+        finally:
+            LIB, OBJ = saved
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()

@@ -34,21 +34,15 @@ struct CamDev {
   float dk[3];    // k1-k4, k2-k5, k3-k6  (numerator minus denominator of the rational term)
   float kd[3];    // k4, k5, k6
   float p1, p2;
+  float tp1, tp2; // 2*p1, 2*p2
   float s[4];     // s1..s4
-};
-
-// fp64 camera for the Jacobi fallback / exact mode: un-centred P = K [R|t], plus cv2 intrinsics.
-struct CamDev64 {
-  double P[12];
-  double R[9];
-  double t[3];
-  double fx, fy, cx, cy;
-  double dist[12];
 };
 
 SKA_HD float rcp_fast(float x) {
 #if defined(__CUDA_ARCH__)
-  return __fdividef(1.0f, x);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU.RCP, <= 1 ulp
+  return r;
 #else
   return 1.0f / x;
 #endif
@@ -65,14 +59,16 @@ SKA_HD float sqrt_fast(float x) {
 
 // One DLT row pair for one view: a = u*P2 - P0, b = v*P2 - P1 (4 entries each).  The products are
 // fused (single rounding of the exact u*P2h - P0h, so the cancellation between u*r3 and cx*r3
-// costs nothing) and the lo parts of P' restore the bits fp32 P' lost.
-template <bool USE_LO>
+// costs nothing).  LO selects how much of the fp32-rounding of P' is restored from the lo parts:
+// 0 = none, 1 = translation column only (the ~1e4-magnitude entries that set the px-error floor),
+// 2 = all columns.
+template <int LO>
 SKA_HD void dlt_rows(const CamDev& c, float u, float v, float a[4], float b[4]) {
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     float ah = fmaf(u, c.Ph[8 + m], -c.Ph[m]);
     float bh = fmaf(v, c.Ph[8 + m], -c.Ph[4 + m]);
-    if (USE_LO) {
+    if (LO == 2 || (LO == 1 && m == 3)) {
       ah += fmaf(u, c.Pl[8 + m], -c.Pl[m]);
       bh += fmaf(v, c.Pl[8 + m], -c.Pl[4 + m]);
     }
@@ -99,6 +95,9 @@ SKA_HD void sym4_rank1(Sym4& M, const float r[4], float w2) {
   M.m23 = fmaf(s2, r[3], M.m23);
   M.m33 = fmaf(s3, r[3], M.m33);
 }
+// trace(M33^-1) from the LDL^T factors: an upper bound of 1/lambda_min(M33).
+struct Ldl3;
+
 SKA_HD void sym4_rank1_unit(Sym4& M, const float r[4]) {
   M.m00 = fmaf(r[0], r[0], M.m00);
   M.m01 = fmaf(r[0], r[1], M.m01);
@@ -113,7 +112,7 @@ SKA_HD void sym4_rank1_unit(Sym4& M, const float r[4]) {
 }
 
 // LDL^T of a symmetric 3x3 (a00 a01 a02 a11 a12 a22), reciprocal pivots kept.
-struct Ldl3 {
+struct Ldl3 {  // (forward declared above)
   float l10, l20, l21, r0, r1, r2;
   bool pos;  // all pivots > 0  <=>  matrix positive definite
 };
@@ -130,6 +129,11 @@ SKA_HD Ldl3 ldl3(float a00, float a01, float a02, float a11, float a12, float a2
   f.r2 = rcp_fast(d2);
   f.pos = (a00 > 0.f) & (d1 > 0.f) & (d2 > 0.f);
   return f;
+}
+SKA_HD float ldl3_inv_trace(const Ldl3& f) {
+  // M^-1 = L^-T D^-1 L^-1 with L^-1 = [[1,0,0],[-l10,1,0],[l10*l21-l20,-l21,1]]
+  const float q = fmaf(f.l10, f.l21, -f.l20);
+  return fmaf(f.r2, fmaf(q, q, fmaf(f.l21, f.l21, 1.0f)), fmaf(f.r1, fmaf(f.l10, f.l10, 1.0f), f.r0));
 }
 SKA_HD void ldl3_solve(const Ldl3& f, float b0, float b1, float b2, float& x0, float& x1, float& x2) {
   const float y1 = fmaf(-f.l10, b0, b1);
@@ -154,6 +158,7 @@ SKA_HD void ldl3_solve(const Ldl3& f, float b0, float b1, float b2, float& x0, f
 struct SecularState {
   float y0, y1, y2;  // centred solution
   float lam;
+  float step2;       // squared length of the last step (contraction monitor)
   bool ok;
 };
 
@@ -172,9 +177,13 @@ SKA_HD bool secular_step(const Sym4& M, const float cx, const float cy, const fl
   s.y0 = n0;
   s.y1 = n1;
   s.y2 = n2;
+  // accept only in the fast-contraction regime (this step < 1/10 of the previous one): a small
+  // step alone proves nothing when convergence is slow (near-degenerate geometry)
+  const bool contracting = step2 <= 0.01f * s.step2;
   s.lam = lam;
+  s.step2 = step2;
   s.ok = f.pos;
-  return f.pos && (step2 <= kSecularTol2 * nrm2);
+  return f.pos && contracting && (step2 <= kSecularTol2 * nrm2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -239,15 +248,23 @@ SKA_HD void jacobi4_smallest(T a[4][4], T vec[4], int sweeps) {
 // ---------------------------------------------------------------------------------------------
 // cv2.projectPoints distortion increment on normalised coordinates: returns (x'' - x, y'' - y).
 // rad - 1 is formed as ((k1-k4) r2 + (k2-k5) r4 + (k3-k6) r6) / den so no bits are lost to 1 + ...
+// PRISM adds the thin-prism terms s1..s4.
+template <bool PRISM>
 SKA_HD void distort_delta(const CamDev& c, float x, float y, float& dx, float& dy) {
-  const float xx = x * x, yy = y * y, xy = x * y;
-  const float r2 = xx + yy;
+  const float xx = x * x, xy = x * y;
+  const float r2 = fmaf(y, y, xx);
   const float num = r2 * fmaf(r2, fmaf(r2, c.dk[2], c.dk[1]), c.dk[0]);
   const float den = fmaf(r2, fmaf(r2, fmaf(r2, c.kd[2], c.kd[1]), c.kd[0]), 1.0f);
   const float radm1 = num * rcp_fast(den);
-  const float r4 = r2 * r2;
-  dx = fmaf(x, radm1, fmaf(2.0f * c.p1, xy, fmaf(c.p2, fmaf(2.0f, xx, r2), fmaf(c.s[0], r2, c.s[1] * r4))));
-  dy = fmaf(y, radm1, fmaf(2.0f * c.p2, xy, fmaf(c.p1, fmaf(2.0f, yy, r2), fmaf(c.s[2], r2, c.s[3] * r4))));
+  float tx = c.p2 * fmaf(2.0f, xx, r2);
+  float ty = c.p1 * fmaf(2.0f * y, y, r2);
+  if (PRISM) {
+    const float r4 = r2 * r2;
+    tx = fmaf(c.s[0], r2, fmaf(c.s[1], r4, tx));
+    ty = fmaf(c.s[2], r2, fmaf(c.s[3], r4, ty));
+  }
+  dx = fmaf(x, radm1, fmaf(c.tp1, xy, tx));
+  dy = fmaf(y, radm1, fmaf(c.tp2, xy, ty));
 }
 
 SKA_HD void distort64(const double* d /*12*/, double x, double y, double& xd, double& yd) {

@@ -10,8 +10,9 @@ namespace ska {
 
 // returns SKA_OK / SKA_EINVAL / SKA_EUNSUPPORTED; fills the fp32 centred camera and the fp64 P.
 // needs_dist_path is set when scoring must take the distortion/skew branch.
+// dist_level: 0 = pinhole scoring, 1 = rational + tangential, 2 = thin prism and/or skew as well.
 inline int prep_camera(const SkaCamera& in, const double c[3], bool pinhole_reproj, CamDev& out, double P64[12],
-                       bool& needs_dist_path, const char** why) {
+                       int& dist_level, const char** why) {
   const double k22 = in.K[8];
   if (!(fabs(k22) > 0.0) || !isfinite(k22)) {
     *why = "K[2][2] must be finite and non-zero";
@@ -65,8 +66,11 @@ inline int prep_camera(const SkaCamera& in, const double c[3], bool pinhole_repr
   out.kd[2] = (float)(z * d[7]);
   out.p1 = (float)(z * d[2]);
   out.p2 = (float)(z * d[3]);
+  out.tp1 = (float)(2.0 * z * d[2]);
+  out.tp2 = (float)(2.0 * z * d[3]);
   for (int i = 0; i < 4; ++i) out.s[i] = (float)(z * d[8 + i]);
-  needs_dist_path = any || (K[1] != 0.0);
+  const bool prism = any && (d[8] != 0.0 || d[9] != 0.0 || d[10] != 0.0 || d[11] != 0.0);
+  dist_level = (prism || K[1] != 0.0) ? 2 : (any ? 1 : 0);
   return SKA_OK;
 }
 

@@ -1,12 +1,15 @@
 // ska_triangulate_impl.cuh - fused weighted V-view DLT triangulation + reprojection scoring, sm_100a.
 //
-// One thread owns PTS consecutive (frame, joint) points; a warp therefore owns a contiguous group
-// of 32*PTS points whose keypoints are one 128-bit (PTS=2) or 64-bit (PTS=1) load per lane and
-// view, fully coalesced.  Cameras are compile-time-indexed kernel parameters (constant bank), so
-// every P'/K/distortion coefficient is an immediate FFMA operand - no loads, no shared memory.
-// The 4x4 normal matrix, the secular iteration and the per-view scoring stay in registers; X is
-// staged through shared memory per warp so the 12-byte/point output leaves as 128-bit stores.
-// HBM-bound by design: 8V (+4V conf) bytes in, 12 + 4V bytes out per point, nothing re-read.
+// Persistent kernel: grid = (#SMs x resident CTAs), each CTA walks tiles of kBlock*PTS points with
+// a register prefetch of the NEXT tile's keypoints issued before the current tile is solved, so the
+// HBM latency of the only loads hides behind ~800 instructions of arithmetic.  One thread owns PTS
+// consecutive (frame, joint) points; a warp therefore owns a contiguous group of 32*PTS points
+// whose keypoints are one 128-bit (PTS=2) or 64-bit (PTS=1) load per lane and view, coalesced.
+// Cameras are compile-time-indexed kernel parameters (constant bank): every P'/K/distortion
+// coefficient is an FFMA constant operand - no loads, no shared memory.  The 4x4 normal matrix,
+// the secular iteration and the per-view scoring stay in registers; X is staged through shared
+// memory per warp so the 12-byte/point output leaves as 128-bit stores.
+// Traffic by design: 8V (+4V conf) bytes in, 12 + 4V bytes out per point, nothing re-read.
 //
 // Replaces: triangulation/triangulate.py:60-68,76-116; vggt/triangulate.py:19-34,64-71;
 //           triangulation/reproject.py:49-83,243-244 (file:line in the reference checkout).
@@ -23,12 +26,12 @@ struct TriParams {
   CamDev cam[V];
   double P64[V][12];
   float c[3];
-  uint32_t solver;
   uint32_t weight_sqrt;
   uint32_t frame_major;  // 1: offsets need (t, j); 0: flat point index
   uint32_t x_vec;        // X base 16-byte aligned -> staged 128-bit stores
   int32_t J;
   int64_t N;             // T*J points
+  int64_t n_tiles;
   int64_t k_sV, k_sT;    // kpts / proj strides in floats (view, frame)
   int64_t c_sV, c_sT;    // conf / err strides in floats
   const float* kpts;
@@ -41,18 +44,14 @@ struct TriParams {
 
 constexpr int kBlock = 256;
 
-template <int V, int PTS, bool CONF, int DIST, uint32_t SOLVER>
-__global__ void __launch_bounds__(kBlock) tri_kernel(const __grid_constant__ TriParams<V> prm) {
-  __shared__ __align__(16) float sX[kBlock / 32][32 * PTS * 3];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t N = prm.N;
-  const int64_t warp_first = ((int64_t)blockIdx.x * kBlock + warp * 32) * PTS;
-  const int64_t i_raw = warp_first + (int64_t)lane * PTS;
-  // out-of-range lanes recompute the last point(s): every lane stays alive for the warp votes
-  const int64_t i0 = (i_raw + PTS <= N) ? i_raw : (N - PTS);
-  const bool live = (i_raw + PTS <= N);
+template <int V, int PTS, bool CONF>
+struct TileInputs {
+  float u[PTS][V], v[PTS][V], c[PTS][V];
+};
 
-  int64_t koff, coff;  // offsets of point i0 within view 0
+// offsets (in floats) of this thread's first point of a tile, within view 0
+template <int V, int PTS>
+__device__ __forceinline__ void point_offsets(const TriParams<V>& prm, int64_t i0, int64_t& koff, int64_t& coff) {
   if (prm.frame_major) {
     const uint32_t t = (uint32_t)i0 / (uint32_t)prm.J;
     const uint32_t j = (uint32_t)i0 - t * (uint32_t)prm.J;
@@ -62,112 +61,194 @@ __global__ void __launch_bounds__(kBlock) tri_kernel(const __grid_constant__ Tri
     koff = 2 * i0;
     coff = i0;
   }
+}
 
-  float u[PTS][V], v[PTS][V], w2[PTS][V];
+// first point of this thread in `tile`, clamped so out-of-range lanes recompute the last point(s)
+// and every lane stays alive for the warp votes
+template <int PTS>
+__device__ __forceinline__ int64_t thread_point(int64_t tile, int64_t N, bool& live) {
+  const int64_t i_raw = (tile * kBlock + threadIdx.x) * PTS;
+  live = (i_raw + PTS <= N);
+  return live ? i_raw : (N - PTS);
+}
+
+template <int V, int PTS, bool CONF>
+__device__ __forceinline__ void load_tile(const TriParams<V>& prm, int64_t koff, int64_t coff, TileInputs<V, PTS, CONF>& in) {
 #pragma unroll
   for (int k = 0; k < V; ++k) {
     const float* kp = prm.kpts + koff + (int64_t)k * prm.k_sV;
     if (PTS == 2) {
       const float4 q = __ldcs(reinterpret_cast<const float4*>(kp));
-      u[0][k] = q.x; v[0][k] = q.y; u[PTS - 1][k] = q.z; v[PTS - 1][k] = q.w;
+      in.u[0][k] = q.x; in.v[0][k] = q.y; in.u[PTS - 1][k] = q.z; in.v[PTS - 1][k] = q.w;
     } else {
       const float2 q = __ldcs(reinterpret_cast<const float2*>(kp));
-      u[0][k] = q.x; v[0][k] = q.y;
+      in.u[0][k] = q.x; in.v[0][k] = q.y;
     }
-    if (CONF && prm.conf != nullptr) {
-      const float* cp = prm.conf + coff + (int64_t)k * prm.c_sV;
-      float c0, c1 = 0.f;
-      if (PTS == 2) {
-        const float2 q = __ldcs(reinterpret_cast<const float2*>(cp));
-        c0 = q.x; c1 = q.y;
+    if (CONF) {
+      if (prm.conf != nullptr) {
+        const float* cp = prm.conf + coff + (int64_t)k * prm.c_sV;
+        if (PTS == 2) {
+          const float2 q = __ldcs(reinterpret_cast<const float2*>(cp));
+          in.c[0][k] = q.x; in.c[PTS - 1][k] = q.y;
+        } else {
+          in.c[0][k] = __ldcs(cp);
+        }
       } else {
-        c0 = __ldcs(cp);
+#pragma unroll
+        for (int p = 0; p < PTS; ++p) in.c[p][k] = 1.0f;
       }
-      w2[0][k] = prm.weight_sqrt ? c0 : c0 * c0;
-      if (PTS == 2) w2[PTS - 1][k] = prm.weight_sqrt ? c1 : c1 * c1;
-    } else {
-#pragma unroll
-      for (int p = 0; p < PTS; ++p) w2[p][k] = 1.0f;
-    }
-  }
-
-  float X[PTS][3], du[PTS][V], dv[PTS][V];
-  uint8_t st[PTS];
-  tri_points<V, PTS, CONF, DIST, SOLVER>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], u, v, w2, X, du, dv, st);
-
-  // ---- per-view error / reprojection, coalesced
-#pragma unroll
-  for (int k = 0; k < V; ++k) {
-    if (prm.err != nullptr && live) {
-      float* ep = prm.err + coff + (int64_t)k * prm.c_sV;
-      const float e0 = sqrt_fast(fmaf(du[0][k], du[0][k], dv[0][k] * dv[0][k]));
-      if (PTS == 2) {
-        const float e1 = sqrt_fast(fmaf(du[PTS - 1][k], du[PTS - 1][k], dv[PTS - 1][k] * dv[PTS - 1][k]));
-        __stcs(reinterpret_cast<float2*>(ep), make_float2(e0, e1));
-      } else {
-        __stcs(ep, e0);
-      }
-    }
-    if (prm.proj != nullptr && live) {
-      float* pp = prm.proj + koff + (int64_t)k * prm.k_sV;
-      if (PTS == 2) {
-        __stcs(reinterpret_cast<float4*>(pp), make_float4(u[0][k] + du[0][k], v[0][k] + dv[0][k],
-                                                          u[PTS - 1][k] + du[PTS - 1][k], v[PTS - 1][k] + dv[PTS - 1][k]));
-      } else {
-        __stcs(reinterpret_cast<float2*>(pp), make_float2(u[0][k] + du[0][k], v[0][k] + dv[0][k]));
-      }
-    }
-  }
-  if (prm.status != nullptr && live) {
-#pragma unroll
-    for (int p = 0; p < PTS; ++p) prm.status[i0 + p] = st[p];
-  }
-
-  // ---- X: (N,3) f32.  Stage the warp's 32*PTS*3 floats, then 128-bit stores.
-  float* sx = sX[warp];
-#pragma unroll
-  for (int p = 0; p < PTS; ++p) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) sx[(lane * PTS + p) * 3 + k] = X[p][k];
-  }
-  __syncwarp();
-  const int64_t remain = N - warp_first;  // points of this warp that exist (may be <= 0)
-  if (remain > 0) {
-    const int npts = remain < 32 * PTS ? (int)remain : 32 * PTS;
-    const int nfl = npts * 3;
-    float* gx = prm.X + warp_first * 3;
-    if (prm.x_vec) {  // warp_first*3 floats is a multiple of 96 floats -> 16-byte aligned
-      const int nvec = nfl >> 2;
-      for (int q = lane; q < nvec; q += 32)
-        __stcs(reinterpret_cast<float4*>(gx) + q, reinterpret_cast<const float4*>(sx)[q]);
-      for (int q = (nvec << 2) + lane; q < nfl; q += 32) gx[q] = sx[q];
-    } else {
-      for (int q = lane; q < nfl; q += 32) gx[q] = sx[q];
     }
   }
 }
 
-template <int V, int PTS, bool CONF, int DIST, uint32_t SOLVER = kSolverSecular>
-static cudaError_t launch(const TriParams<V>& prm, cudaStream_t stream) {
-  const int64_t per_block = (int64_t)kBlock * PTS;
-  const int64_t blocks = (prm.N + per_block - 1) / per_block;
-  tri_kernel<V, PTS, CONF, DIST, SOLVER><<<(unsigned)blocks, kBlock, 0, stream>>>(prm);
+template <int V, int PTS, bool CONF, int DIST, uint32_t SOLVER, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) tri_kernel(const __grid_constant__ TriParams<V> prm) {
+  __shared__ __align__(16) float sX[kBlock / 32][32 * PTS * 3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t N = prm.N;
+
+  int64_t tile = blockIdx.x;
+  if (tile >= prm.n_tiles) return;
+  bool live;
+  int64_t i0 = thread_point<PTS>(tile, N, live);
+  int64_t koff, coff;
+  point_offsets<V, PTS>(prm, i0, koff, coff);
+  TileInputs<V, PTS, CONF> cur;
+  load_tile<V, PTS, CONF>(prm, koff, coff, cur);
+
+  for (;;) {
+    // ---- prefetch the next tile of this CTA into registers (loads stay in flight during the solve)
+    const int64_t ntile = tile + gridDim.x;
+    const bool more = ntile < prm.n_tiles;
+    bool nlive = false;
+    int64_t ni0 = 0, nkoff = 0, ncoff = 0;
+    TileInputs<V, PTS, CONF> nxt;
+    if (more) {
+      ni0 = thread_point<PTS>(ntile, N, nlive);
+      point_offsets<V, PTS>(prm, ni0, nkoff, ncoff);
+      load_tile<V, PTS, CONF>(prm, nkoff, ncoff, nxt);
+    }
+
+    float w2[PTS][V];
+#pragma unroll
+    for (int p = 0; p < PTS; ++p)
+#pragma unroll
+      for (int k = 0; k < V; ++k) w2[p][k] = CONF ? (prm.weight_sqrt ? cur.c[p][k] : cur.c[p][k] * cur.c[p][k]) : 1.0f;
+
+    PointSource src;
+    src.kpts = prm.kpts + koff;
+    src.conf = (prm.conf != nullptr) ? prm.conf + coff : nullptr;
+    src.k_sV = prm.k_sV;
+    src.c_sV = prm.c_sV;
+    src.weight_sqrt = prm.weight_sqrt;
+
+    float X[PTS][3], du[PTS][V], dv[PTS][V];
+    uint8_t st[PTS];
+    tri_points<V, PTS, CONF, DIST, SOLVER>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], cur.u, cur.v, w2, src, X, du,
+                                           dv, st);
+
+    // ---- per-view error / reprojection, coalesced
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      if (prm.err != nullptr && live) {
+        float* ep = prm.err + coff + (int64_t)k * prm.c_sV;
+        const float e0 = sqrt_fast(fmaf(du[0][k], du[0][k], dv[0][k] * dv[0][k]));
+        if (PTS == 2) {
+          const float e1 = sqrt_fast(fmaf(du[PTS - 1][k], du[PTS - 1][k], dv[PTS - 1][k] * dv[PTS - 1][k]));
+          __stcs(reinterpret_cast<float2*>(ep), make_float2(e0, e1));
+        } else {
+          __stcs(ep, e0);
+        }
+      }
+      if (prm.proj != nullptr && live) {
+        float* pp = prm.proj + koff + (int64_t)k * prm.k_sV;
+        if (PTS == 2) {
+          __stcs(reinterpret_cast<float4*>(pp),
+                 make_float4(cur.u[0][k] + du[0][k], cur.v[0][k] + dv[0][k], cur.u[PTS - 1][k] + du[PTS - 1][k],
+                             cur.v[PTS - 1][k] + dv[PTS - 1][k]));
+        } else {
+          __stcs(reinterpret_cast<float2*>(pp), make_float2(cur.u[0][k] + du[0][k], cur.v[0][k] + dv[0][k]));
+        }
+      }
+    }
+    if (prm.status != nullptr && live) {
+#pragma unroll
+      for (int p = 0; p < PTS; ++p) prm.status[i0 + p] = st[p];
+    }
+
+    // ---- X: (N,3) f32.  Stage the warp's 32*PTS*3 floats, then 128-bit stores.
+    float* sx = sX[warp];
+    __syncwarp();  // previous tile's readers are done with sx
+#pragma unroll
+    for (int p = 0; p < PTS; ++p) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) sx[(lane * PTS + p) * 3 + k] = X[p][k];
+    }
+    __syncwarp();
+    const int64_t warp_first = (tile * kBlock + warp * 32) * PTS;
+    const int64_t remain = N - warp_first;  // points of this warp that exist (may be <= 0)
+    if (remain > 0) {
+      const int npts = remain < 32 * PTS ? (int)remain : 32 * PTS;
+      const int nfl = npts * 3;
+      float* gx = prm.X + warp_first * 3;
+      if (prm.x_vec) {  // warp_first*3 floats is a multiple of 96 floats -> 16-byte aligned
+        const int nvec = nfl >> 2;
+        for (int q = lane; q < nvec; q += 32)
+          __stcs(reinterpret_cast<float4*>(gx) + q, reinterpret_cast<const float4*>(sx)[q]);
+        for (int q = (nvec << 2) + lane; q < nfl; q += 32) gx[q] = sx[q];
+      } else {
+        for (int q = lane; q < nfl; q += 32) gx[q] = sx[q];
+      }
+    }
+
+    if (!more) break;
+    tile = ntile;
+    i0 = ni0;
+    koff = nkoff;
+    coff = ncoff;
+    live = nlive;
+    cur = nxt;
+  }
+}
+
+#ifndef SKA_MINB_SMALL
+#define SKA_MINB_SMALL 2  // V <= 4: resident CTAs per SM the register allocator must allow
+#endif
+#ifndef SKA_MINB_LARGE
+#define SKA_MINB_LARGE 1  // V >= 5
+#endif
+template <int V, int PTS, bool CONF, int DIST, uint32_t SOLVER = kSolverSecular, int MINB = (V <= 4 ? SKA_MINB_SMALL : SKA_MINB_LARGE)>
+static cudaError_t launch(TriParams<V>& prm, cudaStream_t stream) {
+  auto kern = tri_kernel<V, PTS, CONF, DIST, SOLVER, MINB>;
+  const int64_t per_tile = (int64_t)kBlock * PTS;
+  prm.n_tiles = (prm.N + per_tile - 1) / per_tile;
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaError_t ce = cudaGetDevice(&dev);
+  if (ce != cudaSuccess) return ce;
+  ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (ce != cudaSuccess) return ce;
+  ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0);
+  if (ce != cudaSuccess) return ce;
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)sms * per_sm;  // one wave of resident CTAs, each walks tiles
+  if (grid > prm.n_tiles) grid = prm.n_tiles;
+  kern<<<(unsigned)grid, kBlock, 0, stream>>>(prm);
   return cudaGetLastError();
 }
 
 template <int V>
 static int dispatch(const TriArgs& a) {
   TriParams<V> prm;
-  bool dist = false;
+  int dist = 0;  // max distortion level over the views: 0 pinhole, 1 rational+tangential, 2 prism/skew
   for (int v = 0; v < V; ++v) {
-    bool d = false;
+    int d = 0;
     const char* why = "";
     const int rc = prep_camera(a.cams[v], a.centre, (a.flags & SKA_PINHOLE_REPROJ) != 0, prm.cam[v], prm.P64[v], d, &why);
     if (rc != SKA_OK) return set_error(rc, why);
-    dist = dist || d;
+    dist = d > dist ? d : dist;
   }
   for (int k = 0; k < 3; ++k) prm.c[k] = (float)a.centre[k];
-  prm.solver = a.flags & SKA_SOLVER_MASK;
+  const uint32_t solver = a.flags & SKA_SOLVER_MASK;
   prm.weight_sqrt = (a.flags & SKA_WEIGHT_SQRT) ? 1u : 0u;
   prm.J = a.J;
   prm.N = a.T * (int64_t)a.J;
@@ -194,17 +275,23 @@ static int dispatch(const TriArgs& a) {
   prm.x_vec = al(a.X, 16) ? 1u : 0u;
   const bool conf = (a.conf != nullptr);
   // 128-bit path: flat point index, even point count, vector-aligned streams, modest register need
+#ifdef SKA_FORCE_PTS1
+  const bool pts2 = false && (V <= 4) && (prm.N % 2 == 0) && al(a.kpts, 16) && al(a.conf, 8) && al(a.err, 8) && al(a.proj, 16);
+#else
   const bool pts2 = !fm && (V <= 4) && (prm.N % 2 == 0) && al(a.kpts, 16) && al(a.conf, 8) && al(a.err, 8) && al(a.proj, 16);
+#endif
   cudaError_t ce;
   cudaStream_t s = (cudaStream_t)a.stream;
 #define SKA_GO(PTS)                                                                      \
   (conf ? (dist ? launch<V, PTS, true, 1>(prm, s) : launch<V, PTS, true, 0>(prm, s))     \
         : (dist ? launch<V, PTS, false, 1>(prm, s) : launch<V, PTS, false, 0>(prm, s)))
-  if (prm.solver == kSolverJacobi64) {
-    // exact / measurement solvers: one generic instantiation (weights and distortion always on)
-    ce = launch<V, 1, true, 1, kSolverJacobi64>(prm, s);
-  } else if (prm.solver == kSolverJacobi32) {
-    ce = launch<V, 1, true, 1, kSolverJacobi32>(prm, s);
+  if (solver == kSolverJacobi64) {
+    // exact / measurement solvers: one generic instantiation (weights and full distortion always on)
+    ce = launch<V, 1, true, 2, kSolverJacobi64, 1>(prm, s);
+  } else if (solver == kSolverJacobi32) {
+    ce = launch<V, 1, true, 2, kSolverJacobi32, 1>(prm, s);
+  } else if (dist >= 2) {
+    ce = launch<V, 1, true, 2, kSolverSecular, 1>(prm, s);  // thin prism / skew: rare, one generic instantiation
   } else if constexpr (V <= 4) {
     ce = pts2 ? SKA_GO(2) : SKA_GO(1);
   } else {

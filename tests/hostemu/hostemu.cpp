@@ -21,14 +21,15 @@ static int run(const SkaCamera* cams, const double* centre, const float* kpts, c
   }
   CamDev cam[V];
   double P64[V][12];
-  bool dist = false;
+  int dist = 0;
   for (int v = 0; v < V; ++v) {
-    bool d;
+    int d;
     const char* why = "";
     int rc = prep_camera(cams[v], c, (flags & SKA_PINHOLE_REPROJ) != 0, cam[v], P64[v], d, &why);
     if (rc) return rc;
-    dist = dist || d;
+    dist = d > dist ? d : dist;
   }
+  const int lo = (flags >> 8) & 3;  // test hook: lo-part level of the DLT rows (default 1)
   const uint32_t solver = flags & SKA_SOLVER_MASK;
   for (int64_t i = 0; i < N; ++i) {
     float u[V], vv[V], w2[V], du[V], dv[V], Xp[3];
@@ -46,18 +47,31 @@ static int run(const SkaCamera* cams, const double* centre, const float* kpts, c
     float(*XO)[3] = (float(*)[3])Xp;
     float(*DU)[V] = (float(*)[V])du;
     float(*DV)[V] = (float(*)[V])dv;
-#define GO(CONF, DIST)                                                                                         \
+    PointSource src;
+    src.kpts = kpts + 2 * i;
+    src.conf = conf ? conf + i : nullptr;
+    src.k_sV = 2 * N;
+    src.c_sV = N;
+    src.weight_sqrt = (flags & SKA_WEIGHT_SQRT) ? 1u : 0u;
+#define GO3(CONF, DIST, LO)                                                                                    \
   do {                                                                                                         \
-    if (solver == kSolverSecular) tri_points<V, 1, CONF, DIST, kSolverSecular>(cam, P64, cx, cy, cz, U, VV, W, XO, DU, DV, &st); \
-    else if (solver == kSolverJacobi64) tri_points<V, 1, CONF, DIST, kSolverJacobi64>(cam, P64, cx, cy, cz, U, VV, W, XO, DU, DV, &st); \
-    else tri_points<V, 1, CONF, DIST, kSolverJacobi32>(cam, P64, cx, cy, cz, U, VV, W, XO, DU, DV, &st);      \
+    if (solver == kSolverSecular) tri_points<V, 1, CONF, DIST, kSolverSecular, LO>(cam, P64, cx, cy, cz, U, VV, W, src, XO, DU, DV, &st); \
+    else if (solver == kSolverJacobi64) tri_points<V, 1, CONF, DIST, kSolverJacobi64, LO>(cam, P64, cx, cy, cz, U, VV, W, src, XO, DU, DV, &st); \
+    else tri_points<V, 1, CONF, DIST, kSolverJacobi32, LO>(cam, P64, cx, cy, cz, U, VV, W, src, XO, DU, DV, &st); \
+  } while (0)
+#define GO(CONF, DIST)                                  \
+  do {                                                  \
+    if (lo == 1) GO3(CONF, DIST, 0);                    \
+    else if (lo == 2) GO3(CONF, DIST, 2);               \
+    else GO3(CONF, DIST, 1);                            \
   } while (0)
     if (conf) {
-      if (dist) GO(true, 1); else GO(true, 0);
+      if (dist == 2) GO(true, 2); else if (dist == 1) GO(true, 1); else GO(true, 0);
     } else {
-      if (dist) GO(false, 1); else GO(false, 0);
+      if (dist == 2) GO(false, 2); else if (dist == 1) GO(false, 1); else GO(false, 0);
     }
 #undef GO
+#undef GO3
     for (int k = 0; k < 3; ++k) X[3 * i + k] = Xp[k];
     if (err)
       for (int v = 0; v < V; ++v) err[v * N + i] = sqrtf(du[v] * du[v] + dv[v] * dv[v]);

@@ -50,7 +50,8 @@ def test_hostemu_matches_oracle(rig, T, J, use_conf, dist, solver):
     assert np.abs(err - eo).max() < POINT_TOL
     rm = lambda e: np.sqrt(np.mean(np.asarray(e, np.float64) ** 2))
     assert abs(rm(err) - rm(eo)) < RMSE_TOL
-    assert (st == 0).all()
+    # the near-degenerate FIXED rig sends its worst-conditioned points (<2%) to the fp64 path
+    assert (st <= 1).all() and (st == 1).mean() <= (0.02 if rig == "2a" else 0.0)
 
 
 def test_hostemu_fallback_certificate():

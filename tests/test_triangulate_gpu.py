@@ -70,7 +70,9 @@ def test_parity_with_oracle(cuda, rig, T, J, use_conf, dist, layout):
     assert np.abs(err - eo).max() < POINT_TOL
     assert abs(_rmse(err) - _rmse(eo)) < RMSE_TOL
     assert np.abs(proj - po).max() < 5e-4  # f32 storage of ~1e3 px values (ulp 6e-5) + POINT_TOL
-    assert (res.status.cpu().numpy() == 0).all()
+    st = res.status.cpu().numpy()
+    # the near-degenerate FIXED rig sends its worst-conditioned points (<2%) to the fp64 path
+    assert (st <= 1).all() and (st == 1).mean() <= (0.02 if rig == "2a" else 0.0)
 
 
 @pytest.mark.parametrize("solver", ["jacobi64", "jacobi32"])

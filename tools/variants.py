@@ -1,0 +1,43 @@
+"""Build experimental variants of libska.so (different launch bounds / points per thread) so one
+gpurun call can time them side by side:  python tools/variants.py build ; python tools/variants.py run"""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+VARIANTS = {
+    "minb2_pts2": ["-DSKA_MINB_SMALL=2"],
+    "minb2_pts1": ["-DSKA_MINB_SMALL=2", "-DSKA_FORCE_PTS1"],
+    "minb3_pts2": ["-DSKA_MINB_SMALL=3"],
+    "minb3_pts1": ["-DSKA_MINB_SMALL=3", "-DSKA_FORCE_PTS1"],
+    "minb1_pts2": ["-DSKA_MINB_SMALL=1"],
+    "minb4_pts1": ["-DSKA_MINB_SMALL=4", "-DSKA_FORCE_PTS1"],
+}
+LIBDIR = ROOT / "skiing_analysis_pytorch_b200" / "lib"
+
+
+def main():
+    cmd = sys.argv[1]
+    names = sys.argv[2:] or list(VARIANTS)
+    if cmd == "build":
+        from skiing_analysis_pytorch_b200 import build
+
+        for n in names:
+            print(n, build.build(out=LIBDIR / f"libska_{n}.so", extra_flags=VARIANTS[n]))
+    else:
+        extra = os.environ.get("BENCH_ARGS", "--steps 20 --warmup 3 --no-cpu-baseline").split()
+        for n in names:
+            env = dict(os.environ, SKA_LIB_PATH=str(LIBDIR / f"libska_{n}.so"))
+            r = subprocess.run([sys.executable, str(ROOT / "bench.py"), *extra], env=env, capture_output=True, text=True)
+            try:
+                j = json.loads(r.stdout.strip().splitlines()[-1])
+                print(f"{n:12s} ms/step {j['ms_per_step']:.4f}  frac {j['roofline']['frac']:.3f}")
+            except Exception:
+                print(n, "FAILED", r.stdout[-300:], r.stderr[-300:])
+
+
+if __name__ == "__main__":
+    main()
