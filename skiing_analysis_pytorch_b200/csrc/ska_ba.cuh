@@ -1,0 +1,147 @@
+// ska_ba.cuh - device-side pieces shared by the bundle-adjustment kernels.
+//
+// Cost and projection are the reference's (bundle_adjustment/loss.py:17-94):
+//   X_c = R X + t;  Z = max(z, 1e-6);  (x, y) = X_c.xy / Z;  (u, v) = (K [x, y, 1])[:2]  (full K)
+//   F = sum_tcj conf/(sum conf + 1e-6) |(u, v) - x2d|^2
+// The LM algorithm on top of it is specified in oracle/lm.py / DESIGN.md section 5 (the reference's
+// run_local_ba is an undefined symbol, vggt/multi_view_process.py:553).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ska {
+
+constexpr int kBaBlock = 256;
+constexpr float kZMin = 1e-6f;
+
+// fp64 camera state as it lives in device memory: R(9) t(3) K(9) pad(3)
+constexpr int kCamStride = 24;
+
+struct CamF {
+  float R[9], t[3];
+  float k00, k01, k02, k10, k11, k12;
+};
+
+__device__ __forceinline__ void load_cam(const double* __restrict__ s, CamF& c) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c.R[i] = (float)s[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c.t[i] = (float)s[9 + i];
+  const double k22 = s[12 + 8];
+  c.k00 = (float)(s[12 + 0] / k22); c.k01 = (float)(s[12 + 1] / k22); c.k02 = (float)(s[12 + 2] / k22);
+  c.k10 = (float)(s[12 + 3] / k22); c.k11 = (float)(s[12 + 4] / k22); c.k12 = (float)(s[12 + 5] / k22);
+}
+
+// One observation: residual e, Jacobian rows of (u,v) w.r.t. X_c (ju, jv) and p = R X.
+struct ObsLin {
+  float eu, ev;
+  float ju[3], jv[3];
+  float p[3];
+  bool clamped;
+};
+
+__device__ __forceinline__ void project_lin(const CamF& c, const float X[3], float uo, float vo, ObsLin& o) {
+  o.p[0] = fmaf(c.R[0], X[0], fmaf(c.R[1], X[1], c.R[2] * X[2]));
+  o.p[1] = fmaf(c.R[3], X[0], fmaf(c.R[4], X[1], c.R[5] * X[2]));
+  o.p[2] = fmaf(c.R[6], X[0], fmaf(c.R[7], X[1], c.R[8] * X[2]));
+  const float xc = o.p[0] + c.t[0], yc = o.p[1] + c.t[1], zc = o.p[2] + c.t[2];
+  o.clamped = zc < kZMin;
+  const float iz = 1.0f / fmaxf(zc, kZMin);
+  const float x = xc * iz, y = yc * iz;
+  const float fu = fmaf(c.k00, x, c.k01 * y), fv = fmaf(c.k10, x, c.k11 * y);
+  o.eu = (fu + c.k02) - uo;
+  o.ev = (fv + c.k12) - vo;
+  const float live = o.clamped ? 0.0f : 1.0f;  // d/dz vanishes while the clamp is active (autograd of loss.py:67)
+  o.ju[0] = c.k00 * iz; o.ju[1] = c.k01 * iz; o.ju[2] = -fu * iz * live;
+  o.jv[0] = c.k10 * iz; o.jv[1] = c.k11 * iz; o.jv[2] = -fv * iz * live;
+}
+
+// residual only (trial cost)
+__device__ __forceinline__ float project_err2(const CamF& c, const float X[3], float uo, float vo, bool& clamped) {
+  const float xc = fmaf(c.R[0], X[0], fmaf(c.R[1], X[1], fmaf(c.R[2], X[2], c.t[0])));
+  const float yc = fmaf(c.R[3], X[0], fmaf(c.R[4], X[1], fmaf(c.R[5], X[2], c.t[1])));
+  const float zc = fmaf(c.R[6], X[0], fmaf(c.R[7], X[1], fmaf(c.R[8], X[2], c.t[2])));
+  clamped = zc < kZMin;
+  const float iz = 1.0f / fmaxf(zc, kZMin);
+  const float x = xc * iz, y = yc * iz;
+  const float eu = fmaf(c.k00, x, fmaf(c.k01, y, c.k02)) - uo;
+  const float ev = fmaf(c.k10, x, fmaf(c.k11, y, c.k12)) - vo;
+  return fmaf(eu, eu, ev * ev);
+}
+
+// point Jacobian rows A_u = ju R, A_v = jv R
+__device__ __forceinline__ void point_rows(const CamF& c, const ObsLin& o, float au[3], float av[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    au[k] = fmaf(o.ju[0], c.R[k], fmaf(o.ju[1], c.R[3 + k], o.ju[2] * c.R[6 + k]));
+    av[k] = fmaf(o.jv[0], c.R[k], fmaf(o.jv[1], c.R[3 + k], o.jv[2] * c.R[6 + k]));
+  }
+}
+
+// camera Jacobian rows B_u = [p x ju | ju], B_v = [p x jv | jv]  (left-multiplicative d_omega, additive d_t)
+__device__ __forceinline__ void camera_rows(const ObsLin& o, float bu[6], float bv[6]) {
+  bu[0] = o.p[1] * o.ju[2] - o.p[2] * o.ju[1];
+  bu[1] = o.p[2] * o.ju[0] - o.p[0] * o.ju[2];
+  bu[2] = o.p[0] * o.ju[1] - o.p[1] * o.ju[0];
+  bv[0] = o.p[1] * o.jv[2] - o.p[2] * o.jv[1];
+  bv[1] = o.p[2] * o.jv[0] - o.p[0] * o.jv[2];
+  bv[2] = o.p[0] * o.jv[1] - o.p[1] * o.jv[0];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    bu[3 + k] = o.ju[k];
+    bv[3 + k] = o.jv[k];
+  }
+}
+
+// Cholesky of the damped 3x3 point block, lower factor with inverted diagonal.
+struct Chol3 {
+  float i0, l10, l20, i1, l21, i2;
+};
+__device__ __forceinline__ Chol3 chol3(float h00, float h01, float h02, float h11, float h12, float h22) {
+  Chol3 f;
+  f.i0 = rsqrtf(h00);
+  f.l10 = h01 * f.i0;
+  f.l20 = h02 * f.i0;
+  f.i1 = rsqrtf(fmaf(-f.l10, f.l10, h11));
+  f.l21 = fmaf(-f.l20, f.l10, h12) * f.i1;
+  f.i2 = rsqrtf(fmaf(-f.l21, f.l21, fmaf(-f.l20, f.l20, h22)));
+  return f;
+}
+// y = L^-1 b
+__device__ __forceinline__ void chol3_fwd(const Chol3& f, float b0, float b1, float b2, float& y0, float& y1, float& y2) {
+  y0 = b0 * f.i0;
+  y1 = fmaf(-f.l10, y0, b1) * f.i1;
+  y2 = fmaf(-f.l21, y1, fmaf(-f.l20, y0, b2)) * f.i2;
+}
+// x = L^-T y
+__device__ __forceinline__ void chol3_bwd(const Chol3& f, float y0, float y1, float y2, float& x0, float& x1, float& x2) {
+  x2 = y2 * f.i2;
+  x1 = fmaf(-f.l21, x2, y1) * f.i1;
+  x0 = fmaf(-f.l20, x2, fmaf(-f.l10, x1, y0)) * f.i0;
+}
+
+// Deterministic block reduction of NV doubles per thread: warp shuffles, then a fixed-order sum of
+// the per-warp values in shared memory.  Result valid in thread 0.  `scratch` holds (kBaBlock/32)*NV doubles.
+template <int NV>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) scratch[warp * NV + i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += scratch[w * NV + i];
+      v[i] = s;
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace ska
