@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SKA_ABI_VERSION 1
+#define SKA_ABI_VERSION 2
 
 #define SKA_OK 0
 #define SKA_EINVAL -1       /* null pointer / bad size / bad enum */
@@ -90,6 +90,70 @@ int ska_triangulate_reproject_f32(const SkaCamera* cams, int32_t V, const double
                                   const double* d_Rt_frames, const float* d_kpts, const float* d_conf,
                                   int64_t T, int32_t J, int32_t layout, uint32_t flags, float* d_X,
                                   float* d_err, float* d_proj, uint8_t* d_status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bundle adjustment: Levenberg-Marquardt with Schur complement over a whole clip.
+ * Fills the slot of the reference's undefined optimiser
+ *   run_local_ba(K, R_init, t_init, X3d_init, x2d, conf2d, num_iters, lr, device, mode)
+ *                                                       vggt/multi_view_process.py:553-564, :546-551
+ * on the cost the reference does define:
+ *   project_points + reprojection_loss                  bundle_adjustment/loss.py:17-94
+ * Algorithm (oracle/lm.py is the fp64 specification): residual r = sqrt(conf/(sum conf + 1e-6)) (pi_c(X) - x2d),
+ * pi = loss.py's projection (Z clamp at 1e-6, full 3x3 K); parameters = every point X (T,J,3) and, per
+ * camera c >= 1, [d_omega(3), d_t(3)] with R <- exp([d_omega]x) R, t <- t + d_t (camera 0 is the gauge);
+ * Marquardt damping lam*diag(H) on both blocks; Schur complement onto the cameras; Cholesky;
+ * back-substitution; accept iff the cost decreases; Nielsen gain-ratio damping update.
+ *
+ * One LM trial = ska_ba_linearize_f32 -> [all-reduce d_red over ranks] -> ska_ba_solve_f64 ->
+ * ska_ba_backsub_f32 -> [all-reduce d_red2] -> ska_ba_control_f64.  Nothing synchronises with the host;
+ * the sequence can be captured in a CUDA graph.  All state lives in caller-owned device buffers:
+ */
+#define SKA_BA_CAM_DOUBLES 24   /* per camera: R(9) row-major, t(3), K(9), pad(3) */
+#define SKA_BA_CTRL_DOUBLES 16
+#define SKA_BA_HIST_DOUBLES 8   /* iter, cost, trial_cost, lambda, rho, accepted, n_clamped, pred */
+#define SKA_BA_RED2_DOUBLES 4   /* trial cost, predicted decrease of the points, clamped count, pad (unscaled sums) */
+/* d_ctrl slots the caller initialises (all others 0): */
+#define SKA_BA_CTRL_LAMBDA 0    /* initial damping, oracle default 1e-3 */
+#define SKA_BA_CTRL_NU 1        /* 2.0 */
+#define SKA_BA_CTRL_SUMCONF 2   /* global sum of conf over ALL ranks (ska_ba_sum_f32 + all-reduce) */
+#define SKA_BA_CTRL_CUR 3       /* which half of d_Xpp holds the current points (0) */
+#define SKA_BA_CTRL_ITER 4      /* next history row (0) */
+#define SKA_BA_CTRL_COST 7      /* out: cost at the current point */
+#define SKA_BA_CTRL_ACCEPTED 8  /* out: last decision */
+
+#define SKA_BA_FORCE_WIDE 1u    /* flags: run the shared-memory SYRK linearisation even for C == 2 (testing) */
+
+typedef struct SkaBaProblem {
+  int32_t C;            /* cameras, 2..SKA_MAX_VIEWS */
+  int32_t J;            /* joints per frame */
+  int64_t T;            /* frames of THIS rank's shard */
+  int32_t layout;       /* SKA_LAYOUT_FRAME_MAJOR: x2d (T,C,J,2), conf (T,C,J) = loss.py's; or VIEW_MAJOR */
+  uint32_t flags;
+  const float* d_x2d;
+  const float* d_conf;
+  float* d_Xpp;         /* [2][T*J*3]: point ping-pong, half d_ctrl[CUR] is current */
+  double* d_cams;       /* [2][C][SKA_BA_CAM_DOUBLES]: slot 0 current, slot 1 trial */
+  double* d_ctrl;       /* [SKA_BA_CTRL_DOUBLES] */
+  double* d_red;        /* [ska_ba_red_doubles(C)]: packed reduced system of this rank (all-reduce payload):
+                           Sw upper triangle (n(n+1)/2, n = 6(C-1)), bw (n), gc (n), Hcc upper triangles (21 per
+                           free camera), cost, clamped count - all sums with raw conf weights */
+  double* d_red2;       /* [SKA_BA_RED2_DOUBLES] */
+  double* d_delta;      /* [C*6] camera step of the current trial */
+  double* d_hist;       /* nullable [max_iters][SKA_BA_HIST_DOUBLES] */
+  void* d_workspace;    /* >= ska_ba_workspace_bytes(C), 16-byte aligned */
+  size_t ws_bytes;
+} SkaBaProblem;
+
+int32_t ska_ba_red_doubles(int32_t C);
+size_t ska_ba_workspace_bytes(int32_t C);
+/* d_out[0] = sum of x[0..count) in fp64, fixed summation order (sum of confidences) */
+int ska_ba_sum_f32(const float* d_x, int64_t count, double* d_out, void* d_workspace, size_t ws_bytes, void* stream);
+int ska_ba_linearize_f32(const SkaBaProblem* p, void* stream);
+/* free_mask: bit (6*c + r) set = parameter r of camera c is optimised (r: 0..2 d_omega, 3..5 d_t);
+ * bits of camera 0 are ignored (gauge).  Modes of vggt/multi_view_process.py:338. */
+int ska_ba_solve_f64(const SkaBaProblem* p, uint64_t free_mask, void* stream);
+int ska_ba_backsub_f32(const SkaBaProblem* p, void* stream);
+int ska_ba_control_f64(const SkaBaProblem* p, void* stream);
 
 #ifdef __cplusplus
 }

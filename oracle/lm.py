@@ -35,6 +35,25 @@ ZMIN = 1e-6
 LAMBDA0 = 1e-3
 
 
+# golden set G6 (tests/golden/g6_lm_history.npz): name -> (rig, T, J, mode); BASELINE configs 3 and 5 at reduced T
+G6_CASES = {"c3": ("2b", 200, 17, "full"), "c5": ("8", 24, 70, "full"), "c3_t": ("2b", 120, 17, "pose_cam_t"),
+            "c4cam": ("4", 60, 17, "full")}
+
+
+def make_problem(rig: str, T: int, J: int, seed: int = 0):
+    """Deterministic BA test problem: GT rig perturbed by N(0,0.01) rad /
+    N(0,0.05) m (camera 0 untouched), points = DLT of the noisy observations under the perturbed rig.
+    Returns (clip, R0, t0, X0)."""
+    from skiing_analysis_pytorch_b200 import synth
+
+    clip = synth.make_clip(rig, T, J, seed=seed)
+    R0, t0 = synth.perturb_cameras(clip.R, clip.t, seed=seed + 1)
+    V = len(R0)
+    P = np.stack([G.make_P(clip.K[v], R0[v], t0[v]) for v in range(V)])
+    X0 = G.dlt_triangulate(P, clip.x_vm.reshape(V, -1, 2)).reshape(T, J, 3)
+    return clip, R0, t0, X0
+
+
 def free_mask(C: int, mode: str = "full") -> np.ndarray:
     """(C,6) bool: which of [d_omega(3), d_t(3)] are optimised. Camera 0 is always fixed.
     Modes follow the names at vggt/multi_view_process.py:338 / configs/vggt.yaml:52."""

@@ -12,6 +12,9 @@ tests only ever read the .npz files.  Golden sets:
       bundle_adjustment.reproject.reproject_points mode A on two non-identity cameras (quirk Q3)
   G3  bundle_adjustment.loss.project_points / reprojection_loss for every accepted shape, f32+f64
   G4  camera_smooth / baseline_reg / bone_length / pose_temporal scalars
+  G6  LM history of oracle/lm.py on BASELINE configs 3 and 5 at reduced T, with the REFERENCE's
+      reprojection_loss evaluated at the initial and final state of each solve (pins the cost the
+      LM minimises; the trajectory itself has no reference implementation - "parity unpinned")
 """
 from __future__ import annotations
 
@@ -148,11 +151,36 @@ def g3_g4():
     np.savez_compressed(OUT / "g3_g4_loss.npz", **out)
 
 
+
+
+def g6():
+    import torch
+
+    from oracle import lm
+
+    loss = ref_import.load("bundle_adjustment.loss")
+    out = {}
+    for name, (rig, T, J, mode) in lm.G6_CASES.items():
+        clip, R0, t0, X0 = lm.make_problem(rig, T, J)
+        R, t, X, hist = lm.run_lm(X0, R0, t0, clip.K, clip.x_fm, clip.conf_fm, num_iters=10, mode=mode)
+        tt_ = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(torch.float64)
+        ref0 = loss.reprojection_loss(tt_(X0), tt_(R0), tt_(t0), tt_(clip.K), tt_(clip.x_fm), tt_(clip.conf_fm)).item()
+        ref1 = loss.reprojection_loss(tt_(X), tt_(R), tt_(t), tt_(clip.K), tt_(clip.x_fm), tt_(clip.conf_fm)).item()
+        out[f"{name}_hist"] = np.array([[h["iter"], h["cost"], h["trial_cost"], h["lam"], h["rho"], h["accepted"], h["n_clamped"], h["pred"]] for h in hist])
+        out[f"{name}_R"] = R
+        out[f"{name}_t"] = t
+        out[f"{name}_X_head"] = X[:4]
+        out[f"{name}_ref_loss_init"] = ref0
+        out[f"{name}_ref_loss_final"] = ref1
+    np.savez_compressed(OUT / "g6_lm_history.npz", **out)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     g1()
     g2()
     g3_g4()
+    g6()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

@@ -5,8 +5,9 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
-MAX_VIEWS = 16
+ABI_VERSION = 2
+MAX_VIEWS = 8
+MAX_BA_VIEWS = 8
 
 LAYOUT_VIEW_MAJOR = 0
 LAYOUT_FRAME_MAJOR = 1
@@ -19,9 +20,13 @@ PINHOLE_REPROJ = 8
 
 SOLVERS = {"secular": SOLVER_SECULAR, "jacobi64": SOLVER_JACOBI64, "jacobi32": SOLVER_JACOBI32}
 
-CTRL_LAMBDA, CTRL_NU, CTRL_COST, CTRL_SUMCONF, CTRL_ACCEPTED, CTRL_ITER = range(6)
-CTRL_SIZE = 8
-HIST_SIZE = 8
+BA_CAM_DOUBLES = 24
+BA_CTRL_DOUBLES = 16
+BA_HIST_DOUBLES = 8
+BA_RED2_DOUBLES = 4
+BA_CTRL_LAMBDA, BA_CTRL_NU, BA_CTRL_SUMCONF, BA_CTRL_CUR, BA_CTRL_ITER = 0, 1, 2, 3, 4
+BA_CTRL_COST, BA_CTRL_ACCEPTED = 7, 8
+BA_FORCE_WIDE = 1
 
 ERRORS = {-1: "SKA_EINVAL", -2: "SKA_EUNSUPPORTED", -3: "SKA_EALIGN", -4: "SKA_EWORKSPACE"}
 
@@ -33,6 +38,36 @@ class SkaCamera(C.Structure):
         ("t", C.c_double * 3),
         ("dist", C.c_double * 14),
     ]
+
+
+class SkaBaProblem(C.Structure):
+    _fields_ = [
+        ("C", C.c_int32),
+        ("J", C.c_int32),
+        ("T", C.c_int64),
+        ("layout", C.c_int32),
+        ("flags", C.c_uint32),
+        ("d_x2d", C.c_void_p),
+        ("d_conf", C.c_void_p),
+        ("d_Xpp", C.c_void_p),
+        ("d_cams", C.c_void_p),
+        ("d_ctrl", C.c_void_p),
+        ("d_red", C.c_void_p),
+        ("d_red2", C.c_void_p),
+        ("d_delta", C.c_void_p),
+        ("d_hist", C.c_void_p),
+        ("d_workspace", C.c_void_p),
+        ("ws_bytes", C.c_size_t),
+    ]
+
+
+def red_layout(n_cams: int) -> dict:
+    """Offsets inside the packed reduced system d_red (include/ska.h)."""
+    nc = n_cams - 1
+    n = 6 * nc
+    ns = n * (n + 1) // 2
+    return dict(n=n, sw=0, bw=ns, gc=ns + n, hcc=ns + 2 * n, cost=ns + 2 * n + 21 * nc, clamp=ns + 2 * n + 21 * nc + 1,
+                size=ns + 2 * n + 21 * nc + 2)
 
 
 def make_cameras(K, R, t, dist=None):

@@ -33,6 +33,13 @@ _SIGS = {
         [C.POINTER(_cabi.SkaCamera), C.c_int32, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint32,
          _vp, _vp, _vp, _vp, _vp],
     ),
+    "ska_ba_red_doubles": (C.c_int32, [C.c_int32]),
+    "ska_ba_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "ska_ba_sum_f32": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_size_t, _vp]),
+    "ska_ba_linearize_f32": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), _vp]),
+    "ska_ba_solve_f64": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), C.c_uint64, _vp]),
+    "ska_ba_backsub_f32": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), _vp]),
+    "ska_ba_control_f64": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), _vp]),
 }
 
 

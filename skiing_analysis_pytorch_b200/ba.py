@@ -1,0 +1,279 @@
+"""Levenberg-Marquardt bundle adjustment driver (host side).
+
+All arithmetic runs in libska.so (ska_ba_* entry points, include/ska.h): linearise + Schur
+accumulation, reduced-system Cholesky, back-substitution + trial cost, and the accept/reject
+controller are CUDA kernels; this module owns the device buffers, enqueues the four launches of a
+trial on the current stream and - when the clip is sharded over ranks - all-reduces the two tiny
+fp64 payloads with torch.distributed (NCCL on GPUs).  Nothing here synchronises with the host until
+the caller reads the results, so a whole solve can be captured in a CUDA graph (``graph=True``).
+
+Fills the slot of the reference's undefined ``run_local_ba`` (vggt/multi_view_process.py:553-564)
+on the cost the reference defines in bundle_adjustment/loss.py:17-94.  Algorithm spec: oracle/lm.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi, _lib
+
+MODES = ("pose_only", "pose_cam_t", "full")  # vggt/multi_view_process.py:338, configs/vggt.yaml:52
+
+
+def free_mask(n_cams: int, mode: str = "full") -> int:
+    """Bit (6*c + r) set = parameter r of camera c is optimised (r 0..2 rotation, 3..5 translation).
+    Camera 0 is the gauge and never moves.  pose_only: points only; pose_cam_t: points + camera
+    translations; full: points + rotations + translations."""
+    if mode not in MODES:
+        raise ValueError(f"unknown mode {mode!r}; expected one of {MODES}")
+    per_cam = {"pose_only": 0, "pose_cam_t": 0b111000, "full": 0b111111}[mode]
+    m = 0
+    for c in range(1, n_cams):
+        m |= per_cam << (6 * c)
+    return m
+
+
+def _stream_ptr(dev) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class BundleAdjuster:
+    """One BA problem resident on one GPU (this rank's frame shard).
+
+    x2d   (T,C,J,2) float32 CUDA [layout "TCJ2", the reference's] or (C,T,J,2) ["CTJ2"]
+    conf  (T,C,J) / (C,T,J) float32 CUDA
+    K     (C,3,3) | (3,3); R0 (C,3,3); t0 (C,3): host arrays, world->camera, shared over the clip
+    X0    (T,J,3) CUDA tensor (any float dtype) - e.g. the output of triangulate_reproject
+    group torch.distributed process group when the clip is sharded by frame range over ranks
+    """
+
+    def __init__(self, x2d, conf, K, R0, t0, X0, *, layout: str = "TCJ2", mode: str = "full", lam0: float = 1e-3,
+                 max_iters: int = 64, group=None, force_wide: bool = False):
+        if not (x2d.is_cuda and conf.is_cuda and X0.is_cuda):
+            raise RuntimeError("x2d, conf and X0 must be CUDA tensors: this package has no CPU path")
+        if x2d.dtype != torch.float32 or conf.dtype != torch.float32:
+            raise TypeError("x2d and conf must be float32")
+        if x2d.dim() != 4 or x2d.shape[-1] != 2:
+            raise ValueError(f"x2d must be 4-D with last dim 2, got {tuple(x2d.shape)}")
+        if layout == "TCJ2":
+            T, Cn, J, _ = x2d.shape
+            self.layout = _cabi.LAYOUT_FRAME_MAJOR
+            cshape = (T, Cn, J)
+        elif layout == "CTJ2":
+            Cn, T, J, _ = x2d.shape
+            self.layout = _cabi.LAYOUT_VIEW_MAJOR
+            cshape = (Cn, T, J)
+        else:
+            raise ValueError("layout must be 'TCJ2' or 'CTJ2'")
+        if tuple(conf.shape) != cshape:
+            raise ValueError(f"conf shape {tuple(conf.shape)} does not match {cshape}")
+        if tuple(X0.shape) != (T, J, 3):
+            raise ValueError(f"X0 must be ({T},{J},3), got {tuple(X0.shape)}")
+        if not 2 <= Cn <= _cabi.MAX_BA_VIEWS:
+            raise ValueError(f"need 2..{_cabi.MAX_BA_VIEWS} cameras, got {Cn}")
+        R0 = np.asarray(R0, np.float64)
+        t0 = np.asarray(t0, np.float64).reshape(Cn, 3)
+        K = np.asarray(K, np.float64)
+        K = np.broadcast_to(K, (Cn, 3, 3)) if K.ndim == 2 else K.reshape(Cn, 3, 3)
+        if R0.shape != (Cn, 3, 3):
+            raise ValueError(f"R0 must be ({Cn},3,3), got {R0.shape}")
+        self.T, self.C, self.J = T, Cn, J
+        self.N = T * J
+        self.dev = x2d.device
+        self.group = group
+        self.mask = free_mask(Cn, mode)
+        self.mode = mode
+        self.max_iters = int(max_iters)
+        self.x2d = x2d.contiguous()
+        self.conf = conf.contiguous()
+        self.lib = _lib.load()
+        dev = self.dev
+        f64 = dict(dtype=torch.float64, device=dev)
+        cams = np.zeros((2, Cn, _cabi.BA_CAM_DOUBLES))
+        for s in range(2):
+            cams[s, :, 0:9] = R0.reshape(Cn, 9)
+            cams[s, :, 9:12] = t0
+            cams[s, :, 12:21] = K.reshape(Cn, 9)
+        self.cams = torch.from_numpy(cams).to(dev)
+        self.Xpp = torch.empty((2, max(self.N, 1), 3), dtype=torch.float32, device=dev)
+        if self.N:
+            self.Xpp[0, : self.N].copy_(X0.reshape(-1, 3))
+        ctrl = np.zeros(_cabi.BA_CTRL_DOUBLES)
+        ctrl[_cabi.BA_CTRL_LAMBDA] = lam0
+        ctrl[_cabi.BA_CTRL_NU] = 2.0
+        self.ctrl = torch.from_numpy(ctrl).to(dev)
+        self.red = torch.zeros(int(self.lib.ska_ba_red_doubles(Cn)), **f64)
+        self.red2 = torch.zeros(_cabi.BA_RED2_DOUBLES, **f64)
+        self.delta = torch.zeros(Cn * 6, **f64)
+        self.hist = torch.zeros((self.max_iters, _cabi.BA_HIST_DOUBLES), **f64)
+        with torch.cuda.device(dev):
+            ws = int(self.lib.ska_ba_workspace_bytes(Cn))
+        self.ws = torch.empty(ws, dtype=torch.uint8, device=dev)
+        self.prob = _cabi.SkaBaProblem(
+            C=Cn, J=J, T=T, layout=self.layout, flags=(_cabi.BA_FORCE_WIDE if force_wide else 0),
+            d_x2d=self.x2d.data_ptr(), d_conf=self.conf.data_ptr(), d_Xpp=self.Xpp.data_ptr(),
+            d_cams=self.cams.data_ptr(), d_ctrl=self.ctrl.data_ptr(), d_red=self.red.data_ptr(),
+            d_red2=self.red2.data_ptr(), d_delta=self.delta.data_ptr(), d_hist=self.hist.data_ptr(),
+            d_workspace=self.ws.data_ptr(), ws_bytes=ws,
+        )
+        self._graph = None
+        self.iters_done = 0
+        # global sum of confidences (loss.py:94 denominator), computed on the device
+        sum_out = C.c_void_p(self.ctrl.data_ptr() + 8 * _cabi.BA_CTRL_SUMCONF)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.ska_ba_sum_f32(C.c_void_p(self.conf.data_ptr()), self.conf.numel(), sum_out,
+                                               C.c_void_p(self.ws.data_ptr()), ws, _stream_ptr(dev)))
+        self._allreduce(self.ctrl[_cabi.BA_CTRL_SUMCONF: _cabi.BA_CTRL_SUMCONF + 1])
+
+    # ------------------------------------------------------------------ pieces of one trial
+    def _allreduce(self, t: torch.Tensor):
+        if self._distributed():
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+
+    def _world(self) -> int:
+        return torch.distributed.get_world_size(self.group)
+
+    def linearize(self):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.ska_ba_linearize_f32(C.byref(self.prob), _stream_ptr(self.dev)))
+
+    def solve(self):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.ska_ba_solve_f64(C.byref(self.prob), C.c_uint64(self.mask), _stream_ptr(self.dev)))
+
+    def backsub(self):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.ska_ba_backsub_f32(C.byref(self.prob), _stream_ptr(self.dev)))
+
+    def control(self):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.ska_ba_control_f64(C.byref(self.prob), _stream_ptr(self.dev)))
+
+    def trial(self):
+        """Enqueue one LM trial (accepted or rejected on the device)."""
+        self.linearize()
+        self._allreduce(self.red)
+        self.solve()
+        self.backsub()
+        self._allreduce(self.red2)
+        self.control()
+
+    # ------------------------------------------------------------------ driver
+    def run(self, num_iters: int, graph: bool = False):
+        """Enqueue `num_iters` trials.  graph=True captures one trial in a CUDA graph (single-GPU
+        solves only: the all-reduce stays outside captured regions) and replays it."""
+        if self.iters_done + num_iters > self.max_iters:
+            raise ValueError(f"history buffer holds {self.max_iters} trials; raise max_iters")
+        if graph and self._distributed():
+            graph = False
+        if graph:
+            if self._graph is None:
+                self.trial()  # warm-up outside capture (module load, attribute setting)
+                num_iters -= 1
+                self.iters_done += 1
+                g = torch.cuda.CUDAGraph()
+                s = torch.cuda.Stream(self.dev)
+                s.wait_stream(torch.cuda.current_stream(self.dev))
+                with torch.cuda.stream(s):
+                    with torch.cuda.graph(g, stream=s):
+                        self.trial()
+                torch.cuda.current_stream(self.dev).wait_stream(s)
+                self._graph = g
+                # capture does not execute: the captured trial still has to run num_iters times
+            for _ in range(num_iters):
+                self._graph.replay()
+        else:
+            for _ in range(num_iters):
+                self.trial()
+        self.iters_done += num_iters
+        return self
+
+    def _distributed(self) -> bool:
+        return torch.distributed.is_available() and torch.distributed.is_initialized() and self._world() > 1
+
+    # ------------------------------------------------------------------ results (synchronise)
+    @property
+    def history(self):
+        h = self.hist[: self.iters_done].cpu().numpy()
+        keys = ("iter", "cost", "trial_cost", "lam", "rho", "accepted", "n_clamped", "pred")
+        out = []
+        for row in h:
+            d = dict(zip(keys, (float(x) for x in row)))
+            d["iter"] = int(d["iter"])
+            d["accepted"] = bool(d["accepted"])
+            d["n_clamped"] = int(d["n_clamped"])
+            out.append(d)
+        return out
+
+    @property
+    def X(self) -> torch.Tensor:
+        cur = int(self.ctrl[_cabi.BA_CTRL_CUR].item())
+        return self.Xpp[cur, : self.N].view(self.T, self.J, 3)
+
+    @property
+    def R(self) -> np.ndarray:
+        return self.cams[0, :, 0:9].cpu().numpy().reshape(self.C, 3, 3)
+
+    @property
+    def t(self) -> np.ndarray:
+        return self.cams[0, :, 9:12].cpu().numpy()
+
+    @property
+    def cost(self) -> float:
+        return float(self.ctrl[_cabi.BA_CTRL_COST].item())
+
+
+def ba_solve(x2d, conf, K, R0, t0, X0, num_iters: int = 20, **kw):
+    """Convenience wrapper: build a BundleAdjuster, run `num_iters` trials, return it."""
+    graph = kw.pop("graph", False)
+    kw.setdefault("max_iters", num_iters)
+    return BundleAdjuster(x2d, conf, K, R0, t0, X0, **kw).run(num_iters, graph=graph)
+
+
+def _mean_rotation(R: np.ndarray) -> np.ndarray:
+    """Chordal mean of rotations (T,3,3) -> (3,3): SVD projection of the arithmetic mean."""
+    U, _, Vt = np.linalg.svd(R.mean(0))
+    D = np.diag([1.0, 1.0, np.sign(np.linalg.det(U @ Vt))])
+    return U @ D @ Vt
+
+
+def run_local_ba(K_torch, R_init_torch, t_init_torch, X3d_init_torch, x2d_torch, conf2d_torch, num_iters=200, lr=1e-3,
+                 device="cuda", mode="pose_only"):
+    """The optimiser the reference calls but never defines (vggt/multi_view_process.py:553-564;
+    argument shapes :546-551).  Returns (R_opt (T,C,3,3), t_opt (T,C,3), X_opt (T,J,3), history).
+
+    Static-rig LM: the per-frame cameras the reference passes are averaged into one camera set
+    shared over the clip (chordal mean rotation, mean translation), optimised with the
+    Schur-complement LM of this package, and broadcast back over the T frames.  `lr` is accepted for
+    signature compatibility and used as the initial damping lambda0 (a first-order learning rate has
+    no meaning for LM).  `num_iters` first-order iterations are capped at 64 LM trials (LM converges
+    in ~10).  Per-frame free cameras are SURVEY row N1 (not built)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("run_local_ba runs on a CUDA device: this package has no CPU path")
+    R = R_init_torch.detach().cpu().numpy().astype(np.float64)
+    t = t_init_torch.detach().cpu().numpy().astype(np.float64)
+    if R.ndim == 4:
+        Tn, Cn = R.shape[:2]
+        R0 = np.stack([_mean_rotation(R[:, c]) for c in range(Cn)])
+        t0 = t.mean(0)
+    elif R.ndim == 3:
+        Cn = R.shape[0]
+        R0, t0 = R, t
+        Tn = x2d_torch.shape[0]
+    else:
+        raise ValueError(f"Unsupported R shape: {R.shape}")
+    K = K_torch.detach().cpu().numpy().astype(np.float64)
+    x2d = x2d_torch.detach().to(dev, torch.float32)
+    conf = conf2d_torch.detach().to(dev, torch.float32)
+    X0 = X3d_init_torch.detach().to(dev, torch.float32)
+    iters = int(max(1, min(int(num_iters), 64)))
+    ba = ba_solve(x2d, conf, K, R0, t0, X0, num_iters=iters, mode=mode, lam0=float(lr))
+    out_dtype = R_init_torch.dtype
+    R_opt = torch.from_numpy(np.broadcast_to(ba.R[None], (Tn, Cn, 3, 3)).copy()).to(dev, out_dtype)
+    t_opt = torch.from_numpy(np.broadcast_to(ba.t[None], (Tn, Cn, 3)).copy()).to(dev, out_dtype)
+    X_opt = ba.X.to(X3d_init_torch.dtype).clone()
+    return R_opt, t_opt, X_opt, ba.history

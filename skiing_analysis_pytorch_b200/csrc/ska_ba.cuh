@@ -5,6 +5,11 @@
 //   F = sum_tcj conf/(sum conf + 1e-6) |(u, v) - x2d|^2
 // The LM algorithm on top of it is specified in oracle/lm.py / DESIGN.md section 5 (the reference's
 // run_local_ba is an undefined symbol, vggt/multi_view_process.py:553).
+//
+// Scaling: every accumulated quantity (Hpp, gp, W, Hcc, gc, Sw, bw, cost) is linear in the
+// observation weight w = conf * s, s = 1/(sum conf + 1e-6).  The kernels accumulate with the raw
+// conf and the fp64 solve / control kernels apply s once, so fp32 never sees the ~1e-9 weights of
+// a 1e8-observation clip.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -16,6 +21,21 @@ constexpr float kZMin = 1e-6f;
 
 // fp64 camera state as it lives in device memory: R(9) t(3) K(9) pad(3)
 constexpr int kCamStride = 24;
+
+// device control block (doubles); one per solve, owned by the caller
+enum : int {
+  kCtrlLambda = 0,   // damping used by the NEXT linearise / solve / backsub
+  kCtrlNu = 1,       // Nielsen growth factor
+  kCtrlSumConf = 2,  // global sum of conf (all ranks)
+  kCtrlCur = 3,      // which half of the X ping-pong buffer is current (0/1)
+  kCtrlIter = 4,     // trial counter = history row to write
+  kCtrlPredCam = 5,  // camera part of the predicted decrease (written by solve)
+  kCtrlOk = 6,       // 1 if the reduced system was positive definite (written by solve)
+  kCtrlCost = 7,     // cost at the current point (written by control)
+  kCtrlAccepted = 8, // last decision
+  kCtrlSize = 16
+};
+constexpr int kHistRow = 8;  // iter, cost, trial_cost, lambda, rho, accepted, n_clamped, pred
 
 struct CamF {
   float R[9], t[3];
@@ -93,19 +113,47 @@ __device__ __forceinline__ void camera_rows(const ObsLin& o, float bu[6], float 
   }
 }
 
+// Symmetric 3x3 point block accumulator + gradient
+struct PointBlock {
+  float h00, h01, h02, h11, h12, h22, g0, g1, g2;
+};
+__device__ __forceinline__ void pb_zero(PointBlock& b) { b.h00 = b.h01 = b.h02 = b.h11 = b.h12 = b.h22 = b.g0 = b.g1 = b.g2 = 0.f; }
+__device__ __forceinline__ void pb_add(PointBlock& b, float cw, const float au[3], const float av[3], float eu, float ev) {
+  const float u0 = cw * au[0], u1 = cw * au[1], u2 = cw * au[2];
+  const float v0 = cw * av[0], v1 = cw * av[1], v2 = cw * av[2];
+  b.h00 = fmaf(u0, au[0], fmaf(v0, av[0], b.h00));
+  b.h01 = fmaf(u0, au[1], fmaf(v0, av[1], b.h01));
+  b.h02 = fmaf(u0, au[2], fmaf(v0, av[2], b.h02));
+  b.h11 = fmaf(u1, au[1], fmaf(v1, av[1], b.h11));
+  b.h12 = fmaf(u1, au[2], fmaf(v1, av[2], b.h12));
+  b.h22 = fmaf(u2, au[2], fmaf(v2, av[2], b.h22));
+  b.g0 = fmaf(u0, eu, fmaf(v0, ev, b.g0));
+  b.g1 = fmaf(u1, eu, fmaf(v1, ev, b.g1));
+  b.g2 = fmaf(u2, eu, fmaf(v2, ev, b.g2));
+}
+
 // Cholesky of the damped 3x3 point block, lower factor with inverted diagonal.
 struct Chol3 {
   float i0, l10, l20, i1, l21, i2;
+  bool ok;
 };
 __device__ __forceinline__ Chol3 chol3(float h00, float h01, float h02, float h11, float h12, float h22) {
   Chol3 f;
   f.i0 = rsqrtf(h00);
   f.l10 = h01 * f.i0;
   f.l20 = h02 * f.i0;
-  f.i1 = rsqrtf(fmaf(-f.l10, f.l10, h11));
+  const float d1 = fmaf(-f.l10, f.l10, h11);
+  f.i1 = rsqrtf(d1);
   f.l21 = fmaf(-f.l20, f.l10, h12) * f.i1;
-  f.i2 = rsqrtf(fmaf(-f.l21, f.l21, fmaf(-f.l20, f.l20, h22)));
+  const float d2 = fmaf(-f.l21, f.l21, fmaf(-f.l20, f.l20, h22));
+  f.i2 = rsqrtf(d2);
+  // a point nobody observes (all conf 0) or a rank-deficient block has no step and no Schur term
+  f.ok = (h00 > 0.f) && (d1 > 0.f) && (d2 > 0.f) && (d2 <= 3.0e38f);
   return f;
+}
+__device__ __forceinline__ Chol3 chol3_damped(const PointBlock& b, float lam) {
+  const float s = 1.0f + lam;
+  return chol3(b.h00 * s, b.h01, b.h02, b.h11 * s, b.h12, b.h22 * s);
 }
 // y = L^-1 b
 __device__ __forceinline__ void chol3_fwd(const Chol3& f, float b0, float b1, float b2, float& y0, float& y1, float& y2) {
@@ -120,28 +168,41 @@ __device__ __forceinline__ void chol3_bwd(const Chol3& f, float y0, float y1, fl
   x0 = fmaf(-f.l20, x2, fmaf(-f.l10, x1, y0)) * f.i0;
 }
 
-// Deterministic block reduction of NV doubles per thread: warp shuffles, then a fixed-order sum of
-// the per-warp values in shared memory.  Result valid in thread 0.  `scratch` holds (kBaBlock/32)*NV doubles.
+// Deterministic block reduction of NV values per thread: fp64 warp shuffles, then a fixed-order sum
+// of the per-warp values in shared memory; thread k < NV writes column k of `out`.  No atomics.
+// `scratch` holds (blockDim/32)*NV doubles.
 template <int NV>
-__device__ __forceinline__ void block_reduce(double (&v)[NV], double* scratch) {
+__device__ __forceinline__ void block_reduce_store(const float (&v)[NV], double* scratch, double* out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    double x = v[i];
+    double x = (double)v[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
     if (lane == 0) scratch[warp * NV + i] = x;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      double s = 0.0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += scratch[w * NV + i];
-      v[i] = s;
-    }
+  const int nw = (int)(blockDim.x >> 5);
+  for (int i = threadIdx.x; i < NV; i += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += scratch[w * NV + i];
+    out[i] = s;
   }
   __syncthreads();
+}
+
+// Observation addressing for both layouts: frame-major (T,C,J,.) is the reference's
+// (bundle_adjustment/loss.py x2d / conf2d), view-major (C,T,J,.) is the triangulation layout.
+struct ObsLayout {
+  int64_t k_sT, k_sV;  // strides in floats for x2d
+  int64_t c_sT, c_sV;  // strides in floats for conf
+  int32_t J;
+};
+__device__ __forceinline__ void obs_offsets(const ObsLayout& L, int64_t i, int64_t& koff, int64_t& coff) {
+  const uint32_t t = (uint32_t)i / (uint32_t)L.J;
+  const uint32_t j = (uint32_t)i - t * (uint32_t)L.J;
+  koff = (int64_t)t * L.k_sT + 2 * (int64_t)j;
+  coff = (int64_t)t * L.c_sT + (int64_t)j;
 }
 
 }  // namespace ska

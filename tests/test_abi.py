@@ -25,7 +25,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/ska.h but not exported by libska.so"
     assert sorted(_lib.exported_symbols()) == syms, "ctypes signature table and header disagree"
-    assert lib.ska_abi_version() == 1
+    assert lib.ska_abi_version() == 2
     assert lib.ska_build_arch() == b"sm_100a"
 
 
