@@ -136,3 +136,46 @@ def perturb_cameras(R, t, seed: int = 1, rot_sigma: float = 0.01, trans_sigma: f
         R2[c] = so3_exp(rng.normal(0.0, rot_sigma, 3)) @ R[c]
         t2[c] = t[c] + rng.normal(0.0, trans_sigma, 3)
     return R2, t2
+
+
+def make_clip_device(rig_name: str, T: int, J: int, device, seed: int = 0, noise_px: float = 1.0, layout: str = "TCJ2",
+                     chunk_frames: int = 65536):
+    """Same statistical model as make_clip but generated on the GPU with torch (synthetic-data
+    plumbing for the full-size benchmark shapes: 1M frames x 70 joints x 8 views is 560M observations,
+    minutes of numpy on the host).  Returns dict(x2d, conf, X, R, t, K) with x2d (T,C,J,2) / conf (T,C,J)
+    for layout "TCJ2" or (C,T,J,2) / (C,T,J) for "CTJ2"; R, t, K are host fp64 arrays."""
+    import torch
+
+    R, t = rig(rig_name)
+    V = len(R)
+    K = np.broadcast_to(K_CALIB, (V, 3, 3)).copy()
+    g = torch.Generator(device=device).manual_seed(seed)
+    f64 = dict(dtype=torch.float64, device=device)
+    template = torch.randn(J, 3, generator=g, **f64) * 0.4
+    Rt = torch.tensor(R, **f64)
+    tt = torch.tensor(t, **f64)
+    Kt = torch.tensor(K, **f64)
+    fm = layout == "TCJ2"
+    x2d = torch.empty((T, V, J, 2) if fm else (V, T, J, 2), dtype=torch.float32, device=device)
+    conf = torch.empty((T, V, J) if fm else (V, T, J), dtype=torch.float32, device=device)
+    X = torch.empty((T, J, 3), **f64)
+    for a in range(0, T, chunk_frames):
+        b = min(T, a + chunk_frames)
+        tt_ = torch.arange(a, b, **f64)
+        root = torch.stack([1.5 * torch.sin(2 * np.pi * tt_ / 300), 0.3 * torch.sin(2 * np.pi * tt_ / 90),
+                            10.0 + 1.0 * torch.cos(2 * np.pi * tt_ / 240)], -1)
+        Xc = root[:, None, :] + template[None] + torch.randn(b - a, J, 3, generator=g, **f64) * 0.02
+        X[a:b] = Xc
+        cam = torch.einsum("vab,tjb->tvja", Rt, Xc) + tt[None, :, None, :]
+        xy = cam[..., :2] / cam[..., 2:3]
+        u = Kt[None, :, None, 0, 0] * xy[..., 0] + Kt[None, :, None, 0, 1] * xy[..., 1] + Kt[None, :, None, 0, 2]
+        v = Kt[None, :, None, 1, 1] * xy[..., 1] + Kt[None, :, None, 1, 2]
+        obs = (torch.stack([u, v], -1) + torch.randn(b - a, V, J, 2, generator=g, **f64) * noise_px).float()
+        cf = (torch.rand(b - a, V, J, generator=g, device=device) * 0.8 + 0.2).float()
+        if fm:
+            x2d[a:b] = obs
+            conf[a:b] = cf
+        else:
+            x2d[:, a:b] = obs.permute(1, 0, 2, 3)
+            conf[:, a:b] = cf.permute(1, 0, 2)
+    return dict(x2d=x2d, conf=conf, X=X, R=R, t=t, K=K)
