@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=20000)
+    ap.add_argument("--ba-iters", type=int, default=20)
     return ap.parse_args()
 
 
@@ -240,6 +241,84 @@ def recorded_traffic(key: str):
     return None
 
 
+BA_CONFIGS = {
+    # name: (rig, total frames, joints) - BASELINE.json configs[2] and configs[4]
+    "config3": ("2b", 100_000, 17),
+    "config5": ("8", 1_000_000, 70),
+}
+
+
+def ba_cpu_iteration_rate(frames=1500, joints=17, rig="2b", iters=3):
+    """LM iterations/s of the fp64 numpy Schur-LM oracle (oracle/lm.py) on `frames` frames; the
+    reference has no LM of its own (run_local_ba is undefined), so this port is the CPU arm."""
+    from oracle import lm
+
+    clip, R0, t0, X0 = lm.make_problem(rig, frames, joints)
+    t0_ = time.perf_counter()
+    lm.run_lm(X0, R0, t0, clip.K, clip.x_fm, clip.conf_fm, num_iters=iters)
+    return iters / (time.perf_counter() - t0_)
+
+
+def run_ba(a, dev, world, rank, barrier, dist):
+    """BA LM iterations/s (second half of BASELINE's metric).  Strong scaling: the clip's frames are
+    split over the ranks; per LM trial the packed reduced camera system and the 3 trial scalars are
+    all-reduced (NCCL)."""
+    import torch
+
+    from skiing_analysis_pytorch_b200 import api, ba, synth
+
+    out = {}
+    peak, _ = hbm_peak()
+    for name, (rig, T_total, J) in BA_CONFIGS.items():
+        T = T_total // world
+        d = synth.make_clip_device(rig, T, J, dev, seed=100 + rank)
+        R0, t0 = synth.perturb_cameras(d["R"], d["t"], seed=1)
+        C = len(R0)
+        kv = d["x2d"].permute(1, 0, 2, 3).contiguous()
+        X0 = api.triangulate_reproject(kv, d["K"], R0, t0, want=("X",)).X  # BA init = DLT under the perturbed rig
+        del kv
+        iters = a.ba_iters
+        s = ba.BundleAdjuster(d["x2d"], d["conf"], d["K"], R0, t0, X0, max_iters=iters + 8)
+        graph = world == 1
+        s.run(4, graph=graph)  # warm-up trials (also captures the graph)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s.run(iters, graph=graph)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item()) / iters
+        hist = s.history
+        alg = T * J * (2 * 12 * C + 36)  # per rank: two streaming passes over the observations + X read twice, written once
+        out[name] = {
+            "metric": "ba_lm_iterations_per_sec",
+            "value": 1e3 / ms,
+            "unit": "iters/s",
+            "ms_per_iter": ms,
+            "scaling": "strong",
+            "frames_total": T * world,
+            "frames_per_gpu": T,
+            "joints": J,
+            "cameras": C,
+            "free_params_per_camera": 6,
+            "launches_per_iter": 6,
+            "cuda_graph": graph,
+            "cost_first": hist[0]["cost"],
+            "cost_last": s.cost,
+            "accepted": int(sum(h["accepted"] for h in hist)),
+            "trials": len(hist),
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "bytes_per_iter_per_gpu": alg,
+                         "note": "fp32-issue-bound, not HBM-bound: see DESIGN.md section 6"},
+        }
+        del s, d, X0
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -373,6 +452,20 @@ def run_ours(a):
             "sample": f"first {frames} frames x {J} joints of the same clip, single-process per-frame "
             "cv2.triangulatePoints + cv2.projectPoints loop (oracle/reference_path.py), as the reference runs it",
         }
+    if not a.no_ba:
+        del d_k, d_c, outs, h_k, h_c, h_X, h_err, host_out
+        api._HOST_PIPE_CACHE.clear()
+        torch.cuda.empty_cache()
+        line["ba"] = run_ba(a, dev, world, rank, barrier, dist)
+        line["gpu_launches_ba_per_iter"] = 6
+        if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
+            r = ba_cpu_iteration_rate()
+            line["ba"]["cpu_baseline"] = {
+                "value": r, "unit": "iters/s at 1500 frames x 17 joints x 2 cameras", "cores": 1, "kind": "port",
+                "extrapolated_config3_iters_per_sec": r * 1500 / 100_000,
+                "sample": "3 LM trials of the fp64 numpy Schur-LM oracle (oracle/lm.py) on a 1500-frame config-3 clip; cost is "
+                "linear in the frame count",
+            }
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
