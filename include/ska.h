@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SKA_ABI_VERSION 2
+#define SKA_ABI_VERSION 3
 
 #define SKA_OK 0
 #define SKA_EINVAL -1       /* null pointer / bad size / bad enum */
@@ -36,6 +36,7 @@ extern "C" {
 #define SKA_EWORKSPACE -4   /* workspace too small */
 
 #define SKA_MAX_VIEWS 8
+#define SKA_MAX_BONES 16 /* bundle_adjustment/loss.py:118-131 lists 12 */
 
 /* memory layout of per-observation tensors */
 #define SKA_LAYOUT_VIEW_MAJOR 0  /* kpts (V,T,J,2), conf/err (V,T,J): the reference's separate
@@ -75,9 +76,7 @@ const char* ska_build_arch(void);
  *   triangulate_point / loop   vggt/triangulate.py:19-34, :64-71    (np.linalg.svd per joint)
  *   reproject_points + errors  triangulation/reproject.py:49-83, :243-244 (cv2.projectPoints, |proj-kpt|)
  *   the per-frame loop         triangulation/triangulate.py:76-116
- * cams[V]   host; static rig.  If d_Rt_frames != NULL it holds per-frame world->camera extrinsics
- *           (T,V,12) fp64 device = [R row-major (9), t (3)] and cams[v].R/t are ignored
- *           (process_triangulate passes per-frame R[i],T[i]: triangulate.py:76-82).
+ * cams[V]   host; static rig shared by every frame (per-frame extrinsics: the _frames_ variant below).
  * centre    host[3] or NULL: numerical conditioning origin only (results do not depend on it
  *           beyond rounding); NULL = least-squares intersection of the optical axes.
  * d_kpts    pixels, layout per `layout`; d_conf nullable (NULL = unit weights = reference behaviour).
@@ -86,10 +85,97 @@ const char* ska_build_arch(void);
  * d_status  nullable (T,J) uint8 out: 0 = fast path certified, 1 = Jacobi fallback used,
  *           2 = non-finite result.
  * Alignment: d_kpts 8 B, everything else 4 B (16 B on all of them enables the 128-bit path). */
-int ska_triangulate_reproject_f32(const SkaCamera* cams, int32_t V, const double* centre,
-                                  const double* d_Rt_frames, const float* d_kpts, const float* d_conf,
-                                  int64_t T, int32_t J, int32_t layout, uint32_t flags, float* d_X,
-                                  float* d_err, float* d_proj, uint8_t* d_status, void* stream);
+int ska_triangulate_reproject_f32(const SkaCamera* cams, int32_t V, const double* centre, const float* d_kpts,
+                                  const float* d_conf, int64_t T, int32_t J, int32_t layout, uint32_t flags,
+                                  float* d_X, float* d_err, float* d_proj, uint8_t* d_status, void* stream);
+
+/* Same, with PER-FRAME extrinsics: process_triangulate hands every frame its own R[i], T[i]
+ * (triangulation/triangulate.py:76-82; vggt/multi_view_process.py:220-234 likewise).
+ * d_Rt_frames  (T,V,12) fp64 device = [R row-major (9), t (3)] world->camera per frame and view;
+ *              cams[v].K / dist are shared over the clip, cams[v].R / t are ignored.
+ * d_workspace  >= ska_tri_frames_workspace_bytes(V, T), 16-byte aligned: the per-frame kernel-side
+ *              cameras (a prep kernel builds them on the device with the same fp64 code the host
+ *              uses for a static rig; conditioning origin chosen per frame).
+ * Solver flags are ignored (fp32 secular path with fp64 fallback). */
+size_t ska_tri_frames_workspace_bytes(int32_t V, int64_t T);
+int ska_triangulate_reproject_frames_f32(const SkaCamera* cams, int32_t V, const double* d_Rt_frames,
+                                         const float* d_kpts, const float* d_conf, int64_t T, int32_t J,
+                                         int32_t layout, uint32_t flags, float* d_X, float* d_err, float* d_proj,
+                                         uint8_t* d_status, void* d_workspace, size_t ws_bytes, void* stream);
+
+/* cv2-style reprojection of GIVEN 3D points (no triangulation) into V cameras, with the rational /
+ * tangential / thin-prism distortion model, computed in fp64 like cv2.projectPoints and stored as
+ * float32 pixels.  Replaces
+ *   reproject_points   triangulation/reproject.py:49-83; bundle_adjustment/reproject.py:74-153
+ *                      (== vggt/reproject.py, front_side/side/reproject.py, fuse/side/reproject.py)
+ * d_X (T,J,3) f32 in the coordinates cams[v] maps from; d_proj like kpts in `layout`, nullable;
+ * d_err (needs d_kpts) = |proj_f32 - kpt| per view as reproject.py:243-244, nullable. */
+int ska_reproject_points_f32(const SkaCamera* cams, int32_t V, const float* d_X, const float* d_kpts, int64_t T,
+                             int32_t J, int32_t layout, float* d_proj, float* d_err, void* stream);
+
+/* nan-aware per-(frame, view) statistics of the pixel errors: d_stats (T,V,4) f32 =
+ * [rmse, mean, median, max] (np.nanmean / nanmedian / nanmax of triangulation/reproject.py:254-261);
+ * all-NaN rows give NaN.  d_err in `layout` ((V,T,J) or (T,V,J)); J <= 1024. */
+int ska_frame_stats_f32(const float* d_err, int64_t T, int32_t J, int32_t V, int32_t layout, float* d_stats,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * bundle_adjustment/loss.py as kernels.  All pointers are device pointers in the caller's dtype
+ * (f32 / f64 variants).  Cameras: d_R (.,C,3,3), d_t (.,C,3), d_K (.,C,3,3) with a FRAME STRIDE in
+ * elements: 0 = one camera set shared over the clip (loss.py's (C,3,3) inputs), 9*C / 3*C / 9*C =
+ * per-frame cameras ((T,C,3,3) inputs); the three strides are independent (loss.py:40-50, :74-79).
+ *
+ * project_points     loss.py:17-84:  d_out (T,C,J,2); Z clamp at 1e-6 (:67), rows 0-1 of the full K. */
+int ska_project_points_f32(const float* d_X, int64_t T, int32_t J, int32_t C, const float* d_R, int64_t R_frame_stride,
+                           const float* d_t, int64_t t_frame_stride, const float* d_K, int64_t K_frame_stride,
+                           float* d_out, void* stream);
+int ska_project_points_f64(const double* d_X, int64_t T, int32_t J, int32_t C, const double* d_R, int64_t R_frame_stride,
+                           const double* d_t, int64_t t_frame_stride, const double* d_K, int64_t K_frame_stride,
+                           double* d_out, void* stream);
+/* reprojection_loss  loss.py:90-94, value and analytic gradient in one pass over the observations.
+ * d_sums[4] (fp64): [sum conf |proj - x2d|^2, sum conf, #clamped observations, 0];
+ *                   loss = w * d_sums[0] / (d_sums[1] + 1e-6).
+ * d_gX (T,J,3), d_gR / d_gt / d_gK shaped like d_R / d_t / d_K: nullable; UNSCALED gradients
+ * sum conf J^T e - multiply by 2 w / (d_sums[1] + 1e-6) (what torch.autograd derives from loss.py).
+ * d_conf == NULL selects vector-Jacobian mode: d_x2d then holds a cotangent g (T,C,J,2) of
+ * project_points' output and the gradients are sum J^T g (the backward of project_points). */
+size_t ska_loss_workspace_bytes(int32_t C);
+int ska_reprojection_loss_f32(const float* d_X, int64_t T, int32_t J, int32_t C, const float* d_R, int64_t R_frame_stride,
+                              const float* d_t, int64_t t_frame_stride, const float* d_K, int64_t K_frame_stride,
+                              const float* d_x2d, const float* d_conf, double* d_sums, float* d_gX, float* d_gR,
+                              float* d_gt, float* d_gK, void* d_workspace, size_t ws_bytes, void* stream);
+int ska_reprojection_loss_f64(const double* d_X, int64_t T, int32_t J, int32_t C, const double* d_R, int64_t R_frame_stride,
+                              const double* d_t, int64_t t_frame_stride, const double* d_K, int64_t K_frame_stride,
+                              const double* d_x2d, const double* d_conf, double* d_sums, double* d_gX, double* d_gR,
+                              double* d_gt, double* d_gK, void* d_workspace, size_t ws_bytes, void* stream);
+/* Regularisers (loss.py:97-155): raw fp64 sums + UNSCALED gradients (nullable); the caller applies
+ * w / count.  d_workspace >= ska_reg_workspace_bytes().
+ *   pose_temporal   :153-155  d_sum[0] = sum_{t<T-1} |X[t+1]-X[t]|^2            count = (T-1)*J*3
+ *   bone_length     :134-150  d_ref == NULL: d_sums[b] = sum_t len[t][b] (the caller forms the mean);
+ *                             else d_sums[0] = sum_{t,b} (len - d_ref[b])^2      count = T*n_bones
+ *                             bone_i / bone_j: HOST index arrays (BONES, :118-131), n_bones <= SKA_MAX_BONES;
+ *                             d_sums holds SKA_MAX_BONES doubles
+ *   camera_centre   :97-100   d_C (n,3) = -R^T t
+ *   camera_smooth   :103-106  cameras (D0, M): d_sum[0] = sum_{d<D0-1,m} |C[d+1][m]-C[d][m]|^2   count = (D0-1)*M*3
+ *   baseline_reg    :109-114  cameras (T, C>=2): d_mean == NULL: d_sum[0] = sum_t |C0-C1|;
+ *                             else d_sum[0] = sum_t (|C0-C1| - d_mean[0])^2      count = T */
+size_t ska_reg_workspace_bytes(void);
+int ska_pose_temporal_f32(const float* d_X, int64_t T, int32_t J, double* d_sum, float* d_gX, void* d_workspace, size_t ws_bytes, void* stream);
+int ska_pose_temporal_f64(const double* d_X, int64_t T, int32_t J, double* d_sum, double* d_gX, void* d_workspace, size_t ws_bytes, void* stream);
+int ska_bone_length_f32(const float* d_X, int64_t T, int32_t J, const int32_t* bone_i, const int32_t* bone_j, int32_t n_bones,
+                        const double* d_ref, double* d_sums, float* d_gX, void* d_workspace, size_t ws_bytes, void* stream);
+int ska_bone_length_f64(const double* d_X, int64_t T, int32_t J, const int32_t* bone_i, const int32_t* bone_j, int32_t n_bones,
+                        const double* d_ref, double* d_sums, double* d_gX, void* d_workspace, size_t ws_bytes, void* stream);
+int ska_camera_centre_f32(const float* d_R, const float* d_t, int64_t n, float* d_C, void* stream);
+int ska_camera_centre_f64(const double* d_R, const double* d_t, int64_t n, double* d_C, void* stream);
+int ska_camera_smooth_f32(const float* d_R, const float* d_t, int64_t D0, int64_t M, double* d_sum, float* d_gR, float* d_gt,
+                          void* d_workspace, size_t ws_bytes, void* stream);
+int ska_camera_smooth_f64(const double* d_R, const double* d_t, int64_t D0, int64_t M, double* d_sum, double* d_gR, double* d_gt,
+                          void* d_workspace, size_t ws_bytes, void* stream);
+int ska_baseline_reg_f32(const float* d_R, const float* d_t, int64_t T, int32_t C, const double* d_mean, double* d_sum,
+                         float* d_gR, float* d_gt, void* d_workspace, size_t ws_bytes, void* stream);
+int ska_baseline_reg_f64(const double* d_R, const double* d_t, int64_t T, int32_t C, const double* d_mean, double* d_sum,
+                         double* d_gR, double* d_gt, void* d_workspace, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Bundle adjustment: Levenberg-Marquardt with Schur complement over a whole clip.

@@ -5,9 +5,10 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_VIEWS = 8
 MAX_BA_VIEWS = 8
+MAX_BONES = 16
 
 LAYOUT_VIEW_MAJOR = 0
 LAYOUT_FRAME_MAJOR = 1
@@ -82,6 +83,8 @@ def make_cameras(K, R, t, dist=None):
     K = np.broadcast_to(K, (V, 3, 3)) if K.ndim == 2 else K.reshape(V, 3, 3)
     if dist is None:
         dists = [None] * V
+    elif isinstance(dist, (list, tuple)) and len(dist) == V and any(d is None or np.ndim(d) >= 1 for d in dist):
+        dists = list(dist)  # one entry (vector or None) per view
     else:
         try:
             arr = np.asarray(dist, np.float64)

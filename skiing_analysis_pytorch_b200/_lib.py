@@ -30,9 +30,21 @@ _SIGS = {
     "ska_build_arch": (C.c_char_p, []),
     "ska_triangulate_reproject_f32": (
         C.c_int,
-        [C.POINTER(_cabi.SkaCamera), C.c_int32, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint32,
+        [C.POINTER(_cabi.SkaCamera), C.c_int32, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint32,
          _vp, _vp, _vp, _vp, _vp],
     ),
+    "ska_tri_frames_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
+    "ska_triangulate_reproject_frames_f32": (
+        C.c_int,
+        [C.POINTER(_cabi.SkaCamera), C.c_int32, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint32,
+         _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp],
+    ),
+    "ska_reproject_points_f32": (
+        C.c_int, [C.POINTER(_cabi.SkaCamera), C.c_int32, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp]
+    ),
+    "ska_frame_stats_f32": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
+    "ska_loss_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "ska_reg_workspace_bytes": (C.c_size_t, []),
     "ska_ba_red_doubles": (C.c_int32, [C.c_int32]),
     "ska_ba_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "ska_ba_sum_f32": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_size_t, _vp]),
@@ -41,6 +53,19 @@ _SIGS = {
     "ska_ba_backsub_f32": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), _vp]),
     "ska_ba_control_f64": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), _vp]),
 }
+for _sfx in ("f32", "f64"):
+    _i64, _i32 = C.c_int64, C.c_int32
+    _SIGS[f"ska_project_points_{_sfx}"] = (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp])
+    _SIGS[f"ska_reprojection_loss_{_sfx}"] = (
+        C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]
+    )
+    _SIGS[f"ska_pose_temporal_{_sfx}"] = (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, C.c_size_t, _vp])
+    _SIGS[f"ska_bone_length_{_sfx}"] = (
+        C.c_int, [_vp, _i64, _i32, C.POINTER(_i32), C.POINTER(_i32), _i32, _vp, _vp, _vp, _vp, C.c_size_t, _vp]
+    )
+    _SIGS[f"ska_camera_centre_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _vp, _vp])
+    _SIGS[f"ska_camera_smooth_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, C.c_size_t, _vp])
+    _SIGS[f"ska_baseline_reg_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp])
 
 
 def exported_symbols():

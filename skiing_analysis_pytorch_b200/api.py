@@ -60,7 +60,9 @@ def triangulate_reproject(
     kpts  (V,T,J,2) [layout "VTJ2"] or (T,V,J,2) [layout "TVJ2"], float32 CUDA, pixels.
     conf  matching (V,T,J) / (T,V,J) or None (unit weights = the reference's behaviour,
           triangulation/triangulate.py:65-67).
-    K     (3,3) or (V,3,3); R (V,3,3), t (V,3): world->camera, host arrays (fp64 kept).
+    K     (3,3) or (V,3,3); R (V,3,3), t (V,3): world->camera, host arrays (fp64 kept) - a static rig.
+          R (T,V,3,3), t (T,V,3) [host arrays or CUDA tensors]: PER-FRAME extrinsics, what
+          process_triangulate passes (triangulation/triangulate.py:76-82); K / dist stay shared.
     dist  None | (n,) OpenCV coefficients shared by all views | list per view; used for SCORING only
           (the reference triangulates raw pixels and reprojects with distortion - quirk Q1,
           triangulate.py:82 vs :103-105).
@@ -98,11 +100,17 @@ def triangulate_reproject(
         raise ValueError("weight_power must be 1.0 (row weight = conf) or 0.5 (row weight = sqrt(conf))")
     if pinhole_reproj:
         flags |= _cabi.PINHOLE_REPROJ
-    R = np.asarray(R, np.float64)
-    if R.shape != (V, 3, 3):
-        raise ValueError(f"R must be ({V},3,3), got {R.shape}")
-    cams = _cabi.make_cameras(K, R, t, dist)
     dev = kpts.device
+    Rt_frames = None
+    if (torch.is_tensor(R) and R.dim() == 4) or (not torch.is_tensor(R) and np.ndim(R) == 4):
+        Rt_frames = _pack_frame_extrinsics(R, t, T, V, dev)
+        cams = _cabi.make_cameras(K, np.broadcast_to(np.eye(3), (V, 3, 3)), np.zeros((V, 3)), dist)
+    else:
+        R = np.asarray(R.detach().cpu() if torch.is_tensor(R) else R, np.float64)
+        if R.shape != (V, 3, 3):
+            raise ValueError(f"R must be ({V},3,3) or ({T},{V},3,3), got {R.shape}")
+        t = t.detach().cpu() if torch.is_tensor(t) else t
+        cams = _cabi.make_cameras(K, R, t, dist)
     out = out or {}
     X = out.get("X")
     if X is None:
@@ -124,12 +132,102 @@ def triangulate_reproject(
     if T == 0:  # empty clip: nothing to launch (an empty tensor has a NULL data pointer)
         return TriangulationResult(X=X, err=err, proj=proj, status=status)
     with torch.cuda.device(dev):
-        rc = lib.ska_triangulate_reproject_f32(
-            cams, V, cptr, None, _ptr(kpts), _ptr(conf), T, J, lay, flags, _ptr(X), _ptr(err), _ptr(proj),
-            _ptr(status), _stream_ptr(dev),
-        )
+        if Rt_frames is not None:
+            ws_bytes = int(lib.ska_tri_frames_workspace_bytes(V, T))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            rc = lib.ska_triangulate_reproject_frames_f32(
+                cams, V, _ptr(Rt_frames), _ptr(kpts), _ptr(conf), T, J, lay, flags, _ptr(X), _ptr(err), _ptr(proj),
+                _ptr(status), _ptr(ws), ws_bytes, _stream_ptr(dev),
+            )
+            ws.record_stream(torch.cuda.current_stream(dev))
+        else:
+            rc = lib.ska_triangulate_reproject_f32(
+                cams, V, cptr, _ptr(kpts), _ptr(conf), T, J, lay, flags, _ptr(X), _ptr(err), _ptr(proj),
+                _ptr(status), _stream_ptr(dev),
+            )
     _lib.check(rc)
     return TriangulationResult(X=X, err=err, proj=proj, status=status)
+
+
+def _pack_frame_extrinsics(R, t, T: int, V: int, dev) -> torch.Tensor:
+    """(T,V,3,3) + (T,V,3) -> (T,V,12) fp64 CUDA [R row-major | t] (include/ska.h d_Rt_frames)."""
+    Rt = torch.as_tensor(np.asarray(R, np.float64) if not torch.is_tensor(R) else R).to(dev, torch.float64)
+    tt = torch.as_tensor(np.asarray(t, np.float64) if not torch.is_tensor(t) else t).to(dev, torch.float64)
+    if tuple(Rt.shape) != (T, V, 3, 3):
+        raise ValueError(f"per-frame R must be ({T},{V},3,3), got {tuple(Rt.shape)}")
+    tt = tt.reshape(T, V, 3)
+    return torch.cat([Rt.reshape(T, V, 9), tt], dim=-1).contiguous()
+
+
+def reproject_points(
+    X: torch.Tensor,
+    K,
+    R,
+    t,
+    dist=None,
+    kpts: Optional[torch.Tensor] = None,
+    *,
+    layout: str = "VTJ2",
+    want: Sequence[str] = ("proj",),
+):
+    """cv2.projectPoints-style reprojection of GIVEN points X (T,J,3) f32 CUDA into V cameras
+    (world->camera R (V,3,3), t (V,3), K (3,3)|(V,3,3), dist as in triangulate_reproject), computed
+    in fp64 on the device and returned as float32 pixels like cv2 does.
+    Returns (proj, err): proj (V,T,J,2) | (T,V,J,2), err = |proj - kpts| per view (needs kpts), or None.
+    Batch form of triangulation/reproject.py:49-83 / bundle_adjustment/reproject.py:74-153."""
+    _require_cuda(X, "X")
+    if X.dim() != 3 or X.shape[-1] != 3:
+        raise ValueError(f"X must be (T,J,3), got {tuple(X.shape)}")
+    X = X.to(torch.float32).contiguous()
+    T, J, _ = X.shape
+    R = np.asarray(R, np.float64)
+    V = R.shape[0]
+    cams = _cabi.make_cameras(K, R, t, dist)
+    if layout == "VTJ2":
+        lay, kshape, eshape = _cabi.LAYOUT_VIEW_MAJOR, (V, T, J, 2), (V, T, J)
+    elif layout == "TVJ2":
+        lay, kshape, eshape = _cabi.LAYOUT_FRAME_MAJOR, (T, V, J, 2), (T, V, J)
+    else:
+        raise ValueError(f"layout must be 'VTJ2' or 'TVJ2', got {layout!r}")
+    dev = X.device
+    if kpts is not None:
+        _require_cuda(kpts, "kpts")
+        if tuple(kpts.shape) != kshape:
+            raise ValueError(f"kpts shape {tuple(kpts.shape)} does not match {kshape}")
+        kpts = kpts.to(torch.float32).contiguous()
+    proj = torch.empty(kshape, dtype=torch.float32, device=dev) if "proj" in want else None
+    err = None
+    if "err" in want:
+        if kpts is None:
+            raise ValueError("want='err' needs kpts")
+        err = torch.empty(eshape, dtype=torch.float32, device=dev)
+    if T > 0:
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ska_reproject_points_f32(cams, V, _ptr(X), _ptr(kpts), T, J, lay, _ptr(proj), _ptr(err),
+                                                            _stream_ptr(dev)))
+    return proj, err
+
+
+def frame_stats(err: torch.Tensor, *, layout: str = "VTJ2") -> torch.Tensor:
+    """nan-aware per-(frame, view) statistics of pixel errors: (T,V,4) f32 = [rmse, mean, median, max]
+    (the scalars of reproject_and_visualize, triangulation/reproject.py:254-261)."""
+    _require_cuda(err, "err")
+    if err.dim() != 3:
+        raise ValueError(f"err must be 3-D, got {tuple(err.shape)}")
+    err = err.to(torch.float32).contiguous()
+    if layout == "VTJ2":
+        V, T, J = err.shape
+        lay = _cabi.LAYOUT_VIEW_MAJOR
+    elif layout == "TVJ2":
+        T, V, J = err.shape
+        lay = _cabi.LAYOUT_FRAME_MAJOR
+    else:
+        raise ValueError(f"layout must be 'VTJ2' or 'TVJ2', got {layout!r}")
+    out = torch.empty((T, V, 4), dtype=torch.float32, device=err.device)
+    if T > 0:
+        with torch.cuda.device(err.device):
+            _lib.check(_lib.load().ska_frame_stats_f32(_ptr(err), T, J, V, lay, _ptr(out), _stream_ptr(err.device)))
+    return out
 
 
 _HOST_PIPE_CACHE: dict = {}

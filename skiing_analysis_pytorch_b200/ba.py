@@ -40,7 +40,78 @@ def _stream_ptr(dev) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-class BundleAdjuster:
+def frame_shard(total_frames: int, world: int, rank: int):
+    """Contiguous frame range [t0, t1) of `rank` when a clip is sharded over `world` ranks (points
+    are private to a frame, so BA and triangulation shard by frame range)."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, rem = divmod(int(total_frames), int(world))
+    t0 = rank * base + min(rank, rem)
+    return t0, t0 + base + (1 if rank < rem else 0)
+
+
+class LMSequencer:
+    """Engine-agnostic sequencing of LM trials over a frame-sharded clip.
+
+    A trial is  linearize -> all-reduce(red) -> solve -> backsub -> all-reduce(red2) -> control;
+    every rank holds its own frame range, runs the identical reduced solve and controller on the
+    reduced sums, and therefore takes the identical accept/reject decision without any further
+    communication.  Subclasses provide the four steps and the two payload tensors `red` / `red2`
+    (the CUDA engine below; an fp64 numpy engine in tests/ exercises this class over gloo)."""
+
+    group = None
+    max_iters = 0
+    iters_done = 0
+    _graph = None
+
+    def _distributed(self) -> bool:
+        return (torch.distributed.is_available() and torch.distributed.is_initialized()
+                and torch.distributed.get_world_size(self.group) > 1)
+
+    def _allreduce(self, t: torch.Tensor):
+        if self._distributed():
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+
+    def trial(self):
+        """Enqueue one LM trial (accepted or rejected by the controller)."""
+        self.linearize()
+        self._allreduce(self.red)
+        self.solve()
+        self.backsub()
+        self._allreduce(self.red2)
+        self.control()
+
+    def run(self, num_iters: int, graph: bool = False):
+        """Enqueue `num_iters` trials.  graph=True captures one trial in a CUDA graph (single-GPU
+        solves only: the all-reduce stays outside captured regions) and replays it."""
+        if self.iters_done + num_iters > self.max_iters:
+            raise ValueError(f"history buffer holds {self.max_iters} trials; raise max_iters")
+        if graph and self._distributed():
+            graph = False
+        if graph:
+            if self._graph is None:
+                self.trial()  # warm-up outside capture (module load, attribute setting)
+                num_iters -= 1
+                self.iters_done += 1
+                g = torch.cuda.CUDAGraph()
+                s = torch.cuda.Stream(self.dev)
+                s.wait_stream(torch.cuda.current_stream(self.dev))
+                with torch.cuda.stream(s):
+                    with torch.cuda.graph(g, stream=s):
+                        self.trial()
+                torch.cuda.current_stream(self.dev).wait_stream(s)
+                self._graph = g
+                # capture does not execute: the captured trial still has to run num_iters times
+            for _ in range(num_iters):
+                self._graph.replay()
+        else:
+            for _ in range(num_iters):
+                self.trial()
+        self.iters_done += num_iters
+        return self
+
+
+class BundleAdjuster(LMSequencer):
     """One BA problem resident on one GPU (this rank's frame shard).
 
     x2d   (T,C,J,2) float32 CUDA [layout "TCJ2", the reference's] or (C,T,J,2) ["CTJ2"]
@@ -129,13 +200,6 @@ class BundleAdjuster:
         self._allreduce(self.ctrl[_cabi.BA_CTRL_SUMCONF: _cabi.BA_CTRL_SUMCONF + 1])
 
     # ------------------------------------------------------------------ pieces of one trial
-    def _allreduce(self, t: torch.Tensor):
-        if self._distributed():
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
-
-    def _world(self) -> int:
-        return torch.distributed.get_world_size(self.group)
-
     def linearize(self):
         with torch.cuda.device(self.dev):
             _lib.check(self.lib.ska_ba_linearize_f32(C.byref(self.prob), _stream_ptr(self.dev)))
@@ -151,48 +215,6 @@ class BundleAdjuster:
     def control(self):
         with torch.cuda.device(self.dev):
             _lib.check(self.lib.ska_ba_control_f64(C.byref(self.prob), _stream_ptr(self.dev)))
-
-    def trial(self):
-        """Enqueue one LM trial (accepted or rejected on the device)."""
-        self.linearize()
-        self._allreduce(self.red)
-        self.solve()
-        self.backsub()
-        self._allreduce(self.red2)
-        self.control()
-
-    # ------------------------------------------------------------------ driver
-    def run(self, num_iters: int, graph: bool = False):
-        """Enqueue `num_iters` trials.  graph=True captures one trial in a CUDA graph (single-GPU
-        solves only: the all-reduce stays outside captured regions) and replays it."""
-        if self.iters_done + num_iters > self.max_iters:
-            raise ValueError(f"history buffer holds {self.max_iters} trials; raise max_iters")
-        if graph and self._distributed():
-            graph = False
-        if graph:
-            if self._graph is None:
-                self.trial()  # warm-up outside capture (module load, attribute setting)
-                num_iters -= 1
-                self.iters_done += 1
-                g = torch.cuda.CUDAGraph()
-                s = torch.cuda.Stream(self.dev)
-                s.wait_stream(torch.cuda.current_stream(self.dev))
-                with torch.cuda.stream(s):
-                    with torch.cuda.graph(g, stream=s):
-                        self.trial()
-                torch.cuda.current_stream(self.dev).wait_stream(s)
-                self._graph = g
-                # capture does not execute: the captured trial still has to run num_iters times
-            for _ in range(num_iters):
-                self._graph.replay()
-        else:
-            for _ in range(num_iters):
-                self.trial()
-        self.iters_done += num_iters
-        return self
-
-    def _distributed(self) -> bool:
-        return torch.distributed.is_available() and torch.distributed.is_initialized() and self._world() > 1
 
     # ------------------------------------------------------------------ results (synchronise)
     @property

@@ -25,20 +25,25 @@ int ska_abi_version(void) { return SKA_ABI_VERSION; }
 const char* ska_last_error(void) { return g_err; }
 const char* ska_build_arch(void) { return "sm_100a"; }
 
-int ska_triangulate_reproject_f32(const SkaCamera* cams, int32_t V, const double* centre, const double* d_Rt_frames,
-                                  const float* d_kpts, const float* d_conf, int64_t T, int32_t J, int32_t layout,
-                                  uint32_t flags, float* d_X, float* d_err, float* d_proj, uint8_t* d_status,
-                                  void* stream) {
+static int check_tri_common(const SkaCamera* cams, int32_t V, const float* d_kpts, const float* d_conf, int64_t T, int32_t J,
+                            int32_t layout, uint32_t flags, float* d_X, float* d_err, float* d_proj) {
   if (cams == nullptr || d_kpts == nullptr || d_X == nullptr) return set_error(SKA_EINVAL, "cams, d_kpts and d_X must not be NULL");
   if (V < 2 || V > SKA_MAX_VIEWS) return set_error(SKA_EINVAL, "V must be in 2..SKA_MAX_VIEWS");
   if (T < 0 || J < 1) return set_error(SKA_EINVAL, "T must be >= 0 and J >= 1");
   if (layout != SKA_LAYOUT_VIEW_MAJOR && layout != SKA_LAYOUT_FRAME_MAJOR) return set_error(SKA_EINVAL, "bad layout");
   if ((flags & SKA_SOLVER_MASK) == 3u) return set_error(SKA_EINVAL, "bad solver");
   if (T * (int64_t)J >= (int64_t)1 << 31) return set_error(SKA_EINVAL, "T*J must be < 2^31 per call; shard the clip");
-  if (d_Rt_frames != nullptr) return set_error(SKA_EUNSUPPORTED, "per-frame extrinsics: use ska_triangulate_reproject_perframe_f32");
   auto al = [](const void* p, uintptr_t n) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % n) == 0; };
   if (!al(d_kpts, 8) || !al(d_proj, 8)) return set_error(SKA_EALIGN, "d_kpts / d_proj must be 8-byte aligned");
   if (!al(d_conf, 4) || !al(d_err, 4) || !al(d_X, 4)) return set_error(SKA_EALIGN, "float pointers must be 4-byte aligned");
+  return SKA_OK;
+}
+
+int ska_triangulate_reproject_f32(const SkaCamera* cams, int32_t V, const double* centre, const float* d_kpts,
+                                  const float* d_conf, int64_t T, int32_t J, int32_t layout, uint32_t flags, float* d_X,
+                                  float* d_err, float* d_proj, uint8_t* d_status, void* stream) {
+  const int rc = check_tri_common(cams, V, d_kpts, d_conf, T, J, layout, flags, d_X, d_err, d_proj);
+  if (rc != SKA_OK) return rc;
   if (T == 0) return SKA_OK;
   TriArgs a;
   a.cams = cams;
@@ -51,6 +56,41 @@ int ska_triangulate_reproject_f32(const SkaCamera* cams, int32_t V, const double
   } else {
     default_centre(cams, V, a.centre);
   }
+  a.Rt_frames = nullptr;
+  a.kpts = d_kpts;
+  a.conf = d_conf;
+  a.T = T;
+  a.J = J;
+  a.layout = layout;
+  a.flags = flags;
+  a.X = d_X;
+  a.err = d_err;
+  a.proj = d_proj;
+  a.status = d_status;
+  a.stream = stream;
+  a.workspace = nullptr;
+  a.ws_bytes = 0;
+  return triangulate_dispatch(a);
+}
+
+size_t ska_tri_frames_workspace_bytes(int32_t V, int64_t T) {
+  if (V < 2 || V > SKA_MAX_VIEWS || T < 0) return 0;
+  return tri_frames_workspace(V, T);
+}
+
+int ska_triangulate_reproject_frames_f32(const SkaCamera* cams, int32_t V, const double* d_Rt_frames, const float* d_kpts,
+                                         const float* d_conf, int64_t T, int32_t J, int32_t layout, uint32_t flags,
+                                         float* d_X, float* d_err, float* d_proj, uint8_t* d_status, void* d_workspace,
+                                         size_t ws_bytes, void* stream) {
+  const int rc = check_tri_common(cams, V, d_kpts, d_conf, T, J, layout, flags, d_X, d_err, d_proj);
+  if (rc != SKA_OK) return rc;
+  if (T == 0) return SKA_OK;
+  if (d_Rt_frames == nullptr) return set_error(SKA_EINVAL, "d_Rt_frames must not be NULL");
+  if (reinterpret_cast<uintptr_t>(d_Rt_frames) % 8 != 0) return set_error(SKA_EALIGN, "d_Rt_frames must be 8-byte aligned");
+  TriArgs a;
+  a.cams = cams;
+  a.V = V;
+  a.centre[0] = a.centre[1] = a.centre[2] = 0.0;
   a.Rt_frames = d_Rt_frames;
   a.kpts = d_kpts;
   a.conf = d_conf;
@@ -63,8 +103,99 @@ int ska_triangulate_reproject_f32(const SkaCamera* cams, int32_t V, const double
   a.proj = d_proj;
   a.status = d_status;
   a.stream = stream;
+  a.workspace = d_workspace;
+  a.ws_bytes = ws_bytes;
   return triangulate_dispatch(a);
 }
+
+int ska_reproject_points_f32(const SkaCamera* cams, int32_t V, const float* d_X, const float* d_kpts, int64_t T, int32_t J,
+                             int32_t layout, float* d_proj, float* d_err, void* stream) {
+  if (cams == nullptr || d_X == nullptr) return set_error(SKA_EINVAL, "cams and d_X must not be NULL");
+  if (V < 1 || V > SKA_MAX_VIEWS) return set_error(SKA_EINVAL, "V must be in 1..SKA_MAX_VIEWS");
+  if (T < 0 || J < 1) return set_error(SKA_EINVAL, "T must be >= 0 and J >= 1");
+  if (layout != SKA_LAYOUT_VIEW_MAJOR && layout != SKA_LAYOUT_FRAME_MAJOR) return set_error(SKA_EINVAL, "bad layout");
+  if (d_err != nullptr && d_kpts == nullptr) return set_error(SKA_EINVAL, "d_err needs d_kpts");
+  if (d_proj == nullptr && d_err == nullptr) return set_error(SKA_EINVAL, "nothing to compute: d_proj and d_err are both NULL");
+  auto al = [](const void* p, uintptr_t n) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % n) == 0; };
+  if (!al(d_kpts, 8) || !al(d_proj, 8)) return set_error(SKA_EALIGN, "d_kpts / d_proj must be 8-byte aligned");
+  if (T == 0) return SKA_OK;
+  return project_cv(cams, V, d_X, d_kpts, T, J, layout, d_proj, d_err, (cudaStream_t)stream);
+}
+
+int ska_frame_stats_f32(const float* d_err, int64_t T, int32_t J, int32_t V, int32_t layout, float* d_stats, void* stream) {
+  if (T < 0 || J < 1 || V < 1) return set_error(SKA_EINVAL, "T >= 0, J >= 1, V >= 1");
+  if (layout != SKA_LAYOUT_VIEW_MAJOR && layout != SKA_LAYOUT_FRAME_MAJOR) return set_error(SKA_EINVAL, "bad layout");
+  if (T == 0) return SKA_OK;
+  if (d_err == nullptr || d_stats == nullptr) return set_error(SKA_EINVAL, "d_err and d_stats must not be NULL");
+  return frame_stats(d_err, T, J, V, layout, d_stats, (cudaStream_t)stream);
+}
+
+// ---- loss.py entry points: thin typed wrappers over the templates
+#define SKA_LOSS_CHECK()                                                                                     \
+  do {                                                                                                       \
+    if (T < 0 || J < 1 || C < 1) return set_error(SKA_EINVAL, "T >= 0, J >= 1, C >= 1");                     \
+    if (T > 0 && (d_X == nullptr || d_R == nullptr || d_t == nullptr || d_K == nullptr))                     \
+      return set_error(SKA_EINVAL, "d_X, d_R, d_t and d_K must not be NULL");                                \
+    if (R_frame_stride != 0 && R_frame_stride != 9 * (int64_t)C) return set_error(SKA_EINVAL, "R frame stride must be 0 or 9*C"); \
+    if (t_frame_stride != 0 && t_frame_stride != 3 * (int64_t)C) return set_error(SKA_EINVAL, "t frame stride must be 0 or 3*C"); \
+    if (K_frame_stride != 0 && K_frame_stride != 9 * (int64_t)C) return set_error(SKA_EINVAL, "K frame stride must be 0 or 9*C"); \
+  } while (0)
+
+#define SKA_DEFINE_LOSS(SFX, S)                                                                                                   \
+  int ska_project_points_##SFX(const S* d_X, int64_t T, int32_t J, int32_t C, const S* d_R, int64_t R_frame_stride, const S* d_t, \
+                               int64_t t_frame_stride, const S* d_K, int64_t K_frame_stride, S* d_out, void* stream) {            \
+    SKA_LOSS_CHECK();                                                                                                             \
+    if (T > 0 && d_out == nullptr) return set_error(SKA_EINVAL, "d_out must not be NULL");                                        \
+    return project_points<S>(d_X, T, J, C, d_R, R_frame_stride, d_t, t_frame_stride, d_K, K_frame_stride, d_out,                  \
+                             (cudaStream_t)stream);                                                                               \
+  }                                                                                                                               \
+  int ska_reprojection_loss_##SFX(const S* d_X, int64_t T, int32_t J, int32_t C, const S* d_R, int64_t R_frame_stride,            \
+                                  const S* d_t, int64_t t_frame_stride, const S* d_K, int64_t K_frame_stride, const S* d_x2d,     \
+                                  const S* d_conf, double* d_sums, S* d_gX, S* d_gR, S* d_gt, S* d_gK, void* d_workspace,         \
+                                  size_t ws_bytes, void* stream) {                                                                \
+    SKA_LOSS_CHECK();                                                                                                             \
+    if (d_sums == nullptr || d_workspace == nullptr) return set_error(SKA_EINVAL, "d_sums and d_workspace must not be NULL");     \
+    if (T > 0 && d_x2d == nullptr) return set_error(SKA_EINVAL, "d_x2d must not be NULL");                                        \
+    return reprojection_loss<S>(d_X, T, J, C, d_R, R_frame_stride, d_t, t_frame_stride, d_K, K_frame_stride, d_x2d, d_conf,       \
+                                d_sums, d_gX, d_gR, d_gt, d_gK, d_workspace, ws_bytes, (cudaStream_t)stream);                     \
+  }                                                                                                                               \
+  int ska_pose_temporal_##SFX(const S* d_X, int64_t T, int32_t J, double* d_sum, S* d_gX, void* d_workspace, size_t ws_bytes,     \
+                              void* stream) {                                                                                     \
+    if (T < 0 || J < 1 || d_sum == nullptr || d_workspace == nullptr || (T > 0 && d_X == nullptr))                                \
+      return set_error(SKA_EINVAL, "bad arguments");                                                                              \
+    return pose_temporal<S>(d_X, T, J, d_sum, d_gX, d_workspace, ws_bytes, (cudaStream_t)stream);                                 \
+  }                                                                                                                               \
+  int ska_bone_length_##SFX(const S* d_X, int64_t T, int32_t J, const int32_t* bone_i, const int32_t* bone_j, int32_t n_bones,    \
+                            const double* d_ref, double* d_sums, S* d_gX, void* d_workspace, size_t ws_bytes, void* stream) {     \
+    if (T < 0 || J < 1 || d_sums == nullptr || d_workspace == nullptr || (T > 0 && d_X == nullptr) ||                             \
+        (n_bones > 0 && (bone_i == nullptr || bone_j == nullptr)))                                                                \
+      return set_error(SKA_EINVAL, "bad arguments");                                                                              \
+    return bone_length<S>(d_X, T, J, bone_i, bone_j, n_bones, d_ref, d_sums, d_gX, d_workspace, ws_bytes, (cudaStream_t)stream);  \
+  }                                                                                                                               \
+  int ska_camera_centre_##SFX(const S* d_R, const S* d_t, int64_t n, S* d_C, void* stream) {                                      \
+    if (n < 0 || (n > 0 && (d_R == nullptr || d_t == nullptr || d_C == nullptr))) return set_error(SKA_EINVAL, "bad arguments");  \
+    return camera_centre<S>(d_R, d_t, n, d_C, (cudaStream_t)stream);                                                              \
+  }                                                                                                                               \
+  int ska_camera_smooth_##SFX(const S* d_R, const S* d_t, int64_t D0, int64_t M, double* d_sum, S* d_gR, S* d_gt,                 \
+                              void* d_workspace, size_t ws_bytes, void* stream) {                                                 \
+    if (D0 < 0 || M < 0 || d_sum == nullptr || d_workspace == nullptr || (D0 * M > 0 && (d_R == nullptr || d_t == nullptr)))      \
+      return set_error(SKA_EINVAL, "bad arguments");                                                                              \
+    return camera_smooth<S>(d_R, d_t, D0, M, d_sum, d_gR, d_gt, d_workspace, ws_bytes, (cudaStream_t)stream);                     \
+  }                                                                                                                               \
+  int ska_baseline_reg_##SFX(const S* d_R, const S* d_t, int64_t T, int32_t C, const double* d_mean, double* d_sum, S* d_gR,      \
+                             S* d_gt, void* d_workspace, size_t ws_bytes, void* stream) {                                         \
+    if (T < 0 || d_sum == nullptr || d_workspace == nullptr || (T > 0 && (d_R == nullptr || d_t == nullptr)))                     \
+      return set_error(SKA_EINVAL, "bad arguments");                                                                              \
+    return baseline_reg<S>(d_R, d_t, T, C, d_mean, d_sum, d_gR, d_gt, d_workspace, ws_bytes, (cudaStream_t)stream);               \
+  }
+
+SKA_DEFINE_LOSS(f32, float)
+SKA_DEFINE_LOSS(f64, double)
+#undef SKA_DEFINE_LOSS
+#undef SKA_LOSS_CHECK
+
+size_t ska_loss_workspace_bytes(int32_t C) { return C < 1 ? 0 : loss_workspace_bytes(C); }
+size_t ska_reg_workspace_bytes(void) { return reg_workspace_bytes(); }
 
 static int check_problem(const SkaBaProblem* p, bool need_points) {
   if (p == nullptr) return set_error(SKA_EINVAL, "problem must not be NULL");

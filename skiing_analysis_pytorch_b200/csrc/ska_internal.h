@@ -26,9 +26,12 @@ struct TriArgs {
   float* proj;
   uint8_t* status;
   void* stream;
+  void* workspace;  // per-frame cameras only
+  size_t ws_bytes;
 };
 
 int triangulate_dispatch(const TriArgs& a);
+size_t tri_frames_workspace(int V, int64_t T);
 
 // bundle adjustment (ska_ba.cu / ska_ba_wide.cu)
 int ba_red_size(int C);
@@ -40,5 +43,32 @@ int ba_backsub(const SkaBaProblem& p, cudaStream_t s);
 int ba_solve(int C, uint64_t free_mask, const double* red, double* cams, double* ctrl, double* delta, void* stream);
 int ba_control(int C, const double* red, const double* red2, double* cams, double* ctrl, double* hist, void* stream);
 int launch_reduce(const double* partials, int rows, int ncol, double* out, cudaStream_t s);
+
+
+// standalone projection / losses (ska_project.cu, ska_losses.cu)
+int project_cv(const SkaCamera* cams, int V, const float* X, const float* kpts, int64_t T, int J, int layout, float* proj,
+               float* err, cudaStream_t s);
+int frame_stats(const float* err, int64_t T, int J, int V, int layout, float* out, cudaStream_t s);
+template <typename S>
+int project_points(const S* X, int64_t T, int J, int C, const S* R, int64_t R_sT, const S* t, int64_t t_sT, const S* K,
+                   int64_t K_sT, S* out, cudaStream_t s);
+size_t loss_workspace_bytes(int C);
+template <typename S>
+int reprojection_loss(const S* X, int64_t T, int J, int C, const S* R, int64_t R_sT, const S* t, int64_t t_sT, const S* K,
+                      int64_t K_sT, const S* x2d, const S* conf, double* sums, S* gX, S* gR, S* gt, S* gK, void* ws,
+                      size_t ws_bytes, cudaStream_t s);
+size_t reg_workspace_bytes();
+template <typename S>
+int pose_temporal(const S* X, int64_t T, int J, double* sum, S* gX, void* ws, size_t ws_bytes, cudaStream_t s);
+template <typename S>
+int bone_length(const S* X, int64_t T, int J, const int32_t* bi, const int32_t* bj, int nb, const double* ref, double* sums,
+                S* gX, void* ws, size_t ws_bytes, cudaStream_t s);
+template <typename S>
+int camera_centre(const S* R, const S* t, int64_t n, S* C, cudaStream_t s);
+template <typename S>
+int camera_smooth(const S* R, const S* t, int64_t D0, int64_t M, double* sum, S* gR, S* gt, void* ws, size_t ws_bytes, cudaStream_t s);
+template <typename S>
+int baseline_reg(const S* R, const S* t, int64_t T, int Cn, const double* mean, double* sum, S* gR, S* gt, void* ws, size_t ws_bytes,
+                 cudaStream_t s);
 
 }  // namespace ska

@@ -1,4 +1,5 @@
-// ska_prep.h - host-side (fp64) preparation of kernel-side cameras.  Host only.
+// ska_prep.h - fp64 preparation of kernel-side cameras.  Runs on the host for a static rig (once per
+// call) and on the device for per-frame extrinsics (tri_prep_frames kernel): same code, SKA_HD.
 #pragma once
 #include <math.h>
 #include <string.h>
@@ -11,7 +12,7 @@ namespace ska {
 // returns SKA_OK / SKA_EINVAL / SKA_EUNSUPPORTED; fills the fp32 centred camera and the fp64 P.
 // needs_dist_path is set when scoring must take the distortion/skew branch.
 // dist_level: 0 = pinhole scoring, 1 = rational + tangential, 2 = thin prism and/or skew as well.
-inline int prep_camera(const SkaCamera& in, const double c[3], bool pinhole_reproj, CamDev& out, double P64[12],
+SKA_HD int prep_camera(const SkaCamera& in, const double c[3], bool pinhole_reproj, CamDev& out, double P64[12],
                        int& dist_level, const char** why) {
   const double k22 = in.K[8];
   if (!(fabs(k22) > 0.0) || !isfinite(k22)) {
@@ -76,7 +77,7 @@ inline int prep_camera(const SkaCamera& in, const double c[3], bool pinhole_repr
 
 // Default conditioning origin: the point closest (least squares) to all optical axes, regularised
 // towards the mean camera centre along directions the axes do not determine (parallel axes).
-inline void default_centre(const SkaCamera* cams, int V, double c[3]) {
+SKA_HD void default_centre(const SkaCamera* cams, int V, double c[3]) {
   double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, b[3] = {0, 0, 0}, mean[3] = {0, 0, 0};
   for (int v = 0; v < V; ++v) {
     const double* R = cams[v].R;
@@ -109,7 +110,8 @@ inline void default_centre(const SkaCamera* cams, int V, double c[3]) {
   }
   double M[3][3];
   for (int col = 0; col < 3; ++col) {
-    memcpy(M, A, sizeof(M));
+    for (int r = 0; r < 3; ++r)
+      for (int q = 0; q < 3; ++q) M[r][q] = A[r][q];
     for (int r = 0; r < 3; ++r) M[r][col] = b[r];
     const double dc = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
                       M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);

@@ -2,4 +2,5 @@
 #include "ska_triangulate_impl.cuh"
 namespace ska {
 int tri_dispatch_v2(const TriArgs& a) { return dispatch<2>(a); }
+size_t tri_frames_ws_v2(int64_t T) { return frames_ws_bytes<2>(T); }
 }  // namespace ska

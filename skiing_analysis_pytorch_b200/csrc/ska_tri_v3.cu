@@ -2,4 +2,5 @@
 #include "ska_triangulate_impl.cuh"
 namespace ska {
 int tri_dispatch_v3(const TriArgs& a) { return dispatch<3>(a); }
+size_t tri_frames_ws_v3(int64_t T) { return frames_ws_bytes<3>(T); }
 }  // namespace ska

@@ -2,4 +2,5 @@
 #include "ska_triangulate_impl.cuh"
 namespace ska {
 int tri_dispatch_v4(const TriArgs& a) { return dispatch<4>(a); }
+size_t tri_frames_ws_v4(int64_t T) { return frames_ws_bytes<4>(T); }
 }  // namespace ska

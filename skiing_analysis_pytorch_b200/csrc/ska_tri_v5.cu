@@ -2,4 +2,5 @@
 #include "ska_triangulate_impl.cuh"
 namespace ska {
 int tri_dispatch_v5(const TriArgs& a) { return dispatch<5>(a); }
+size_t tri_frames_ws_v5(int64_t T) { return frames_ws_bytes<5>(T); }
 }  // namespace ska

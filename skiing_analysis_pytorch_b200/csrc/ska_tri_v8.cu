@@ -2,4 +2,5 @@
 #include "ska_triangulate_impl.cuh"
 namespace ska {
 int tri_dispatch_v8(const TriArgs& a) { return dispatch<8>(a); }
+size_t tri_frames_ws_v8(int64_t T) { return frames_ws_bytes<8>(T); }
 }  // namespace ska

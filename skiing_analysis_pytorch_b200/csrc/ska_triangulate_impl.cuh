@@ -236,8 +236,178 @@ static cudaError_t launch(TriParams<V>& prm, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Per-frame extrinsics (process_triangulate passes R[i], T[i] per frame: triangulate.py:76-82).
+// tri_prep_frames: one thread per frame turns the frame's fp64 [R|t] (T,V,12) into the same
+// kernel-side camera the static path prepares on the host (prep_camera / default_centre, identical
+// code) and stores it in the caller's workspace; tri_frames_kernel then runs the very same
+// tri_points<> arithmetic with cameras read through L1 (the ~J threads of a frame share them).
+template <int V>
+struct FrameCams {
+  CamDev cam[V];
+  double P64[V][12];
+  float c[4];
+};
+
+template <int V>
+struct StaticCams {
+  SkaCamera cam[V];
+};
+
+template <int V>
+__global__ void __launch_bounds__(128) tri_prep_frames(const __grid_constant__ StaticCams<V> st, const double* __restrict__ Rt,
+                                                      int64_t T, uint32_t pinhole, FrameCams<V>* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  SkaCamera cams[V];
+#pragma unroll 1
+  for (int v = 0; v < V; ++v) {
+    cams[v] = st.cam[v];
+    const double* s = Rt + (t * V + v) * 12;
+    for (int k = 0; k < 9; ++k) cams[v].R[k] = s[k];
+    for (int k = 0; k < 3; ++k) cams[v].t[k] = s[9 + k];
+  }
+  double c[3];
+  default_centre(cams, V, c);
+  FrameCams<V>& o = out[t];
+#pragma unroll 1
+  for (int v = 0; v < V; ++v) {
+    int d = 0;
+    const char* why = "";
+    CamDev cd;
+    double P[12];
+    prep_camera(cams[v], c, pinhole != 0, cd, P, d, &why);  // K / dist were validated on the host
+    o.cam[v] = cd;
+    for (int k = 0; k < 12; ++k) o.P64[v][k] = P[k];
+  }
+  o.c[0] = (float)c[0];
+  o.c[1] = (float)c[1];
+  o.c[2] = (float)c[2];
+  o.c[3] = 0.f;
+}
+
+template <int V>
+struct TriFrameParams {
+  const FrameCams<V>* frames;
+  uint32_t weight_sqrt, frame_major;
+  int32_t J;
+  int64_t N;
+  int64_t k_sV, k_sT, c_sV, c_sT;
+  const float* kpts;
+  const float* conf;
+  float* X;
+  float* err;
+  float* proj;
+  uint8_t* status;
+};
+
+template <int V>
+__global__ void __launch_bounds__(128) tri_frames_kernel(const TriFrameParams<V> prm) {
+  const int64_t i_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i_raw < prm.N;
+  const int64_t i = live ? i_raw : prm.N - 1;  // every lane stays alive for the warp votes
+  const uint32_t t = (uint32_t)i / (uint32_t)prm.J;
+  const uint32_t j = (uint32_t)i - t * (uint32_t)prm.J;
+  int64_t koff, coff;
+  if (prm.frame_major) {
+    koff = (int64_t)t * prm.k_sT + 2 * (int64_t)j;
+    coff = (int64_t)t * prm.c_sT + (int64_t)j;
+  } else {
+    koff = 2 * i;
+    coff = i;
+  }
+  float u[1][V], v[1][V], w2[1][V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const float2 q = __ldg(reinterpret_cast<const float2*>(prm.kpts + koff + (int64_t)k * prm.k_sV));
+    u[0][k] = q.x;
+    v[0][k] = q.y;
+    float c = 1.0f;
+    if (prm.conf != nullptr) c = __ldg(prm.conf + coff + (int64_t)k * prm.c_sV);
+    w2[0][k] = prm.weight_sqrt ? c : c * c;
+  }
+  PointSource src;
+  src.kpts = prm.kpts + koff;
+  src.conf = (prm.conf != nullptr) ? prm.conf + coff : nullptr;
+  src.k_sV = prm.k_sV;
+  src.c_sV = prm.c_sV;
+  src.weight_sqrt = prm.weight_sqrt;
+  const FrameCams<V>& fc = prm.frames[t];
+  float X[1][3], du[1][V], dv[1][V];
+  uint8_t st[1];
+  tri_points<V, 1, true, 2, kSolverSecular>(fc.cam, fc.P64, fc.c[0], fc.c[1], fc.c[2], u, v, w2, src, X, du, dv, st);
+  if (!live) return;
+  prm.X[3 * i] = X[0][0];
+  prm.X[3 * i + 1] = X[0][1];
+  prm.X[3 * i + 2] = X[0][2];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    if (prm.err != nullptr) prm.err[coff + (int64_t)k * prm.c_sV] = sqrt_fast(fmaf(du[0][k], du[0][k], dv[0][k] * dv[0][k]));
+    if (prm.proj != nullptr)
+      *reinterpret_cast<float2*>(prm.proj + koff + (int64_t)k * prm.k_sV) = make_float2(u[0][k] + du[0][k], v[0][k] + dv[0][k]);
+  }
+  if (prm.status != nullptr) prm.status[i] = st[0];
+}
+
+template <int V>
+static int dispatch_frames(const TriArgs& a) {
+  if (a.ws_bytes < (size_t)a.T * sizeof(FrameCams<V>) || a.workspace == nullptr)
+    return set_error(SKA_EWORKSPACE, "workspace too small (see ska_tri_frames_workspace_bytes)");
+  if (reinterpret_cast<uintptr_t>(a.workspace) % 16 != 0) return set_error(SKA_EALIGN, "workspace must be 16-byte aligned");
+  StaticCams<V> st;
+  const double origin[3] = {0.0, 0.0, 0.0};
+  for (int v = 0; v < V; ++v) {  // validate K / dist once on the host (R, t are per frame)
+    CamDev tmp;
+    double P[12];
+    int d = 0;
+    const char* why = "";
+    const int rc = prep_camera(a.cams[v], origin, (a.flags & SKA_PINHOLE_REPROJ) != 0, tmp, P, d, &why);
+    if (rc != SKA_OK) return set_error(rc, why);
+    st.cam[v] = a.cams[v];
+  }
+  cudaStream_t s = (cudaStream_t)a.stream;
+  FrameCams<V>* frames = reinterpret_cast<FrameCams<V>*>(a.workspace);
+  tri_prep_frames<V><<<(unsigned)((a.T + 127) / 128), 128, 0, s>>>(st, a.Rt_frames, a.T, (a.flags & SKA_PINHOLE_REPROJ) ? 1u : 0u, frames);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return set_error((int)ce, cudaGetErrorString(ce));
+  TriFrameParams<V> prm;
+  prm.frames = frames;
+  prm.weight_sqrt = (a.flags & SKA_WEIGHT_SQRT) ? 1u : 0u;
+  prm.J = a.J;
+  prm.N = a.T * (int64_t)a.J;
+  const bool fm = (a.layout == SKA_LAYOUT_FRAME_MAJOR);
+  prm.frame_major = fm ? 1u : 0u;
+  if (fm) {
+    prm.k_sV = 2 * (int64_t)a.J;
+    prm.k_sT = 2 * (int64_t)a.J * V;
+    prm.c_sV = a.J;
+    prm.c_sT = (int64_t)a.J * V;
+  } else {
+    prm.k_sV = 2 * prm.N;
+    prm.k_sT = 2 * (int64_t)a.J;
+    prm.c_sV = prm.N;
+    prm.c_sT = a.J;
+  }
+  prm.kpts = a.kpts;
+  prm.conf = a.conf;
+  prm.X = a.X;
+  prm.err = a.err;
+  prm.proj = a.proj;
+  prm.status = a.status;
+  tri_frames_kernel<V><<<(unsigned)((prm.N + 127) / 128), 128, 0, s>>>(prm);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) return set_error((int)ce, cudaGetErrorString(ce));
+  return SKA_OK;
+}
+
+template <int V>
+static size_t frames_ws_bytes(int64_t T) {
+  return (size_t)T * sizeof(FrameCams<V>);
+}
+
 template <int V>
 static int dispatch(const TriArgs& a) {
+  if (a.Rt_frames != nullptr) return dispatch_frames<V>(a);
   TriParams<V> prm;
   int dist = 0;  // max distortion level over the views: 0 pinhole, 1 rational+tangential, 2 prism/skew
   for (int v = 0; v < V; ++v) {

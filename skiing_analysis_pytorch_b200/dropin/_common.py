@@ -1,0 +1,148 @@
+"""Helpers shared by the drop-in shims: device choice, host<->device marshalling for the per-frame
+signatures (J <= 70 points per call: a GPU round trip, kept for API parity - throughput comes from
+the clip-level entry points), the reprojection panel and its statistics."""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+
+def device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: skiing_analysis_pytorch_b200 has no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def f32(a) -> np.ndarray:
+    """The reference's _as_float32 (triangulation/reproject.py:63-75): every input is down-cast."""
+    return np.asarray(a, dtype=np.float32)
+
+
+def nan_stats(err: np.ndarray) -> dict:
+    """rmse / mean / median / max exactly as reproject.py:254-261 (nan-aware, float64)."""
+    return {
+        "rmse": float(np.sqrt(np.nanmean(err**2))),
+        "mean": float(np.nanmean(err)),
+        "median": float(np.nanmedian(err)),
+        "max": float(np.nanmax(err)),
+    }
+
+
+def _bgr_u8(img) -> np.ndarray:
+    im = np.asarray(img.cpu() if torch.is_tensor(img) else img)
+    if im.ndim == 2:
+        im = np.stack([im] * 3, axis=-1)
+    elif im.ndim == 3 and im.shape[2] == 1:
+        im = np.repeat(im, 3, axis=2)
+    elif not (im.ndim == 3 and im.shape[2] == 3):
+        raise ValueError(f"Unsupported image shape: {im.shape}")
+    if im.dtype != np.uint8:
+        im = np.clip(im, 0, 255)
+        im = (im * 255.0).astype(np.uint8) if im.max() <= 1.0 else im.astype(np.uint8)
+    return np.ascontiguousarray(im)
+
+
+def render_reprojection_panel(
+    img1,
+    img2,
+    kptL,
+    kptR,
+    proj_L,
+    proj_R,
+    joint_names: Optional[Sequence[str]] = None,
+    circle_r: int = 5,
+    thickness: int = 2,
+    align_height: bool = True,
+    title_left: str = "Left/Cam1 (Green=Observed, Red=Reprojected)",
+    title_right: str = "Right/Cam2",
+):
+    """Host-side visualisation (NOT accelerated): observed keypoints in green,
+    reprojections in red, error vectors in cyan, both views side by side with an RMSE banner.
+    Same signature and return value (vis_left, vis_right, panel) as
+    triangulation/reproject.py:86-200 / bundle_adjustment/reproject.py:156-278."""
+    import cv2
+
+    views = [_bgr_u8(img1), _bgr_u8(img2)]
+    if align_height and views[0].shape[0] != views[1].shape[0]:
+        h = max(v.shape[0] for v in views)
+        views = [v if v.shape[0] == h else cv2.resize(v, (int(v.shape[1] * h / v.shape[0]), h), interpolation=cv2.INTER_LINEAR)
+                 for v in views]
+    green, red, cyan, white = (0, 255, 0), (0, 0, 255), (255, 255, 0), (255, 255, 255)
+    font = cv2.FONT_HERSHEY_SIMPLEX
+    drawn, banners = [], []
+    for vis, obs, rep, title in zip(views, (kptL, kptR), (proj_L, proj_R), (title_left, title_right)):
+        vis = vis.copy()
+        h, w = vis.shape[:2]
+        obs = np.asarray(obs, dtype=float).reshape(-1, 2)
+        rep = np.asarray(rep, dtype=float).reshape(-1, 2)
+        rep_c = np.stack([np.clip(rep[:, 0], 0, w - 1), np.clip(rep[:, 1], 0, h - 1)], axis=1)
+        for j in range(len(obs)):
+            if not (np.isfinite(obs[j]).all() and np.isfinite(rep_c[j]).all()):
+                continue
+            o = (int(round(obs[j, 0])), int(round(obs[j, 1])))
+            r = (int(round(rep_c[j, 0])), int(round(rep_c[j, 1])))
+            cv2.circle(vis, o, circle_r, green, thickness, cv2.LINE_AA)
+            cv2.circle(vis, r, circle_r, red, thickness, cv2.LINE_AA)
+            cv2.line(vis, o, r, cyan, 1, cv2.LINE_AA)
+            name = str(joint_names[j]) if joint_names is not None and j < len(joint_names) else str(j)
+            cv2.putText(vis, name, (o[0] + 6, o[1] - 6), font, 0.45, green, 1, cv2.LINE_AA)
+        e = np.linalg.norm(rep - obs, axis=1)
+        s = nan_stats(e)
+        banners.append(f"{title} | RMSE={s['rmse']:.2f}px  (mean={s['mean']:.2f}, med={s['median']:.2f}, max={s['max']:.2f})")
+        drawn.append(vis)
+    visL, visR = drawn
+    panel = np.zeros((max(visL.shape[0], visR.shape[0]), visL.shape[1] + visR.shape[1], 3), np.uint8)
+    panel[: visL.shape[0], : visL.shape[1]] = visL
+    panel[: visR.shape[0], visL.shape[1]:] = visR
+    cv2.putText(panel, banners[0], (20, 30), font, 0.7, white, 2, cv2.LINE_AA)
+    cv2.putText(panel, banners[1], (visL.shape[1] + 20, 30), font, 0.7, white, 2, cv2.LINE_AA)
+    return visL, visR, panel
+
+
+def report(proj_L, proj_R, kptL, kptR, errL=None, errR=None) -> dict:
+    """The statistics half of reproject_and_visualize (reproject.py:243-261): per-joint error in
+    float64 from float32 projections (quirk Q6) + nan-aware scalars."""
+    if errL is None:
+        errL = np.linalg.norm(proj_L - np.asarray(kptL, float), axis=1)
+    if errR is None:
+        errR = np.linalg.norm(proj_R - np.asarray(kptR, float), axis=1)
+    out = {"proj_L": proj_L, "proj_R": proj_R, "err_L": errL, "err_R": errR}
+    for side, e in (("L", errL), ("R", errR)):
+        s = nan_stats(e)
+        out[f"rmse_{side}"] = s["rmse"]
+        out[f"mean_err_{side}"] = s["mean"]
+        out[f"median_err_{side}"] = s["median"]
+        out[f"max_err_{side}"] = s["max"]
+    return out
+
+
+def visualize(img1, img2, proj, kptL, kptR, joint_names, circle_r, thickness, out_path) -> dict:
+    """Panel + statistics + imwrite; returns the dict of reproject.py:249-266 (same keys)."""
+    import cv2
+
+    visL, visR, panel = render_reprojection_panel(img1, img2, kptL, kptR, proj["proj_L"], proj["proj_R"],
+                                                  joint_names=joint_names, circle_r=circle_r, thickness=thickness)
+    res = report(proj["proj_L"], proj["proj_R"], kptL, kptR)
+    Path(out_path).parent.mkdir(parents=True, exist_ok=True)
+    cv2.imwrite(str(out_path), panel)
+    res.update(out_path=str(out_path), vis_left=visL, vis_right=visR, panel=panel)
+    return res
+
+
+def reproject_pair(X3, K1, dist1, K2, dist2, R_rel, t_rel) -> dict:
+    """cam1 = identity with (K1, dist1), cam2 = (R_rel, t_rel) with (K2, dist2); float32 in,
+    float32 (J,2) out - the arithmetic of reproject_points on the GPU (ska_reproject_points_f32)."""
+    from .. import api
+
+    dev = device()
+    X = torch.from_numpy(np.ascontiguousarray(f32(X3).reshape(1, -1, 3))).to(dev)
+    K = np.stack([f32(K1).reshape(3, 3), f32(K2).reshape(3, 3)]).astype(np.float64)
+    R = np.stack([np.eye(3), f32(R_rel).reshape(3, 3).astype(np.float64)])
+    t = np.stack([np.zeros(3), f32(t_rel).reshape(3).astype(np.float64)])
+    dists = [None if d is None else f32(d).reshape(-1).astype(np.float64) for d in (dist1, dist2)]
+    proj, _ = api.reproject_points(X, K, R, t, dists, want=("proj",))
+    p = proj.cpu().numpy()
+    return {"proj_L": p[0, 0], "proj_R": p[1, 0]}

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../skiing_analysis_pytorch_b200/csrc/ska_prep.h"
+#include "../../skiing_analysis_pytorch_b200/csrc/ska_project.cuh"
 #include "../../skiing_analysis_pytorch_b200/csrc/ska_tri_point.cuh"
 
 using namespace ska;
@@ -89,5 +90,29 @@ extern "C" int hostemu_triangulate(const SkaCamera* cams, int32_t V, const doubl
     case 4: return run<4>(cams, centre, kpts, conf, N, flags, X, err, status);
     case 8: return run<8>(cams, centre, kpts, conf, N, flags, X, err, status);
     default: return SKA_EUNSUPPORTED;
+  }
+}
+
+// cv2-style projection (ska_project.cuh project_cv64): cam = R(9) t(3) fx fy cx cy d(12)
+extern "C" void hostemu_project_cv(const double* cam, const double* X, int64_t N, double* uv) {
+  CamCv64 c;
+  for (int k = 0; k < 9; ++k) c.R[k] = cam[k];
+  for (int k = 0; k < 3; ++k) c.t[k] = cam[9 + k];
+  c.fx = cam[12]; c.fy = cam[13]; c.cx = cam[14]; c.cy = cam[15];
+  for (int k = 0; k < 12; ++k) c.d[k] = cam[16 + k];
+  for (int64_t i = 0; i < N; ++i) project_cv64(c, X[3 * i], X[3 * i + 1], X[3 * i + 2], uv[2 * i], uv[2 * i + 1]);
+}
+
+// loss.py projection + adjoint for one camera (ska_project.cuh): per point outputs
+//   uv (N,2), gXc (N,3), gK (N,6) for the cotangent g (N,2)
+extern "C" void hostemu_project_loss(const double* R, const double* t, const double* K, const double* X, const double* g,
+                                     int64_t N, double* uv, double* gXc, double* gK, uint8_t* clamped) {
+  for (int64_t i = 0; i < N; ++i) {
+    LossObs<double> o;
+    project_loss<double>(R, t, K, X + 3 * i, o);
+    uv[2 * i] = o.u;
+    uv[2 * i + 1] = o.v;
+    clamped[i] = o.clamped ? 1 : 0;
+    project_loss_adjoint<double>(K, o, g[2 * i], g[2 * i + 1], gXc + 3 * i, gK + 6 * i);
   }
 }

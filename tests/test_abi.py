@@ -25,7 +25,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/ska.h but not exported by libska.so"
     assert sorted(_lib.exported_symbols()) == syms, "ctypes signature table and header disagree"
-    assert lib.ska_abi_version() == 2
+    assert lib.ska_abi_version() == 3
     assert lib.ska_build_arch() == b"sm_100a"
 
 
@@ -50,7 +50,7 @@ def test_argument_errors_without_gpu():
     R, t = synth.rig("2b")
     cams = _cabi.make_cameras(synth.K_CALIB, R, t)
     fake = C.c_void_p(256)
-    args = lambda **kw: [kw.get("cams", cams), kw.get("V", 2), None, None, kw.get("kpts", fake), None, kw.get("T", 1),
+    args = lambda **kw: [kw.get("cams", cams), kw.get("V", 2), None, kw.get("kpts", fake), None, kw.get("T", 1),
                          kw.get("J", 17), kw.get("layout", 0), kw.get("flags", 0), kw.get("X", fake), None, None, None, None]
     assert lib.ska_triangulate_reproject_f32(*args(V=1)) == -1
     assert lib.ska_triangulate_reproject_f32(*args(V=9)) == -1
@@ -65,6 +65,22 @@ def test_argument_errors_without_gpu():
     assert lib.ska_triangulate_reproject_f32(*args(cams=tilted)) == -2
     with pytest.raises(ValueError):
         _cabi.make_cameras(synth.K_CALIB, R, t, [0.1] * 6)
+    # per-frame extrinsics: workspace contract
+    assert lib.ska_tri_frames_workspace_bytes(2, 10) > 0 and lib.ska_tri_frames_workspace_bytes(9, 10) == 0
+    fargs = [cams, 2, fake, fake, None, 4, 17, 0, 0, fake, None, None, None, fake, 16, None]
+    assert lib.ska_triangulate_reproject_frames_f32(*fargs) == -4  # workspace too small
+    fargs[2] = None
+    assert lib.ska_triangulate_reproject_frames_f32(*fargs) == -1
+    # standalone reprojection / statistics / losses
+    assert lib.ska_reproject_points_f32(cams, 2, fake, None, 1, 17, 0, None, None, None) == -1  # nothing to compute
+    assert lib.ska_reproject_points_f32(cams, 2, fake, None, 1, 17, 0, None, fake, None) == -1  # err needs kpts
+    assert lib.ska_reproject_points_f32(cams, 2, fake, None, 0, 17, 0, fake, None, None) == 0
+    assert lib.ska_frame_stats_f32(None, 0, 17, 2, 0, None, None) == 0
+    assert lib.ska_project_points_f32(fake, 1, 17, 2, fake, 5, fake, 0, fake, 0, fake, None) == -1  # bad stride
+    assert lib.ska_project_points_f64(fake, 0, 17, 2, fake, 0, fake, 0, fake, 0, fake, None) == 0
+    assert lib.ska_reprojection_loss_f32(fake, 1, 17, 2, fake, 0, fake, 0, fake, 0, fake, fake, None, None, None, None, None,
+                                         fake, 0, None) == -1
+    assert lib.ska_loss_workspace_bytes(2) > 0 and lib.ska_reg_workspace_bytes() > 0
 
 
 def test_api_refuses_cpu_tensors():

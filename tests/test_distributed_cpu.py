@@ -1,0 +1,102 @@
+"""world_size-2 (and 3) gloo runs of the product's LM sequencer on the CPU-only box: each rank owns a
+contiguous frame range, the packed reduced camera system and the trial scalars are all-reduced, and
+every rank must reproduce the single-process fp64 oracle trajectory (oracle/lm.py) exactly to
+rounding.  The compute engine here is the numpy oracle (tests/oracle_engine.py); the sequencing,
+sharding and collectives are the product's (skiing_analysis_pytorch_b200/ba.py)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, rig, T, J, mode, iters, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    from oracle import lm
+    from skiing_analysis_pytorch_b200.ba import frame_shard
+    from tests.oracle_engine import OracleBundleAdjuster
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        clip, R0, t0, X0 = lm.make_problem(rig, T, J)
+        a, b = frame_shard(T, world, rank)
+        ba = OracleBundleAdjuster(clip.x_fm[a:b], clip.conf_fm[a:b], clip.K, R0, t0, X0[a:b], mode=mode, max_iters=iters)
+        ba.run(iters)
+        np.savez(Path(out_dir) / f"rank{rank}.npz", R=ba.R, t=ba.t, X=ba.X, a=a, b=b,
+                 hist=np.array([[h["cost"], h["trial_cost"], h["lam"], h["rho"], float(h["accepted"]), h["pred"]] for h in ba.history]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,rig,T,J,mode", [(2, "2b", 41, 17, "full"), (3, "4", 20, 17, "pose_cam_t"), (2, "8", 9, 70, "full")])
+def test_sharded_lm_over_gloo_matches_single_process_oracle(tmp_path, world, rig, T, J, mode):
+    from oracle import lm
+
+    iters = 6
+    mp.spawn(_worker, args=(world, _free_port(), rig, T, J, mode, iters, str(tmp_path)), nprocs=world, join=True)
+    clip, R0, t0, X0 = lm.make_problem(rig, T, J)
+    R, t, X, hist = lm.run_lm(X0, R0, t0, clip.K, clip.x_fm, clip.conf_fm, num_iters=iters, mode=mode)
+    ref = np.array([[h["cost"], h["trial_cost"], h["lam"], h["rho"], float(h["accepted"]), h["pred"]] for h in hist])
+    outs = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    for o in outs:
+        # LM cost trajectory: north-star tolerance 1e-4 relative per iteration; the fp64 engines agree far tighter
+        np.testing.assert_allclose(o["hist"][:, :2], ref[:, :2], rtol=1e-9)
+        # identical accept / reject decisions wherever the decision is not rounding noise (at the
+        # optimum F_trial - F is ~1e-13 F and its sign is arbitrary); compare up to the first such trial
+        decisive = np.abs(ref[:, 0] - ref[:, 1]) > 1e-9 * ref[:, 0]
+        n_ok = len(decisive) if decisive.all() else int(np.argmin(decisive))
+        assert n_ok >= 3
+        np.testing.assert_array_equal(o["hist"][:n_ok, 4], ref[:n_ok, 4])
+        np.testing.assert_allclose(o["hist"][:n_ok, 2], ref[:n_ok, 2], rtol=1e-6)  # damping trajectory
+        if n_ok < len(decisive):
+            continue
+        np.testing.assert_allclose(o["R"], R, atol=1e-9)
+        np.testing.assert_allclose(o["t"], t, atol=1e-8)
+        np.testing.assert_allclose(o["X"], X.reshape(-1, 3)[int(o["a"]) * J: int(o["b"]) * J], atol=1e-7)
+    # every rank took the same decisions and holds the same cameras
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o["hist"], outs[0]["hist"])
+        np.testing.assert_array_equal(o["R"], outs[0]["R"])
+    assert sum(int(o["b"]) - int(o["a"]) for o in outs) == T
+
+
+def test_frame_shard_partitions_the_clip():
+    from skiing_analysis_pytorch_b200.ba import frame_shard
+
+    for T in (0, 1, 7, 100, 1_000_003):
+        for world in (1, 2, 3, 8):
+            r = [frame_shard(T, world, k) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == T
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+    with pytest.raises(ValueError):
+        frame_shard(10, 2, 2)
+
+
+def test_single_process_oracle_engine_equals_run_lm():
+    """The engine adapter itself (payload pack / unpack) is faithful: world = 1, no process group."""
+    from oracle import lm
+    from tests.oracle_engine import OracleBundleAdjuster
+
+    clip, R0, t0, X0 = lm.make_problem("3", 12, 17)
+    ba = OracleBundleAdjuster(clip.x_fm, clip.conf_fm, clip.K, R0, t0, X0, max_iters=5).run(5)
+    _, _, _, hist = lm.run_lm(X0, R0, t0, clip.K, clip.x_fm, clip.conf_fm, num_iters=5)
+    np.testing.assert_allclose([h["cost"] for h in ba.history], [h["cost"] for h in hist], rtol=1e-10)
+    np.testing.assert_allclose([h["trial_cost"] for h in ba.history], [h["trial_cost"] for h in hist], rtol=1e-10)
+    assert [h["accepted"] for h in ba.history] == [h["accepted"] for h in hist]
+    assert torch.is_tensor(ba.red) and ba.red.dtype == torch.float64

@@ -91,3 +91,62 @@ def test_hostemu_nan_propagates():
     X, err, st = hostemu.triangulate(cams, 2, x)
     assert np.isnan(X[5]).all() and st[5] == 2
     assert np.isfinite(np.delete(X, 5, axis=0)).all()
+
+
+def test_hostemu_cv_projection_matches_oracle():
+    """ska_project.cuh project_cv64 (the standalone reprojection kernel's arithmetic) vs the fp64 oracle."""
+    import ctypes as C
+
+    lib = C.CDLL(str(hostemu.build()))
+    rng = np.random.default_rng(0)
+    R, t = synth.rig("3")
+    X = synth.CENTRE + rng.normal(0, 0.5, (200, 3))
+    for dist in (None, synth.DIST_CALIB, np.r_[synth.DIST_CALIB[:8], 1e-3, -2e-3, 3e-3, 1e-3]):
+        d = np.zeros(12) if dist is None else np.asarray(dist, float)[:12]
+        K = synth.K_CALIB
+        cam = np.r_[R[1].ravel(), t[1], K[0, 0], K[1, 1], K[0, 2], K[1, 2], d]
+        uv = np.zeros((200, 2))
+        lib.hostemu_project_cv(cam.ctypes.data_as(C.c_void_p), np.ascontiguousarray(X).ctypes.data_as(C.c_void_p), C.c_int64(200),
+                               uv.ctypes.data_as(C.c_void_p))
+        ref = G.project_cv(X, R[1], t[1], K, None if dist is None else d)
+        assert np.abs(uv - ref).max() < 1e-9
+
+
+def test_hostemu_loss_projection_and_adjoint_match_autograd():
+    """ska_project.cuh project_loss / project_loss_adjoint vs torch.autograd on the plain restatement."""
+    import ctypes as C
+
+    import torch
+
+    from tests import torch_ref as TR
+
+    lib = C.CDLL(str(hostemu.build()))
+    rng = np.random.default_rng(1)
+    R, t = synth.rig("3")
+    K = synth.K_CALIB.copy()
+    K[0, 1] = 0.7  # skew is honoured (loss.py:74-82)
+    N = 64
+    X = synth.CENTRE + rng.normal(0, 0.5, (N, 3))
+    X[0] = [0.0, 0.0, -5.0]  # behind camera 0... for camera 1 pick a point behind it too
+    X[1] = -R[1].T @ t[1] - 2.0 * R[1].T @ np.array([0, 0, 1.0])
+    g = rng.normal(0, 1, (N, 2))
+    uv, gXc, gK, cl = np.zeros((N, 2)), np.zeros((N, 3)), np.zeros((N, 6)), np.zeros(N, np.uint8)
+    p = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+    lib.hostemu_project_loss(p(R[1]), p(t[1]), p(K), p(X), p(g), C.c_int64(N), p(uv), p(gXc), p(gK), p(cl))
+    Xt = torch.tensor(X[None], requires_grad=True)
+    Rt = torch.tensor(R[1][None], requires_grad=True)
+    tt = torch.tensor(t[1][None], requires_grad=True)
+    Kt = torch.tensor(K[None], requires_grad=True)
+    proj = TR.project_points(Xt, Rt, tt, Kt)  # (1,1,N,2)
+    assert np.abs(proj.detach().numpy()[0, 0] - uv).max() <= 1e-9 * np.abs(uv).max()
+    assert cl[1] == 1 and cl[2:].sum() == 0
+    (proj[0, 0] * torch.tensor(g)).sum().backward()
+    gX = gXc @ R[1]                      # gX = R^T gXc per point
+    scale = lambda a: np.abs(a).max() + 1e-30
+    assert np.abs(gX - Xt.grad.numpy()[0]).max() <= 1e-9 * scale(gX)
+    assert np.abs(gXc.sum(0) - tt.grad.numpy()[0]).max() <= 1e-9 * scale(gXc.sum(0))
+    gR = np.einsum("nr,nk->rk", gXc, X)
+    assert np.abs(gR - Rt.grad.numpy()[0]).max() <= 1e-9 * scale(gR)
+    gKs = gK.sum(0)
+    assert np.abs(gKs - Kt.grad.numpy()[0, :2].ravel()).max() <= 1e-9 * scale(gKs)
+    assert np.abs(Kt.grad.numpy()[0, 2]).max() == 0.0
