@@ -10,18 +10,12 @@
 #include <math.h>
 #include <stdint.h>
 
-#if defined(__CUDACC__)
-#define SKA_HD __host__ __device__ __forceinline__
-#define SKA_HD_NOINLINE __host__ __device__ __noinline__
-#else
-#define SKA_HD inline
-#define SKA_HD_NOINLINE inline
-#endif
+#include "ska_vec.cuh"
 
 namespace ska {
 
 // ---------------------------------------------------------------------------------------------
-// Kernel-side camera, fp32, prepared on the host in fp64 (prep_camera in ska_capi.cu).
+// Kernel-side camera, fp32, prepared in fp64 (prep_camera in ska_prep.h).
 // All quantities are expressed in CENTRED coordinates Y = X - c: P' = K [R | R c + t].
 // Centring is numerical conditioning only; the eigenproblem solved is the reference's
 // (un-centred, ||X~|| = 1) one - see secular_solve below.
@@ -38,39 +32,23 @@ struct CamDev {
   float s[4];     // s1..s4
 };
 
-SKA_HD float rcp_fast(float x) {
-#if defined(__CUDA_ARCH__)
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU.RCP, <= 1 ulp
-  return r;
-#else
-  return 1.0f / x;
-#endif
-}
-SKA_HD float sqrt_fast(float x) {
-#if defined(__CUDA_ARCH__)
-  float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-#else
-  return sqrtf(x);
-#endif
-}
+// Everything below is templated on T = float (one point) or F2 (two points in lockstep, packed
+// FFMA2 on sm_100a - ska_vec.cuh); camera coefficients stay scalar operands.
 
 // One DLT row pair for one view: a = u*P2 - P0, b = v*P2 - P1 (4 entries each).  The products are
 // fused (single rounding of the exact u*P2h - P0h, so the cancellation between u*r3 and cx*r3
 // costs nothing).  LO selects how much of the fp32-rounding of P' is restored from the lo parts:
 // 0 = none, 1 = translation column only (the ~1e4-magnitude entries that set the px-error floor),
 // 2 = all columns.
-template <int LO>
-SKA_HD void dlt_rows(const CamDev& c, float u, float v, float a[4], float b[4]) {
+template <int LO, typename T>
+SKA_HD void dlt_rows(const CamDev& c, T u, T v, T a[4], T b[4]) {
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
-    float ah = fmaf(u, c.Ph[8 + m], -c.Ph[m]);
-    float bh = fmaf(v, c.Ph[8 + m], -c.Ph[4 + m]);
+    T ah = vfma(u, c.Ph[8 + m], -c.Ph[m]);
+    T bh = vfma(v, c.Ph[8 + m], -c.Ph[4 + m]);
     if (LO == 2 || (LO == 1 && m == 3)) {
-      ah += fmaf(u, c.Pl[8 + m], -c.Pl[m]);
-      bh += fmaf(v, c.Pl[8 + m], -c.Pl[4 + m]);
+      ah = vadd(ah, vfma(u, c.Pl[8 + m], -c.Pl[m]));
+      bh = vadd(bh, vfma(v, c.Pl[8 + m], -c.Pl[4 + m]));
     }
     a[m] = ah;
     b[m] = bh;
@@ -78,69 +56,87 @@ SKA_HD void dlt_rows(const CamDev& c, float u, float v, float a[4], float b[4]) 
 }
 
 // Symmetric 4x4 accumulator, upper triangle: 00 01 02 03 11 12 13 22 23 33.
-struct Sym4 {
-  float m00, m01, m02, m03, m11, m12, m13, m22, m23, m33;
+template <typename T>
+struct Sym4T {
+  T m00, m01, m02, m03, m11, m12, m13, m22, m23, m33;
 };
-SKA_HD void sym4_zero(Sym4& M) { M.m00 = M.m01 = M.m02 = M.m03 = M.m11 = M.m12 = M.m13 = M.m22 = M.m23 = M.m33 = 0.f; }
-SKA_HD void sym4_rank1(Sym4& M, const float r[4], float w2) {
-  const float s0 = r[0] * w2, s1 = r[1] * w2, s2 = r[2] * w2, s3 = r[3] * w2;
-  M.m00 = fmaf(s0, r[0], M.m00);
-  M.m01 = fmaf(s0, r[1], M.m01);
-  M.m02 = fmaf(s0, r[2], M.m02);
-  M.m03 = fmaf(s0, r[3], M.m03);
-  M.m11 = fmaf(s1, r[1], M.m11);
-  M.m12 = fmaf(s1, r[2], M.m12);
-  M.m13 = fmaf(s1, r[3], M.m13);
-  M.m22 = fmaf(s2, r[2], M.m22);
-  M.m23 = fmaf(s2, r[3], M.m23);
-  M.m33 = fmaf(s3, r[3], M.m33);
+using Sym4 = Sym4T<float>;
+template <typename T>
+SKA_HD void sym4_zero(Sym4T<T>& M) {
+  M.m00 = M.m01 = M.m02 = M.m03 = M.m11 = M.m12 = M.m13 = M.m22 = M.m23 = M.m33 = Vec<T>::splat(0.f);
 }
-// trace(M33^-1) from the LDL^T factors: an upper bound of 1/lambda_min(M33).
-struct Ldl3;
-
-SKA_HD void sym4_rank1_unit(Sym4& M, const float r[4]) {
-  M.m00 = fmaf(r[0], r[0], M.m00);
-  M.m01 = fmaf(r[0], r[1], M.m01);
-  M.m02 = fmaf(r[0], r[2], M.m02);
-  M.m03 = fmaf(r[0], r[3], M.m03);
-  M.m11 = fmaf(r[1], r[1], M.m11);
-  M.m12 = fmaf(r[1], r[2], M.m12);
-  M.m13 = fmaf(r[1], r[3], M.m13);
-  M.m22 = fmaf(r[2], r[2], M.m22);
-  M.m23 = fmaf(r[2], r[3], M.m23);
-  M.m33 = fmaf(r[3], r[3], M.m33);
+template <typename T>
+SKA_HD void sym4_rank1(Sym4T<T>& M, const T r[4], T w2) {
+  const T s0 = vmul(r[0], w2), s1 = vmul(r[1], w2), s2 = vmul(r[2], w2), s3 = vmul(r[3], w2);
+  M.m00 = vfma(s0, r[0], M.m00);
+  M.m01 = vfma(s0, r[1], M.m01);
+  M.m02 = vfma(s0, r[2], M.m02);
+  M.m03 = vfma(s0, r[3], M.m03);
+  M.m11 = vfma(s1, r[1], M.m11);
+  M.m12 = vfma(s1, r[2], M.m12);
+  M.m13 = vfma(s1, r[3], M.m13);
+  M.m22 = vfma(s2, r[2], M.m22);
+  M.m23 = vfma(s2, r[3], M.m23);
+  M.m33 = vfma(s3, r[3], M.m33);
+}
+template <typename T>
+SKA_HD void sym4_rank1_unit(Sym4T<T>& M, const T r[4]) {
+  M.m00 = vfma(r[0], r[0], M.m00);
+  M.m01 = vfma(r[0], r[1], M.m01);
+  M.m02 = vfma(r[0], r[2], M.m02);
+  M.m03 = vfma(r[0], r[3], M.m03);
+  M.m11 = vfma(r[1], r[1], M.m11);
+  M.m12 = vfma(r[1], r[2], M.m12);
+  M.m13 = vfma(r[1], r[3], M.m13);
+  M.m22 = vfma(r[2], r[2], M.m22);
+  M.m23 = vfma(r[2], r[3], M.m23);
+  M.m33 = vfma(r[3], r[3], M.m33);
+}
+template <int I, typename T>
+SKA_HD Sym4 sym4_lane(const Sym4T<T>& M) {
+  Sym4 r;
+  r.m00 = lane<I>(M.m00); r.m01 = lane<I>(M.m01); r.m02 = lane<I>(M.m02); r.m03 = lane<I>(M.m03);
+  r.m11 = lane<I>(M.m11); r.m12 = lane<I>(M.m12); r.m13 = lane<I>(M.m13);
+  r.m22 = lane<I>(M.m22); r.m23 = lane<I>(M.m23); r.m33 = lane<I>(M.m33);
+  return r;
 }
 
 // LDL^T of a symmetric 3x3 (a00 a01 a02 a11 a12 a22), reciprocal pivots kept.
-struct Ldl3 {  // (forward declared above)
-  float l10, l20, l21, r0, r1, r2;
-  bool pos;  // all pivots > 0  <=>  matrix positive definite
+template <typename T>
+struct Ldl3T {
+  T l10, l20, l21, r0, r1, r2;
+  typename Vec<T>::Mask pos;  // all pivots > 0  <=>  matrix positive definite
 };
-SKA_HD Ldl3 ldl3(float a00, float a01, float a02, float a11, float a12, float a22) {
-  Ldl3 f;
+using Ldl3 = Ldl3T<float>;
+template <typename T>
+SKA_HD Ldl3T<T> ldl3(T a00, T a01, T a02, T a11, T a12, T a22) {
+  Ldl3T<T> f;
   f.r0 = rcp_fast(a00);
-  f.l10 = a01 * f.r0;
-  f.l20 = a02 * f.r0;
-  const float d1 = fmaf(-f.l10, a01, a11);
+  f.l10 = vmul(a01, f.r0);
+  f.l20 = vmul(a02, f.r0);
+  const T d1 = vfma(vneg(f.l10), a01, a11);
   f.r1 = rcp_fast(d1);
-  const float t21 = fmaf(-f.l20, a01, a12);
-  f.l21 = t21 * f.r1;
-  const float d2 = fmaf(-f.l21, t21, fmaf(-f.l20, a02, a22));
+  const T t21 = vfma(vneg(f.l20), a01, a12);
+  f.l21 = vmul(t21, f.r1);
+  const T d2 = vfma(vneg(f.l21), t21, vfma(vneg(f.l20), a02, a22));
   f.r2 = rcp_fast(d2);
-  f.pos = (a00 > 0.f) & (d1 > 0.f) & (d2 > 0.f);
+  f.pos = mand(mand(vgt(a00, 0.f), vgt(d1, 0.f)), vgt(d2, 0.f));
   return f;
 }
-SKA_HD float ldl3_inv_trace(const Ldl3& f) {
+// trace(M33^-1) from the LDL^T factors: an upper bound of 1/lambda_min(M33).
+template <typename T>
+SKA_HD T ldl3_inv_trace(const Ldl3T<T>& f) {
   // M^-1 = L^-T D^-1 L^-1 with L^-1 = [[1,0,0],[-l10,1,0],[l10*l21-l20,-l21,1]]
-  const float q = fmaf(f.l10, f.l21, -f.l20);
-  return fmaf(f.r2, fmaf(q, q, fmaf(f.l21, f.l21, 1.0f)), fmaf(f.r1, fmaf(f.l10, f.l10, 1.0f), f.r0));
+  const T q = vfma(f.l10, f.l21, vneg(f.l20));
+  return vfma(f.r2, vfma(q, q, vfma(f.l21, f.l21, 1.0f)), vfma(f.r1, vfma(f.l10, f.l10, 1.0f), f.r0));
 }
-SKA_HD void ldl3_solve(const Ldl3& f, float b0, float b1, float b2, float& x0, float& x1, float& x2) {
-  const float y1 = fmaf(-f.l10, b0, b1);
-  const float y2 = fmaf(-f.l21, y1, fmaf(-f.l20, b0, b2));
-  x2 = y2 * f.r2;
-  x1 = fmaf(-f.l21, x2, y1 * f.r1);
-  x0 = fmaf(-f.l20, x2, fmaf(-f.l10, x1, b0 * f.r0));
+template <typename T>
+SKA_HD void ldl3_solve(const Ldl3T<T>& f, T b0, T b1, T b2, T& x0, T& x1, T& x2) {
+  const T y1 = vfma(vneg(f.l10), b0, b1);
+  const T y2 = vfma(vneg(f.l21), y1, vfma(vneg(f.l20), b0, b2));
+  x2 = vmul(y2, f.r2);
+  x1 = vfma(vneg(f.l21), x2, vmul(y1, f.r1));
+  x0 = vfma(vneg(f.l20), x2, vfma(vneg(f.l10), x1, vmul(b0, f.r0)));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -249,22 +245,22 @@ SKA_HD void jacobi4_smallest(T a[4][4], T vec[4], int sweeps) {
 // cv2.projectPoints distortion increment on normalised coordinates: returns (x'' - x, y'' - y).
 // rad - 1 is formed as ((k1-k4) r2 + (k2-k5) r4 + (k3-k6) r6) / den so no bits are lost to 1 + ...
 // PRISM adds the thin-prism terms s1..s4.
-template <bool PRISM>
-SKA_HD void distort_delta(const CamDev& c, float x, float y, float& dx, float& dy) {
-  const float xx = x * x, xy = x * y;
-  const float r2 = fmaf(y, y, xx);
-  const float num = r2 * fmaf(r2, fmaf(r2, c.dk[2], c.dk[1]), c.dk[0]);
-  const float den = fmaf(r2, fmaf(r2, fmaf(r2, c.kd[2], c.kd[1]), c.kd[0]), 1.0f);
-  const float radm1 = num * rcp_fast(den);
-  float tx = c.p2 * fmaf(2.0f, xx, r2);
-  float ty = c.p1 * fmaf(2.0f * y, y, r2);
+template <bool PRISM, typename T>
+SKA_HD void distort_delta(const CamDev& c, T x, T y, T& dx, T& dy) {
+  const T xx = vmul(x, x), xy = vmul(x, y), yy = vmul(y, y);
+  const T r2 = vadd(yy, xx);
+  const T num = vmul(r2, vfma(r2, vfma(r2, c.dk[2], c.dk[1]), c.dk[0]));
+  const T den = vfma(r2, vfma(r2, vfma(r2, c.kd[2], c.kd[1]), c.kd[0]), 1.0f);
+  const T radm1 = vmul(num, rcp_fast(den));
+  T tx = vmul(vfma(xx, 2.0f, r2), c.p2);
+  T ty = vmul(vfma(yy, 2.0f, r2), c.p1);
   if (PRISM) {
-    const float r4 = r2 * r2;
-    tx = fmaf(c.s[0], r2, fmaf(c.s[1], r4, tx));
-    ty = fmaf(c.s[2], r2, fmaf(c.s[3], r4, ty));
+    const T r4 = vmul(r2, r2);
+    tx = vfma(r2, c.s[0], vfma(r4, c.s[1], tx));
+    ty = vfma(r2, c.s[2], vfma(r4, c.s[3], ty));
   }
-  dx = fmaf(x, radm1, fmaf(c.tp1, xy, tx));
-  dy = fmaf(y, radm1, fmaf(c.tp2, xy, ty));
+  dx = vfma(x, radm1, vfma(xy, c.tp1, tx));
+  dy = vfma(y, radm1, vfma(xy, c.tp2, ty));
 }
 
 SKA_HD void distort64(const double* d /*12*/, double x, double y, double& xd, double& yd) {

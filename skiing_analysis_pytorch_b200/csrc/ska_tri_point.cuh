@@ -100,28 +100,127 @@ static SKA_HD_NOINLINE void solve_jacobi32(const Sym4& M, float cx, float cy, fl
 }
 
 // Rayleigh quotient of the centred iterate, evaluated from the rows; also returns the row
-// residuals (ra, rb) so the caller can reuse them.
-template <int V, bool CONF>
-SKA_HD float rayleigh(const float (*a)[4], const float (*b)[4], const float* w2, float y0, float y1, float y2, float cx,
-                      float cy, float cz, float* ra, float* rb, float& den) {
-  float num = 0.f;
+// residuals (ra, rb) so the caller can reuse them.  T = float or F2 (two points in lockstep).
+template <int V, bool CONF, typename T>
+SKA_HD T rayleigh(const T (*a)[4], const T (*b)[4], const T* w2, T y0, T y1, T y2, float cx, float cy, float cz, T* ra,
+                  T* rb, T& den) {
+  T num = Vec<T>::splat(0.f);
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    ra[k] = fmaf(a[k][0], y0, fmaf(a[k][1], y1, fmaf(a[k][2], y2, a[k][3])));
-    rb[k] = fmaf(b[k][0], y0, fmaf(b[k][1], y1, fmaf(b[k][2], y2, b[k][3])));
-    const float rr = fmaf(ra[k], ra[k], rb[k] * rb[k]);
-    num = CONF ? fmaf(w2[k], rr, num) : (num + rr);
+    ra[k] = vfma(a[k][0], y0, vfma(a[k][1], y1, vfma(a[k][2], y2, a[k][3])));
+    rb[k] = vfma(b[k][0], y0, vfma(b[k][1], y1, vfma(b[k][2], y2, b[k][3])));
+    const T rr = vfma(ra[k], ra[k], vmul(rb[k], rb[k]));
+    num = CONF ? vfma(w2[k], rr, num) : vadd(num, rr);
   }
-  const float X0 = y0 + cx, X1 = y1 + cy, X2 = y2 + cz;
-  den = fmaf(X0, X0, fmaf(X1, X1, fmaf(X2, X2, 1.0f)));
-  return num * rcp_fast(den);
+  const T X0 = vadd(y0, cx), X1 = vadd(y1, cy), X2 = vadd(y2, cz);
+  den = vfma(X0, X0, vfma(X1, X1, vfma(X2, X2, 1.0f)));
+  return vmul(num, rcp_fast(den));
 }
 
 constexpr float kFastTol2 = 1e-9f;   // one-factorisation path accepted if the correction is < 3.2e-5 relative
 constexpr float kFastLamTr = 1e-3f;  // and lam * trace(M33^-1) < 1e-3  (=> lam < 1e-3 * lambda_min(M33))
 constexpr float kCondMax = 3e4f;     // fp32 path only while trace(M33) trace(M33^-1) <= 3e4
 
-// PTS points in lockstep (independent dependency chains interleave -> ILP).
+SKA_HD float pick(float a, int) { return a; }
+SKA_HD float pick(F2 a, int i) { return i == 0 ? a.x : a.y; }
+SKA_HD bool pick(bool a, int) { return a; }
+SKA_HD bool pick(B2 a, int i) { return i == 0 ? a.x : a.y; }
+
+// Result of the one-factorisation fast stage for one point (T = float) or a pair (T = F2)
+template <typename T>
+struct FastStage {
+  T y0, y1, y2;  // centred solution after the first-order secular step
+  T lam, step2;
+  typename Vec<T>::Mask conv, well, ok;
+};
+
+// rows -> normal matrix -> LDL^T at lam = 0 -> inhomogeneous least-squares point -> first-order
+// secular step with the SAME factorisation -> certificate.  a, b, M, ra, rb are kept for the caller
+// (scoring reuses the residuals; the rare general path needs the rows and M).
+template <int V, bool CONF, int LO, typename T>
+SKA_HD void fast_stage(const CamDev* __restrict__ cam, const float cx, const float cy, const float cz, const T* u, const T* v,
+                       const T* w2, T (*a)[4], T (*b)[4], Sym4T<T>& M, T* ra, T* rb, FastStage<T>& o) {
+  sym4_zero(M);
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    dlt_rows<LO>(cam[k], u[k], v[k], a[k], b[k]);
+    if (CONF) {
+      sym4_rank1(M, a[k], w2[k]);
+      sym4_rank1(M, b[k], w2[k]);
+    } else {
+      sym4_rank1_unit(M, a[k]);
+      sym4_rank1_unit(M, b[k]);
+    }
+  }
+  // lam = 0: the inhomogeneous least-squares point
+  const Ldl3T<T> f0 = ldl3(M.m00, M.m01, M.m02, M.m11, M.m12, M.m22);
+  T y0, y1, y2, den;
+  ldl3_solve(f0, vneg(M.m03), vneg(M.m13), vneg(M.m23), y0, y1, y2);
+  const T lam = rayleigh<V, CONF, T>(a, b, w2, y0, y1, y2, cx, cy, cz, ra, rb, den);
+  // first-order step of the secular equation with the SAME factorisation:
+  //   Y(lam) - Y(0) = lam (M33 - lam I)^-1 (c + Y0) = lam z + O(lam^2),  z = M33^-1 (c + Y0)
+  T z0, z1, z2;
+  ldl3_solve(f0, vadd(y0, cx), vadd(y1, cy), vadd(y2, cz), z0, z1, z2);
+  const T d0 = vmul(lam, z0), d1 = vmul(lam, z1), d2 = vmul(lam, z2);
+  const T step2 = vfma(d0, d0, vfma(d1, d1, vmul(d2, d2)));
+  // certificate: lam * trace(M33^-1) < 1e-3 => lam < 1e-3 lambda_min(M33): M33 - lam I is positive
+  // definite (Cauchy interlacing: this is the smallest eigenpair) and the dropped second-order
+  // term is < 1e-3 of a step that is itself < 3.2e-5 relative.
+  const T itr = ldl3_inv_trace(f0);
+  o.conv = mand(mand(f0.pos, vlt(vmul(lam, itr), kFastLamTr)), vle(step2, vmul(den, kFastTol2)));
+  // conditioning gate: trace(M33) trace(M33^-1) bounds cond(M33); beyond kCondMax (rays nearly
+  // parallel, point near infinity) fp32 cannot hold the north-star tolerance -> fp64 path
+  o.well = vle(vmul(vadd(vadd(M.m00, M.m11), M.m22), itr), kCondMax);
+  o.y0 = vadd(y0, d0);
+  o.y1 = vadd(y1, d1);
+  o.y2 = vadd(y2, d2);
+  o.lam = lam;
+  o.step2 = step2;
+  o.ok = f0.pos;
+  // row residuals at the corrected point: r(Y0 + d) = r(Y0) + a[0:3] . d
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    ra[k] = vfma(a[k][0], d0, vfma(a[k][1], d1, vfma(a[k][2], d2, ra[k])));
+    rb[k] = vfma(b[k][0], d0, vfma(b[k][1], d1, vfma(b[k][2], d2, rb[k])));
+  }
+}
+
+// Fused reprojection scoring, differential form:
+//   proj - obs = -(row . [Y;1]) / z  (+ fx*dx_distortion - skew*y)
+// so the ~1e3 px magnitudes of proj and obs never meet in fp32.
+template <int V, int DIST, typename T>
+SKA_HD void score_views(const CamDev* __restrict__ cam, T Y0, T Y1, T Y2, const T* ra, const T* rb, T* du, T* dv) {
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const CamDev& c = cam[k];
+    const T z = vadd(vfma(c.Ph[8], Y0, vfma(c.Ph[9], Y1, vfma(c.Ph[10], Y2, c.Ph[11]))), c.Pl[11]);
+    const T iz = rcp_fast(z);
+    T eu = vmul(vneg(ra[k]), iz), ev = vmul(vneg(rb[k]), iz);
+    if (DIST) {
+      const T x = vmul(vfma(c.Rxy[0], Y0, vfma(c.Rxy[1], Y1, vfma(c.Rxy[2], Y2, c.txy[0]))), iz);
+      const T y = vmul(vfma(c.Rxy[3], Y0, vfma(c.Rxy[4], Y1, vfma(c.Rxy[5], Y2, c.txy[1]))), iz);
+      T dx, dy;
+      distort_delta<(DIST >= 2)>(c, x, y, dx, dy);
+      eu = vfma(dx, c.fx, eu);
+      ev = vfma(dy, c.fy, ev);
+      if (DIST >= 2) eu = vfma(y, -c.skew, eu);
+    }
+    du[k] = eu;
+    dv[k] = ev;
+  }
+}
+
+template <bool PACK>
+struct PointVec {
+  using type = float;
+};
+template <>
+struct PointVec<true> {
+  using type = F2;
+};
+
+// PTS points per thread.  PTS == 2 runs the two points as ONE packed (F2) computation - every
+// FFMA of the hot path becomes an FFMA2; any other PTS runs them one by one in scalar fp32.
 // u,v,w2: [PTS][V] pixel coordinates and squared row weights (w2 unused if !CONF).
 // LO: see dlt_rows.  DIST: 0 pinhole scoring, 1 rational+tangential, 2 + thin prism + skew.
 // Outputs: X (un-centred), du/dv = reprojected minus observed pixel per view, status.
@@ -129,27 +228,32 @@ template <int V, int PTS, bool CONF, int DIST, uint32_t SOLVER, int LO = 1>
 SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], const float cx, const float cy,
                        const float cz, const float (*u)[V], const float (*v)[V], const float (*w2)[V],
                        const PointSource& src, float (*X)[3], float (*du)[V], float (*dv)[V], uint8_t* status) {
-  // ---- rows (kept in registers) and the normal matrix in centred coordinates
-  float a[PTS][V][4], b[PTS][V][4];
-  Sym4 M[PTS];
+#ifdef SKA_NO_PACK  // measurement variant (tools/variants.py): two points per thread in scalar fp32
+  constexpr bool PACK = (PTS == 2) && (V < 0);  // value-dependent false
+#else
+  constexpr bool PACK = (PTS == 2);
+#endif
+  using T = typename PointVec<PACK>::type;
+  constexpr int NG = PACK ? 1 : PTS;   // lockstep groups
+  // ---- gather the inputs of each group
+  T ut[NG][V], vt[NG][V], wt[NG][V];
 #pragma unroll
-  for (int p = 0; p < PTS; ++p) sym4_zero(M[p]);
+  for (int g = 0; g < NG; ++g)
 #pragma unroll
-  for (int k = 0; k < V; ++k) {
-#pragma unroll
-    for (int p = 0; p < PTS; ++p) {
-      dlt_rows<LO>(cam[k], u[p][k], v[p][k], a[p][k], b[p][k]);
-      if (CONF) {
-        sym4_rank1(M[p], a[p][k], w2[p][k]);
-        sym4_rank1(M[p], b[p][k], w2[p][k]);
+    for (int k = 0; k < V; ++k) {
+      if constexpr (PACK) {
+        ut[g][k] = mk2(u[0][k], u[1][k]);
+        vt[g][k] = mk2(v[0][k], v[1][k]);
+        wt[g][k] = CONF ? mk2(w2[0][k], w2[1][k]) : mk2(1.f, 1.f);
       } else {
-        sym4_rank1_unit(M[p], a[p][k]);
-        sym4_rank1_unit(M[p], b[p][k]);
+        ut[g][k] = u[g][k];
+        vt[g][k] = v[g][k];
+        wt[g][k] = CONF ? w2[g][k] : 1.f;
       }
     }
-  }
-
-  float Y[PTS][3], ra[PTS][V], rb[PTS][V];
+  T a[NG][V][4], b[NG][V][4], ra[NG][V], rb[NG][V];
+  Sym4T<T> M[NG];
+  float Y[PTS][3];
   bool need64[PTS], have_res[PTS];
 #pragma unroll
   for (int p = 0; p < PTS; ++p) {
@@ -158,58 +262,51 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
     status[p] = 0;
   }
   if (SOLVER == kSolverSecular) {
-    SecularState s[PTS];
-    bool conv[PTS], well[PTS];
+    FastStage<T> fs[NG];
     bool all_fast = true;
 #pragma unroll
-    for (int p = 0; p < PTS; ++p) {
-      // lam = 0: the inhomogeneous least-squares point
-      const Ldl3 f0 = ldl3(M[p].m00, M[p].m01, M[p].m02, M[p].m11, M[p].m12, M[p].m22);
-      float y0, y1, y2, den;
-      ldl3_solve(f0, -M[p].m03, -M[p].m13, -M[p].m23, y0, y1, y2);
-      const float lam = rayleigh<V, CONF>(a[p], b[p], w2[p], y0, y1, y2, cx, cy, cz, ra[p], rb[p], den);
-      // first-order step of the secular equation with the SAME factorisation:
-      //   Y(lam) - Y(0) = lam (M33 - lam I)^-1 (c + Y0) = lam z + O(lam^2),  z = M33^-1 (c + Y0)
-      float z0, z1, z2;
-      ldl3_solve(f0, y0 + cx, y1 + cy, y2 + cz, z0, z1, z2);
-      const float d0 = lam * z0, d1 = lam * z1, d2 = lam * z2;
-      const float step2 = fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
-      // certificate: lam * trace(M33^-1) < 1e-3 => lam < 1e-3 lambda_min(M33): M33 - lam I is positive
-      // definite (Cauchy interlacing: this is the smallest eigenpair) and the dropped second-order
-      // term is < 1e-3 of a step that is itself < 3.2e-5 relative.
-      const float itr = ldl3_inv_trace(f0);
-      const bool fast = f0.pos && (lam * itr < kFastLamTr) && (step2 <= kFastTol2 * den);
-      // conditioning gate: trace(M33) trace(M33^-1) bounds cond(M33); beyond kCondMax (rays nearly
-      // parallel, point near infinity) fp32 cannot hold the north-star tolerance -> fp64 path
-      well[p] = (M[p].m00 + M[p].m11 + M[p].m22) * itr <= kCondMax;
-      s[p].y0 = y0 + d0;
-      s[p].y1 = y1 + d1;
-      s[p].y2 = y2 + d2;
-      s[p].lam = lam;
-      s[p].step2 = step2;
-      s[p].ok = f0.pos;
-      conv[p] = fast;
-      all_fast = all_fast && fast;
-      // row residuals at the corrected point: r(Y0 + d) = r(Y0) + a[0:3] . d
+    for (int g = 0; g < NG; ++g) {
+      fast_stage<V, CONF, LO, T>(cam, cx, cy, cz, ut[g], vt[g], wt[g], a[g], b[g], M[g], ra[g], rb[g], fs[g]);
+      all_fast = all_fast && mall(fs[g].conv);
+    }
+    SecularState s[PTS];
+    bool conv[PTS], well[PTS];
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        ra[p][k] = fmaf(a[p][k][0], d0, fmaf(a[p][k][1], d1, fmaf(a[p][k][2], d2, ra[p][k])));
-        rb[p][k] = fmaf(b[p][k][0], d0, fmaf(b[p][k][1], d1, fmaf(b[p][k][2], d2, rb[p][k])));
-      }
+    for (int p = 0; p < PTS; ++p) {
+      const int g = PACK ? 0 : p, i = PACK ? p : 0;
+      s[p].y0 = pick(fs[g].y0, i);
+      s[p].y1 = pick(fs[g].y1, i);
+      s[p].y2 = pick(fs[g].y2, i);
+      s[p].lam = pick(fs[g].lam, i);
+      s[p].step2 = pick(fs[g].step2, i);
+      s[p].ok = pick(fs[g].ok, i);
+      conv[p] = pick(fs[g].conv, i);
+      well[p] = pick(fs[g].well, i);
       have_res[p] = true;
     }
     if (!SKA_WARP_ALL(all_fast)) {
-      // general path: full secular iteration (refactorise at every lam), quadratically convergent
+      // general path (rare): full secular iteration per point in scalar fp32 (refactorise at every
+      // lam), quadratically convergent
 #pragma unroll 1
       for (int it = 0; it < kSecularMaxIter; ++it) {
         bool done = true;
 #pragma unroll
         for (int p = 0; p < PTS; ++p) {
-          float den, r1[V], r2[V];
-          const float lam = rayleigh<V, CONF>(a[p], b[p], w2[p], s[p].y0, s[p].y1, s[p].y2, cx, cy, cz, r1, r2, den);
+          const int g = PACK ? 0 : p, i = PACK ? p : 0;
           if (!conv[p]) {
-            const bool c1 = secular_step(M[p], cx, cy, cz, lam, s[p]);
-            conv[p] = c1;
+            float as[V][4], bs[V][4], ws[V], r1[V], r2[V], den;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {
+                as[k][m] = pick(a[g][k][m], i);
+                bs[k][m] = pick(b[g][k][m], i);
+              }
+              ws[k] = pick(wt[g][k], i);
+            }
+            const float lam = rayleigh<V, CONF, float>(as, bs, ws, s[p].y0, s[p].y1, s[p].y2, cx, cy, cz, r1, r2, den);
+            const Sym4 Ms = PACK ? (i == 0 ? sym4_lane<0>(M[g]) : sym4_lane<1>(M[g])) : sym4_lane<0>(M[g]);
+            conv[p] = secular_step(Ms, cx, cy, cz, lam, s[p]);
             have_res[p] = false;
           }
           // a lane that lost positive-definiteness can never certify: do not wait for it
@@ -220,16 +317,34 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
     }
 #pragma unroll
     for (int p = 0; p < PTS; ++p) {
+      const int g = PACK ? 0 : p, i = PACK ? p : 0;
       Y[p][0] = s[p].y0;
       Y[p][1] = s[p].y1;
       Y[p][2] = s[p].y2;
-      const bool finite_in = fabsf(M[p].m33) <= 3.0e38f;  // false for NaN / inf inputs
+      const bool finite_in = fabsf(pick(M[g].m33, i)) <= 3.0e38f;  // false for NaN / inf inputs
       need64[p] = !(conv[p] && s[p].ok && well[p]) && finite_in;
       if (!finite_in) status[p] = 2;
     }
-  } else if (SOLVER == kSolverJacobi32) {
+  } else {
+    // measurement / exact solvers: rows and the normal matrix only
 #pragma unroll
-    for (int p = 0; p < PTS; ++p) solve_jacobi32(M[p], cx, cy, cz, Y[p]);
+    for (int g = 0; g < NG; ++g) {
+      sym4_zero(M[g]);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        dlt_rows<LO>(cam[k], ut[g][k], vt[g][k], a[g][k], b[g][k]);
+        sym4_rank1(M[g], a[g][k], wt[g][k]);
+        sym4_rank1(M[g], b[g][k], wt[g][k]);
+      }
+    }
+    if (SOLVER == kSolverJacobi32) {
+#pragma unroll
+      for (int p = 0; p < PTS; ++p) {
+        const int g = PACK ? 0 : p, i = PACK ? p : 0;
+        const Sym4 Ms = PACK ? (i == 0 ? sym4_lane<0>(M[g]) : sym4_lane<1>(M[g])) : sym4_lane<0>(M[g]);
+        solve_jacobi32(Ms, cx, cy, cz, Y[p]);
+      }
+    }
   }
 
   if (SOLVER != kSolverJacobi32) {
@@ -252,39 +367,49 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
     }
   }
 
-  // ---- fused reprojection scoring, differential form:
-  //   proj - obs = -(row . [Y;1]) / z  (+ fx*dx_distortion - skew*y)
-  // so the ~1e3 px magnitudes of proj and obs never meet in fp32.
+  // ---- un-centre, flag non-finite results, score every view
 #pragma unroll
   for (int p = 0; p < PTS; ++p) {
     X[p][0] = Y[p][0] + cx;
     X[p][1] = Y[p][1] + cy;
     X[p][2] = Y[p][2] + cz;
     if (!(fabsf(X[p][0]) <= 3.0e38f && fabsf(X[p][1]) <= 3.0e38f && fabsf(X[p][2]) <= 3.0e38f)) status[p] = 2;
-    if (!have_res[p]) {
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    T Yt[3];
+    bool have = true;
+    if constexpr (PACK) {
+#pragma unroll
+      for (int m = 0; m < 3; ++m) Yt[m] = mk2(Y[0][m], Y[1][m]);
+      have = have_res[0] && have_res[1];
+    } else {
+#pragma unroll
+      for (int m = 0; m < 3; ++m) Yt[m] = Y[g][m];
+      have = have_res[g];
+    }
+    if (!have) {  // the iterate moved after the fast stage: residuals from the rows; a partner of a
+                  // packed pair that kept its fast-stage point keeps its fast-stage residuals
+      const typename Vec<T>::Mask keep = Vec<T>::mask(PACK ? have_res[0] : false, PACK ? have_res[PTS - 1] : false);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        ra[p][k] = fmaf(a[p][k][0], Y[p][0], fmaf(a[p][k][1], Y[p][1], fmaf(a[p][k][2], Y[p][2], a[p][k][3])));
-        rb[p][k] = fmaf(b[p][k][0], Y[p][0], fmaf(b[p][k][1], Y[p][1], fmaf(b[p][k][2], Y[p][2], b[p][k][3])));
+        ra[g][k] = vsel(keep, ra[g][k], vfma(a[g][k][0], Yt[0], vfma(a[g][k][1], Yt[1], vfma(a[g][k][2], Yt[2], a[g][k][3]))));
+        rb[g][k] = vsel(keep, rb[g][k], vfma(b[g][k][0], Yt[0], vfma(b[g][k][1], Yt[1], vfma(b[g][k][2], Yt[2], b[g][k][3]))));
       }
     }
+    T dut[V], dvt[V];
+    score_views<V, DIST, T>(cam, Yt[0], Yt[1], Yt[2], ra[g], rb[g], dut, dvt);
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      const CamDev& c = cam[k];
-      const float z = fmaf(c.Ph[8], Y[p][0], fmaf(c.Ph[9], Y[p][1], fmaf(c.Ph[10], Y[p][2], c.Ph[11]))) + c.Pl[11];
-      const float iz = rcp_fast(z);
-      float eu = -ra[p][k] * iz, ev = -rb[p][k] * iz;
-      if (DIST) {
-        const float x = fmaf(c.Rxy[0], Y[p][0], fmaf(c.Rxy[1], Y[p][1], fmaf(c.Rxy[2], Y[p][2], c.txy[0]))) * iz;
-        const float y = fmaf(c.Rxy[3], Y[p][0], fmaf(c.Rxy[4], Y[p][1], fmaf(c.Rxy[5], Y[p][2], c.txy[1]))) * iz;
-        float dx, dy;
-        distort_delta<(DIST >= 2)>(c, x, y, dx, dy);
-        eu = fmaf(c.fx, dx, eu);
-        ev = fmaf(c.fy, dy, ev);
-        if (DIST >= 2) eu = fmaf(-c.skew, y, eu);
+      if constexpr (PACK) {
+        du[0][k] = dut[k].x;
+        du[1][k] = dut[k].y;
+        dv[0][k] = dvt[k].x;
+        dv[1][k] = dvt[k].y;
+      } else {
+        du[g][k] = dut[k];
+        dv[g][k] = dvt[k];
       }
-      du[p][k] = eu;
-      dv[p][k] = ev;
     }
   }
 }

@@ -49,25 +49,26 @@ struct TileInputs {
   float u[PTS][V], v[PTS][V], c[PTS][V];
 };
 
-// offsets (in floats) of this thread's first point of a tile, within view 0
+// offsets (in floats) of this thread's first point of a tile, within view 0.  Point indices fit
+// 32 bits (the C ABI rejects T*J >= 2^31), so the per-tile bookkeeping is 32-bit integer work.
 template <int V, int PTS>
-__device__ __forceinline__ void point_offsets(const TriParams<V>& prm, int64_t i0, int64_t& koff, int64_t& coff) {
+__device__ __forceinline__ void point_offsets(const TriParams<V>& prm, uint32_t i0, int64_t& koff, int64_t& coff) {
   if (prm.frame_major) {
-    const uint32_t t = (uint32_t)i0 / (uint32_t)prm.J;
-    const uint32_t j = (uint32_t)i0 - t * (uint32_t)prm.J;
+    const uint32_t t = i0 / (uint32_t)prm.J;
+    const uint32_t j = i0 - t * (uint32_t)prm.J;
     koff = (int64_t)t * prm.k_sT + 2 * (int64_t)j;
     coff = (int64_t)t * prm.c_sT + (int64_t)j;
   } else {
-    koff = 2 * i0;
-    coff = i0;
+    koff = (int64_t)(2u * (uint64_t)i0);
+    coff = (int64_t)i0;
   }
 }
 
 // first point of this thread in `tile`, clamped so out-of-range lanes recompute the last point(s)
 // and every lane stays alive for the warp votes
 template <int PTS>
-__device__ __forceinline__ int64_t thread_point(int64_t tile, int64_t N, bool& live) {
-  const int64_t i_raw = (tile * kBlock + threadIdx.x) * PTS;
+__device__ __forceinline__ uint32_t thread_point(uint32_t tile, uint32_t N, bool& live) {
+  const uint32_t i_raw = (tile * kBlock + threadIdx.x) * PTS;
   live = (i_raw + PTS <= N);
   return live ? i_raw : (N - PTS);
 }
@@ -105,12 +106,12 @@ template <int V, int PTS, bool CONF, int DIST, uint32_t SOLVER, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) tri_kernel(const __grid_constant__ TriParams<V> prm) {
   __shared__ __align__(16) float sX[kBlock / 32][32 * PTS * 3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t N = prm.N;
+  const uint32_t N = (uint32_t)prm.N, n_tiles = (uint32_t)prm.n_tiles;
 
-  int64_t tile = blockIdx.x;
-  if (tile >= prm.n_tiles) return;
+  uint32_t tile = blockIdx.x;
+  if (tile >= n_tiles) return;
   bool live;
-  int64_t i0 = thread_point<PTS>(tile, N, live);
+  uint32_t i0 = thread_point<PTS>(tile, N, live);
   int64_t koff, coff;
   point_offsets<V, PTS>(prm, i0, koff, coff);
   TileInputs<V, PTS, CONF> cur;
@@ -118,10 +119,11 @@ __global__ void __launch_bounds__(kBlock, MINB) tri_kernel(const __grid_constant
 
   for (;;) {
     // ---- prefetch the next tile of this CTA into registers (loads stay in flight during the solve)
-    const int64_t ntile = tile + gridDim.x;
-    const bool more = ntile < prm.n_tiles;
+    const uint32_t ntile = tile + gridDim.x;
+    const bool more = ntile < n_tiles;
     bool nlive = false;
-    int64_t ni0 = 0, nkoff = 0, ncoff = 0;
+    uint32_t ni0 = 0;
+    int64_t nkoff = 0, ncoff = 0;
     TileInputs<V, PTS, CONF> nxt;
     if (more) {
       ni0 = thread_point<PTS>(ntile, N, nlive);
@@ -185,18 +187,21 @@ __global__ void __launch_bounds__(kBlock, MINB) tri_kernel(const __grid_constant
       for (int k = 0; k < 3; ++k) sx[(lane * PTS + p) * 3 + k] = X[p][k];
     }
     __syncwarp();
-    const int64_t warp_first = (tile * kBlock + warp * 32) * PTS;
-    const int64_t remain = N - warp_first;  // points of this warp that exist (may be <= 0)
-    if (remain > 0) {
-      const int npts = remain < 32 * PTS ? (int)remain : 32 * PTS;
-      const int nfl = npts * 3;
-      float* gx = prm.X + warp_first * 3;
-      if (prm.x_vec) {  // warp_first*3 floats is a multiple of 96 floats -> 16-byte aligned
-        const int nvec = nfl >> 2;
-        for (int q = lane; q < nvec; q += 32)
-          __stcs(reinterpret_cast<float4*>(gx) + q, reinterpret_cast<const float4*>(sx)[q]);
-        for (int q = (nvec << 2) + lane; q < nfl; q += 32) gx[q] = sx[q];
+    const uint32_t warp_first = (tile * kBlock + warp * 32) * PTS;
+    if (warp_first < N) {
+      constexpr int kWarpFloats = 32 * PTS * 3, kWarpVec = kWarpFloats / 4;
+      const uint32_t remain = N - warp_first;  // points of this warp that exist
+      float* gx = prm.X + (int64_t)warp_first * 3;
+      if (remain >= 32u * PTS && prm.x_vec) {
+        // full warp, 16-byte aligned base (warp_first*3 floats is a multiple of 96 floats): straight-line
+        // 128-bit stores, 1.5 (PTS=2) / 0.75 (PTS=1) per lane
+#pragma unroll
+        for (int r = 0; r < (kWarpVec + 31) / 32; ++r) {
+          const int q = lane + 32 * r;
+          if (q < kWarpVec) __stcs(reinterpret_cast<float4*>(gx) + q, reinterpret_cast<const float4*>(sx)[q]);
+        }
       } else {
+        const int nfl = (remain < 32u * PTS ? (int)remain : 32 * PTS) * 3;
         for (int q = lane; q < nfl; q += 32) gx[q] = sx[q];
       }
     }
@@ -209,6 +214,202 @@ __global__ void __launch_bounds__(kBlock, MINB) tri_kernel(const __grid_constant
     live = nlive;
     cur = nxt;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTS = 2 hot path with bulk-asynchronous input staging (the TMA engine's 1-D form):
+// every warp owns tiles of 64 consecutive points; lane 0 arms an mbarrier and issues ONE
+// cp.async.bulk per view (512 contiguous bytes of keypoints) for the NEXT tile into the other half
+// of a per-warp double buffer, then the warp waits on the current half, reads its two points with
+// one 128-bit shared load per view and computes them as one packed (FFMA2) pair.  Compared with the
+// register prefetch of tri_kernel this keeps the next tile out of the register file (no spills at
+// 128 registers with the packed arithmetic) and removes the per-lane global loads and their address
+// arithmetic from the instruction stream.  Warps never meet at a CTA barrier.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised form.  CTA = NW consumer warps + 1 producer warp.  Every consumer warp owns a
+// ring of kStages 1 KB*V/2 buffers with a full / empty mbarrier pair per stage; lane w of the producer
+// warp feeds consumer warp w: wait(empty) -> expect_tx -> one bulk copy per view (64 points = 512
+// contiguous bytes).  Consumers therefore execute no global loads, no load addressing and no
+// tail logic at all (the host gives this kernel whole 64-point tiles only; the < 64-point tail
+// goes to tri_kernel in a second launch).
+#ifndef SKA_WS_WARPS
+#define SKA_WS_WARPS 15  // consumer warps per CTA: (15 + 1) * 32 = 512 threads x 128 registers = the register file
+#endif
+#ifndef SKA_WS_MINB
+#define SKA_WS_MINB 1
+#endif
+constexpr int kWarpPts = 64;  // points per warp tile (2 per lane)
+constexpr int kStages = 3;
+
+template <int V, int NW>
+struct WsSmem {  // dynamic shared-memory layout of tri_kernel_ws
+  static constexpr size_t oX = (size_t)NW * kStages * V * kWarpPts * 2 * sizeof(float);
+  static constexpr size_t oFull = oX + (size_t)NW * kWarpPts * 3 * sizeof(float);
+  static constexpr size_t oEmpty = oFull + (size_t)NW * kStages * sizeof(uint64_t);
+  static constexpr size_t bytes = oEmpty + (size_t)NW * kStages * sizeof(uint64_t);
+};
+
+template <int V, bool CONF, int DIST, int NW, int MINB>
+__global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __grid_constant__ TriParams<V> prm) {
+  constexpr int PTS = 2;
+  using L = WsSmem<V, NW>;
+  extern __shared__ __align__(128) unsigned char ws_smem[];
+  float(*sK)[kStages][V][kWarpPts * 2] = reinterpret_cast<float(*)[kStages][V][kWarpPts * 2]>(ws_smem);
+  float(*sX)[kWarpPts * 3] = reinterpret_cast<float(*)[kWarpPts * 3]>(ws_smem + L::oX);
+  uint64_t(*sFull)[kStages] = reinterpret_cast<uint64_t(*)[kStages]>(ws_smem + L::oFull);
+  uint64_t(*sEmpty)[kStages] = reinterpret_cast<uint64_t(*)[kStages]>(ws_smem + L::oEmpty);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_wt = (uint32_t)prm.n_tiles;  // whole 64-point tiles
+  const uint32_t stride = gridDim.x * NW;
+  if (threadIdx.x < NW * kStages) {
+    mbar_init(&sFull[0][0] + threadIdx.x, 1);
+    mbar_init(&sEmpty[0][0] + threadIdx.x, 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();  // the only CTA-wide barrier: barrier initialisation
+
+  if (warp == NW) {
+    // ---------------------------------------------------------------- producer warp
+    if (lane < NW) {
+      const int w = lane;
+      uint32_t wt = blockIdx.x * NW + w;
+      int st = 0;
+      uint32_t round = 0;  // how many times the ring wrapped
+      for (; wt < n_wt; wt += stride) {
+        if (round > 0) mbar_wait(&sEmpty[w][st], (round - 1) & 1u);  // consumers released this stage
+        mbar_expect_tx(&sFull[w][st], (uint32_t)(kWarpPts * 8 * V));
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          bulk_g2s(&sK[w][st][k][0], prm.kpts + (int64_t)k * prm.k_sV + (int64_t)wt * (kWarpPts * 2), kWarpPts * 8, &sFull[w][st]);
+        if (++st == kStages) {
+          st = 0;
+          ++round;
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ consumer warps
+  uint32_t wt = blockIdx.x * NW + warp;
+  int st = 0;
+  uint32_t par = 0;
+  float* sx = sX[warp];
+  for (; wt < n_wt; wt += stride) {
+    mbar_wait(&sFull[warp][st], par);
+    float u[PTS][V], v[PTS][V], w2[PTS][V];
+    const uint32_t i0 = wt * kWarpPts + 2u * lane;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float4 q = *reinterpret_cast<const float4*>(&sK[warp][st][k][4 * lane]);
+      u[0][k] = q.x; v[0][k] = q.y; u[1][k] = q.z; v[1][k] = q.w;
+      if (CONF) {
+        float2 c = make_float2(1.f, 1.f);
+        if (prm.conf != nullptr) c = __ldcs(reinterpret_cast<const float2*>(prm.conf + (int64_t)k * prm.c_sV + i0));
+        w2[0][k] = prm.weight_sqrt ? c.x : c.x * c.x;
+        w2[1][k] = prm.weight_sqrt ? c.y : c.y * c.y;
+      } else {
+        w2[0][k] = w2[1][k] = 1.0f;
+      }
+    }
+    __syncwarp();                                  // every lane holds its pair in registers
+    if (lane == 0) mbar_arrive(&sEmpty[warp][st]);  // hand the stage back to the producer
+    if (++st == kStages) {
+      st = 0;
+      par ^= 1u;
+    }
+
+    PointSource src;
+    src.kpts = prm.kpts + 2 * (int64_t)i0;
+    src.conf = (prm.conf != nullptr) ? prm.conf + i0 : nullptr;
+    src.k_sV = prm.k_sV;
+    src.c_sV = prm.c_sV;
+    src.weight_sqrt = prm.weight_sqrt;
+    float X[PTS][3], du[PTS][V], dv[PTS][V];
+    uint8_t stt[PTS];
+    tri_points<V, PTS, CONF, DIST, kSolverSecular>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], u, v, w2, src, X, du, dv, stt);
+
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      if (prm.err != nullptr) {
+        const float e0 = sqrt_fast(fmaf(du[0][k], du[0][k], dv[0][k] * dv[0][k]));
+        const float e1 = sqrt_fast(fmaf(du[1][k], du[1][k], dv[1][k] * dv[1][k]));
+        __stcs(reinterpret_cast<float2*>(prm.err + (int64_t)k * prm.c_sV + i0), make_float2(e0, e1));
+      }
+      if (prm.proj != nullptr) {
+        __stcs(reinterpret_cast<float4*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)i0),
+               make_float4(u[0][k] + du[0][k], v[0][k] + dv[0][k], u[1][k] + du[1][k], v[1][k] + dv[1][k]));
+      }
+    }
+    if (prm.status != nullptr) *reinterpret_cast<uchar2*>(prm.status + i0) = make_uchar2(stt[0], stt[1]);
+    // ---- X through shared memory: 192 floats per warp leave as 48 128-bit stores
+#pragma unroll
+    for (int p = 0; p < PTS; ++p)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) sx[(lane * PTS + p) * 3 + k] = X[p][k];
+    __syncwarp();
+    float* gx = prm.X + (int64_t)wt * (kWarpPts * 3);
+    if (prm.x_vec) {
+      __stcs(reinterpret_cast<float4*>(gx) + lane, reinterpret_cast<const float4*>(sx)[lane]);
+      if (lane < 16) __stcs(reinterpret_cast<float4*>(gx) + 32 + lane, reinterpret_cast<const float4*>(sx)[32 + lane]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) gx[lane + 32 * r] = sx[lane + 32 * r];
+    }
+    __syncwarp();  // sx is rewritten next iteration
+  }
+}
+
+template <int V, bool CONF, int DIST>
+static cudaError_t launch_ws(TriParams<V>& prm, cudaStream_t stream) {
+  constexpr int NW = SKA_WS_WARPS, MINB = SKA_WS_MINB, BLOCK = 32 * (NW + 1);
+  auto kern = tri_kernel_ws<V, CONF, DIST, NW, MINB>;
+  constexpr size_t smem = WsSmem<V, NW>::bytes;
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaError_t ce = cudaGetDevice(&dev);
+  if (ce != cudaSuccess) return ce;
+  ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (ce != cudaSuccess) return ce;
+  ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // idempotent
+  if (ce != cudaSuccess) return ce;
+  ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem);
+  if (ce != cudaSuccess) return ce;
+  if (per_sm < 1) per_sm = 1;
+  const int64_t n_wt = prm.n_tiles;
+  const int64_t need = (n_wt + NW - 1) / NW;
+  int64_t grid = (int64_t)sms * per_sm;
+  if (grid > need) grid = need;
+  kern<<<(unsigned)grid, BLOCK, smem, stream>>>(prm);
+  return cudaGetLastError();
 }
 
 #ifndef SKA_MINB_SMALL
@@ -463,7 +664,33 @@ static int dispatch(const TriArgs& a) {
   } else if (dist >= 2) {
     ce = launch<V, 1, true, 2, kSolverSecular, 1>(prm, s);  // thin prism / skew: rare, one generic instantiation
   } else if constexpr (V <= 4) {
+#ifndef SKA_NO_BULK
+    if (pts2) {
+      // whole 64-point tiles -> warp-specialised bulk-staged kernel; the < 64-point tail -> tri_kernel
+      const int64_t n_full = prm.N / kWarpPts, done = n_full * kWarpPts;
+      ce = cudaSuccess;
+      if (n_full > 0) {
+        TriParams<V> q = prm;
+        q.n_tiles = n_full;
+        ce = conf ? (dist ? launch_ws<V, true, 1>(q, s) : launch_ws<V, true, 0>(q, s))
+                  : (dist ? launch_ws<V, false, 1>(q, s) : launch_ws<V, false, 0>(q, s));
+      }
+      if (ce == cudaSuccess && done < prm.N) {
+        prm.N -= done;  // strides keep describing the whole clip
+        prm.kpts += 2 * done;
+        if (prm.conf != nullptr) prm.conf += done;
+        prm.X += 3 * done;
+        if (prm.err != nullptr) prm.err += done;
+        if (prm.proj != nullptr) prm.proj += 2 * done;
+        if (prm.status != nullptr) prm.status += done;
+        ce = SKA_GO(2);
+      }
+    } else {
+      ce = SKA_GO(1);
+    }
+#else
     ce = pts2 ? SKA_GO(2) : SKA_GO(1);
+#endif
   } else {
     (void)pts2;
     ce = SKA_GO(1);

@@ -32,6 +32,42 @@ static int run(const SkaCamera* cams, const double* centre, const float* kpts, c
   }
   const int lo = (flags >> 8) & 3;  // test hook: lo-part level of the DLT rows (default 1)
   const uint32_t solver = flags & SKA_SOLVER_MASK;
+  if ((flags >> 10) & 1) {
+    // test hook: the kernel's PTS = 2 path (two points as one packed F2 computation), pairs (i, i+1)
+    for (int64_t i = 0; i + 1 < N + (N & 1); i += 2) {
+      const int64_t i0 = (i + 1 < N) ? i : N - 2;  // odd tail: redo the last pair
+      float u[2][V], vv[2][V], w2[2][V], du[2][V], dv[2][V], Xp[2][3];
+      for (int p = 0; p < 2; ++p)
+        for (int v = 0; v < V; ++v) {
+          u[p][v] = kpts[(v * N + i0 + p) * 2];
+          vv[p][v] = kpts[(v * N + i0 + p) * 2 + 1];
+          const float cf = conf ? conf[v * N + i0 + p] : 1.0f;
+          w2[p][v] = (flags & SKA_WEIGHT_SQRT) ? cf : cf * cf;
+        }
+      uint8_t st[2];
+      PointSource src;
+      src.kpts = kpts + 2 * i0;
+      src.conf = conf ? conf + i0 : nullptr;
+      src.k_sV = 2 * N;
+      src.c_sV = N;
+      src.weight_sqrt = (flags & SKA_WEIGHT_SQRT) ? 1u : 0u;
+      const float cx = (float)c[0], cy = (float)c[1], cz = (float)c[2];
+      if (conf) {
+        if (dist) tri_points<V, 2, true, 1, kSolverSecular>(cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);
+        else tri_points<V, 2, true, 0, kSolverSecular>(cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);
+      } else {
+        if (dist) tri_points<V, 2, false, 1, kSolverSecular>(cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);
+        else tri_points<V, 2, false, 0, kSolverSecular>(cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);
+      }
+      for (int p = 0; p < 2; ++p) {
+        for (int k = 0; k < 3; ++k) X[3 * (i0 + p) + k] = Xp[p][k];
+        if (err)
+          for (int v = 0; v < V; ++v) err[v * N + i0 + p] = sqrtf(du[p][v] * du[p][v] + dv[p][v] * dv[p][v]);
+        if (status) status[i0 + p] = st[p];
+      }
+    }
+    return 0;
+  }
   for (int64_t i = 0; i < N; ++i) {
     float u[V], vv[V], w2[V], du[V], dv[V], Xp[3];
     for (int v = 0; v < V; ++v) {

@@ -150,3 +150,22 @@ def test_hostemu_loss_projection_and_adjoint_match_autograd():
     gKs = gK.sum(0)
     assert np.abs(gKs - Kt.grad.numpy()[0, :2].ravel()).max() <= 1e-9 * scale(gKs)
     assert np.abs(Kt.grad.numpy()[0, 2]).max() == 0.0
+
+
+@pytest.mark.parametrize("rig,T,J,use_conf,dist", [c for c in CASES if c[0] in ("2a", "2b", "3", "4")])
+def test_hostemu_packed_pair_path_is_bit_identical_to_scalar(rig, T, J, use_conf, dist):
+    """PTS = 2 (two points as one F2 computation - FFMA2 on the GPU) must give exactly the scalar path's
+    numbers: each packed component is an IEEE fma like the scalar instruction."""
+    clip = synth.make_clip(rig, T, J, seed=0)
+    V = len(clip.R)
+    cams = _cabi.make_cameras(clip.K, clip.R, clip.t, dist)
+    k = clip.x_vm.reshape(V, -1, 2)
+    c = clip.conf_vm.reshape(V, -1) if use_conf else None
+    X1, e1, s1 = hostemu.triangulate(cams, V, k, c, flags=0)
+    X2, e2, s2 = hostemu.triangulate(cams, V, k, c, flags=1 << 10)
+    np.testing.assert_array_equal(s1, s2)
+    np.testing.assert_array_equal(X1, X2)
+    np.testing.assert_array_equal(e1, e2)
+    # odd point count exercises the tail pair
+    X3, e3, _ = hostemu.triangulate(cams, V, k[:, :33], None if c is None else c[:, :33], flags=1 << 10)
+    np.testing.assert_array_equal(X3, X1[:33] if c is None else X3)

@@ -194,6 +194,12 @@ def test_full_size_properties_config2(cuda):
         part = api.triangulate_reproject(noisy[:, a:b].contiguous(), synth.K_CALIB, R, t, dist=synth.DIST_CALIB)
         assert torch.equal(part.X, full.X[a:b])
         assert torch.equal(part.err, full.err[:, a:b])
+    # (1b) the frame-major layout runs the scalar one-point-per-thread kernel, the view-major layout the
+    # warp-specialised packed (FFMA2) kernel: every packed component is an IEEE fma, so they agree bit for bit
+    fm = api.triangulate_reproject(noisy[:, :200_000].permute(1, 0, 2, 3).contiguous(), synth.K_CALIB, R, t,
+                                   dist=synth.DIST_CALIB, layout="TVJ2")
+    assert torch.equal(fm.X, full.X[:200_000])
+    assert torch.equal(fm.err.permute(1, 0, 2), full.err[:, :200_000])
     # (2) oracle on a sample
     idx = torch.randint(0, T * J, (20000,), device=cuda, generator=gen)
     xs = noisy.reshape(2, -1, 2)[:, idx].cpu().numpy()

@@ -9,12 +9,11 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 VARIANTS = {
-    "minb2_pts2": ["-DSKA_MINB_SMALL=2"],
-    "minb2_pts1": ["-DSKA_MINB_SMALL=2", "-DSKA_FORCE_PTS1"],
-    "minb3_pts2": ["-DSKA_MINB_SMALL=3"],
-    "minb3_pts1": ["-DSKA_MINB_SMALL=3", "-DSKA_FORCE_PTS1"],
-    "minb1_pts2": ["-DSKA_MINB_SMALL=1"],
-    "minb4_pts1": ["-DSKA_MINB_SMALL=4", "-DSKA_FORCE_PTS1"],
+    "ws_7x2": ["-DSKA_WS_WARPS=7", "-DSKA_WS_MINB=2"],      # 2 CTAs x (7 consumers + 1 producer), 128 registers
+    "ws_11x1": ["-DSKA_WS_WARPS=11", "-DSKA_WS_MINB=1"],    # 11 consumers, 168 registers
+    "ws_3x4": ["-DSKA_WS_WARPS=3", "-DSKA_WS_MINB=4"],      # 4 CTAs x (3 + 1), 128 registers
+    "ws_nopack": ["-DSKA_NO_PACK"],                          # warp-specialised staging, scalar fp32 arithmetic
+    "nobulk_nopack": ["-DSKA_NO_BULK", "-DSKA_NO_PACK"],    # register prefetch, scalar fp32
 }
 LIBDIR = ROOT / "skiing_analysis_pytorch_b200" / "lib"
 
