@@ -312,7 +312,8 @@ def run_ba(a, dev, world, rank, barrier, dist):
             "trials": len(hist),
             "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "bytes_per_iter_per_gpu": alg,
-                         "note": "fp32-issue-bound, not HBM-bound: see DESIGN.md section 6"},
+                         "note": ("latency / issue-bound (22 us of HBM time per trial)" if C == 2 else
+                                  "CUDA-core (fp32 FMA pipe) bound: ~5k FMA per point") + ", not HBM-bound: DESIGN.md section 6"},
         }
         del s, d, X0
         torch.cuda.empty_cache()
@@ -429,7 +430,7 @@ def run_ours(a):
         "gpu_launches": a.steps,
         "roofline": {
             "bound": "hbm",
-            "kernel": "ska::tri_kernel",
+            "kernel": "ska::tri_kernel_ws (warp-specialised bulk-async staging, packed FFMA2 pairs)",
             "achieved": achieved,
             "peak": peak,
             "peak_source": peak_src,

@@ -60,12 +60,13 @@ class LMSequencer:
     (the CUDA engine below; an fp64 numpy engine in tests/ exercises this class over gloo)."""
 
     group = None
+    local_only = False  # True: never all-reduce even inside an initialised process group (unsharded solve)
     max_iters = 0
     iters_done = 0
     _graph = None
 
     def _distributed(self) -> bool:
-        return (torch.distributed.is_available() and torch.distributed.is_initialized()
+        return (not self.local_only and torch.distributed.is_available() and torch.distributed.is_initialized()
                 and torch.distributed.get_world_size(self.group) > 1)
 
     def _allreduce(self, t: torch.Tensor):
@@ -119,10 +120,13 @@ class BundleAdjuster(LMSequencer):
     K     (C,3,3) | (3,3); R0 (C,3,3); t0 (C,3): host arrays, world->camera, shared over the clip
     X0    (T,J,3) CUDA tensor (any float dtype) - e.g. the output of triangulate_reproject
     group torch.distributed process group when the clip is sharded by frame range over ranks
+          (None = the default group when torch.distributed is initialised with world size > 1);
+          local_only=True solves this rank's data alone, without any collective
     """
 
     def __init__(self, x2d, conf, K, R0, t0, X0, *, layout: str = "TCJ2", mode: str = "full", lam0: float = 1e-3,
-                 max_iters: int = 64, group=None, force_wide: bool = False):
+                 max_iters: int = 64, group=None, force_wide: bool = False, local_only: bool = False):
+        self.local_only = bool(local_only)
         if not (x2d.is_cuda and conf.is_cuda and X0.is_cuda):
             raise RuntimeError("x2d, conf and X0 must be CUDA tensors: this package has no CPU path")
         if x2d.dtype != torch.float32 or conf.dtype != torch.float32:

@@ -246,20 +246,26 @@ __global__ void __launch_bounds__(kBaBlock, 2) ba_backsub_kernel(const BaKernelA
 }
 
 // ------------------------------------------------------------------------------------------------
-// fixed-order column sums of the per-CTA partial rows: out[col] = sum_r partials[r][col]
-__global__ void ba_reduce_columns(const double* __restrict__ partials, int rows, int ncol, double* __restrict__ out) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+// fixed-order column sums of the per-CTA partial rows: out[col] = sum_r partials[r][col].
+// One warp per column: lane l sums rows l, l+32, ... (independent loads, a handful per lane - a serial
+// walk over ~300 rows is a 20-microsecond chain of dependent L2 round trips), then a fixed shuffle tree.
+constexpr int kRedCols = 8;  // columns (= warps) per CTA
+__global__ void __launch_bounds__(32 * kRedCols) ba_reduce_columns(const double* __restrict__ partials, int rows, int ncol,
+                                                                   double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int col = blockIdx.x * kRedCols + (threadIdx.x >> 5);
   if (col >= ncol) return;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four interleaved chains, combined in a fixed order
-  int r = 0;
-  for (; r + 4 <= rows; r += 4) {
+  double s0 = 0.0, s1 = 0.0;
+  int r = lane;
+  for (; r + 32 < rows; r += 64) {
     s0 += partials[(int64_t)r * ncol + col];
-    s1 += partials[(int64_t)(r + 1) * ncol + col];
-    s2 += partials[(int64_t)(r + 2) * ncol + col];
-    s3 += partials[(int64_t)(r + 3) * ncol + col];
+    s1 += partials[(int64_t)(r + 32) * ncol + col];
   }
-  for (; r < rows; ++r) s0 += partials[(int64_t)r * ncol + col];
-  out[col] = (s0 + s1) + (s2 + s3);
+  if (r < rows) s0 += partials[(int64_t)r * ncol + col];
+  double s = s0 + s1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) out[col] = s;
 }
 
 // plain sum of a float array (sum of confidences), same deterministic scheme
@@ -400,57 +406,65 @@ __global__ void __launch_bounds__(64) ba_solve_kernel(int C, uint64_t free_mask,
   __syncthreads();
   // delta (C,6) with the gauge camera's zeros, and the trial cameras in slot 1
   for (int i = tid; i < 6 * C; i += nt) delta[i] = (i < 6) ? 0.0 : d[i - 6];
-  for (int c = tid; c < C; c += nt) {
+  // trial cameras: K (and camera 0 entirely) copied by all threads, then R / t of the free cameras
+  for (int k = tid; k < C * kCamStride; k += nt)
+    if (k < kCamStride || (k % kCamStride) >= 12) cams[C * kCamStride + k] = cams[k];
+  for (int c = 1 + tid; c < C; c += nt) {
     const double* src = cams + c * kCamStride;
     double* dst = cams + (C + c) * kCamStride;
-    for (int k = 0; k < kCamStride; ++k) dst[k] = src[k];
-    if (c >= 1) {
-      const double* dc = d + 6 * (c - 1);
-      so3_exp_left(dc, src, dst);
-      for (int k = 0; k < 3; ++k) dst[9 + k] = src[9 + k] + dc[3 + k];
-    }
+    const double* dc = d + 6 * (c - 1);
+    so3_exp_left(dc, src, dst);
+    for (int k = 0; k < 3; ++k) dst[9 + k] = src[9 + k] + dc[3 + k];
   }
 }
 
-// LM controller: gain ratio, accept / reject, Nielsen update (oracle/lm.py run_lm / nielsen_update)
-__global__ void ba_control_kernel(int C, const double* __restrict__ red, const double* __restrict__ red2, double* cams, double* ctrl,
-                                  double* hist) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// LM controller: gain ratio, accept / reject, Nielsen update (oracle/lm.py run_lm / nielsen_update).
+// One warp: lane 0 decides, all lanes commit the trial cameras (a serial copy by one thread is a
+// chain of dependent global round trips - microseconds in a 100-microsecond trial).
+__global__ void __launch_bounds__(32) ba_control_kernel(int C, const double* __restrict__ red, const double* __restrict__ red2,
+                                                        double* cams, double* ctrl, double* hist) {
+  if (blockIdx.x != 0) return;
   const RedLayout L(C);
-  const double s = 1.0 / (ctrl[kCtrlSumConf] + 1e-6);
-  const double F = s * red[L.oCost], Ft = s * red2[0];
-  const double pred = ctrl[kCtrlPredCam] + s * red2[1];
-  const double lam = ctrl[kCtrlLambda], nu = ctrl[kCtrlNu];
-  const bool ok = ctrl[kCtrlOk] > 0.5;
-  const double rho = pred > 0.0 ? (F - Ft) / pred : 0.0;
-  const bool accepted = ok && isfinite(Ft) && (Ft < F);
-  const int it = (int)ctrl[kCtrlIter];
-  if (hist != nullptr) {
-    double* h = hist + (int64_t)it * kHistRow;
-    h[0] = (double)it;
-    h[1] = F;
-    h[2] = Ft;
-    h[3] = lam;
-    h[4] = rho;
-    h[5] = accepted ? 1.0 : 0.0;
-    h[6] = red[L.oClamp];
-    h[7] = pred;
+  int accepted_i = 0;
+  if (threadIdx.x == 0) {
+    const double s = 1.0 / (ctrl[kCtrlSumConf] + 1e-6);
+    const double F = s * red[L.oCost], Ft = s * red2[0];
+    const double pred = ctrl[kCtrlPredCam] + s * red2[1];
+    const double lam = ctrl[kCtrlLambda], nu = ctrl[kCtrlNu];
+    const bool ok = ctrl[kCtrlOk] > 0.5;
+    const double rho = pred > 0.0 ? (F - Ft) / pred : 0.0;
+    const bool accepted = ok && isfinite(Ft) && (Ft < F);
+    const int it = (int)ctrl[kCtrlIter];
+    if (hist != nullptr) {
+      double* h = hist + (int64_t)it * kHistRow;
+      h[0] = (double)it;
+      h[1] = F;
+      h[2] = Ft;
+      h[3] = lam;
+      h[4] = rho;
+      h[5] = accepted ? 1.0 : 0.0;
+      h[6] = red[L.oClamp];
+      h[7] = pred;
+    }
+    if (accepted) {
+      const double q = 2.0 * rho - 1.0;
+      const double f = 1.0 - q * q * q;
+      ctrl[kCtrlLambda] = lam * (f > 1.0 / 3.0 ? f : 1.0 / 3.0);
+      ctrl[kCtrlNu] = 2.0;
+      ctrl[kCtrlCur] = 1.0 - ctrl[kCtrlCur];
+      ctrl[kCtrlCost] = Ft;
+    } else {
+      ctrl[kCtrlLambda] = lam * nu;
+      ctrl[kCtrlNu] = 2.0 * nu;
+      ctrl[kCtrlCost] = F;
+    }
+    ctrl[kCtrlAccepted] = accepted ? 1.0 : 0.0;
+    ctrl[kCtrlIter] = (double)(it + 1);
+    accepted_i = accepted ? 1 : 0;
   }
-  if (accepted) {
-    const double q = 2.0 * rho - 1.0;
-    const double f = 1.0 - q * q * q;
-    ctrl[kCtrlLambda] = lam * (f > 1.0 / 3.0 ? f : 1.0 / 3.0);
-    ctrl[kCtrlNu] = 2.0;
-    ctrl[kCtrlCur] = 1.0 - ctrl[kCtrlCur];
-    ctrl[kCtrlCost] = Ft;
-    for (int k = 0; k < C * kCamStride; ++k) cams[k] = cams[C * kCamStride + k];
-  } else {
-    ctrl[kCtrlLambda] = lam * nu;
-    ctrl[kCtrlNu] = 2.0 * nu;
-    ctrl[kCtrlCost] = F;
-  }
-  ctrl[kCtrlAccepted] = accepted ? 1.0 : 0.0;
-  ctrl[kCtrlIter] = (double)(it + 1);
+  accepted_i = __shfl_sync(0xffffffffu, accepted_i, 0);
+  if (accepted_i)
+    for (int k = threadIdx.x; k < C * kCamStride; k += 32) cams[k] = cams[C * kCamStride + k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -503,7 +517,7 @@ static int fill_layout(const SkaBaProblem& in, BaKernelArgs& a) {
 }
 
 int launch_reduce(const double* partials, int rows, int ncol, double* out, cudaStream_t s) {
-  ba_reduce_columns<<<(ncol + 127) / 128, 128, 0, s>>>(partials, rows, ncol, out);
+  ba_reduce_columns<<<(ncol + kRedCols - 1) / kRedCols, 32 * kRedCols, 0, s>>>(partials, rows, ncol, out);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }

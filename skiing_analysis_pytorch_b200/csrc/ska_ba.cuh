@@ -52,6 +52,13 @@ __device__ __forceinline__ void load_cam(const double* __restrict__ s, CamF& c) 
   c.k10 = (float)(s[12 + 3] / k22); c.k11 = (float)(s[12 + 4] / k22); c.k12 = (float)(s[12 + 5] / k22);
 }
 
+// 1/z: one MUFU.RCP plus one Newton step (full fp32 accuracy, a third of the IEEE-division sequence)
+__device__ __forceinline__ float ba_rcp(float z) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(z));
+  return fmaf(r, fmaf(-z, r, 1.0f), r);
+}
+
 // One observation: residual e, Jacobian rows of (u,v) w.r.t. X_c (ju, jv) and p = R X.
 struct ObsLin {
   float eu, ev;
@@ -66,7 +73,7 @@ __device__ __forceinline__ void project_lin(const CamF& c, const float X[3], flo
   o.p[2] = fmaf(c.R[6], X[0], fmaf(c.R[7], X[1], c.R[8] * X[2]));
   const float xc = o.p[0] + c.t[0], yc = o.p[1] + c.t[1], zc = o.p[2] + c.t[2];
   o.clamped = zc < kZMin;
-  const float iz = 1.0f / fmaxf(zc, kZMin);
+  const float iz = ba_rcp(fmaxf(zc, kZMin));
   const float x = xc * iz, y = yc * iz;
   const float fu = fmaf(c.k00, x, c.k01 * y), fv = fmaf(c.k10, x, c.k11 * y);
   o.eu = (fu + c.k02) - uo;
@@ -82,7 +89,7 @@ __device__ __forceinline__ float project_err2(const CamF& c, const float X[3], f
   const float yc = fmaf(c.R[3], X[0], fmaf(c.R[4], X[1], fmaf(c.R[5], X[2], c.t[1])));
   const float zc = fmaf(c.R[6], X[0], fmaf(c.R[7], X[1], fmaf(c.R[8], X[2], c.t[2])));
   clamped = zc < kZMin;
-  const float iz = 1.0f / fmaxf(zc, kZMin);
+  const float iz = ba_rcp(fmaxf(zc, kZMin));
   const float x = xc * iz, y = yc * iz;
   const float eu = fmaf(c.k00, x, fmaf(c.k01, y, c.k02)) - uo;
   const float ev = fmaf(c.k10, x, fmaf(c.k11, y, c.k12)) - vo;
@@ -147,8 +154,10 @@ __device__ __forceinline__ Chol3 chol3(float h00, float h01, float h02, float h1
   f.l21 = fmaf(-f.l20, f.l10, h12) * f.i1;
   const float d2 = fmaf(-f.l21, f.l21, fmaf(-f.l20, f.l20, h22));
   f.i2 = rsqrtf(d2);
-  // a point nobody observes (all conf 0) or a rank-deficient block has no step and no Schur term
+  // a point nobody observes (all conf 0) or a rank-deficient block has no step and no Schur term:
+  // its factor is zeroed so that chol3_fwd / chol3_bwd return exact zeros without a branch
   f.ok = (h00 > 0.f) && (d1 > 0.f) && (d2 > 0.f) && (d2 <= 3.0e38f);
+  if (!f.ok) f.i0 = f.l10 = f.l20 = f.i1 = f.l21 = f.i2 = 0.f;
   return f;
 }
 __device__ __forceinline__ Chol3 chol3_damped(const PointBlock& b, float lam) {

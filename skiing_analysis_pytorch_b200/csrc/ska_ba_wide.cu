@@ -2,15 +2,18 @@
 // registers): the Schur accumulation is a skinny SYRK, done warp-cooperatively from shared memory.
 //
 // Each warp owns 32 points per tile.
-//   phase 1  thread = point: pass A over the cameras builds the damped 3x3 point block and its
-//            Cholesky; pass B re-projects and writes, per free camera c,
-//              Y_c = L^-1 W_c (3 x 6)                          -> Yt[col][3*lane + k]      (transposed)
-//              sqrt(conf) [B_u | e_u | -A_u dp0], same for v   -> Bt[c][col][2*lane + {0,1}]
-//            with dp0 = -Hd^-1 gp (the point's own step with the cameras frozen).
-//   phase 2a lane = one 6x6 block (a, b), a <= b, of Sw = sum Y^T Y: 36 fp32 accumulators, operands
+//   phase 1  thread = point: pass A over the cameras builds the damped 3x3 point block, its Cholesky
+//            and dp0 = -Hd^-1 gp (the point's own step with the cameras frozen); pass B re-projects
+//            each free camera c and
+//              - writes Y_c = L^-1 W_c (3 x 6) transposed into the warp's staging buffer
+//                Yt[col][3*lane + k] (the only shared-memory staging: 16.8 KB per warp at C = 8),
+//              - forms the camera's 33 per-point sums-to-be (Hcc upper triangle 21, gc 6, bw 6) in
+//                registers and reduces them over the 32 points with a TRANSPOSING butterfly: 5
+//                exchange steps of 16/8/4/2/1 values leave lane i holding the warp total of value i
+//                (31 shuffles for 32 values instead of 160).
+//   phase 2  lane = one 6x6 block (a, b), a <= b, of Sw = sum Y^T Y: 36 fp32 accumulators, operands
 //            read as 128-bit shared loads of 4 consecutive rows of one column (padded column stride:
 //            conflict free), 144 FMA per 12 loads.
-//   phase 2b lane = (camera, column pair) of [Hcc | gc | bw] = sum B^T [B | e | -A dp0].
 // Every kFlush tiles the per-lane fp32 accumulators are folded into the CTA's fp64 packed reduced
 // system in shared memory in a fixed warp order (no atomics, deterministic); the CTA writes one
 // fp64 partial row, ba_reduce_columns (ska_ba.cu) sums the rows in a fixed order.
@@ -38,8 +41,6 @@ struct BaKernelArgsW {
 
 constexpr int kFlush = 16;
 constexpr int kYStride = 100;  // 96 rows + 4: column stride = 4 banks mod 32
-constexpr int kBColStride = 68;  // 64 rows + 4
-constexpr int kBCamStride = 8 * kBColStride + 4;
 
 constexpr int largest_div(int n, int cap) {
   int best = 1;
@@ -48,22 +49,36 @@ constexpr int largest_div(int n, int cap) {
   return best;
 }
 
+#ifndef SKA_BA_WIDE_WARPS
+#define SKA_BA_WIDE_WARPS 12  // 384 threads x <= 168 registers = the whole register file, one CTA per SM
+#endif
+
 template <int C>
 struct Wide {
   static constexpr int NC = C - 1, n = 6 * NC, nS = n * (n + 1) / 2;
   static constexpr int oBw = nS, oGc = nS + n, oHcc = nS + 2 * n, oCost = oHcc + 21 * NC, oClamp = oCost + 1, size = oClamp + 1;
   static constexpr int NP = NC * (NC + 1) / 2;              // 6x6 block pairs a <= b
-  static constexpr int SL_A = largest_div(24, 32 / NP);     // row slices in phase 2a (24 chunks of 4 rows)
+  static constexpr int SL_A = largest_div(24, 32 / NP);     // row slices in phase 2 (24 chunks of 4 rows)
   static constexpr int CH_A = 24 / SL_A;
-  static constexpr int NQ = 4 * NC;                         // (camera, column pair) lanes in phase 2b
-  static constexpr int SL_B = largest_div(16, 32 / NQ);     // 16 chunks of 4 rows
-  static constexpr int CH_B = 16 / SL_B;
-  static constexpr int W = C >= 7 ? 6 : 8;                  // warps per CTA
-  static constexpr int y_floats = n * kYStride;
-  static constexpr int b_floats = NC * kBCamStride;
-  static constexpr int warp_floats = y_floats + b_floats;
+  static constexpr int W = SKA_BA_WIDE_WARPS;               // warps per CTA
+  static constexpr int warp_floats = n * kYStride;
   static constexpr size_t smem = (size_t)W * warp_floats * sizeof(float) + (size_t)size * sizeof(double) + C * sizeof(CamF);
 };
+
+// lane i ends up with the sum over the warp of v[i] (i < 32); v is destroyed
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
 
 template <int C>
 __global__ void __launch_bounds__(32 * Wide<C>::W, 1) ba_linearize_wide_kernel(const BaKernelArgsW a) {
@@ -74,7 +89,6 @@ __global__ void __launch_bounds__(32 * Wide<C>::W, 1) ba_linearize_wide_kernel(c
   CamF* s_cam = reinterpret_cast<CamF*>(s_red + L::size);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* Yt = s_warp + (size_t)warp * L::warp_floats;
-  float* Bt = Yt + L::y_floats;
 
   if (threadIdx.x < C) load_cam(a.cams + threadIdx.x * kCamStride, s_cam[threadIdx.x]);
   for (int k = threadIdx.x; k < L::size; k += blockDim.x) s_red[k] = 0.0;
@@ -83,7 +97,7 @@ __global__ void __launch_bounds__(32 * Wide<C>::W, 1) ba_linearize_wide_kernel(c
   const int cur = (int)a.ctrl[kCtrlCur];
   const float* X = a.Xpp + (int64_t)cur * 3 * a.N;
 
-  // phase-2a role: block pair and row slice
+  // phase-2 role: block pair and row slice
   int pa = 0, pb_ = 0;
   const int pair = lane % L::NP, slice_a = lane / L::NP;
   {
@@ -99,18 +113,14 @@ __global__ void __launch_bounds__(32 * Wide<C>::W, 1) ba_linearize_wide_kernel(c
     }
   }
   const bool act_a = slice_a < L::SL_A;
-  // phase-2b role
-  const int cq = lane % L::NQ, slice_b = lane / L::NQ;
-  const int cam_b = cq >> 2, q_b = cq & 3;
-  const bool act_b = slice_b < L::SL_B;
 
-  float accS[6][6], accB[6][2];
+  float accS[6][6], accH[L::NC], accX[L::NC];  // accH: lane i = entry i of the camera's 33 sums; accX: entry 32
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
+  for (int k = 0; k < 6; ++k)
 #pragma unroll
     for (int l = 0; l < 6; ++l) accS[k][l] = 0.f;
-    accB[k][0] = accB[k][1] = 0.f;
-  }
+#pragma unroll
+  for (int c = 0; c < L::NC; ++c) accH[c] = accX[c] = 0.f;
   float cost = 0.f, nclamp = 0.f;
   int since = 0;
 
@@ -155,7 +165,7 @@ __global__ void __launch_bounds__(32 * Wide<C>::W, 1) ba_linearize_wide_kernel(c
       chol3_fwd(f, -pb.g0, -pb.g1, -pb.g2, y0, y1, y2);
       chol3_bwd(f, y0, y1, y2, d0, d1, d2);
     }
-    __syncwarp();  // previous tile's phase 2 is done with the staging buffers
+    __syncwarp();  // previous tile's phase 2 is done with the staging buffer
 #pragma unroll
     for (int c = 1; c < C; ++c) {
       ObsLin ol;
@@ -164,26 +174,32 @@ __global__ void __launch_bounds__(32 * Wide<C>::W, 1) ba_linearize_wide_kernel(c
       point_rows(s_cam[c], ol, au, av);
       camera_rows(ol, bu, bv);
       const float w = cw[c];
-      const float sw = sqrtf(w);
-      float* bt = Bt + (c - 1) * kBCamStride + 2 * lane;
+      float s33[32], s32;
+      const float adu = -fmaf(au[0], d0, fmaf(au[1], d1, au[2] * d2));
+      const float adv = -fmaf(av[0], d0, fmaf(av[1], d1, av[2] * d2));
+      int q = 0;
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
         const float su = w * bu[r], sv = w * bv[r];
-        float y0 = 0.f, y1 = 0.f, y2 = 0.f;
-        if (f.ok) chol3_fwd(f, fmaf(su, au[0], sv * av[0]), fmaf(su, au[1], sv * av[1]), fmaf(su, au[2], sv * av[2]), y0, y1, y2);
+        float y0, y1, y2;  // a point without a factor has a zeroed one: Y = 0 without a branch
+        chol3_fwd(f, fmaf(su, au[0], sv * av[0]), fmaf(su, au[1], sv * av[1]), fmaf(su, au[2], sv * av[2]), y0, y1, y2);
         float* yt = Yt + (6 * (c - 1) + r) * kYStride + 3 * lane;
         yt[0] = y0;
         yt[1] = y1;
         yt[2] = y2;
-        *reinterpret_cast<float2*>(bt + r * kBColStride) = make_float2(sw * bu[r], sw * bv[r]);
+#pragma unroll
+        for (int s2 = r; s2 < 6; ++s2, ++q) s33[q] = fmaf(su, bu[s2], sv * bv[s2]);  // Hcc upper triangle, 21 entries
+        s33[21 + r] = fmaf(su, ol.eu, sv * ol.ev);                                   // gc
+        if (r < 5) s33[27 + r] = fmaf(su, adu, sv * adv);                            // bw (entries 27..31)
+        else s32 = fmaf(su, adu, sv * adv);                                          // bw[5] = entry 32
       }
-      const float adu = fmaf(au[0], d0, fmaf(au[1], d1, au[2] * d2));
-      const float adv = fmaf(av[0], d0, fmaf(av[1], d1, av[2] * d2));
-      *reinterpret_cast<float2*>(bt + 6 * kBColStride) = make_float2(sw * ol.eu, sw * ol.ev);
-      *reinterpret_cast<float2*>(bt + 7 * kBColStride) = make_float2(-sw * adu, -sw * adv);
+      accH[c - 1] += transpose_reduce32(s33, lane);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s32 += __shfl_xor_sync(0xffffffffu, s32, o);
+      accX[c - 1] += s32;
     }
     __syncwarp();
-    // ---------------------------------------------------------------- phase 2a: Sw block (pa, pb_)
+    // ---------------------------------------------------------------- phase 2: Sw block (pa, pb_)
     if (act_a) {
       const float* ya = Yt + (6 * pa) * kYStride + 4 * slice_a * L::CH_A;
       const float* yb = Yt + (6 * pb_) * kYStride + 4 * slice_a * L::CH_A;
@@ -200,23 +216,6 @@ __global__ void __launch_bounds__(32 * Wide<C>::W, 1) ba_linearize_wide_kernel(c
 #pragma unroll
           for (int l = 0; l < 6; ++l)
             accS[k][l] = fmaf(A4[k].x, B4[l].x, fmaf(A4[k].y, B4[l].y, fmaf(A4[k].z, B4[l].z, fmaf(A4[k].w, B4[l].w, accS[k][l]))));
-      }
-    }
-    // ---------------------------------------------------------------- phase 2b: [Hcc | gc | bw]
-    if (act_b) {
-      const float* bc = Bt + cam_b * kBCamStride + 4 * slice_b * L::CH_B;
-#pragma unroll 2
-      for (int ch = 0; ch < L::CH_B; ++ch) {
-        float4 R4[6], Q4[2];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) R4[k] = *reinterpret_cast<const float4*>(bc + k * kBColStride + 4 * ch);
-        Q4[0] = *reinterpret_cast<const float4*>(bc + (2 * q_b) * kBColStride + 4 * ch);
-        Q4[1] = *reinterpret_cast<const float4*>(bc + (2 * q_b + 1) * kBColStride + 4 * ch);
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            accB[k][j] = fmaf(R4[k].x, Q4[j].x, fmaf(R4[k].y, Q4[j].y, fmaf(R4[k].z, Q4[j].z, fmaf(R4[k].w, Q4[j].w, accB[k][j]))));
       }
     }
     // ---------------------------------------------------------------- periodic fp64 fold
@@ -245,23 +244,13 @@ __global__ void __launch_bounds__(32 * Wide<C>::W, 1) ba_linearize_wide_kernel(c
             }
             __syncwarp();
           }
-          for (int sl = 0; sl < L::SL_B; ++sl) {
-            if (act_b && slice_b == sl) {
+          // lane i holds entry i of every camera's [Hcc (21) | gc (6) | bw (6)]; entry 32 is on every lane
+          const int o33 = lane < 21 ? L::oHcc + lane : (lane < 27 ? L::oGc + (lane - 21) : L::oBw + (lane - 27));
+          const int s33 = lane < 21 ? 21 : 6;
 #pragma unroll
-              for (int k = 0; k < 6; ++k)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                  const int col = 2 * q_b + j;
-                  if (col < 6) {
-                    if (col >= k) s_red[L::oHcc + 21 * cam_b + (k * 6 - (k * (k - 1)) / 2 + (col - k))] += (double)accB[k][j];
-                  } else if (col == 6) {
-                    s_red[L::oGc + 6 * cam_b + k] += (double)accB[k][j];
-                  } else {
-                    s_red[L::oBw + 6 * cam_b + k] += (double)accB[k][j];
-                  }
-                }
-            }
-            __syncwarp();
+          for (int c = 0; c < L::NC; ++c) {
+            s_red[o33 + s33 * c] += (double)accH[c];
+            if (lane == 0) s_red[L::oBw + 6 * c + 5] += (double)accX[c];
           }
           if (lane == 0) {
             s_red[L::oCost] += dc;
@@ -271,11 +260,11 @@ __global__ void __launch_bounds__(32 * Wide<C>::W, 1) ba_linearize_wide_kernel(c
       }
       __syncthreads();
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
+      for (int k = 0; k < 6; ++k)
 #pragma unroll
         for (int l = 0; l < 6; ++l) accS[k][l] = 0.f;
-        accB[k][0] = accB[k][1] = 0.f;
-      }
+#pragma unroll
+      for (int c = 0; c < L::NC; ++c) accH[c] = accX[c] = 0.f;
     }
   }
   __syncthreads();

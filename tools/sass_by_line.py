@@ -37,14 +37,17 @@ def main():
     rows = list(csv.reader(io.StringIO(raw)))
     hdr = rows[1]
     ia, isrc, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed")
+    ismp = hdr.index("# Samples")
     data = [r for r in rows[2:] if r and r[ia].startswith("0x")]
     base = int(data[0][ia], 16)
-    prof = {int(r[ia], 16) - base: (r[isrc].strip(), int(r[iex])) for r in data}
+    prof = {int(r[ia], 16) - base: (r[isrc].strip(), int(r[iex]), int(r[ismp] or 0)) for r in data}
     op = lambda t: [w for w in t.split() if not w.startswith("@")][0]
     agg, aggop, mism, total = collections.Counter(), collections.defaultdict(collections.Counter), 0, 0
+    smp = collections.Counter()
     for off, txt, line in ins:
         if off in prof:
-            ptxt, ex = prof[off]
+            ptxt, ex, ns = prof[off]
+            smp[line] += ns
             mism += op(ptxt) != op(txt)
             agg[line] += ex
             aggop[line][op(txt).split(".")[0]] += ex
@@ -59,7 +62,7 @@ def main():
                 cache[f] = []
         s = cache[f][l - 1].strip()[:90] if l - 1 < len(cache[f]) else ""
         ops = " ".join(f"{k}:{v / units:.0f}" for k, v in aggop[(f, l)].most_common(4))
-        print(f"{ex / units:7.1f} {Path(f).name}:{l}: {s}   [{ops}]")
+        print(f"{ex / units:7.1f} {100.0 * smp[(f, l)] / max(1, sum(smp.values())):5.1f}%smp {Path(f).name}:{l}: {s}   [{ops}]")
 
 
 if __name__ == "__main__":
