@@ -327,7 +327,7 @@ __device__ void so3_exp_left(const double w[3], const double* R, double* Rn) {
     for (int c = 0; c < 3; ++c) Rn[3 * r + c] = E[3 * r] * R[c] + E[3 * r + 1] * R[3 + c] + E[3 * r + 2] * R[6 + c];
 }
 
-__global__ void __launch_bounds__(64) ba_solve_kernel(int C, uint64_t free_mask, const double* __restrict__ red, double* cams,
+__global__ void __launch_bounds__(256) ba_solve_kernel(int C, uint64_t free_mask, const double* __restrict__ red, double* cams,
                                                       double* ctrl, double* delta) {
   __shared__ double S[kMaxN][kMaxN + 1];
   __shared__ double b[kMaxN], hd[kMaxN], gc[kMaxN], d[kMaxN];
@@ -380,26 +380,34 @@ __global__ void __launch_bounds__(64) ba_solve_kernel(int C, uint64_t free_mask,
     }
     __syncthreads();
   }
-  // forward / backward substitution (n <= 42: one thread)
+  // forward / backward substitution, column oriented: thread 0 finishes one unknown, every thread
+  // eliminates it from its rows (a single-thread triangular solve is ~n^2 dependent shared-memory
+  // round trips: 27 us at n = 42)
+  for (int i = tid; i < n; i += nt) d[i] = b[i];
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    if (tid == 0) d[k] = d[k] / S[k][k];
+    __syncthreads();
+    const double dk = d[k];
+    for (int i = k + 1 + tid; i < n; i += nt) d[i] -= S[i][k] * dk;
+    __syncthreads();
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    if (tid == 0) d[k] = d[k] / S[k][k];
+    __syncthreads();
+    const double dk = d[k];
+    for (int i = tid; i < k; i += nt) d[i] -= S[k][i] * dk;
+    __syncthreads();
+  }
   if (tid == 0) {
-    for (int i = 0; i < n; ++i) {
-      double v = b[i];
-      for (int k = 0; k < i; ++k) v -= S[i][k] * d[k];
-      d[i] = v / S[i][i];
-    }
-    for (int i = n - 1; i >= 0; --i) {
-      double v = d[i];
-      for (int k = i + 1; k < n; ++k) v -= S[k][i] * d[k];
-      d[i] = v / S[i][i];
-    }
     double pred = 0.0;
+    bool fin = true;
+    for (int i = 0; i < n; ++i) fin = fin && isfinite(d[i]);
     for (int i = 0; i < n; ++i) {
       const bool fi = (free_mask >> (6 + i)) & 1ull;
       if (!s_ok || !isfinite(d[i])) d[i] = 0.0;
       if (fi) pred += d[i] * (lam * hd[i] * d[i] - gc[i]);
     }
-    bool fin = true;
-    for (int i = 0; i < n; ++i) fin = fin && isfinite(d[i]);
     ctrl[kCtrlOk] = (s_ok && fin) ? 1.0 : 0.0;
     ctrl[kCtrlPredCam] = pred;
   }
@@ -567,7 +575,7 @@ int ba_backsub(const SkaBaProblem& in, cudaStream_t s) {
 }
 
 int ba_solve(int C, uint64_t free_mask, const double* red, double* cams, double* ctrl, double* delta, void* stream) {
-  ba_solve_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(C, free_mask, red, cams, ctrl, delta);
+  ba_solve_kernel<<<1, C <= 3 ? 64 : 256, 0, (cudaStream_t)stream>>>(C, free_mask, red, cams, ctrl, delta);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }
