@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-ba", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=20000)
     ap.add_argument("--ba-iters", type=int, default=20)
+    ap.add_argument("--e2e-chunk", type=int, default=65536, help="frames per H2D -> kernel -> D2H chunk of the host pipeline")
+    ap.add_argument("--e2e-streams", type=int, default=3)
     return ap.parse_args()
 
 
@@ -379,13 +381,14 @@ def run_ours(a):
         h_err = torch.empty((V, T, J), dtype=torch.float32).pin_memory()
         host_out = {"X": h_X, "err": h_err}
         e2e_steps = max(3, min(a.steps, 10))
+        kw_host = dict(kw, chunk_frames=a.e2e_chunk, n_streams=a.e2e_streams)
         for _ in range(2):
-            api.triangulate_reproject_host(h_k, conf=h_c, out=host_out, **kw)
+            api.triangulate_reproject_host(h_k, conf=h_c, out=host_out, **kw_host)
         barrier()
         ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev2.record()
         for _ in range(e2e_steps):
-            api.triangulate_reproject_host(h_k, conf=h_c, out=host_out, **kw)
+            api.triangulate_reproject_host(h_k, conf=h_c, out=host_out, **kw_host)
         ev3.record()
         barrier()
         e2e_ms = ev2.elapsed_time(ev3)

@@ -188,26 +188,27 @@ SKA_HD void fast_stage(const CamDev* __restrict__ cam, const float cx, const flo
 // Fused reprojection scoring, differential form:
 //   proj - obs = -(row . [Y;1]) / z  (+ fx*dx_distortion - skew*y)
 // so the ~1e3 px magnitudes of proj and obs never meet in fp32.
+template <int DIST, typename T>
+SKA_HD void score_view(const CamDev& c, T Y0, T Y1, T Y2, T ra, T rb, T& eu, T& ev) {
+  const T z = vadd(vfma(c.Ph[8], Y0, vfma(c.Ph[9], Y1, vfma(c.Ph[10], Y2, c.Ph[11]))), c.Pl[11]);
+  const T iz = rcp_fast(z);
+  eu = vmul(vneg(ra), iz);
+  ev = vmul(vneg(rb), iz);
+  if (DIST) {
+    const T x = vmul(vfma(c.Rxy[0], Y0, vfma(c.Rxy[1], Y1, vfma(c.Rxy[2], Y2, c.txy[0]))), iz);
+    const T y = vmul(vfma(c.Rxy[3], Y0, vfma(c.Rxy[4], Y1, vfma(c.Rxy[5], Y2, c.txy[1]))), iz);
+    T dx, dy;
+    distort_delta<(DIST >= 2)>(c, x, y, dx, dy);
+    eu = vfma(dx, c.fx, eu);
+    ev = vfma(dy, c.fy, ev);
+    if (DIST >= 2) eu = vfma(y, -c.skew, eu);
+  }
+}
+
 template <int V, int DIST, typename T>
 SKA_HD void score_views(const CamDev* __restrict__ cam, T Y0, T Y1, T Y2, const T* ra, const T* rb, T* du, T* dv) {
 #pragma unroll
-  for (int k = 0; k < V; ++k) {
-    const CamDev& c = cam[k];
-    const T z = vadd(vfma(c.Ph[8], Y0, vfma(c.Ph[9], Y1, vfma(c.Ph[10], Y2, c.Ph[11]))), c.Pl[11]);
-    const T iz = rcp_fast(z);
-    T eu = vmul(vneg(ra[k]), iz), ev = vmul(vneg(rb[k]), iz);
-    if (DIST) {
-      const T x = vmul(vfma(c.Rxy[0], Y0, vfma(c.Rxy[1], Y1, vfma(c.Rxy[2], Y2, c.txy[0]))), iz);
-      const T y = vmul(vfma(c.Rxy[3], Y0, vfma(c.Rxy[4], Y1, vfma(c.Rxy[5], Y2, c.txy[1]))), iz);
-      T dx, dy;
-      distort_delta<(DIST >= 2)>(c, x, y, dx, dy);
-      eu = vfma(dx, c.fx, eu);
-      ev = vfma(dy, c.fy, ev);
-      if (DIST >= 2) eu = vfma(y, -c.skew, eu);
-    }
-    du[k] = eu;
-    dv[k] = ev;
-  }
+  for (int k = 0; k < V; ++k) score_view<DIST, T>(cam[k], Y0, Y1, Y2, ra[k], rb[k], du[k], dv[k]);
 }
 
 template <bool PACK>
@@ -411,6 +412,163 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
         dv[g][k] = dvt[k];
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming form of the same arithmetic for many views (V >= 5): nothing per view is kept in
+// registers.  The observations are re-read through `obs(k, u, v, w2)` (shared memory in the
+// kernel) and the DLT rows are recomputed in each of three passes over the views
+//   pass 1  rows -> normal matrix M
+//   pass 2  rows -> Rayleigh quotient at the inhomogeneous least-squares point
+//   pass 3  rows -> residuals at the final point -> scoring -> emit(k, u, v, du, dv)
+// which costs 24 more FMAs per view than tri_points<> but needs ~90 registers for ANY V, so an
+// 8-view point pair fits the packed (F2) path and three times as many warps stay resident.
+// T = float (one point) or F2 (two points in lockstep); src addresses the thread's first point in
+// global memory for the fp64 fallback (second point: +2 floats / +1 float).
+template <int V, bool CONF, int DIST, typename T, typename Obs, typename Emit, int LO = 1>
+SKA_HD void tri_points_stream(const CamDev* __restrict__ cam, const double (*P64)[12], const float cx, const float cy,
+                              const float cz, const Obs& obs, const PointSource& src, float (*X)[3], uint8_t* status,
+                              Emit& emit) {
+  constexpr int NP = Vec<T>::N;
+#ifndef SKA_STREAM_UNROLL
+#define SKA_STREAM_UNROLL 1
+#endif
+  // the view loops stay ROLLED for many views: unrolled, the scheduler interleaves all V views' rows
+  // (8 views x 8 row entries x 2 registers) and spills; rolled, one view is live at a time
+  constexpr int kU = (V >= 5) ? SKA_STREAM_UNROLL : V;
+  Sym4T<T> M;
+  sym4_zero(M);
+#pragma unroll kU
+  for (int k = 0; k < V; ++k) {
+    T u, v, w2, a[4], b[4];
+    obs(k, u, v, w2);
+    dlt_rows<LO>(cam[k], u, v, a, b);
+    if (CONF) {
+      sym4_rank1(M, a, w2);
+      sym4_rank1(M, b, w2);
+    } else {
+      sym4_rank1_unit(M, a);
+      sym4_rank1_unit(M, b);
+    }
+  }
+  const Ldl3T<T> f0 = ldl3(M.m00, M.m01, M.m02, M.m11, M.m12, M.m22);
+  T y0, y1, y2;
+  ldl3_solve(f0, vneg(M.m03), vneg(M.m13), vneg(M.m23), y0, y1, y2);
+  T num = Vec<T>::splat(0.f);
+#pragma unroll kU
+  for (int k = 0; k < V; ++k) {
+    T u, v, w2, a[4], b[4];
+    obs(k, u, v, w2);
+    dlt_rows<LO>(cam[k], u, v, a, b);
+    const T ra = vfma(a[0], y0, vfma(a[1], y1, vfma(a[2], y2, a[3])));
+    const T rb = vfma(b[0], y0, vfma(b[1], y1, vfma(b[2], y2, b[3])));
+    const T rr = vfma(ra, ra, vmul(rb, rb));
+    num = CONF ? vfma(w2, rr, num) : vadd(num, rr);
+  }
+  const T X0 = vadd(y0, cx), X1 = vadd(y1, cy), X2 = vadd(y2, cz);
+  const T den = vfma(X0, X0, vfma(X1, X1, vfma(X2, X2, 1.0f)));
+  const T lam = vmul(num, rcp_fast(den));
+  T z0, z1, z2;
+  ldl3_solve(f0, X0, X1, X2, z0, z1, z2);
+  const T d0 = vmul(lam, z0), d1 = vmul(lam, z1), d2 = vmul(lam, z2);
+  const T step2 = vfma(d0, d0, vfma(d1, d1, vmul(d2, d2)));
+  const T itr = ldl3_inv_trace(f0);
+  const typename Vec<T>::Mask fast = mand(mand(f0.pos, vlt(vmul(lam, itr), kFastLamTr)), vle(step2, vmul(den, kFastTol2)));
+  const typename Vec<T>::Mask wellm = vle(vmul(vadd(vadd(M.m00, M.m11), M.m22), itr), kCondMax);
+  const T Yf0 = vadd(y0, d0), Yf1 = vadd(y1, d1), Yf2 = vadd(y2, d2);
+
+  SecularState s[NP];
+  bool conv[NP], well[NP], need64[NP];
+  float Y[NP][3];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    s[p].y0 = pick(Yf0, p);
+    s[p].y1 = pick(Yf1, p);
+    s[p].y2 = pick(Yf2, p);
+    s[p].lam = pick(lam, p);
+    s[p].step2 = pick(step2, p);
+    s[p].ok = pick(f0.pos, p);
+    conv[p] = pick(fast, p);
+    well[p] = pick(wellm, p);
+    status[p] = 0;
+  }
+  if (!SKA_WARP_ALL(mall(fast))) {
+    // general path (rare): full secular iteration per point in scalar fp32
+#pragma unroll 1
+    for (int it = 0; it < kSecularMaxIter; ++it) {
+      bool done = true;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        if (!conv[p]) {
+          float nm = 0.f;
+#pragma unroll 1
+          for (int k = 0; k < V; ++k) {
+            T u, v, w2;
+            obs(k, u, v, w2);
+            float a[4], b[4];
+            dlt_rows<LO>(cam[k], pick(u, p), pick(v, p), a, b);
+            const float ra = fmaf(a[0], s[p].y0, fmaf(a[1], s[p].y1, fmaf(a[2], s[p].y2, a[3])));
+            const float rb = fmaf(b[0], s[p].y0, fmaf(b[1], s[p].y1, fmaf(b[2], s[p].y2, b[3])));
+            const float rr = fmaf(ra, ra, rb * rb);
+            nm = CONF ? fmaf(pick(w2, p), rr, nm) : nm + rr;
+          }
+          const float Xa = s[p].y0 + cx, Xb = s[p].y1 + cy, Xc = s[p].y2 + cz;
+          const float lm = nm * rcp_fast(fmaf(Xa, Xa, fmaf(Xb, Xb, fmaf(Xc, Xc, 1.0f))));
+          const Sym4 Ms = (p == 0) ? sym4_lane<0>(M) : sym4_lane<1>(M);
+          conv[p] = secular_step(Ms, cx, cy, cz, lm, s[p]);
+        }
+        done = done && (conv[p] || !s[p].ok);
+      }
+      if (SKA_WARP_ALL(done)) break;
+    }
+  }
+  bool any64 = false;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    Y[p][0] = s[p].y0;
+    Y[p][1] = s[p].y1;
+    Y[p][2] = s[p].y2;
+    const bool finite_in = fabsf(pick(M.m33, p)) <= 3.0e38f;  // false for NaN / inf inputs
+    need64[p] = !(conv[p] && s[p].ok && well[p]) && finite_in;
+    if (!finite_in) status[p] = 2;
+    any64 = any64 || need64[p];
+  }
+  if (SKA_WARP_ANY(any64)) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      if (need64[p]) {
+        const Vec3d Xd = solve_jacobi64<V>(P64, src.kpts + 2 * p, src.conf ? src.conf + p : nullptr, src.k_sV, src.c_sV,
+                                           src.weight_sqrt);
+        Y[p][0] = (float)(Xd.x - (double)cx);
+        Y[p][1] = (float)(Xd.y - (double)cy);
+        Y[p][2] = (float)(Xd.z - (double)cz);
+        status[p] = 1;
+      }
+    }
+  }
+  T Yt[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    if constexpr (NP == 2) Yt[m] = mk2(Y[0][m], Y[NP - 1][m]);
+    else Yt[m] = Y[0][m];
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    X[p][0] = Y[p][0] + cx;
+    X[p][1] = Y[p][1] + cy;
+    X[p][2] = Y[p][2] + cz;
+    if (!(fabsf(X[p][0]) <= 3.0e38f && fabsf(X[p][1]) <= 3.0e38f && fabsf(X[p][2]) <= 3.0e38f)) status[p] = 2;
+  }
+#pragma unroll kU
+  for (int k = 0; k < V; ++k) {
+    T u, v, w2, a[4], b[4], eu, ev;
+    obs(k, u, v, w2);
+    dlt_rows<LO>(cam[k], u, v, a, b);
+    const T ra = vfma(a[0], Yt[0], vfma(a[1], Yt[1], vfma(a[2], Yt[2], a[3])));
+    const T rb = vfma(b[0], Yt[0], vfma(b[1], Yt[1], vfma(b[2], Yt[2], b[3])));
+    score_view<DIST, T>(cam[k], Yt[0], Yt[1], Yt[2], ra, rb, eu, ev);
+    emit(k, u, v, eu, ev);
   }
 }
 

@@ -267,22 +267,77 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 #define SKA_WS_MINB 1
 #endif
 constexpr int kWarpPts = 64;  // points per warp tile (2 per lane)
-constexpr int kStages = 3;
 
-template <int V, int NW>
-struct WsSmem {  // dynamic shared-memory layout of tri_kernel_ws
-  static constexpr size_t oX = (size_t)NW * kStages * V * kWarpPts * 2 * sizeof(float);
-  static constexpr size_t oFull = oX + (size_t)NW * kWarpPts * 3 * sizeof(float);
-  static constexpr size_t oEmpty = oFull + (size_t)NW * kStages * sizeof(uint64_t);
-  static constexpr size_t bytes = oEmpty + (size_t)NW * kStages * sizeof(uint64_t);
+// STREAM = false: the warp copies its pair into registers, releases the stage and runs tri_points<>
+//                 (rows kept in registers; V <= 4).
+// STREAM = true : tri_points_stream<> re-reads the observations from the stage in each of its three
+//                 passes (nothing per view in registers; V >= 5), confidences are staged by the
+//                 producer as well, and the stage is released after the last pass.
+template <int V, bool CONF, bool STREAM>
+struct WsCfg {
+  static constexpr int kStages = STREAM ? 2 : 3;
+  static constexpr bool kStageConf = STREAM && CONF;
+  static constexpr int kViewFloats = kWarpPts * 2 + (kStageConf ? kWarpPts : 0);  // keypoints (+ confidences) of one view
+  static constexpr int kStageFloats = V * kViewFloats;
 };
 
-template <int V, bool CONF, int DIST, int NW, int MINB>
+template <int V, int NW, bool CONF, bool STREAM>
+struct WsSmem {  // dynamic shared-memory layout of tri_kernel_ws
+  using Cf = WsCfg<V, CONF, STREAM>;
+  static constexpr size_t oX = (size_t)NW * Cf::kStages * Cf::kStageFloats * sizeof(float);
+  static constexpr size_t oFull = oX + (size_t)NW * kWarpPts * 3 * sizeof(float);
+  static constexpr size_t oEmpty = oFull + (size_t)NW * Cf::kStages * sizeof(uint64_t);
+  static constexpr size_t bytes = oEmpty + (size_t)NW * Cf::kStages * sizeof(uint64_t);
+};
+
+// observations of the lane's point pair, read from the warp's stage (tri_points_stream)
+template <bool CONF>
+struct StageObs {
+  const float* stage;  // [V][kViewFloats]
+  int view_floats, lane;
+  uint32_t weight_sqrt;
+  __device__ __forceinline__ void operator()(int k, F2& u, F2& v, F2& w2) const {
+    // volatile asm loads: each pass must RE-READ the stage - a plain load would let the compiler keep the
+    // observations (and the rows derived from them) live across the three passes, which is exactly the
+    // register footprint the streaming form exists to avoid
+    const float* p = stage + k * view_floats;
+    float4 q;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(smem_u32(p + 4 * lane)));
+    u = mk2(q.x, q.z);
+    v = mk2(q.y, q.w);
+    if (CONF) {
+      float2 c;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(c.x), "=f"(c.y) : "r"(smem_u32(p + kWarpPts * 2 + 2 * lane)));
+      w2 = weight_sqrt ? mk2(c.x, c.y) : mk2(c.x * c.x, c.y * c.y);
+    } else {
+      w2 = mk2(1.f, 1.f);
+    }
+  }
+};
+
+template <int V>
+struct StreamEmit {  // per-view outputs of tri_points_stream, written as they are produced
+  const TriParams<V>& prm;
+  uint32_t i0;
+  __device__ __forceinline__ void operator()(int k, F2 u, F2 v, F2 du, F2 dv) const {
+    if (prm.err != nullptr) {
+      const float e0 = sqrt_fast(fmaf(du.x, du.x, dv.x * dv.x)), e1 = sqrt_fast(fmaf(du.y, du.y, dv.y * dv.y));
+      __stcs(reinterpret_cast<float2*>(prm.err + (int64_t)k * prm.c_sV + i0), make_float2(e0, e1));
+    }
+    if (prm.proj != nullptr)
+      __stcs(reinterpret_cast<float4*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)i0),
+             make_float4(u.x + du.x, v.x + dv.x, u.y + du.y, v.y + dv.y));
+  }
+};
+
+template <int V, bool CONF, int DIST, int NW, int MINB, bool STREAM>
 __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __grid_constant__ TriParams<V> prm) {
   constexpr int PTS = 2;
-  using L = WsSmem<V, NW>;
+  using Cf = WsCfg<V, CONF, STREAM>;
+  using L = WsSmem<V, NW, CONF, STREAM>;
+  constexpr int kStages = Cf::kStages;
   extern __shared__ __align__(128) unsigned char ws_smem[];
-  float(*sK)[kStages][V][kWarpPts * 2] = reinterpret_cast<float(*)[kStages][V][kWarpPts * 2]>(ws_smem);
+  float* sK = reinterpret_cast<float*>(ws_smem);  // [NW][kStages][V][kViewFloats]
   float(*sX)[kWarpPts * 3] = reinterpret_cast<float(*)[kWarpPts * 3]>(ws_smem + L::oX);
   uint64_t(*sFull)[kStages] = reinterpret_cast<uint64_t(*)[kStages]>(ws_smem + L::oFull);
   uint64_t(*sEmpty)[kStages] = reinterpret_cast<uint64_t(*)[kStages]>(ws_smem + L::oEmpty);
@@ -306,10 +361,16 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
       uint32_t round = 0;  // how many times the ring wrapped
       for (; wt < n_wt; wt += stride) {
         if (round > 0) mbar_wait(&sEmpty[w][st], (round - 1) & 1u);  // consumers released this stage
-        mbar_expect_tx(&sFull[w][st], (uint32_t)(kWarpPts * 8 * V));
+        float* stage = sK + ((size_t)w * kStages + st) * Cf::kStageFloats;
+        mbar_expect_tx(&sFull[w][st], (uint32_t)(Cf::kStageFloats * sizeof(float)));
 #pragma unroll
-        for (int k = 0; k < V; ++k)
-          bulk_g2s(&sK[w][st][k][0], prm.kpts + (int64_t)k * prm.k_sV + (int64_t)wt * (kWarpPts * 2), kWarpPts * 8, &sFull[w][st]);
+        for (int k = 0; k < V; ++k) {
+          bulk_g2s(stage + k * Cf::kViewFloats, prm.kpts + (int64_t)k * prm.k_sV + (int64_t)wt * (kWarpPts * 2), kWarpPts * 8,
+                   &sFull[w][st]);
+          if (Cf::kStageConf)
+            bulk_g2s(stage + k * Cf::kViewFloats + kWarpPts * 2, prm.conf + (int64_t)k * prm.c_sV + (int64_t)wt * kWarpPts,
+                     kWarpPts * 4, &sFull[w][st]);
+        }
         if (++st == kStages) {
           st = 0;
           ++round;
@@ -326,49 +387,56 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
   float* sx = sX[warp];
   for (; wt < n_wt; wt += stride) {
     mbar_wait(&sFull[warp][st], par);
-    float u[PTS][V], v[PTS][V], w2[PTS][V];
+    const float* stage = sK + ((size_t)warp * kStages + st) * Cf::kStageFloats;
     const uint32_t i0 = wt * kWarpPts + 2u * lane;
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-      const float4 q = *reinterpret_cast<const float4*>(&sK[warp][st][k][4 * lane]);
-      u[0][k] = q.x; v[0][k] = q.y; u[1][k] = q.z; v[1][k] = q.w;
-      if (CONF) {
-        float2 c = make_float2(1.f, 1.f);
-        if (prm.conf != nullptr) c = __ldcs(reinterpret_cast<const float2*>(prm.conf + (int64_t)k * prm.c_sV + i0));
-        w2[0][k] = prm.weight_sqrt ? c.x : c.x * c.x;
-        w2[1][k] = prm.weight_sqrt ? c.y : c.y * c.y;
-      } else {
-        w2[0][k] = w2[1][k] = 1.0f;
-      }
-    }
-    __syncwarp();                                  // every lane holds its pair in registers
-    if (lane == 0) mbar_arrive(&sEmpty[warp][st]);  // hand the stage back to the producer
-    if (++st == kStages) {
-      st = 0;
-      par ^= 1u;
-    }
-
     PointSource src;
     src.kpts = prm.kpts + 2 * (int64_t)i0;
     src.conf = (prm.conf != nullptr) ? prm.conf + i0 : nullptr;
     src.k_sV = prm.k_sV;
     src.c_sV = prm.c_sV;
     src.weight_sqrt = prm.weight_sqrt;
-    float X[PTS][3], du[PTS][V], dv[PTS][V];
+    float X[PTS][3];
     uint8_t stt[PTS];
-    tri_points<V, PTS, CONF, DIST, kSolverSecular>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], u, v, w2, src, X, du, dv, stt);
-
+    if constexpr (STREAM) {
+      StageObs<CONF> obs{stage, Cf::kViewFloats, lane, prm.weight_sqrt};
+      StreamEmit<V> emit{prm, i0};
+      tri_points_stream<V, CONF, DIST, F2>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], obs, src, X, stt, emit);
+      __syncwarp();                                  // every lane finished its last pass over the stage
+      if (lane == 0) mbar_arrive(&sEmpty[warp][st]);  // hand it back to the producer
+    } else {
+      float u[PTS][V], v[PTS][V], w2[PTS][V], du[PTS][V], dv[PTS][V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      if (prm.err != nullptr) {
-        const float e0 = sqrt_fast(fmaf(du[0][k], du[0][k], dv[0][k] * dv[0][k]));
-        const float e1 = sqrt_fast(fmaf(du[1][k], du[1][k], dv[1][k] * dv[1][k]));
-        __stcs(reinterpret_cast<float2*>(prm.err + (int64_t)k * prm.c_sV + i0), make_float2(e0, e1));
+      for (int k = 0; k < V; ++k) {
+        const float4 q = *reinterpret_cast<const float4*>(stage + k * Cf::kViewFloats + 4 * lane);
+        u[0][k] = q.x; v[0][k] = q.y; u[1][k] = q.z; v[1][k] = q.w;
+        if (CONF) {
+          float2 c = make_float2(1.f, 1.f);
+          if (prm.conf != nullptr) c = __ldcs(reinterpret_cast<const float2*>(prm.conf + (int64_t)k * prm.c_sV + i0));
+          w2[0][k] = prm.weight_sqrt ? c.x : c.x * c.x;
+          w2[1][k] = prm.weight_sqrt ? c.y : c.y * c.y;
+        } else {
+          w2[0][k] = w2[1][k] = 1.0f;
+        }
       }
-      if (prm.proj != nullptr) {
-        __stcs(reinterpret_cast<float4*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)i0),
-               make_float4(u[0][k] + du[0][k], v[0][k] + dv[0][k], u[1][k] + du[1][k], v[1][k] + dv[1][k]));
+      __syncwarp();                                  // every lane holds its pair in registers
+      if (lane == 0) mbar_arrive(&sEmpty[warp][st]);  // hand the stage back to the producer
+      tri_points<V, PTS, CONF, DIST, kSolverSecular>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], u, v, w2, src, X, du, dv, stt);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        if (prm.err != nullptr) {
+          const float e0 = sqrt_fast(fmaf(du[0][k], du[0][k], dv[0][k] * dv[0][k]));
+          const float e1 = sqrt_fast(fmaf(du[1][k], du[1][k], dv[1][k] * dv[1][k]));
+          __stcs(reinterpret_cast<float2*>(prm.err + (int64_t)k * prm.c_sV + i0), make_float2(e0, e1));
+        }
+        if (prm.proj != nullptr) {
+          __stcs(reinterpret_cast<float4*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)i0),
+                 make_float4(u[0][k] + du[0][k], v[0][k] + dv[0][k], u[1][k] + du[1][k], v[1][k] + dv[1][k]));
+        }
       }
+    }
+    if (++st == kStages) {
+      st = 0;
+      par ^= 1u;
     }
     if (prm.status != nullptr) *reinterpret_cast<uchar2*>(prm.status + i0) = make_uchar2(stt[0], stt[1]);
     // ---- X through shared memory: 192 floats per warp leave as 48 128-bit stores
@@ -389,11 +457,19 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
   }
 }
 
-template <int V, bool CONF, int DIST>
+#ifndef SKA_WS_STREAM_WARPS
+#define SKA_WS_STREAM_WARPS 15
+#endif
+#ifndef SKA_WS_STREAM_MINB
+#define SKA_WS_STREAM_MINB 1
+#endif
+
+template <int V, bool CONF, int DIST, bool STREAM>
 static cudaError_t launch_ws(TriParams<V>& prm, cudaStream_t stream) {
-  constexpr int NW = SKA_WS_WARPS, MINB = SKA_WS_MINB, BLOCK = 32 * (NW + 1);
-  auto kern = tri_kernel_ws<V, CONF, DIST, NW, MINB>;
-  constexpr size_t smem = WsSmem<V, NW>::bytes;
+  constexpr int NW = STREAM ? SKA_WS_STREAM_WARPS : SKA_WS_WARPS, MINB = STREAM ? SKA_WS_STREAM_MINB : SKA_WS_MINB, BLOCK = 32 * (NW + 1);
+  auto kern = tri_kernel_ws<V, CONF, DIST, NW, MINB, STREAM>;
+  constexpr size_t smem = WsSmem<V, NW, CONF, STREAM>::bytes;
+  static_assert(smem <= 227 * 1024, "tri_kernel_ws staging does not fit the SM's shared memory");
   int dev = 0, sms = 0, per_sm = 0;
   cudaError_t ce = cudaGetDevice(&dev);
   if (ce != cudaSuccess) return ce;
@@ -645,17 +721,37 @@ static int dispatch(const TriArgs& a) {
   auto al = [](const void* p, uintptr_t n) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % n) == 0; };
   prm.x_vec = al(a.X, 16) ? 1u : 0u;
   const bool conf = (a.conf != nullptr);
-  // 128-bit path: flat point index, even point count, vector-aligned streams, modest register need
+  // pair path: flat point index, even point count, vector-aligned streams
 #ifdef SKA_FORCE_PTS1
-  const bool pts2 = false && (V <= 4) && (prm.N % 2 == 0) && al(a.kpts, 16) && al(a.conf, 8) && al(a.err, 8) && al(a.proj, 16);
+  const bool pair_ok = false;
 #else
-  const bool pts2 = !fm && (V <= 4) && (prm.N % 2 == 0) && al(a.kpts, 16) && al(a.conf, 8) && al(a.err, 8) && al(a.proj, 16);
+  const bool pair_ok = !fm && (prm.N % 2 == 0) && al(a.kpts, 16) && al(a.conf, 8) && al(a.err, 8) && al(a.proj, 16);
 #endif
+  // V <= 4: warp-specialised kernel, rows in registers (tri_points).  V >= 5: tri_kernel (one point per thread).
+  // The streaming three-pass form (tri_points_stream: nothing per view in registers, packed pairs for any V,
+  // confidences staged by bulk copies) is kept as a measurement variant: on B200 it was SLOWER than tri_kernel at
+  // V = 8 (2.20 vs 1.96 ms on config 4's shard: rolled view loops turn every camera coefficient into an indexed
+  // LDC) and equal at V = 2 (profiles/r01_tri_kernel_variants.txt).
+#if defined(SKA_WS_STREAM_ALL)
+  constexpr bool kStream = true;
+  constexpr bool kWs = true;
+#elif defined(SKA_WS_STREAM_LARGE)
+  constexpr bool kStream = (V >= 5);
+  constexpr bool kWs = true;
+#else
+  constexpr bool kStream = false;
+  constexpr bool kWs = (V <= 4);
+#endif
+  const bool ws_ok = kWs && pair_ok && (!kStream || !conf || (al(a.conf, 16) && prm.N % 4 == 0));
   cudaError_t ce;
   cudaStream_t s = (cudaStream_t)a.stream;
 #define SKA_GO(PTS)                                                                      \
   (conf ? (dist ? launch<V, PTS, true, 1>(prm, s) : launch<V, PTS, true, 0>(prm, s))     \
         : (dist ? launch<V, PTS, false, 1>(prm, s) : launch<V, PTS, false, 0>(prm, s)))
+#define SKA_GO_WS(Q)                                                                                           \
+  (conf ? (dist ? launch_ws<V, true, 1, kStream>(Q, s) : launch_ws<V, true, 0, kStream>(Q, s))                 \
+        : (dist ? launch_ws<V, false, 1, kStream>(Q, s) : launch_ws<V, false, 0, kStream>(Q, s)))
+  constexpr int kTailPts = (V <= 4) ? 2 : 1;  // tri_kernel handles the < 64-point tail
   if (solver == kSolverJacobi64) {
     // exact / measurement solvers: one generic instantiation (weights and full distortion always on)
     ce = launch<V, 1, true, 2, kSolverJacobi64, 1>(prm, s);
@@ -663,38 +759,33 @@ static int dispatch(const TriArgs& a) {
     ce = launch<V, 1, true, 2, kSolverJacobi32, 1>(prm, s);
   } else if (dist >= 2) {
     ce = launch<V, 1, true, 2, kSolverSecular, 1>(prm, s);  // thin prism / skew: rare, one generic instantiation
-  } else if constexpr (V <= 4) {
 #ifndef SKA_NO_BULK
-    if (pts2) {
-      // whole 64-point tiles -> warp-specialised bulk-staged kernel; the < 64-point tail -> tri_kernel
-      const int64_t n_full = prm.N / kWarpPts, done = n_full * kWarpPts;
-      ce = cudaSuccess;
-      if (n_full > 0) {
-        TriParams<V> q = prm;
-        q.n_tiles = n_full;
-        ce = conf ? (dist ? launch_ws<V, true, 1>(q, s) : launch_ws<V, true, 0>(q, s))
-                  : (dist ? launch_ws<V, false, 1>(q, s) : launch_ws<V, false, 0>(q, s));
-      }
-      if (ce == cudaSuccess && done < prm.N) {
-        prm.N -= done;  // strides keep describing the whole clip
-        prm.kpts += 2 * done;
-        if (prm.conf != nullptr) prm.conf += done;
-        prm.X += 3 * done;
-        if (prm.err != nullptr) prm.err += done;
-        if (prm.proj != nullptr) prm.proj += 2 * done;
-        if (prm.status != nullptr) prm.status += done;
-        ce = SKA_GO(2);
-      }
-    } else {
-      ce = SKA_GO(1);
+  } else if (ws_ok) {
+    // whole 64-point tiles -> warp-specialised bulk-staged kernel; the < 64-point tail -> tri_kernel
+    const int64_t n_full = prm.N / kWarpPts, done = n_full * kWarpPts;
+    ce = cudaSuccess;
+    if (n_full > 0) {
+      TriParams<V> q = prm;
+      q.n_tiles = n_full;
+      ce = SKA_GO_WS(q);
     }
-#else
-    ce = pts2 ? SKA_GO(2) : SKA_GO(1);
+    if (ce == cudaSuccess && done < prm.N) {
+      prm.N -= done;  // strides keep describing the whole clip
+      prm.kpts += 2 * done;
+      if (prm.conf != nullptr) prm.conf += done;
+      prm.X += 3 * done;
+      if (prm.err != nullptr) prm.err += done;
+      if (prm.proj != nullptr) prm.proj += 2 * done;
+      if (prm.status != nullptr) prm.status += done;
+      ce = SKA_GO(kTailPts);
+    }
 #endif
+  } else if constexpr (V <= 4) {
+    ce = pair_ok ? SKA_GO(2) : SKA_GO(1);
   } else {
-    (void)pts2;
     ce = SKA_GO(1);
   }
+#undef SKA_GO_WS
 #undef SKA_GO
   if (ce != cudaSuccess) return set_error((int)ce, cudaGetErrorString(ce));
   return SKA_OK;

@@ -9,11 +9,11 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 VARIANTS = {
-    "ws_7x2": ["-DSKA_WS_WARPS=7", "-DSKA_WS_MINB=2"],      # 2 CTAs x (7 consumers + 1 producer), 128 registers
-    "ws_11x1": ["-DSKA_WS_WARPS=11", "-DSKA_WS_MINB=1"],    # 11 consumers, 168 registers
-    "ws_3x4": ["-DSKA_WS_WARPS=3", "-DSKA_WS_MINB=4"],      # 4 CTAs x (3 + 1), 128 registers
-    "ws_nopack": ["-DSKA_NO_PACK"],                          # warp-specialised staging, scalar fp32 arithmetic
-    "nobulk_nopack": ["-DSKA_NO_BULK", "-DSKA_NO_PACK"],    # register prefetch, scalar fp32
+    "stream_all": ["-DSKA_WS_STREAM_ALL"],                                   # V <= 4 through the streaming three-pass form too
+    "stream_u2": ["-DSKA_STREAM_UNROLL=2"],                                  # view loops unrolled by 2 (V >= 5)
+    "stream_w23": ["-DSKA_WS_STREAM_WARPS=23"],                              # 24 warps x 85 registers (V >= 5)
+    "stream_w11": ["-DSKA_WS_STREAM_WARPS=11"],                              # 12 warps x 168 registers (V >= 5)
+    "stream_7x2": ["-DSKA_WS_STREAM_WARPS=7", "-DSKA_WS_STREAM_MINB=2"],     # 2 CTAs x (7 + 1) warps
 }
 LIBDIR = ROOT / "skiing_analysis_pytorch_b200" / "lib"
 
