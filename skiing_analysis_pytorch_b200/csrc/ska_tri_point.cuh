@@ -436,7 +436,7 @@ SKA_HD void tri_points_stream(const CamDev* __restrict__ cam, const double (*P64
 #endif
   // the view loops stay ROLLED for many views: unrolled, the scheduler interleaves all V views' rows
   // (8 views x 8 row entries x 2 registers) and spills; rolled, one view is live at a time
-  constexpr int kU = (V >= 5) ? SKA_STREAM_UNROLL : V;
+  constexpr int kU = (V >= 5 && NP == 2) ? SKA_STREAM_UNROLL : V;  // scalar form: unrolled (coefficients stay constant-bank operands)
   Sym4T<T> M;
   sym4_zero(M);
 #pragma unroll kU

@@ -315,6 +315,39 @@ struct StageObs {
   }
 };
 
+// scalar (one point at a time) counterparts: sub = 0 / 1 selects the lane's first / second point
+template <bool CONF>
+struct StageObs1 {
+  const float* stage;
+  int view_floats, lane, sub;
+  uint32_t weight_sqrt;
+  __device__ __forceinline__ void operator()(int k, float& u, float& v, float& w2) const {
+    const float* p = stage + k * view_floats;
+    float2 q;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(q.x), "=f"(q.y) : "r"(smem_u32(p + 4 * lane + 2 * sub)));
+    u = q.x;
+    v = q.y;
+    if (CONF) {
+      float c;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c) : "r"(smem_u32(p + kWarpPts * 2 + 2 * lane + sub)));
+      w2 = weight_sqrt ? c : c * c;
+    } else {
+      w2 = 1.f;
+    }
+  }
+};
+
+template <int V>
+struct StreamEmit1 {
+  const TriParams<V>& prm;
+  uint32_t i;  // the point's index
+  __device__ __forceinline__ void operator()(int k, float u, float v, float du, float dv) const {
+    if (prm.err != nullptr) __stcs(prm.err + (int64_t)k * prm.c_sV + i, sqrt_fast(fmaf(du, du, dv * dv)));
+    if (prm.proj != nullptr)
+      __stcs(reinterpret_cast<float2*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)i), make_float2(u + du, v + dv));
+  }
+};
+
 template <int V>
 struct StreamEmit {  // per-view outputs of tri_points_stream, written as they are produced
   const TriParams<V>& prm;
@@ -398,9 +431,21 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
     float X[PTS][3];
     uint8_t stt[PTS];
     if constexpr (STREAM) {
+#ifdef SKA_STREAM_SCALAR
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {  // the lane's two points one after the other, scalar fp32, view loops unrolled
+        StageObs1<CONF> obs{stage, Cf::kViewFloats, lane, sub, prm.weight_sqrt};
+        StreamEmit1<V> emit{prm, i0 + sub};
+        PointSource s1 = src;
+        s1.kpts += 2 * sub;
+        if (s1.conf != nullptr) s1.conf += sub;
+        tri_points_stream<V, CONF, DIST, float>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], obs, s1, X + sub, stt + sub, emit);
+      }
+#else
       StageObs<CONF> obs{stage, Cf::kViewFloats, lane, prm.weight_sqrt};
       StreamEmit<V> emit{prm, i0};
       tri_points_stream<V, CONF, DIST, F2>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], obs, src, X, stt, emit);
+#endif
       __syncwarp();                                  // every lane finished its last pass over the stage
       if (lane == 0) mbar_arrive(&sEmpty[warp][st]);  // hand it back to the producer
     } else {

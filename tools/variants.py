@@ -9,11 +9,10 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 VARIANTS = {
-    "stream_all": ["-DSKA_WS_STREAM_ALL"],                                   # V <= 4 through the streaming three-pass form too
-    "stream_u2": ["-DSKA_STREAM_UNROLL=2"],                                  # view loops unrolled by 2 (V >= 5)
-    "stream_w23": ["-DSKA_WS_STREAM_WARPS=23"],                              # 24 warps x 85 registers (V >= 5)
-    "stream_w11": ["-DSKA_WS_STREAM_WARPS=11"],                              # 12 warps x 168 registers (V >= 5)
-    "stream_7x2": ["-DSKA_WS_STREAM_WARPS=7", "-DSKA_WS_STREAM_MINB=2"],     # 2 CTAs x (7 + 1) warps
+    "ss15": ["-DSKA_WS_STREAM_LARGE", "-DSKA_STREAM_SCALAR"],                                # V >= 5: scalar streaming, 15 consumer warps x 128 regs
+    "ss17": ["-DSKA_WS_STREAM_LARGE", "-DSKA_STREAM_SCALAR", "-DSKA_WS_STREAM_WARPS=17"],   # 18 warps x <= 113 regs
+    "ss11": ["-DSKA_WS_STREAM_LARGE", "-DSKA_STREAM_SCALAR", "-DSKA_WS_STREAM_WARPS=11"],   # 12 warps x 168 regs
+    "sp15": ["-DSKA_WS_STREAM_LARGE"],                                                       # V >= 5: packed streaming (rolled loops)
 }
 LIBDIR = ROOT / "skiing_analysis_pytorch_b200" / "lib"
 
