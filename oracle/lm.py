@@ -105,6 +105,17 @@ def cost_only(X, R, t, K, x2d, w):
     return float((w * d).sum()), int((Xc[..., 2] < ZMIN).sum())
 
 
+def _safe_inverse(Hd):
+    """Inverse of the damped 3x3 point blocks; a block that is not positive definite (a point nobody observes:
+    all confidences 0, or a rank-deficient block) gets the ZERO matrix - no step and no Schur term for that
+    point, the rule the CUDA kernels implement with their Cholesky pivot test (ska_ba.cuh chol3)."""
+    ok = np.all(np.isfinite(Hd), axis=(1, 2))
+    ev = np.linalg.eigvalsh(np.where(ok[:, None, None], Hd, np.eye(3)))
+    ok &= ev[:, 0] > 0
+    inv = np.linalg.inv(np.where(ok[:, None, None], Hd, np.eye(3)))
+    return inv * ok[:, None, None]
+
+
 @dataclass
 class Linearisation:
     Hcc: np.ndarray  # (C,6,6) undamped
@@ -132,7 +143,7 @@ def linearise(X, R, t, K, x2d, w, lam, keep_points=False) -> Linearisation:
     gc = np.einsum("ncij,nci->cj", B * w[..., None, None], e)
     W = np.einsum("ncij,ncik->njck", wA, B).reshape(N, 3, 6 * C)
     Hd = Hpp + lam * np.einsum("nii,ij->nij", Hpp, np.eye(3))
-    Hinv = np.linalg.inv(Hd)
+    Hinv = _safe_inverse(Hd)
     HW = np.einsum("nij,njk->nik", Hinv, W)
     Sw = np.einsum("nik,nil->kl", W, HW)
     bw = np.einsum("nik,nij,nj->k", W, Hinv, gp)
@@ -178,7 +189,7 @@ def back_substitute(X, R, t, K, x2d, w, lam, delta_c):
     rhs = np.einsum("ncij,nci->nj", wA, lin_e)  # gp + W delta_c
     diag = np.einsum("nii->ni", Hpp)
     Hd = Hpp + lam * np.einsum("ni,ij->nij", diag, np.eye(3))
-    dp = -np.linalg.solve(Hd, rhs[..., None])[..., 0]
+    dp = -np.einsum("nij,nj->ni", _safe_inverse(Hd), rhs)
     pred_pts = float(np.sum(dp * (lam * diag * dp - gp)))
     return dp, pred_pts
 

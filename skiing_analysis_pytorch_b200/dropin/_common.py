@@ -102,39 +102,26 @@ def render_reprojection_panel(
     return visL, visR, panel
 
 
-def report(proj_L, proj_R, kptL, kptR, errL=None, errR=None) -> dict:
-    """The statistics half of reproject_and_visualize (reproject.py:243-261): per-joint error in
-    float64 from float32 projections (quirk Q6) + nan-aware scalars."""
-    if errL is None:
-        errL = np.linalg.norm(proj_L - np.asarray(kptL, float), axis=1)
-    if errR is None:
-        errR = np.linalg.norm(proj_R - np.asarray(kptR, float), axis=1)
-    out = {"proj_L": proj_L, "proj_R": proj_R, "err_L": errL, "err_R": errR}
-    for side, e in (("L", errL), ("R", errR)):
-        s = nan_stats(e)
-        out[f"rmse_{side}"] = s["rmse"]
-        out[f"mean_err_{side}"] = s["mean"]
-        out[f"median_err_{side}"] = s["median"]
-        out[f"max_err_{side}"] = s["max"]
-    return out
-
-
 def visualize(img1, img2, proj, kptL, kptR, joint_names, circle_r, thickness, out_path) -> dict:
-    """Panel + statistics + imwrite; returns the dict of reproject.py:249-266 (same keys)."""
+    """Panel + statistics + imwrite; returns the dict of reproject.py:249-266 (same keys).
+    `proj` comes from reproject_pair(..., kptL, kptR): projections, per-joint errors and the nan-aware
+    scalars were all computed on the GPU; the host only draws."""
     import cv2
 
     visL, visR, panel = render_reprojection_panel(img1, img2, kptL, kptR, proj["proj_L"], proj["proj_R"],
                                                   joint_names=joint_names, circle_r=circle_r, thickness=thickness)
-    res = report(proj["proj_L"], proj["proj_R"], kptL, kptR)
+    res = dict(proj)
     Path(out_path).parent.mkdir(parents=True, exist_ok=True)
     cv2.imwrite(str(out_path), panel)
     res.update(out_path=str(out_path), vis_left=visL, vis_right=visR, panel=panel)
     return res
 
 
-def reproject_pair(X3, K1, dist1, K2, dist2, R_rel, t_rel) -> dict:
+def reproject_pair(X3, K1, dist1, K2, dist2, R_rel, t_rel, kptL=None, kptR=None) -> dict:
     """cam1 = identity with (K1, dist1), cam2 = (R_rel, t_rel) with (K2, dist2); float32 in,
-    float32 (J,2) out - the arithmetic of reproject_points on the GPU (ska_reproject_points_f32)."""
+    float32 (J,2) out - the arithmetic of reproject_points on the GPU (ska_reproject_points_f32).
+    With the observed keypoints the per-joint errors (float64 like reproject.py:243-244, from float32
+    projections: quirk Q6) and the nan-aware rmse / mean / median / max (ska_frame_stats_f32) come back too."""
     from .. import api
 
     dev = device()
@@ -143,6 +130,18 @@ def reproject_pair(X3, K1, dist1, K2, dist2, R_rel, t_rel) -> dict:
     R = np.stack([np.eye(3), f32(R_rel).reshape(3, 3).astype(np.float64)])
     t = np.stack([np.zeros(3), f32(t_rel).reshape(3).astype(np.float64)])
     dists = [None if d is None else f32(d).reshape(-1).astype(np.float64) for d in (dist1, dist2)]
-    proj, _ = api.reproject_points(X, K, R, t, dists, want=("proj",))
-    p = proj.cpu().numpy()
-    return {"proj_L": p[0, 0], "proj_R": p[1, 0]}
+    if kptL is None:
+        proj, _ = api.reproject_points(X, K, R, t, dists, want=("proj",))
+        p = proj.cpu().numpy()
+        return {"proj_L": p[0, 0], "proj_R": p[1, 0]}
+    k = np.stack([np.asarray(kptL, np.float32).reshape(1, -1, 2), np.asarray(kptR, np.float32).reshape(1, -1, 2)])
+    proj, err = api.reproject_points(X, K, R, t, dists, kpts=torch.from_numpy(k).to(dev), want=("proj", "err"))
+    st = api.frame_stats(err).cpu().numpy().astype(np.float64)  # (1, 2, 4): rmse, mean, median, max
+    p, e = proj.cpu().numpy(), err.cpu().numpy().astype(np.float64)
+    out = {"proj_L": p[0, 0], "proj_R": p[1, 0], "err_L": e[0, 0], "err_R": e[1, 0]}
+    for v, side in enumerate("LR"):
+        out[f"rmse_{side}"] = float(st[0, v, 0])
+        out[f"mean_err_{side}"] = float(st[0, v, 1])
+        out[f"median_err_{side}"] = float(st[0, v, 2])
+        out[f"max_err_{side}"] = float(st[0, v, 3])
+    return out

@@ -27,5 +27,7 @@ def reproject_and_visualize(img1, img2, X3, kptL, kptR, K1, dist1, K2, dist2, R,
                             out_path: str = "/mnt/data/reprojection_compare.jpg") -> Dict[str, object]:
     """triangulation/reproject.py:203-266: reproject, draw, save, return the same dict
     (proj_L/R, err_L/R, rmse_*, mean_err_*, median_err_*, max_err_*, out_path, vis_left/right, panel)."""
-    proj = reproject_points(X3, K1, dist1, K2, dist2, R, T)
+    R_ = _common.f32(R).reshape(3, 3)
+    T_ = _common.f32(T).reshape(3, 1)
+    proj = _common.reproject_pair(X3, K1, dist1, K2, dist2, R_, T_, kptL, kptR)
     return _common.visualize(img1, img2, proj, kptL, kptR, joint_names, circle_r, thickness, out_path)

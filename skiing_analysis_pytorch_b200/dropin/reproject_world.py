@@ -46,5 +46,6 @@ def reproject_and_visualize(img1, img2, X3, kptL, kptR, K1, dist1, K2, dist2, R,
                             joint_names: Optional[Sequence[str]] = None, circle_r: int = 5, thickness: int = 2,
                             out_path: Path = Path("reprojection_panel.jpg")) -> Dict[str, object]:
     """bundle_adjustment/reproject.py:281-350."""
-    proj = reproject_points(X3, K1, dist1, K2, dist2, R, T)
+    R_rel, t_rel = _relative_pose(R, T)
+    proj = _common.reproject_pair(X3, K1, dist1, K2, dist2, R_rel, t_rel, kptL, kptR)
     return _common.visualize(img1, img2, proj, kptL, kptR, joint_names, circle_r, thickness, out_path)

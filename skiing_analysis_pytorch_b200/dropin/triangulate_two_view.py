@@ -68,9 +68,13 @@ def process_triangulate(left_kpts, right_kpts, left_vframes, right_vframes, K, R
     """triangulation/triangulate.py:71-118: returns the list of per-frame (J,3) joints; per frame
     it also writes the 3-D plot (reference's own matplotlib helper, when importable) and the
     reprojection panel, and logs the mean errors.  The numbers come from one fused GPU launch."""
+    from .. import api
+
     res = triangulate_clip(left_kpts, right_kpts, K, R, T)
     X = res.X.cpu().numpy()
     proj = res.proj.cpu().numpy()
+    err = res.err.cpu().numpy().astype(np.float64)
+    stats = api.frame_stats(res.err).cpu().numpy().astype(np.float64)  # (T,2,4): rmse, mean, median, max per frame and view
     try:  # the reference's own viz module (matplotlib); optional
         from triangulation.vis.pose_visualization import visualize_3d_joints
     except Exception:  # pragma: no cover - not installed outside a reference checkout
@@ -85,8 +89,12 @@ def process_triangulate(left_kpts, right_kpts, left_vframes, right_vframes, K, R
             visualize_3d_joints(joints_3d=joints_3d, R=R[i], T=T[i], K=K, image_size=(W, H),
                                 save_path=os.path.join(output_path, f"frame_{i:04d}.png"), title=f"Frame {i} - 3D Joints",
                                 y_up=True)
-        out = _common.visualize(l_frame, r_frame, {"proj_L": proj[0, i], "proj_R": proj[1, i]}, left_kpts[i], right_kpts[i],
-                                None, 5, 2, os.path.join(output_path, "reproj", f"{i:04d}.jpg"))
+        pr = {"proj_L": proj[0, i], "proj_R": proj[1, i], "err_L": err[0, i], "err_R": err[1, i]}
+        for v, side in enumerate("LR"):
+            pr.update({f"rmse_{side}": float(stats[i, v, 0]), f"mean_err_{side}": float(stats[i, v, 1]),
+                       f"median_err_{side}": float(stats[i, v, 2]), f"max_err_{side}": float(stats[i, v, 3])})
+        out = _common.visualize(l_frame, r_frame, pr, left_kpts[i], right_kpts[i], None, 5, 2,
+                                os.path.join(output_path, "reproj", f"{i:04d}.jpg"))
         logger.info(f"Saved to: {out['out_path']}")
         logger.info(f"Reprojection error - Frame {i}: Left {out['mean_err_L']:.2f}px, Right {out['mean_err_R']:.2f}px")
         joints_3d_all.append(joints_3d)

@@ -133,3 +133,17 @@ def test_optimum_agrees_with_scipy_least_squares():
     sol = opt.least_squares(fun, np.zeros(6 + n), method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=200)
     final = min(h["trial_cost"] if h["accepted"] else h["cost"] for h in hist)
     assert abs(2.0 * sol.cost - final) <= 1e-8 * final
+
+
+def test_unobserved_points_have_no_step_and_no_schur_term():
+    """A point with all confidences 0 has a singular block: the specification (shared with the CUDA kernels) is
+    'no step, no contribution' - the solve stays finite and the point stays where it was."""
+    clip, R0, t0, X0 = lm.make_problem("3", 20, 17)
+    conf = clip.conf_fm.copy()
+    conf[4, :, 2] = 0.0
+    conf[9] = 0.0
+    R, t, X, hist = lm.run_lm(X0, R0, t0, clip.K, clip.x_fm, conf, num_iters=5)
+    assert np.isfinite(X).all() and np.isfinite(R).all() and all(np.isfinite(h["trial_cost"]) for h in hist)
+    np.testing.assert_array_equal(X[4, 2], X0[4, 2])
+    np.testing.assert_array_equal(X[9], X0[9])
+    assert hist[-1]["cost"] < 0.1 * hist[0]["cost"]
