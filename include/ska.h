@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SKA_ABI_VERSION 3
+#define SKA_ABI_VERSION 4
 
 #define SKA_OK 0
 #define SKA_EINVAL -1       /* null pointer / bad size / bad enum */
@@ -240,6 +240,38 @@ int ska_ba_linearize_f32(const SkaBaProblem* p, void* stream);
 int ska_ba_solve_f64(const SkaBaProblem* p, uint64_t free_mask, void* stream);
 int ska_ba_backsub_f32(const SkaBaProblem* p, void* stream);
 int ska_ba_control_f64(const SkaBaProblem* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Post-triangulation triage and temporal smoothing (the step right after the path).
+ * Replaces post_triage_single / post_triage_sequence and smooth_skeleton of
+ * triangulation/postprocess.py:54-170 for a whole clip.
+ *
+ * ska_post_triage_f32: cams[2] host (cam 0 = K1 [I|0] in the reference, cam 1 = K2 [R|T]; any world->camera
+ *   pair is accepted); d_X (T,J,3); d_kpts (2,T,J,2) view-major; d_conf (2,T,J) nullable.
+ *   flags: SKA_TRIAGE_UNDISTORT0/1 = undistort that view's pixels with cams[v].dist first
+ *   (cv2.undistortPoints(x, K, d, P=K): 5 fixed-point iterations, float32 result, postprocess.py:93-98).
+ *   A joint is kept iff depth > 0 in both cameras (:47-52), 0.5 (e1 + e2) is finite and <= err_thresh_px (:112)
+ *   and both confidences >= conf_thr (:108-110).  Outputs: d_Xclean (T,J,3) = X or NaN (:115-116);
+ *   d_em (T,J) mean pixel error, nullable; d_flags (T,J) nullable: SKA_TRIAGE_POS | _ERR | _CONF | _KEEP.
+ * ska_frame_flag_counts_u8: d_counts (T,4) int32 = per-frame count of each of the four flag bits
+ *   (pos_depth_ratio, kept_ratio, kept_count of :118-124; rmse / median of d_em via ska_frame_stats_f32, V = 1).
+ * ska_savgol_f32: Savitzky-Golay (scipy.signal.savgol_filter, mode="interp") along T for each of the S = J*3
+ *   series of d_X (T,S), over the series' FINITE samples only (compacted in time, filtered, scattered back;
+ *   non-finite entries stay; series with fewer finite samples than `win` pass through) - smooth_skeleton :54-68.
+ *   win odd <= 25, poly < win.  d_workspace >= ska_savgol_workspace_bytes(T, S).  d_out may not alias d_X. */
+#define SKA_TRIAGE_UNDISTORT0 1u
+#define SKA_TRIAGE_UNDISTORT1 2u
+#define SKA_TRIAGE_POS 1
+#define SKA_TRIAGE_ERR 2
+#define SKA_TRIAGE_CONF 4
+#define SKA_TRIAGE_KEEP 8
+int ska_post_triage_f32(const SkaCamera* cams, const float* d_X, const float* d_kpts, const float* d_conf, int64_t T, int32_t J,
+                        uint32_t flags, double conf_thr, double err_thresh_px, float* d_Xclean, float* d_em, uint8_t* d_flags,
+                        void* stream);
+int ska_frame_flag_counts_u8(const uint8_t* d_flags, int64_t T, int32_t J, int32_t* d_counts, void* stream);
+size_t ska_savgol_workspace_bytes(int64_t T, int32_t S);
+int ska_savgol_f32(const float* d_X, int64_t T, int32_t S, int32_t win, int32_t poly, float* d_out, void* d_workspace,
+                   size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

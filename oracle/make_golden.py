@@ -12,6 +12,7 @@ tests only ever read the .npz files.  Golden sets:
       bundle_adjustment.reproject.reproject_points mode A on two non-identity cameras (quirk Q3)
   G3  bundle_adjustment.loss.project_points / reprojection_loss for every accepted shape, f32+f64
   G4  camera_smooth / baseline_reg / bone_length / pose_temporal scalars
+  G7  triangulation.postprocess.post_triage_sequence / post_triage_single / smooth_skeleton (row N2)
   G6  LM history of oracle/lm.py on BASELINE configs 3 and 5 at reduced T, with the REFERENCE's
       reprojection_loss evaluated at the initial and final state of each solve (pins the cost the
       LM minimises; the trajectory itself has no reference implementation - "parity unpinned")
@@ -175,8 +176,49 @@ def g6():
     np.savez_compressed(OUT / "g6_lm_history.npz", **out)
 
 
+def g7():
+    """triangulation.postprocess.post_triage_sequence / smooth_skeleton of the reference (row N2)."""
+    import warnings
+
+    from oracle import geometry as G
+
+    pp = ref_import.load("triangulation.postprocess")
+    clip = synth.make_clip("2b", 80, 17, seed=21)
+    K, R, t = clip.K[0], clip.R[1], clip.t[1]
+    P = np.stack([G.make_P(K, np.eye(3), np.zeros(3)), G.make_P(K, R, t)])
+    X = G.dlt_triangulate(P, clip.x_vm.reshape(2, -1, 2)).reshape(80, 17, 3).astype(np.float32)
+    X[3, 4] = np.nan                     # a joint the triangulation lost
+    X[10, 2] = [0.0, 0.0, -3.0]          # behind the cameras
+    kL, kR = clip.x_vm[0].copy(), clip.x_vm[1].copy()
+    kL[20, 5] += 40.0                    # a gross outlier
+    out = dict(X=X, kptL=kL, kptR=kR, K=K, R=R, t=t, dist=synth.DIST_CALIB, confL=clip.conf_vm[0], confR=clip.conf_vm[1])
+    cases = {"plain": dict(), "dist": dict(dist1=synth.DIST_CALIB, dist2=synth.DIST_CALIB),
+             "conf_smooth": dict(confL=clip.conf_vm[0], confR=clip.conf_vm[1], smooth=True),
+             "tight_smooth6": dict(err_thresh_px=1.0, smooth=True, sg_win=6, sg_poly=3)}
+    keys = ["rmse_px", "median_err_px", "pos_depth_ratio", "kept_ratio", "kept_count"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name, kw in cases.items():
+            Xc, st = pp.post_triage_sequence(X, kL, kR, K, K, R, t, **kw)
+            out[f"{name}_X"] = Xc
+            out[f"{name}_stats"] = np.array([[s[k] for k in keys] for s in st])
+        Xc1, rep1, keep1 = pp.post_triage_single(X[20], kL[20], kR[20], K, K, R, t, confL=clip.conf_vm[0][20], confR=clip.conf_vm[1][20],
+                                                 return_masks=True)
+        out["single_X"], out["single_keep"], out["single_stats"] = Xc1, keep1, np.array([rep1[k] for k in keys])
+        rng = np.random.default_rng(5)
+        Xs = (synth.skeleton_clip(64, 5, rng)).astype(np.float32)
+        Xs[rng.uniform(size=Xs.shape[:2]) < 0.15] = np.nan
+        Xs[:, 4] = np.nan
+        Xs[:60, 3] = np.nan              # fewer finite samples than the window: left alone
+        out["smooth_in"] = Xs
+        out["smooth_out_9_2"] = pp.smooth_skeleton(Xs, win=9, poly=2)
+        out["smooth_out_8_3"] = pp.smooth_skeleton(Xs, win=8, poly=3)
+    np.savez_compressed(OUT / "g7_post_triage.npz", **out)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    g7()
     g1()
     g2()
     g3_g4()

@@ -5,7 +5,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_VIEWS = 8
 MAX_BA_VIEWS = 8
 MAX_BONES = 16

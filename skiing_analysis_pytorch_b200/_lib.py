@@ -43,6 +43,13 @@ _SIGS = {
         C.c_int, [C.POINTER(_cabi.SkaCamera), C.c_int32, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp]
     ),
     "ska_frame_stats_f32": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
+    "ska_post_triage_f32": (
+        C.c_int,
+        [C.POINTER(_cabi.SkaCamera), _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_uint32, C.c_double, C.c_double, _vp, _vp, _vp, _vp],
+    ),
+    "ska_frame_flag_counts_u8": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp]),
+    "ska_savgol_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "ska_savgol_f32": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_size_t, _vp]),
     "ska_loss_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "ska_reg_workspace_bytes": (C.c_size_t, []),
     "ska_ba_red_doubles": (C.c_int32, [C.c_int32]),

@@ -194,6 +194,35 @@ SKA_DEFINE_LOSS(f64, double)
 #undef SKA_DEFINE_LOSS
 #undef SKA_LOSS_CHECK
 
+int ska_post_triage_f32(const SkaCamera* cams, const float* d_X, const float* d_kpts, const float* d_conf, int64_t T, int32_t J,
+                        uint32_t flags, double conf_thr, double err_thresh_px, float* d_Xclean, float* d_em, uint8_t* d_flags,
+                        void* stream) {
+  if (cams == nullptr) return set_error(SKA_EINVAL, "cams must not be NULL");
+  if (T < 0 || J < 1) return set_error(SKA_EINVAL, "T >= 0, J >= 1");
+  if (flags > 3u) return set_error(SKA_EINVAL, "unknown flag bits");
+  if (T == 0) return SKA_OK;
+  if (d_X == nullptr || d_kpts == nullptr || d_Xclean == nullptr) return set_error(SKA_EINVAL, "d_X, d_kpts and d_Xclean must not be NULL");
+  if (reinterpret_cast<uintptr_t>(d_kpts) % 8 != 0) return set_error(SKA_EALIGN, "d_kpts must be 8-byte aligned");
+  return post_triage(cams, d_X, d_kpts, d_conf, T, J, flags, conf_thr, err_thresh_px, d_Xclean, d_em, d_flags, (cudaStream_t)stream);
+}
+
+int ska_frame_flag_counts_u8(const uint8_t* d_flags, int64_t T, int32_t J, int32_t* d_counts, void* stream) {
+  if (T < 0 || J < 1) return set_error(SKA_EINVAL, "T >= 0, J >= 1");
+  if (T == 0) return SKA_OK;
+  if (d_flags == nullptr || d_counts == nullptr) return set_error(SKA_EINVAL, "d_flags and d_counts must not be NULL");
+  return flag_counts(d_flags, T, J, d_counts, (cudaStream_t)stream);
+}
+
+size_t ska_savgol_workspace_bytes(int64_t T, int32_t S) { return (T < 0 || S < 1) ? 0 : savgol_workspace_bytes(T, S); }
+
+int ska_savgol_f32(const float* d_X, int64_t T, int32_t S, int32_t win, int32_t poly, float* d_out, void* d_workspace,
+                   size_t ws_bytes, void* stream) {
+  if (T < 0 || S < 1) return set_error(SKA_EINVAL, "T >= 0, S >= 1");
+  if (T > 0 && (d_X == nullptr || d_out == nullptr || d_workspace == nullptr)) return set_error(SKA_EINVAL, "d_X, d_out and d_workspace must not be NULL");
+  if (d_X == d_out && T > 0) return set_error(SKA_EINVAL, "d_out must not alias d_X");
+  return savgol(d_X, T, S, win, poly, d_out, d_workspace, ws_bytes, (cudaStream_t)stream);
+}
+
 size_t ska_loss_workspace_bytes(int32_t C) { return C < 1 ? 0 : loss_workspace_bytes(C); }
 size_t ska_reg_workspace_bytes(void) { return reg_workspace_bytes(); }
 

@@ -71,4 +71,12 @@ template <typename S>
 int baseline_reg(const S* R, const S* t, int64_t T, int Cn, const double* mean, double* sum, S* gR, S* gt, void* ws, size_t ws_bytes,
                  cudaStream_t s);
 
+
+// post-triangulation triage + Savitzky-Golay smoothing (ska_post.cu)
+int post_triage(const SkaCamera* cams, const float* X, const float* kpts, const float* conf, int64_t T, int J, uint32_t flags,
+                double conf_thr, double err_thr, float* Xc, float* em, uint8_t* fl, cudaStream_t s);
+int flag_counts(const uint8_t* flags, int64_t T, int J, int32_t* out, cudaStream_t s);
+size_t savgol_workspace_bytes(int64_t T, int S);
+int savgol(const float* X, int64_t T, int S, int win, int poly, float* out, void* ws, size_t ws_bytes, cudaStream_t s);
+
 }  // namespace ska

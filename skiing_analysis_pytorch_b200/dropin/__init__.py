@@ -26,6 +26,7 @@ import types
 MODULE_MAP = {
     "triangulation.triangulate": "triangulate_two_view",
     "triangulation.reproject": "reproject_stereo",
+    "triangulation.postprocess": "postprocess",
     "bundle_adjustment.loss": "ba_loss",
     "bundle_adjustment.reproject": "reproject_world",
     "vggt.triangulate": "triangulate_vggt",

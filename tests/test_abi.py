@@ -25,7 +25,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/ska.h but not exported by libska.so"
     assert sorted(_lib.exported_symbols()) == syms, "ctypes signature table and header disagree"
-    assert lib.ska_abi_version() == 3
+    assert lib.ska_abi_version() == 4
     assert lib.ska_build_arch() == b"sm_100a"
 
 
@@ -81,6 +81,14 @@ def test_argument_errors_without_gpu():
     assert lib.ska_reprojection_loss_f32(fake, 1, 17, 2, fake, 0, fake, 0, fake, 0, fake, fake, None, None, None, None, None,
                                          fake, 0, None) == -1
     assert lib.ska_loss_workspace_bytes(2) > 0 and lib.ska_reg_workspace_bytes() > 0
+    # post-triangulation triage / smoothing
+    assert lib.ska_post_triage_f32(cams, fake, fake, None, 1, 17, 4, 0.3, 2.0, fake, None, None, None) == -1  # unknown flag
+    assert lib.ska_post_triage_f32(cams, fake, fake, None, 0, 17, 0, 0.3, 2.0, fake, None, None, None) == 0
+    assert lib.ska_savgol_workspace_bytes(1000, 51) >= 1000 * 51 * 4
+    assert lib.ska_savgol_f32(fake, 10, 51, 8, 2, C.c_void_p(512), fake, 1 << 30, None) == -2   # even window
+    assert lib.ska_savgol_f32(fake, 10, 51, 9, 9, C.c_void_p(512), fake, 1 << 30, None) == -1   # poly >= window
+    assert lib.ska_savgol_f32(fake, 10, 51, 9, 2, C.c_void_p(512), fake, 16, None) == -4        # workspace
+    assert lib.ska_savgol_f32(fake, 10, 51, 9, 2, fake, fake, 1 << 30, None) == -1              # aliasing
 
 
 def test_api_refuses_cpu_tensors():

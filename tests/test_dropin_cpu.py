@@ -37,6 +37,17 @@ EXPECTED = {
         "triangulate_one_frame": ["K", "R", "T", "kptL", "kptR", "frame_L", "frame_R", "save_dir", "dist", "visualize_3d", "frame_num"],
     },
 }
+EXPECTED["triangulation.postprocess"] = {
+    "build_P": ["K", "R", "t"],
+    "project": ["P", "X3"],
+    "reproj_errors": ["P1", "P2", "X3", "x1_pix", "x2_pix"],
+    "positive_depth_mask": ["R", "T", "X3"],
+    "smooth_skeleton": ["X", "win", "poly"],
+    "post_triage_single": ["X3_frame", "kptL_frame", "kptR_frame", "K1", "K2", "R", "T", "dist1", "dist2", "confL", "confR",
+                           "conf_thr", "err_thresh_px", "return_masks"],
+    "post_triage_sequence": ["X3_seq", "kptL_seq", "kptR_seq", "K1", "K2", "R", "T", "dist1", "dist2", "confL", "confR", "conf_thr",
+                             "err_thresh_px", "smooth", "sg_win", "sg_poly"],
+}
 for _m in ("bundle_adjustment.reproject", "vggt.reproject", "front_side.side.reproject", "fuse.side.reproject"):
     EXPECTED[_m] = EXPECTED["triangulation.reproject"]
 
@@ -81,7 +92,7 @@ def test_signatures_match_the_reference_checkout():
             assert list(rs.parameters) == list(ss.parameters), (name, fn)
             for p in rs.parameters:
                 rd, sd = rs.parameters[p].default, ss.parameters[p].default
-                if rd is inspect.Parameter.empty or isinstance(rd, (int, float, str, bool, type(None))):
+                if rd is inspect.Parameter.empty or isinstance(rd, (int, float, str, bool, type(None))) or sd is inspect.Parameter.empty:
                     assert rd == sd or (rd is sd), (name, fn, p, rd, sd)
     for k in list(sys.modules):
         if k.split(".")[0] in ("triangulation", "bundle_adjustment", "vggt"):
