@@ -86,6 +86,8 @@ def smooth_skeleton(X: torch.Tensor, win: int = 9, poly: int = 2) -> torch.Tenso
     Tn = Xc.shape[0]
     S = int(np.prod(Xc.shape[1:]))
     w = effective_window(Tn, int(win))
+    if int(poly) >= w:
+        raise ValueError("polyorder must be less than window_length.")  # what scipy.signal.savgol_filter raises
     out = torch.empty_like(Xc)
     if Tn == 0:
         return out

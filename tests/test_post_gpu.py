@@ -83,7 +83,7 @@ def test_triage_matches_oracle_on_seeded_clips(cuda, J, with_dist, with_conf):
 
 def test_smoothing_matches_oracle_with_gaps_and_odd_sizes(cuda):
     rng = np.random.default_rng(7)
-    for T, J, win, poly in ((1000, 17, 9, 2), (333, 70, 15, 3), (129, 3, 25, 4), (9, 2, 9, 2), (5, 2, 9, 2)):
+    for T, J, win, poly in ((1000, 17, 9, 2), (334, 70, 15, 3), (130, 3, 25, 4), (333, 5, 9, 2), (9, 2, 9, 2), (5, 2, 9, 2)):  # odd T -> window 3 (postprocess.py:58)
         X = synth.skeleton_clip(T, J, rng).astype(np.float32)
         X[rng.uniform(size=X.shape) < 0.1] = np.nan
         if J > 2:
@@ -93,6 +93,15 @@ def test_smoothing_matches_oracle_with_gaps_and_odd_sizes(cuda):
         out = post.smooth_skeleton(torch.from_numpy(X).to(cuda), win=win, poly=poly).cpu().numpy()
         np.testing.assert_array_equal(np.isnan(out), np.isnan(ref))
         np.testing.assert_allclose(out, ref, rtol=SMOOTH_RTOL, atol=2e-6, equal_nan=True)
+
+
+def test_smoothing_argument_errors(cuda):
+    X = torch.zeros(40, 3, 3, device=cuda)
+    with pytest.raises(ValueError, match="polyorder"):   # scipy's message for the same mistake
+        post.smooth_skeleton(X, win=5, poly=5)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        post.smooth_skeleton(X.cpu())
+    assert tuple(post.smooth_skeleton(X[:0]).shape) == (0, 3, 3)
 
 
 def test_full_size_properties(cuda):
@@ -109,7 +118,9 @@ def test_full_size_properties(cuda):
         assert torch.equal(part.flags, res.flags[a:b])
         assert torch.equal(torch.nan_to_num(part.X_clean, nan=-1.0), torch.nan_to_num(res.X_clean[a:b], nan=-1.0))
     kept = ((res.flags & 8) != 0)
-    assert abs(kept.float().mean().item() - 0.875 ** 2) < 0.05       # both confidences U(0.2,1) >= 0.3
+    assert abs(((res.flags & 4) != 0).float().mean().item() - 0.875 ** 2) < 0.01   # both confidences U(0.2,1) >= 0.3
+    assert ((res.flags & 1) != 0).all()                                           # ground-truth points are in front of both cameras
+    assert 0.6 < kept.float().mean().item() < 0.766                               # minus the 2 px error gate under 1 px noise
     assert res.report[:, 4].sum().item() == kept.sum().item()
     tt = torch.arange(T, device=cuda, dtype=torch.float64) / T
     poly = torch.stack([1.0 + 2.0 * tt - 3.0 * tt * tt, 0.5 - tt, 4.0 * tt * tt], -1)[:, None, :].expand(T, J, 3).float().contiguous()
