@@ -13,7 +13,6 @@ on the cost the reference defines in bundle_adjustment/loss.py:17-94.  Algorithm
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
 
 import numpy as np
 import torch

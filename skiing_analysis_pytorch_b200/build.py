@@ -57,7 +57,6 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: Path 
     nvcc = _nvcc()
     OBJ.mkdir(parents=True, exist_ok=True)
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    dep_m = _deps_mtime()
     hdr_m = max(
         f.stat().st_mtime for f in list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "ska.h"]
     )
@@ -84,7 +83,6 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: Path 
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB)
-    del dep_m
     return LIB
 
 
