@@ -358,7 +358,7 @@ def run_tri_8view(a, dev, world, barrier, dist):
                          "note": "fp32-pipe bound: ~800 FMA-pipe cycles per 32 points = the HBM roofline time"}}
 
 
-def run_ours(a):
+def run_ours(a, out_fd=1):
     import torch
     import torch.distributed as dist
 
@@ -510,7 +510,7 @@ def run_ours(a):
                 "linear in the frame count",
             }
     if rank == 0:
-        print(json.dumps(line))
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -520,7 +520,16 @@ def main():
     a = parse()
     if a.impl == "reference":
         return run_reference(a)
-    return run_ours(a)
+    # stdout carries exactly ONE line (the JSON): libraries that print to fd 1 from C (NCCL's version banner) are sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return run_ours(a, real_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
 
 
 if __name__ == "__main__":
