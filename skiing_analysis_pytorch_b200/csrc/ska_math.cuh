@@ -25,6 +25,8 @@ struct CamDev {
   float Rxy[6];   // rows 0 and 1 of R           (normalised coordinates for the distortion model)
   float txy[2];   // (R c + t).x, .y
   float fx, fy, skew;
+  float ifx, ify;  // 1/fx, 1/fy
+  float ncx, ncy;  // -cx/fx, -cy/fy: normalised coordinate of pixel u = fma(u, ifx, ncx)   (zero skew)
   float dk[3];    // k1-k4, k2-k5, k3-k6  (numerator minus denominator of the rational term)
   float kd[3];    // k4, k5, k6
   float p1, p2;

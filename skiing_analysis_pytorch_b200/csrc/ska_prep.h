@@ -54,6 +54,10 @@ SKA_HD int prep_camera(const SkaCamera& in, const double c[3], bool pinhole_repr
   out.fx = (float)K[0];
   out.fy = (float)K[4];
   out.skew = (float)K[1];
+  out.ifx = (float)(1.0 / K[0]);
+  out.ify = (float)(1.0 / K[4]);
+  out.ncx = (float)(-K[2] / K[0]);
+  out.ncy = (float)(-K[5] / K[4]);
   const double* d = in.dist;
   bool any = false;
   for (int i = 0; i < 12; ++i) any = any || (d[i] != 0.0);

@@ -363,7 +363,9 @@ struct StreamEmit {  // per-view outputs of tri_points_stream, written as they a
   }
 };
 
-template <int V, bool CONF, int DIST, int NW, int MINB, bool STREAM>
+// LEAN: the common output set (X and err, no proj / status, 16-byte aligned X) compiled without the per-tile
+// pointer tests of the general form.
+template <int V, bool CONF, int DIST, int NW, int MINB, bool STREAM, bool LEAN>
 __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __grid_constant__ TriParams<V> prm) {
   constexpr int PTS = 2;
   using Cf = WsCfg<V, CONF, STREAM>;
@@ -468,12 +470,12 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
       tri_points<V, PTS, CONF, DIST, kSolverSecular>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], u, v, w2, src, X, du, dv, stt);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        if (prm.err != nullptr) {
+        if (LEAN || prm.err != nullptr) {
           const float e0 = sqrt_fast(fmaf(du[0][k], du[0][k], dv[0][k] * dv[0][k]));
           const float e1 = sqrt_fast(fmaf(du[1][k], du[1][k], dv[1][k] * dv[1][k]));
           __stcs(reinterpret_cast<float2*>(prm.err + (int64_t)k * prm.c_sV + i0), make_float2(e0, e1));
         }
-        if (prm.proj != nullptr) {
+        if (!LEAN && prm.proj != nullptr) {
           __stcs(reinterpret_cast<float4*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)i0),
                  make_float4(u[0][k] + du[0][k], v[0][k] + dv[0][k], u[1][k] + du[1][k], v[1][k] + dv[1][k]));
         }
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
       st = 0;
       par ^= 1u;
     }
-    if (prm.status != nullptr) *reinterpret_cast<uchar2*>(prm.status + i0) = make_uchar2(stt[0], stt[1]);
+    if (!LEAN && prm.status != nullptr) *reinterpret_cast<uchar2*>(prm.status + i0) = make_uchar2(stt[0], stt[1]);
     // ---- X through shared memory: 192 floats per warp leave as 48 128-bit stores
 #pragma unroll
     for (int p = 0; p < PTS; ++p)
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
       for (int k = 0; k < 3; ++k) sx[(lane * PTS + p) * 3 + k] = X[p][k];
     __syncwarp();
     float* gx = prm.X + (int64_t)wt * (kWarpPts * 3);
-    if (prm.x_vec) {
+    if (LEAN || prm.x_vec) {
       __stcs(reinterpret_cast<float4*>(gx) + lane, reinterpret_cast<const float4*>(sx)[lane]);
       if (lane < 16) __stcs(reinterpret_cast<float4*>(gx) + 32 + lane, reinterpret_cast<const float4*>(sx)[32 + lane]);
     } else {
@@ -509,10 +511,10 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
 #define SKA_WS_STREAM_MINB 1
 #endif
 
-template <int V, bool CONF, int DIST, bool STREAM>
-static cudaError_t launch_ws(TriParams<V>& prm, cudaStream_t stream) {
+template <int V, bool CONF, int DIST, bool STREAM, bool LEAN>
+static cudaError_t launch_ws_impl(TriParams<V>& prm, cudaStream_t stream) {
   constexpr int NW = STREAM ? SKA_WS_STREAM_WARPS : SKA_WS_WARPS, MINB = STREAM ? SKA_WS_STREAM_MINB : SKA_WS_MINB, BLOCK = 32 * (NW + 1);
-  auto kern = tri_kernel_ws<V, CONF, DIST, NW, MINB, STREAM>;
+  auto kern = tri_kernel_ws<V, CONF, DIST, NW, MINB, STREAM, LEAN>;
   constexpr size_t smem = WsSmem<V, NW, CONF, STREAM>::bytes;
   static_assert(smem <= 227 * 1024, "tri_kernel_ws staging does not fit the SM's shared memory");
   int dev = 0, sms = 0, per_sm = 0;
@@ -531,6 +533,12 @@ static cudaError_t launch_ws(TriParams<V>& prm, cudaStream_t stream) {
   if (grid > need) grid = need;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(prm);
   return cudaGetLastError();
+}
+
+template <int V, bool CONF, int DIST, bool STREAM>
+static cudaError_t launch_ws(TriParams<V>& prm, cudaStream_t stream) {
+  const bool lean = !STREAM && prm.err != nullptr && prm.proj == nullptr && prm.status == nullptr && prm.x_vec;
+  return lean ? launch_ws_impl<V, CONF, DIST, STREAM, true>(prm, stream) : launch_ws_impl<V, CONF, DIST, STREAM, false>(prm, stream);
 }
 
 #ifndef SKA_MINB_SMALL
