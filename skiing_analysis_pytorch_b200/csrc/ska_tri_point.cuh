@@ -126,6 +126,27 @@ SKA_HD float pick(F2 a, int i) { return i == 0 ? a.x : a.y; }
 SKA_HD bool pick(bool a, int) { return a; }
 SKA_HD bool pick(B2 a, int i) { return i == 0 ? a.x : a.y; }
 
+// DLT rows of a point (float) or of a packed pair (F2).  The pair's rows are formed with SCALAR FFMAs per point and
+// packed afterwards: the two points' pixels arrive interleaved from memory (u0 v0 u1 v1), so a packed FFMA2 would
+// first need the pair (u0, u1) assembled with two moves - which the register allocator re-does in front of every
+// use (measured: ~40 moves per tile) - and its two camera coefficients loaded (LDC), whereas the scalar FFMA takes
+// both coefficients straight from the constant bank and its result lands in the pair's half for free.
+template <int LO>
+SKA_HD void dlt_rows_pts(const CamDev& c, float u, float v, float a[4], float b[4]) {
+  dlt_rows<LO>(c, u, v, a, b);
+}
+template <int LO>
+SKA_HD void dlt_rows_pts(const CamDev& c, F2 u, F2 v, F2 a[4], F2 b[4]) {
+  float a0[4], b0[4], a1[4], b1[4];
+  dlt_rows<LO>(c, u.x, v.x, a0, b0);
+  dlt_rows<LO>(c, u.y, v.y, a1, b1);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    a[m] = mk2(a0[m], a1[m]);
+    b[m] = mk2(b0[m], b1[m]);
+  }
+}
+
 // Result of the one-factorisation fast stage for one point (T = float) or a pair (T = F2)
 template <typename T>
 struct FastStage {
@@ -143,7 +164,7 @@ SKA_HD void fast_stage(const CamDev* __restrict__ cam, const float cx, const flo
   sym4_zero(M);
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    dlt_rows<LO>(cam[k], u[k], v[k], a[k], b[k]);
+    dlt_rows_pts<LO>(cam[k], u[k], v[k], a[k], b[k]);
     if (CONF) {
       sym4_rank1(M, a[k], w2[k]);
       sym4_rank1(M, b[k], w2[k]);
@@ -188,6 +209,9 @@ SKA_HD void fast_stage(const CamDev* __restrict__ cam, const float cx, const flo
 // Fused reprojection scoring, differential form:
 //   proj - obs = -(row . [Y;1]) / z  (+ fx*dx_distortion - skew*y)
 // so the ~1e3 px magnitudes of proj and obs never meet in fp32.
+SKA_HD float pix_norm(float u, float s, float o) { return fmaf(u, s, o); }
+SKA_HD F2 pix_norm(F2 u, float s, float o) { return mk2(fmaf(u.x, s, o), fmaf(u.y, s, o)); }  // scalar: see dlt_rows_pts
+
 // u, v: the observed pixel (DIST == 1 derives the normalised coordinates from it).
 template <int DIST, typename T>
 SKA_HD void score_view(const CamDev& c, T Y0, T Y1, T Y2, T ra, T rb, T u, T v, T& eu, T& ev) {
@@ -201,8 +225,8 @@ SKA_HD void score_view(const CamDev& c, T Y0, T Y1, T Y2, T ra, T rb, T u, T v, 
       // zero skew: the pinhole reprojection is u + eu, so x = (u + eu - cx) / fx - two FMAs per coordinate
       // instead of a second 3x4 row product (the cancellation u - cx costs 6e-8 in x: nothing after the
       // distortion polynomial's ~0.1 sensitivity)
-      x = vfma(eu, c.ifx, vfma(u, c.ifx, c.ncx));
-      y = vfma(ev, c.ify, vfma(v, c.ify, c.ncy));
+      x = vfma(eu, c.ifx, pix_norm(u, c.ifx, c.ncx));
+      y = vfma(ev, c.ify, pix_norm(v, c.ify, c.ncy));
     } else {
       x = vmul(vfma(c.Rxy[0], Y0, vfma(c.Rxy[1], Y1, vfma(c.Rxy[2], Y2, c.txy[0]))), iz);
       y = vmul(vfma(c.Rxy[3], Y0, vfma(c.Rxy[4], Y1, vfma(c.Rxy[5], Y2, c.txy[1]))), iz);
