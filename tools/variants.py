@@ -9,10 +9,10 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 VARIANTS = {
-    "ss15": ["-DSKA_WS_STREAM_LARGE", "-DSKA_STREAM_SCALAR"],                                # V >= 5: scalar streaming, 15 consumer warps x 128 regs
-    "ss17": ["-DSKA_WS_STREAM_LARGE", "-DSKA_STREAM_SCALAR", "-DSKA_WS_STREAM_WARPS=17"],   # 18 warps x <= 113 regs
-    "ss11": ["-DSKA_WS_STREAM_LARGE", "-DSKA_STREAM_SCALAR", "-DSKA_WS_STREAM_WARPS=11"],   # 12 warps x 168 regs
-    "sp15": ["-DSKA_WS_STREAM_LARGE"],                                                       # V >= 5: packed streaming (rolled loops)
+    "ws13": ["-DSKA_WS_WARPS=13"],   # 14 warps x 146 registers
+    "ws11": ["-DSKA_WS_WARPS=11"],   # 12 warps x 168 registers
+    "ws12": ["-DSKA_WS_WARPS=12"],   # 13 warps x 157 registers
+    "ws14": ["-DSKA_WS_WARPS=14"],   # 15 warps x 136 registers
 }
 LIBDIR = ROOT / "skiing_analysis_pytorch_b200" / "lib"
 
