@@ -266,6 +266,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 #ifndef SKA_WS_MINB
 #define SKA_WS_MINB 1
 #endif
+#ifndef SKA_WS_STAGES
+#define SKA_WS_STAGES 4
+#endif
 constexpr int kWarpPts = 64;  // points per warp tile (2 per lane)
 
 // STREAM = false: the warp copies its pair into registers, releases the stage and runs tri_points<>
@@ -275,7 +278,7 @@ constexpr int kWarpPts = 64;  // points per warp tile (2 per lane)
 //                 producer as well, and the stage is released after the last pass.
 template <int V, bool CONF, bool STREAM>
 struct WsCfg {
-  static constexpr int kStages = STREAM ? 2 : 3;
+  static constexpr int kStages = STREAM ? 2 : (V <= 4 ? SKA_WS_STAGES : 3);  // a warp finishes a tile in ~1.2 us: the ring must cover HBM + TMA latency
   static constexpr bool kStageConf = STREAM && CONF;
   static constexpr int kViewFloats = kWarpPts * 2 + (kStageConf ? kWarpPts : 0);  // keypoints (+ confidences) of one view
   static constexpr int kStageFloats = V * kViewFloats;

@@ -9,10 +9,10 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 VARIANTS = {
-    "ws13": ["-DSKA_WS_WARPS=13"],   # 14 warps x 146 registers
-    "ws11": ["-DSKA_WS_WARPS=11"],   # 12 warps x 168 registers
-    "ws12": ["-DSKA_WS_WARPS=12"],   # 13 warps x 157 registers
-    "ws14": ["-DSKA_WS_WARPS=14"],   # 15 warps x 136 registers
+    "st3": ["-DSKA_WS_STAGES=3"],
+    "st4": ["-DSKA_WS_STAGES=4"],
+    "st8": ["-DSKA_WS_STAGES=8"],
+    "st12": ["-DSKA_WS_STAGES=12"],
 }
 LIBDIR = ROOT / "skiing_analysis_pytorch_b200" / "lib"
 
