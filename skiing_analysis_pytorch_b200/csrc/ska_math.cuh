@@ -142,6 +142,42 @@ SKA_HD void ldl3_solve(const Ldl3T<T>& f, T b0, T b1, T b2, T& x0, T& x1, T& x2)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two views' cameras interleaved: every member is the pair (view 2i, view 2i+1).  Used by the view-pair
+// form of the per-point arithmetic (tri_point_vp): one packed instruction does the same step for two views of
+// ONE point, and each pair of coefficients is one 64-bit constant load.  No skew / thin prism (DIST <= 1).
+struct CamPairDev {
+  F2 Ph[12];
+  F2 Pl3[3];      // lo parts of the translation column: Pl[3], Pl[7], Pl[11]
+  F2 fx, fy, ifx, ify, ncx, ncy;
+  F2 dk[3], kd[3];
+  F2 p1, p2, tp1, tp2;
+  F2 s[4];        // unused (PRISM = false); keeps distort_delta generic
+};
+SKA_HD void make_cam_pair(const CamDev& a, const CamDev& b, CamPairDev& o) {
+  for (int i = 0; i < 12; ++i) o.Ph[i] = mk2(a.Ph[i], b.Ph[i]);
+  o.Pl3[0] = mk2(a.Pl[3], b.Pl[3]);
+  o.Pl3[1] = mk2(a.Pl[7], b.Pl[7]);
+  o.Pl3[2] = mk2(a.Pl[11], b.Pl[11]);
+  o.fx = mk2(a.fx, b.fx); o.fy = mk2(a.fy, b.fy);
+  o.ifx = mk2(a.ifx, b.ifx); o.ify = mk2(a.ify, b.ify);
+  o.ncx = mk2(a.ncx, b.ncx); o.ncy = mk2(a.ncy, b.ncy);
+  for (int i = 0; i < 3; ++i) { o.dk[i] = mk2(a.dk[i], b.dk[i]); o.kd[i] = mk2(a.kd[i], b.kd[i]); }
+  o.p1 = mk2(a.p1, b.p1); o.p2 = mk2(a.p2, b.p2);
+  o.tp1 = mk2(a.tp1, b.tp1); o.tp2 = mk2(a.tp2, b.tp2);
+  for (int i = 0; i < 4; ++i) o.s[i] = mk2(a.s[i], b.s[i]);
+}
+// DLT rows of two views of one point (LO = 1: translation column restored from the lo parts)
+SKA_HD void dlt_rows_vp(const CamPairDev& c, F2 u, F2 v, F2 a[4], F2 b[4]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    a[m] = vfma(u, c.Ph[8 + m], vneg(c.Ph[m]));
+    b[m] = vfma(v, c.Ph[8 + m], vneg(c.Ph[4 + m]));
+  }
+  a[3] = vadd(a[3], vfma(u, c.Pl3[2], vneg(c.Pl3[0])));
+  b[3] = vadd(b[3], vfma(v, c.Pl3[2], vneg(c.Pl3[1])));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Smallest eigenpair of the un-centred DLT normal matrix M = A^T A, computed in centred
 // coordinates.  With X~ = [c + Y; 1] the eigen-equations (M - lam I) X~ = 0 read
 //     (M'33 - lam I) Y = -m'34 + lam c            (rows 1..3, M' = T^T M T, T = [I c; 0 1])
@@ -247,8 +283,8 @@ SKA_HD void jacobi4_smallest(T a[4][4], T vec[4], int sweeps) {
 // cv2.projectPoints distortion increment on normalised coordinates: returns (x'' - x, y'' - y).
 // rad - 1 is formed as ((k1-k4) r2 + (k2-k5) r4 + (k3-k6) r6) / den so no bits are lost to 1 + ...
 // PRISM adds the thin-prism terms s1..s4.
-template <bool PRISM, typename T>
-SKA_HD void distort_delta(const CamDev& c, T x, T y, T& dx, T& dy) {
+template <bool PRISM, typename T, typename CamT>
+SKA_HD void distort_delta(const CamT& c, T x, T y, T& dx, T& dy) {
   const T xx = vmul(x, x), xy = vmul(x, y), yy = vmul(y, y);
   const T r2 = vadd(yy, xx);
   const T num = vmul(r2, vfma(r2, vfma(r2, c.dk[2], c.dk[1]), c.dk[0]));

@@ -607,4 +607,140 @@ SKA_HD void tri_points_stream(const CamDev* __restrict__ cam, const double (*P64
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// View-pair form for many views (even V >= 4): ONE point per call, the per-view work - DLT rows, normal-matrix
+// accumulation, Rayleigh residuals, residual update, scoring - packed over PAIRS OF VIEWS (F2 = views 2i, 2i+1)
+// with interleaved camera constants (CamPairDev); the 3x3 solve, the secular step and the certificate are scalar.
+// Same arithmetic per view as tri_points<V, 1, ...> (each packed half is the scalar IEEE operation); sums over the
+// views are formed as (even views) + (odd views), so results agree with the scalar form to rounding, not bit for bit.
+// The rare general path and the fp64 fallback reuse the scalar per-view code on `cam`.
+template <int V, bool CONF, int DIST, int LO = 1>
+SKA_HD void tri_point_vp(const CamPairDev* __restrict__ camp, const CamDev* __restrict__ cam, const double (*P64)[12],
+                         const float cx, const float cy, const float cz, const float* u, const float* v, const float* w2,
+                         const PointSource& src, float* X, float* du, float* dv, uint8_t& status) {
+  static_assert(V % 2 == 0 && DIST <= 1 && LO == 1, "view-pair form: even V, no skew / thin prism");
+  constexpr int H = V / 2;
+  F2 a[H][4], b[H][4], ra[H], rb[H], u2[H], v2[H], w22[H];
+  Sym4T<F2> M2;
+  sym4_zero(M2);
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    u2[i] = mk2(u[2 * i], u[2 * i + 1]);
+    v2[i] = mk2(v[2 * i], v[2 * i + 1]);
+    w22[i] = CONF ? mk2(w2[2 * i], w2[2 * i + 1]) : mk2(1.f, 1.f);
+    dlt_rows_vp(camp[i], u2[i], v2[i], a[i], b[i]);
+    if (CONF) {
+      sym4_rank1(M2, a[i], w22[i]);
+      sym4_rank1(M2, b[i], w22[i]);
+    } else {
+      sym4_rank1_unit(M2, a[i]);
+      sym4_rank1_unit(M2, b[i]);
+    }
+  }
+  Sym4 M;
+  M.m00 = M2.m00.x + M2.m00.y; M.m01 = M2.m01.x + M2.m01.y; M.m02 = M2.m02.x + M2.m02.y; M.m03 = M2.m03.x + M2.m03.y;
+  M.m11 = M2.m11.x + M2.m11.y; M.m12 = M2.m12.x + M2.m12.y; M.m13 = M2.m13.x + M2.m13.y;
+  M.m22 = M2.m22.x + M2.m22.y; M.m23 = M2.m23.x + M2.m23.y; M.m33 = M2.m33.x + M2.m33.y;
+  // lam = 0: the inhomogeneous least-squares point
+  const Ldl3 f0 = ldl3(M.m00, M.m01, M.m02, M.m11, M.m12, M.m22);
+  float y0, y1, y2;
+  ldl3_solve(f0, -M.m03, -M.m13, -M.m23, y0, y1, y2);
+  F2 num2 = mk2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    ra[i] = vfma(a[i][0], y0, vfma(a[i][1], y1, vfma(a[i][2], y2, a[i][3])));
+    rb[i] = vfma(b[i][0], y0, vfma(b[i][1], y1, vfma(b[i][2], y2, b[i][3])));
+    const F2 rr = vfma(ra[i], ra[i], vmul(rb[i], rb[i]));
+    num2 = CONF ? vfma(w22[i], rr, num2) : vadd(num2, rr);
+  }
+  const float X0 = y0 + cx, X1 = y1 + cy, X2 = y2 + cz;
+  const float den = fmaf(X0, X0, fmaf(X1, X1, fmaf(X2, X2, 1.0f)));
+  const float lam = (num2.x + num2.y) * rcp_fast(den);
+  float z0, z1, z2;
+  ldl3_solve(f0, X0, X1, X2, z0, z1, z2);
+  const float d0 = lam * z0, d1 = lam * z1, d2 = lam * z2;
+  const float step2 = fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
+  const float itr = ldl3_inv_trace(f0);
+  bool conv = f0.pos && (lam * itr < kFastLamTr) && (step2 <= kFastTol2 * den);
+  const bool well = (M.m00 + M.m11 + M.m22) * itr <= kCondMax;
+  SecularState s;
+  s.y0 = y0 + d0;
+  s.y1 = y1 + d1;
+  s.y2 = y2 + d2;
+  s.lam = lam;
+  s.step2 = step2;
+  s.ok = f0.pos;
+  bool have_res = true;
+#pragma unroll
+  for (int i = 0; i < H; ++i) {  // r(Y0 + d) = r(Y0) + a[0:3] . d
+    ra[i] = vfma(a[i][0], d0, vfma(a[i][1], d1, vfma(a[i][2], d2, ra[i])));
+    rb[i] = vfma(b[i][0], d0, vfma(b[i][1], d1, vfma(b[i][2], d2, rb[i])));
+  }
+  status = 0;
+  if (!SKA_WARP_ALL(conv)) {
+    // general path (rare): full secular iteration in scalar fp32 on the scalar cameras
+#pragma unroll 1
+    for (int it = 0; it < kSecularMaxIter; ++it) {
+      if (!conv) {
+        float nm = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < V; ++k) {
+          float as[4], bs[4];
+          dlt_rows<LO>(cam[k], u[k], v[k], as, bs);
+          const float r1 = fmaf(as[0], s.y0, fmaf(as[1], s.y1, fmaf(as[2], s.y2, as[3])));
+          const float r2 = fmaf(bs[0], s.y0, fmaf(bs[1], s.y1, fmaf(bs[2], s.y2, bs[3])));
+          const float rr = fmaf(r1, r1, r2 * r2);
+          nm = CONF ? fmaf(w2[k], rr, nm) : nm + rr;
+        }
+        const float Xa = s.y0 + cx, Xb = s.y1 + cy, Xc = s.y2 + cz;
+        const float lm = nm * rcp_fast(fmaf(Xa, Xa, fmaf(Xb, Xb, fmaf(Xc, Xc, 1.0f))));
+        conv = secular_step(M, cx, cy, cz, lm, s);
+        have_res = false;
+      }
+      if (SKA_WARP_ALL(conv || !s.ok)) break;
+    }
+  }
+  float Y[3] = {s.y0, s.y1, s.y2};
+  const bool finite_in = fabsf(M.m33) <= 3.0e38f;  // false for NaN / inf inputs
+  const bool need64 = !(conv && s.ok && well) && finite_in;
+  if (!finite_in) status = 2;
+  if (SKA_WARP_ANY(need64)) {
+    if (need64) {
+      const Vec3d Xd = solve_jacobi64<V>(P64, src.kpts, src.conf, src.k_sV, src.c_sV, src.weight_sqrt);
+      Y[0] = (float)(Xd.x - (double)cx);
+      Y[1] = (float)(Xd.y - (double)cy);
+      Y[2] = (float)(Xd.z - (double)cz);
+      have_res = false;
+      status = 1;
+    }
+  }
+  X[0] = Y[0] + cx;
+  X[1] = Y[1] + cy;
+  X[2] = Y[2] + cz;
+  if (!(fabsf(X[0]) <= 3.0e38f && fabsf(X[1]) <= 3.0e38f && fabsf(X[2]) <= 3.0e38f)) status = 2;
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    if (!have_res) {
+      ra[i] = vfma(a[i][0], Y[0], vfma(a[i][1], Y[1], vfma(a[i][2], Y[2], a[i][3])));
+      rb[i] = vfma(b[i][0], Y[0], vfma(b[i][1], Y[1], vfma(b[i][2], Y[2], b[i][3])));
+    }
+    const CamPairDev& c = camp[i];
+    const F2 z = vadd(vfma(c.Ph[8], Y[0], vfma(c.Ph[9], Y[1], vfma(c.Ph[10], Y[2], c.Ph[11]))), c.Pl3[2]);
+    const F2 iz = rcp_fast(z);
+    F2 eu = vmul(vneg(ra[i]), iz), ev = vmul(vneg(rb[i]), iz);
+    if (DIST) {
+      const F2 x = vfma(eu, c.ifx, vfma(u2[i], c.ifx, c.ncx));
+      const F2 y = vfma(ev, c.ify, vfma(v2[i], c.ify, c.ncy));
+      F2 dx, dy;
+      distort_delta<false>(c, x, y, dx, dy);
+      eu = vfma(dx, c.fx, eu);
+      ev = vfma(dy, c.fy, ev);
+    }
+    du[2 * i] = eu.x;
+    du[2 * i + 1] = eu.y;
+    dv[2 * i] = ev.x;
+    dv[2 * i + 1] = ev.y;
+  }
+}
+
 }  // namespace ska

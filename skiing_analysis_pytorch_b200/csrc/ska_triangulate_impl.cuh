@@ -24,6 +24,7 @@ namespace ska {
 template <int V>
 struct TriParams {
   CamDev cam[V];
+  CamPairDev camp[V / 2];  // the same cameras interleaved by view pairs (tri_point_vp, even V >= 4)
   double P64[V][12];
   float c[3];
   uint32_t weight_sqrt;
@@ -42,7 +43,10 @@ struct TriParams {
   uint8_t* status;
 };
 
-constexpr int kBlock = 256;
+#ifndef SKA_KBLOCK
+#define SKA_KBLOCK 256
+#endif
+constexpr int kBlock = SKA_KBLOCK;
 
 template <int V, int PTS, bool CONF>
 struct TileInputs {
@@ -146,8 +150,18 @@ __global__ void __launch_bounds__(kBlock, MINB) tri_kernel(const __grid_constant
 
     float X[PTS][3], du[PTS][V], dv[PTS][V];
     uint8_t st[PTS];
-    tri_points<V, PTS, CONF, DIST, SOLVER>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], cur.u, cur.v, w2, src, X, du,
-                                           dv, st);
+#ifndef SKA_NO_VP
+    constexpr bool kVP = (PTS == 1) && (V >= 4) && (V % 2 == 0) && (DIST <= 1) && (SOLVER == kSolverSecular);
+#else
+    constexpr bool kVP = false;
+#endif
+    if constexpr (kVP) {
+      // many views: one point per thread, per-view work packed over pairs of views
+      tri_point_vp<V, CONF, DIST>(prm.camp, prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], cur.u[0], cur.v[0], w2[0], src, X[0],
+                                  du[0], dv[0], st[0]);
+    } else {
+      tri_points<V, PTS, CONF, DIST, SOLVER>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], cur.u, cur.v, w2, src, X, du, dv, st);
+    }
 
     // ---- per-view error / reprojection, coalesced
 #pragma unroll
@@ -751,6 +765,7 @@ static int dispatch(const TriArgs& a) {
     dist = d > dist ? d : dist;
   }
   for (int k = 0; k < 3; ++k) prm.c[k] = (float)a.centre[k];
+  for (int i = 0; i < V / 2; ++i) make_cam_pair(prm.cam[2 * i], prm.cam[2 * i + 1], prm.camp[i]);
   const uint32_t solver = a.flags & SKA_SOLVER_MASK;
   prm.weight_sqrt = (a.flags & SKA_WEIGHT_SQRT) ? 1u : 0u;
   prm.J = a.J;

@@ -32,6 +32,45 @@ static int run(const SkaCamera* cams, const double* centre, const float* kpts, c
   }
   const int lo = (flags >> 8) & 3;  // test hook: lo-part level of the DLT rows (default 1)
   const uint32_t solver = flags & SKA_SOLVER_MASK;
+  if ((flags >> 12) & 1) {
+    // test hook: the view-pair form (tri_point_vp) the kernel uses for even V >= 4
+    if constexpr (V >= 4 && V % 2 == 0) {
+      CamPairDev camp[V / 2];
+      for (int i = 0; i < V / 2; ++i) make_cam_pair(cam[2 * i], cam[2 * i + 1], camp[i]);
+      if (dist > 1) return SKA_EUNSUPPORTED;
+      for (int64_t i = 0; i < N; ++i) {
+        float u[V], vv[V], w2[V], du[V], dv[V], Xp[3];
+        for (int v = 0; v < V; ++v) {
+          u[v] = kpts[(v * N + i) * 2];
+          vv[v] = kpts[(v * N + i) * 2 + 1];
+          const float cf = conf ? conf[v * N + i] : 1.0f;
+          w2[v] = (flags & SKA_WEIGHT_SQRT) ? cf : cf * cf;
+        }
+        uint8_t st;
+        PointSource src;
+        src.kpts = kpts + 2 * i;
+        src.conf = conf ? conf + i : nullptr;
+        src.k_sV = 2 * N;
+        src.c_sV = N;
+        src.weight_sqrt = (flags & SKA_WEIGHT_SQRT) ? 1u : 0u;
+        const float cx = (float)c[0], cy = (float)c[1], cz = (float)c[2];
+        if (conf) {
+          if (dist) tri_point_vp<V, true, 1>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);
+          else tri_point_vp<V, true, 0>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);
+        } else {
+          if (dist) tri_point_vp<V, false, 1>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);
+          else tri_point_vp<V, false, 0>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);
+        }
+        for (int k = 0; k < 3; ++k) X[3 * i + k] = Xp[k];
+        if (err)
+          for (int v = 0; v < V; ++v) err[v * N + i] = sqrtf(du[v] * du[v] + dv[v] * dv[v]);
+        if (status) status[i] = st;
+      }
+      return 0;
+    } else {
+      return SKA_EUNSUPPORTED;
+    }
+  }
   if ((flags >> 11) & 1) {
     // test hook: the streaming three-pass form (tri_points_stream, packed pairs) the kernel uses for V >= 5
     struct HostObs {

@@ -191,3 +191,23 @@ def test_hostemu_streaming_three_pass_form_matches_oracle(rig, T, J, use_conf, d
     np.testing.assert_array_equal(X, X1)       # same solve, bit for bit
     np.testing.assert_array_equal(st, s1)
     assert np.abs(err - e1).max() < 1e-4        # residuals evaluated directly at the final point vs updated (both within POINT_TOL of the oracle)
+
+
+@pytest.mark.parametrize("rig,T,J,use_conf,dist", [c for c in CASES if c[0] in ("4", "8")] + [("8", 16, 17, False, None), ("4", 32, 17, False, synth.DIST_CALIB)])
+def test_hostemu_view_pair_form_matches_oracle(rig, T, J, use_conf, dist):
+    """tri_point_vp (per-view work packed over pairs of views - the even V >= 4 kernel path)."""
+    clip = synth.make_clip(rig, T, J, seed=0)
+    conf = clip.conf_vm if use_conf else None
+    V = len(clip.R)
+    Xo, eo = _oracle(clip, conf, dist)
+    cams = _cabi.make_cameras(clip.K, clip.R, clip.t, dist)
+    k = clip.x_vm.reshape(V, -1, 2)
+    c = None if conf is None else conf.reshape(V, -1)
+    X, err, st = hostemu.triangulate(cams, V, k, c, flags=1 << 12)
+    rel = np.linalg.norm(X - Xo, axis=1) / np.linalg.norm(Xo, axis=1)
+    assert rel.max() < X_REL_HELD < X_REL_TOL
+    assert np.abs(err - eo).max() < POINT_TOL
+    assert abs(np.sqrt((err.astype(np.float64) ** 2).mean()) - np.sqrt((eo ** 2).mean())) < RMSE_TOL
+    assert (st == 0).all()
+    X1, e1, _ = hostemu.triangulate(cams, V, k, c, flags=0)
+    assert (np.linalg.norm(X - X1, axis=1) / np.linalg.norm(X1, axis=1)).max() < 1e-6   # same sums in a different order

@@ -9,10 +9,10 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 VARIANTS = {
-    "st3": ["-DSKA_WS_STAGES=3"],
-    "st4": ["-DSKA_WS_STAGES=4"],
-    "st8": ["-DSKA_WS_STAGES=8"],
-    "st12": ["-DSKA_WS_STAGES=12"],
+    "b128_m3": ["-DSKA_KBLOCK=128", "-DSKA_MINB_LARGE=3"],   # tri_kernel V >= 5: 12 warps x 168 registers
+    "b128_m4": ["-DSKA_KBLOCK=128", "-DSKA_MINB_LARGE=4"],   # 16 warps x 128 registers
+    "b128_m2": ["-DSKA_KBLOCK=128", "-DSKA_MINB_LARGE=2"],   # 8 warps x 255 registers, finer CTAs
+    "b256_m2": ["-DSKA_MINB_LARGE=2"],                        # 16 warps x 128 registers
 }
 LIBDIR = ROOT / "skiing_analysis_pytorch_b200" / "lib"
 
