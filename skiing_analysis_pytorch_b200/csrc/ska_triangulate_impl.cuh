@@ -283,6 +283,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 #ifndef SKA_WS_STAGES
 #define SKA_WS_STAGES 4
 #endif
+#ifndef SKA_WS_STREAM_STAGES
+#define SKA_WS_STREAM_STAGES 3
+#endif
 constexpr int kWarpPts = 64;  // points per warp tile (2 per lane)
 
 // STREAM = false: the warp copies its pair into registers, releases the stage and runs tri_points<>
@@ -290,9 +293,15 @@ constexpr int kWarpPts = 64;  // points per warp tile (2 per lane)
 // STREAM = true : tri_points_stream<> re-reads the observations from the stage in each of its three
 //                 passes (nothing per view in registers; V >= 5), confidences are staged by the
 //                 producer as well, and the stage is released after the last pass.
+#ifdef SKA_STREAM_THREE_PASS
+constexpr bool kStreamThreePass = true;   // measurement variant: tri_points_stream instead of tri_point_vp
+#else
+constexpr bool kStreamThreePass = false;
+#endif
+
 template <int V, bool CONF, bool STREAM>
 struct WsCfg {
-  static constexpr int kStages = STREAM ? 2 : (V <= 4 ? SKA_WS_STAGES : 3);  // a warp finishes a tile in ~1.2 us: the ring must cover HBM + TMA latency
+  static constexpr int kStages = STREAM ? SKA_WS_STREAM_STAGES : (V <= 4 ? SKA_WS_STAGES : 3);  // a warp finishes a tile in ~1.2 us: the ring must cover HBM + TMA latency
   static constexpr bool kStageConf = STREAM && CONF;
   static constexpr int kViewFloats = kWarpPts * 2 + (kStageConf ? kWarpPts : 0);  // keypoints (+ confidences) of one view
   static constexpr int kStageFloats = V * kViewFloats;
@@ -449,7 +458,44 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
     src.weight_sqrt = prm.weight_sqrt;
     float X[PTS][3];
     uint8_t stt[PTS];
-    if constexpr (STREAM) {
+    if constexpr (STREAM && V % 2 == 0 && V >= 4 && DIST <= 1 && !kStreamThreePass) {
+      // many views: the lane's two points one after the other, each with its per-view work packed over pairs of
+      // views (tri_point_vp); observations come from the stage right when they are needed - no prefetch registers,
+      // no global-load addressing in the consumer
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        float u[V], v[V], w2[V], du[V], dv[V], Xp[3];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float* p = stage + k * Cf::kViewFloats;
+          const float2 q = *reinterpret_cast<const float2*>(p + 4 * lane + 2 * sub);
+          u[k] = q.x;
+          v[k] = q.y;
+          if (CONF) {
+            const float c = p[kWarpPts * 2 + 2 * lane + sub];
+            w2[k] = prm.weight_sqrt ? c : c * c;
+          } else {
+            w2[k] = 1.0f;
+          }
+        }
+        PointSource s1 = src;
+        s1.kpts += 2 * sub;
+        if (s1.conf != nullptr) s1.conf += sub;
+        uint8_t st1;
+        tri_point_vp<V, CONF, DIST>(prm.camp, prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], u, v, w2, s1, Xp, du, dv, st1);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          if (prm.err != nullptr) __stcs(prm.err + (int64_t)k * prm.c_sV + i0 + sub, sqrt_fast(fmaf(du[k], du[k], dv[k] * dv[k])));
+          if (prm.proj != nullptr)
+            __stcs(reinterpret_cast<float2*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)(i0 + sub)), make_float2(u[k] + du[k], v[k] + dv[k]));
+        }
+        if (prm.status != nullptr) prm.status[i0 + sub] = st1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sx[(lane * PTS + sub) * 3 + k] = Xp[k];
+      }
+      __syncwarp();                                  // both points done with the stage
+      if (lane == 0) mbar_arrive(&sEmpty[warp][st]);
+    } else if constexpr (STREAM) {
 #ifdef SKA_STREAM_SCALAR
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {  // the lane's two points one after the other, scalar fp32, view loops unrolled
@@ -502,12 +548,14 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
       st = 0;
       par ^= 1u;
     }
-    if (!LEAN && prm.status != nullptr) *reinterpret_cast<uchar2*>(prm.status + i0) = make_uchar2(stt[0], stt[1]);
     // ---- X through shared memory: 192 floats per warp leave as 48 128-bit stores
+    if constexpr (!(STREAM && V % 2 == 0 && V >= 4 && DIST <= 1 && !kStreamThreePass)) {
+      if (!LEAN && prm.status != nullptr) *reinterpret_cast<uchar2*>(prm.status + i0) = make_uchar2(stt[0], stt[1]);
 #pragma unroll
-    for (int p = 0; p < PTS; ++p)
+      for (int p = 0; p < PTS; ++p)
 #pragma unroll
-      for (int k = 0; k < 3; ++k) sx[(lane * PTS + p) * 3 + k] = X[p][k];
+        for (int k = 0; k < 3; ++k) sx[(lane * PTS + p) * 3 + k] = X[p][k];
+    }
     __syncwarp();
     float* gx = prm.X + (int64_t)wt * (kWarpPts * 3);
     if (LEAN || prm.x_vec) {
@@ -522,7 +570,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
 }
 
 #ifndef SKA_WS_STREAM_WARPS
-#define SKA_WS_STREAM_WARPS 15
+#define SKA_WS_STREAM_WARPS 11
 #endif
 #ifndef SKA_WS_STREAM_MINB
 #define SKA_WS_STREAM_MINB 1
@@ -798,17 +846,18 @@ static int dispatch(const TriArgs& a) {
 #else
   const bool pair_ok = !fm && (prm.N % 2 == 0) && al(a.kpts, 16) && al(a.conf, 8) && al(a.err, 8) && al(a.proj, 16);
 #endif
-  // V <= 4: warp-specialised kernel, rows in registers (tri_points).  V >= 5: tri_kernel (one point per thread).
-  // The streaming three-pass form (tri_points_stream: nothing per view in registers, packed pairs for any V,
-  // confidences staged by bulk copies) is kept as a measurement variant: on B200 it was SLOWER than tri_kernel at
-  // V = 8 (2.20 vs 1.96 ms on config 4's shard: rolled view loops turn every camera coefficient into an indexed
-  // LDC) and equal at V = 2 (profiles/r01_tri_kernel_variants.txt).
+  // V <= 4: warp-specialised kernel, point pairs packed, rows in registers (tri_points).
+  // V >= 5 (and everything the pair path cannot take): tri_kernel, one point per thread; for even V its per-view work
+  //   is packed over view pairs (tri_point_vp).
+  // Measured and kept off (profiles/r01_tri_kernel_variants.txt): the warp-specialised kernel with staged confidences
+  //   for V = 6, 8 (SKA_WS_LARGE: view-pair arithmetic, 1.01 vs 0.84 ms at V = 8) and the streaming three-pass form
+  //   (SKA_STREAM_THREE_PASS / SKA_WS_STREAM_ALL: slower at V = 8, equal at V = 2).
 #if defined(SKA_WS_STREAM_ALL)
   constexpr bool kStream = true;
   constexpr bool kWs = true;
-#elif defined(SKA_WS_STREAM_LARGE)
-  constexpr bool kStream = (V >= 5);
-  constexpr bool kWs = true;
+#elif defined(SKA_WS_LARGE)
+  constexpr bool kStream = (V >= 6) && (V % 2 == 0);  // measurement variant: staged observations + view-pair arithmetic
+  constexpr bool kWs = (V <= 4) || kStream;
 #else
   constexpr bool kStream = false;
   constexpr bool kWs = (V <= 4);

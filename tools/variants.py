@@ -9,10 +9,10 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 VARIANTS = {
-    "b128_m3": ["-DSKA_KBLOCK=128", "-DSKA_MINB_LARGE=3"],   # tri_kernel V >= 5: 12 warps x 168 registers
-    "b128_m4": ["-DSKA_KBLOCK=128", "-DSKA_MINB_LARGE=4"],   # 16 warps x 128 registers
-    "b128_m2": ["-DSKA_KBLOCK=128", "-DSKA_MINB_LARGE=2"],   # 8 warps x 255 registers, finer CTAs
-    "b256_m2": ["-DSKA_MINB_LARGE=2"],                        # 16 warps x 128 registers
+    "sw9": ["-DSKA_WS_STREAM_WARPS=9"],     # V = 6, 8 view-pair ws kernel: 10 warps x <= 204 registers
+    "sw10": ["-DSKA_WS_STREAM_WARPS=10"],   # 11 warps x <= 186
+    "sw13": ["-DSKA_WS_STREAM_WARPS=13", "-DSKA_WS_STREAM_STAGES=2"],   # 14 warps x <= 146
+    "nowsl": ["-DSKA_NO_WS_LARGE"],         # V >= 5 in tri_kernel (view pairs, register prefetch)
 }
 LIBDIR = ROOT / "skiing_analysis_pytorch_b200" / "lib"
 
