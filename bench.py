@@ -353,7 +353,7 @@ def run_tri_8view(a, dev, world, barrier, dist):
     ach = bpj * T * J / (ms * 1e-3) / 1e9
     return {"workload": "1M frames x 17 joints x 8 views per GPU, confidence-weighted DLT + distortion scoring", "ms_per_step": ms,
             "value": world * T * J / (ms * 1e-3), "unit": UNIT, "steps": steps,
-            "roofline": {"bound": "hbm", "kernel": "ska::tri_kernel<8,...> (one point per thread)", "achieved": ach, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "ska::tri_kernel<8,...> (one point per thread, per-view work packed over view pairs)", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "bytes_per_joint": bpj,
                          "note": "fp32-pipe bound: ~800 FMA-pipe cycles per 32 points = the HBM roofline time"}}
 
