@@ -354,7 +354,7 @@ def run_tri_8view(a, dev, world, barrier, dist):
     return {"workload": "1M frames x 17 joints x 8 views per GPU, confidence-weighted DLT + distortion scoring", "ms_per_step": ms,
             "value": world * T * J / (ms * 1e-3), "unit": UNIT, "steps": steps,
             "roofline": {"bound": "hbm", "kernel": "ska::tri_kernel<8,...> (one point per thread, per-view work packed over view pairs)", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "bytes_per_joint": bpj,
+                         "unit": "GB/s", "frac": ach / peak, "bytes_per_joint": bpj, "traffic": recorded_traffic("tri_kernel_8view"),
                          "note": "fp32-pipe bound: ~800 FMA-pipe cycles per 32 points = the HBM roofline time"}}
 
 
