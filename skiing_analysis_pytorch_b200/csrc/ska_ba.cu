@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kBaBlock, 2) ba_linearize_reg(const BaKernelAr
     acc[L::oCost] += cost;
     acc[L::oClamp] += (float)ncl;
     const Chol3 f = chol3_damped(pb, lam);
-    if (f.ok) {
+    {  // no branch on f.ok: a point without a factor has a zeroed one (chol3), so Y = 0 and it adds exact zeros
       float yg0, yg1, yg2;
       chol3_fwd(f, pb.g0, pb.g1, pb.g2, yg0, yg1, yg2);
       float Y[3][6];
@@ -219,11 +219,14 @@ __global__ void __launch_bounds__(kBaBlock, 2) ba_backsub_kernel(const BaKernelA
       r2 = fmaf(cw * au[2], lu, fmaf(cw * av[2], lv, r2));
     }
     const Chol3 f = chol3_damped(pb, lam);
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-    if (f.ok) {
+    float d0, d1, d2;
+    {  // branch-free: zeroed factor -> zero step for a point without a factor
       float y0, y1, y2;
       chol3_fwd(f, -r0, -r1, -r2, y0, y1, y2);
       chol3_bwd(f, y0, y1, y2, d0, d1, d2);
+      d0 = f.ok ? d0 : 0.f;  // selects, not a branch (a non-finite residual times the zeroed factor would be NaN)
+      d1 = f.ok ? d1 : 0.f;
+      d2 = f.ok ? d2 : 0.f;
       // predicted decrease of the quadratic model, point part: dp . (lam diag(Hpp) dp - gp)
       acc[1] += d0 * fmaf(lam * pb.h00, d0, -pb.g0) + d1 * fmaf(lam * pb.h11, d1, -pb.g1) + d2 * fmaf(lam * pb.h22, d2, -pb.g2);
     }

@@ -159,11 +159,14 @@ __global__ void __launch_bounds__(32 * Wide<C>::W, 1) ba_linearize_wide_kernel(c
       nclamp += (valid && ol.clamped) ? 1.f : 0.f;
     }
     const Chol3 f = chol3_damped(pb, lam);
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f;  // dp0 = -Hd^-1 gp
-    if (f.ok) {
+    float d0, d1, d2;  // dp0 = -Hd^-1 gp (zero for a point without a factor: chol3 zeroes it)
+    {
       float y0, y1, y2;
       chol3_fwd(f, -pb.g0, -pb.g1, -pb.g2, y0, y1, y2);
       chol3_bwd(f, y0, y1, y2, d0, d1, d2);
+      d0 = f.ok ? d0 : 0.f;
+      d1 = f.ok ? d1 : 0.f;
+      d2 = f.ok ? d2 : 0.f;
     }
     __syncwarp();  // previous tile's phase 2 is done with the staging buffer
 #pragma unroll
