@@ -247,6 +247,7 @@ def recorded_traffic(key: str):
 BA_CONFIGS = {
     # name: (rig, total frames, joints) - BASELINE.json configs[2] and configs[4]
     "config3": ("2b", 100_000, 17),
+    "config3_calib": ("2b", 100_000, 17),  # config 3 with every camera's intrinsics + distortion free (15 parameters per camera)
     "config5": ("8", 1_000_000, 70),
 }
 
@@ -281,7 +282,15 @@ def run_ba(a, dev, world, rank, barrier, dist):
         X0 = api.triangulate_reproject(kv, d["K"], R0, t0, want=("X",)).X  # BA init = DLT under the perturbed rig
         del kv
         iters = a.ba_iters
-        s = ba.BundleAdjuster(d["x2d"], d["conf"], d["K"], R0, t0, X0, max_iters=iters + 8)
+        calib = name.endswith("_calib")
+        if calib:
+            th = synth.perturb_intrinsics(d["K"])
+            K_init, dist_init = synth.theta_to_K_dist(th)
+            X0 = api.triangulate_reproject(d["x2d"].permute(1, 0, 2, 3).contiguous(), K_init, R0, t0, want=("X",)).X
+            s = ba.CalibratingBundleAdjuster(d["x2d"], d["conf"], K_init, R0, t0, X0, dist=dist_init, prior_rho=synth.CALIB_PRIOR_RHO,
+                                             prior_theta=synth.theta_from_K(d["K"]), max_iters=iters + 8)
+        else:
+            s = ba.BundleAdjuster(d["x2d"], d["conf"], d["K"], R0, t0, X0, max_iters=iters + 8)
         graph = world == 1
         s.run(4, graph=graph)  # warm-up trials (also captures the graph)
         barrier()
@@ -296,6 +305,9 @@ def run_ba(a, dev, world, rank, barrier, dist):
         ms = float(ms.item()) / iters
         hist = s.history
         alg = T * J * (2 * 12 * C + 36)  # per rank: two streaming passes over the observations + X read twice, written once
+        note = ("latency / issue-bound (22 us of HBM time per trial)" if C == 2 else "CUDA-core (fp32 FMA pipe) bound: ~5k FMA per point")
+        if calib:
+            note = "issue-bound: the 24 x 24 reduced system + two 17 x 17 camera blocks cost ~4k warp instructions per 32 points"
         out[name] = {
             "metric": "ba_lm_iterations_per_sec",
             "value": 1e3 / ms,
@@ -306,7 +318,9 @@ def run_ba(a, dev, world, rank, barrier, dist):
             "frames_per_gpu": T,
             "joints": J,
             "cameras": C,
-            "free_params_per_camera": 6,
+            "free_params_per_camera": 15 if calib else 6,
+            "parameters": ("points + extrinsics (camera 0 = gauge) + fx fy cx cy k1 k2 p1 p2 k3 of every camera, Gaussian prior on the intrinsics"
+                           if calib else "points + extrinsics (camera 0 = gauge)"),
             "launches_per_iter": 6,
             "cuda_graph": graph,
             "cost_first": hist[0]["cost"],
@@ -315,8 +329,7 @@ def run_ba(a, dev, world, rank, barrier, dist):
             "trials": len(hist),
             "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "bytes_per_iter_per_gpu": alg,
-                         "note": ("latency / issue-bound (22 us of HBM time per trial)" if C == 2 else
-                                  "CUDA-core (fp32 FMA pipe) bound: ~5k FMA per point") + ", not HBM-bound: DESIGN.md section 6"},
+                         "note": note + ", not HBM-bound: DESIGN.md section 6"},
         }
         del s, d, X0
         torch.cuda.empty_cache()

@@ -242,6 +242,38 @@ int ska_ba_backsub_f32(const SkaBaProblem* p, void* stream);
 int ska_ba_control_f64(const SkaBaProblem* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * CALIBRATING bundle adjustment: the same LM with every camera's intrinsics and distortion free as well
+ * (BASELINE config 3: "2 cameras, Rodrigues extrinsics + intrinsics/distortion"; specification: oracle/lm_calib.py).
+ * Projection = cv2.projectPoints' 5-coefficient model the reference reprojects with
+ * (triangulation/reproject.py:77-78, bundle_adjustment/reproject.py:147-148) + loss.py's depth clamp (:67):
+ *   x = X_c.x/Z, y = X_c.y/Z, r2 = x^2 + y^2, rad = 1 + k1 r2 + k2 r2^2 + k3 r2^3
+ *   u = fx (x rad + 2 p1 x y + p2 (r2 + 2 x^2)) + cx,   v = fy (y rad + p1 (r2 + 2 y^2) + 2 p2 x y) + cy
+ * 15 parameters per camera: [d_omega(3), d_t(3), fx, fy, cx, cy, k1, k2, p1, p2, k3]; camera 0's extrinsics are the gauge.
+ * Cost = loss.py's confidence-weighted mean squared error under that projection
+ *        + sum_c sum_k rho_ck (theta_ck - theta0_ck)^2   (optional Gaussian prior on the 9 intrinsics; d_prior).
+ * The SkaBaProblem fields keep their meaning except:
+ *   d_cams  [2][C][SKA_BA_CAM_DOUBLES]: R(9), t(3), theta(9) = fx fy cx cy k1 k2 p1 p2 k3, pad(3)
+ *   d_delta [C * SKA_BA_CALIB_PARAMS]
+ *   d_red   [ska_ba_calib_red_doubles(C)]: upper triangle of Sw (n(n+1)/2, n = 15 C - 6: camera 0 contributes its 9
+ *           intrinsics only), then per camera 160 doubles: the row-major upper triangle (153) of sum w row^T row with
+ *           row = [B(15) | e | a.dp0] - entries (r,s<=14) Hcc, (r,15) gc, (r,16) bw, (15,15) cost - and, in slot 153,
+ *           the count of depth-clamped observations; all sums with raw conf weights
+ *   d_workspace >= ska_ba_calib_workspace_bytes(C)
+ * free_mask: bit (15*c + r) set = parameter r of camera c is optimised (bits 0..5 of camera 0 are ignored).
+ * d_prior: nullable [C][18] = theta0(9), rho(9) per camera.
+ * Built for C == 2 (config 3); other camera counts return SKA_EUNSUPPORTED.  One trial = linearize ->
+ * [all-reduce d_red] -> solve -> backsub -> [all-reduce d_red2] -> control, as above. */
+#define SKA_BA_CALIB_PARAMS 15
+#define SKA_BA_CALIB_INTRINSICS 9
+#define SKA_BA_CALIB_CAM_BLOCK 160
+int32_t ska_ba_calib_red_doubles(int32_t C);
+size_t ska_ba_calib_workspace_bytes(int32_t C);
+int ska_ba_calib_linearize_f32(const SkaBaProblem* p, void* stream);
+int ska_ba_calib_solve_f64(const SkaBaProblem* p, uint64_t free_mask, const double* d_prior, void* stream);
+int ska_ba_calib_backsub_f32(const SkaBaProblem* p, void* stream);
+int ska_ba_calib_control_f64(const SkaBaProblem* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Post-triangulation triage and temporal smoothing (the step right after the path).
  * Replaces post_triage_single / post_triage_sequence and smooth_skeleton of
  * triangulation/postprocess.py:54-170 for a whole clip.

@@ -277,22 +277,8 @@ def dense_step(X, R, t, th, x2d, w, lam, free, th0, rho):
     return full[:n_c].reshape(C, P), full[n_c:].reshape(N, 3)
 
 
-THETA_PERTURB = np.array([1.01, 0.99, 4.0, -3.0, 0.05, -0.02, 1e-3, -1e-3, 0.01])
-PRIOR_RHO = np.array([1e-4, 1e-4, 1e-4, 1e-4, 1.0, 1.0, 1.0, 1.0, 1.0])
-
-
-def perturb_intrinsics(K) -> np.ndarray:
-    """Initial intrinsics of the calibrating BA test / bench problems: fx * 1.01, fy * 0.99, (cx, cy) + (4, -3) px and a
-    small non-zero distortion vector, alternating sign per camera.  The synthetic observations are pinhole under K, so
-    the optimiser has ~1 % focal error, a few px of principal-point error and the distortion to remove."""
-    th = intr_from_K(K)
-    for c in range(len(th)):
-        sg = 1.0 if c % 2 == 0 else -1.0
-        th[c, 0] *= 1.0 + sg * (THETA_PERTURB[0] - 1.0)
-        th[c, 1] *= 1.0 + sg * (THETA_PERTURB[1] - 1.0)
-        th[c, 2:4] += sg * THETA_PERTURB[2:4]
-        th[c, 4:] = sg * THETA_PERTURB[4:]
-    return th
+from skiing_analysis_pytorch_b200.synth import CALIB_PRIOR_RHO as PRIOR_RHO  # noqa: E402  (problem definition shared with bench.py)
+from skiing_analysis_pytorch_b200.synth import perturb_intrinsics  # noqa: E402,F401
 
 
 def make_problem(rig: str, T: int, J: int, seed: int = 0):

@@ -71,6 +71,29 @@ def red_layout(n_cams: int) -> dict:
                 size=ns + 2 * n + 21 * nc + 2)
 
 
+BA_CALIB_PARAMS = 15
+BA_CALIB_INTRINSICS = 9
+BA_CALIB_CAM_BLOCK = 160
+
+
+def calib_red_layout(n_cams: int) -> dict:
+    """Offsets inside the calibrating BA's packed reduced system (include/ska.h): Sw triangle over the n = 15 C - 6
+    free-able parameters, then one 160-double block per camera (upper triangle of the 17 x 17 row products)."""
+    n = BA_CALIB_PARAMS * n_cams - 6
+    ns = n * (n + 1) // 2
+    return dict(n=n, sw=0, cam=ns, size=ns + BA_CALIB_CAM_BLOCK * n_cams)
+
+
+def calib_tri(r: int, s: int) -> int:
+    """Index of entry (r, s), r <= s, in the row-major upper triangle of the 17 x 17 per-camera block."""
+    return r * 17 - (r * (r - 1)) // 2 + (s - r)
+
+
+def calib_col(c: int, r: int) -> int:
+    """Column of parameter r of camera c in the reduced system (camera 0: r >= 6 only)."""
+    return r - 6 if c == 0 else BA_CALIB_INTRINSICS + BA_CALIB_PARAMS * (c - 1) + r
+
+
 def make_cameras(K, R, t, dist=None):
     """Pack V cameras into a ctypes SkaCamera array.
 

@@ -59,6 +59,12 @@ _SIGS = {
     "ska_ba_solve_f64": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), C.c_uint64, _vp]),
     "ska_ba_backsub_f32": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), _vp]),
     "ska_ba_control_f64": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), _vp]),
+    "ska_ba_calib_red_doubles": (C.c_int32, [C.c_int32]),
+    "ska_ba_calib_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "ska_ba_calib_linearize_f32": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), _vp]),
+    "ska_ba_calib_solve_f64": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), C.c_uint64, _vp, _vp]),
+    "ska_ba_calib_backsub_f32": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), _vp]),
+    "ska_ba_calib_control_f64": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), _vp]),
 }
 for _sfx in ("f32", "f64"):
     _i64, _i32 = C.c_int64, C.c_int32

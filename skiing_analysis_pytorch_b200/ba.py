@@ -251,6 +251,117 @@ class BundleAdjuster(LMSequencer):
         return float(self.ctrl[_cabi.BA_CTRL_COST].item())
 
 
+CALIB_MODES = ("full", "extr_focal", "intr_only")
+CALIB_PARAM_NAMES = ("wx", "wy", "wz", "tx", "ty", "tz", "fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3")
+
+
+def calib_free_mask(n_cams: int, mode: str = "full") -> int:
+    """Bit (15*c + r) set = parameter r of camera c is optimised; r indexes CALIB_PARAM_NAMES.  Camera 0's extrinsics
+    are the gauge.  full: all extrinsics (c >= 1) + every camera's 9 intrinsics; extr_focal: extrinsics + fx fy cx cy;
+    intr_only: the 9 intrinsics of every camera with all extrinsics fixed."""
+    if mode not in CALIB_MODES:
+        raise ValueError(f"unknown calibration mode {mode!r}; expected one of {CALIB_MODES}")
+    intr = {"full": 0x7FC0, "extr_focal": 0x03C0, "intr_only": 0x7FC0}[mode]
+    extr = 0 if mode == "intr_only" else 0x3F
+    m = 0
+    for c in range(n_cams):
+        m |= (intr | (extr if c >= 1 else 0)) << (_cabi.BA_CALIB_PARAMS * c)
+    return m
+
+
+class CalibratingBundleAdjuster(BundleAdjuster):
+    """LM over the points, the extrinsics AND every camera's intrinsics + distortion (15 parameters per camera) -
+    BASELINE config 3's "Rodrigues extrinsics + intrinsics/distortion".  Specification: oracle/lm_calib.py.
+
+    Arguments as BundleAdjuster, plus
+      K            (C,3,3) | (3,3) zero-skew intrinsics (fx, fy, cx, cy are read from it)
+      dist         None | (5,) | (C,5): initial [k1, k2, p1, p2, k3] (cv2 order, the model of triangulation/reproject.py:77-78)
+      calib        one of CALIB_MODES, or an explicit integer free mask (calib_free_mask)
+      prior_rho    None | (9,) | (C,9): precision of a Gaussian prior on [fx fy cx cy k1 k2 p1 p2 k3]
+                   (cost += sum rho (theta - prior_theta)^2); prior_theta defaults to the initial intrinsics
+    Built for 2 cameras (config 3); libska returns SKA_EUNSUPPORTED otherwise."""
+
+    def __init__(self, x2d, conf, K, R0, t0, X0, *, dist=None, calib="full", prior_rho=None, prior_theta=None, **kw):
+        kw.pop("mode", None)
+        kw.pop("force_wide", None)
+        super().__init__(x2d, conf, K, R0, t0, X0, **kw)
+        Cn, dev = self.C, self.dev
+        if Cn != 2:
+            raise ValueError("the calibrating BA is built for 2 cameras (BASELINE config 3)")
+        K = np.asarray(K, np.float64)
+        K = np.broadcast_to(K, (Cn, 3, 3)) if K.ndim == 2 else K.reshape(Cn, 3, 3)
+        if np.abs(K[:, 0, 1]).max() > 0 or np.abs(K[:, 1, 0]).max() > 0:
+            raise ValueError("the calibrating BA uses cv2's zero-skew camera matrix")
+        theta = np.zeros((Cn, _cabi.BA_CALIB_INTRINSICS))
+        theta[:, 0], theta[:, 1], theta[:, 2], theta[:, 3] = K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2]
+        if dist is not None:
+            theta[:, 4:] = np.broadcast_to(np.asarray(dist, np.float64), (Cn, 5))
+        cams = self.cams.cpu().numpy()
+        cams[:, :, 12:24] = 0.0
+        cams[:, :, 12:21] = theta[None]
+        self.cams = torch.from_numpy(cams).to(dev)
+        self.mask = calib_free_mask(Cn, calib) if isinstance(calib, str) else int(calib)
+        self.mode = calib
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.prior = None
+        if prior_rho is not None:
+            pr = np.zeros((Cn, 2, _cabi.BA_CALIB_INTRINSICS))
+            pr[:, 0] = theta if prior_theta is None else np.broadcast_to(np.asarray(prior_theta, np.float64), theta.shape)
+            pr[:, 1] = np.broadcast_to(np.asarray(prior_rho, np.float64), theta.shape)
+            self.prior = torch.from_numpy(pr).to(dev)
+        self.red = torch.zeros(int(self.lib.ska_ba_calib_red_doubles(Cn)), **f64)
+        self.delta = torch.zeros(Cn * _cabi.BA_CALIB_PARAMS, **f64)
+        with torch.cuda.device(dev):
+            ws = max(int(self.lib.ska_ba_calib_workspace_bytes(Cn)), self.ws.numel())
+        self.ws = torch.empty(ws, dtype=torch.uint8, device=dev)
+        self.prob.d_cams = self.cams.data_ptr()
+        self.prob.d_red = self.red.data_ptr()
+        self.prob.d_delta = self.delta.data_ptr()
+        self.prob.d_workspace = self.ws.data_ptr()
+        self.prob.ws_bytes = ws
+        self.prob.flags = 0
+
+    def linearize(self):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.ska_ba_calib_linearize_f32(C.byref(self.prob), _stream_ptr(self.dev)))
+
+    def solve(self):
+        pr = C.c_void_p(self.prior.data_ptr()) if self.prior is not None else None
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.ska_ba_calib_solve_f64(C.byref(self.prob), C.c_uint64(self.mask), pr, _stream_ptr(self.dev)))
+
+    def backsub(self):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.ska_ba_calib_backsub_f32(C.byref(self.prob), _stream_ptr(self.dev)))
+
+    def control(self):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.ska_ba_calib_control_f64(C.byref(self.prob), _stream_ptr(self.dev)))
+
+    @property
+    def theta(self) -> np.ndarray:
+        """(C,9) current [fx fy cx cy k1 k2 p1 p2 k3]."""
+        return self.cams[0, :, 12:21].cpu().numpy()
+
+    @property
+    def K(self) -> np.ndarray:
+        th = self.theta
+        K = np.zeros((self.C, 3, 3))
+        K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = th[:, 0], th[:, 1], th[:, 2], th[:, 3], 1.0
+        return K
+
+    @property
+    def dist(self) -> np.ndarray:
+        return self.theta[:, 4:].copy()
+
+
+def ba_calibrate(x2d, conf, K, R0, t0, X0, num_iters: int = 20, **kw):
+    """Convenience wrapper: build a CalibratingBundleAdjuster, run `num_iters` trials, return it."""
+    graph = kw.pop("graph", False)
+    kw.setdefault("max_iters", num_iters)
+    return CalibratingBundleAdjuster(x2d, conf, K, R0, t0, X0, **kw).run(num_iters, graph=graph)
+
+
 def ba_solve(x2d, conf, K, R0, t0, X0, num_iters: int = 20, **kw):
     """Convenience wrapper: build a BundleAdjuster, run `num_iters` trials, return it."""
     graph = kw.pop("graph", False)

@@ -303,33 +303,6 @@ __global__ void __launch_bounds__(kBaBlock) ba_sum_kernel(const float* __restric
 // reduced camera system: one CTA, fp64
 constexpr int kMaxN = 6 * (SKA_MAX_VIEWS - 1);
 
-__device__ void so3_exp_left(const double w[3], const double* R, double* Rn) {
-  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
-  double A, B;
-  if (th2 < 1e-8) {
-    A = 1.0 - th2 / 6.0;
-    B = 0.5 - th2 / 24.0;
-  } else {
-    const double th = sqrt(th2);
-    A = sin(th) / th;
-    B = (1.0 - cos(th)) / th2;
-  }
-  // E = I + A [w]x + B [w]x^2
-  const double wx = w[0], wy = w[1], wz = w[2];
-  double E[9];
-  E[0] = 1.0 - B * (wy * wy + wz * wz);
-  E[1] = -A * wz + B * wx * wy;
-  E[2] = A * wy + B * wx * wz;
-  E[3] = A * wz + B * wx * wy;
-  E[4] = 1.0 - B * (wx * wx + wz * wz);
-  E[5] = -A * wx + B * wy * wz;
-  E[6] = -A * wy + B * wx * wz;
-  E[7] = A * wx + B * wy * wz;
-  E[8] = 1.0 - B * (wx * wx + wy * wy);
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) Rn[3 * r + c] = E[3 * r] * R[c] + E[3 * r + 1] * R[3 + c] + E[3 * r + 2] * R[6 + c];
-}
-
 __global__ void __launch_bounds__(256) ba_solve_kernel(int C, uint64_t free_mask, const double* __restrict__ red, double* cams,
                                                       double* ctrl, double* delta) {
   __shared__ double S[kMaxN][kMaxN + 1];

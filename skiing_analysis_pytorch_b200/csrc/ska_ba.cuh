@@ -33,6 +33,8 @@ enum : int {
   kCtrlOk = 6,       // 1 if the reduced system was positive definite (written by solve)
   kCtrlCost = 7,     // cost at the current point (written by control)
   kCtrlAccepted = 8, // last decision
+  kCtrlPriorCur = 9,    // calibrating BA: intrinsics-prior part of the cost at the current cameras (written by solve)
+  kCtrlPriorTrial = 10, // ... and at the trial cameras
   kCtrlSize = 16
 };
 constexpr int kHistRow = 8;  // iter, cost, trial_cost, lambda, rho, accepted, n_clamped, pred
@@ -198,6 +200,60 @@ __device__ __forceinline__ void block_reduce_store(const float (&v)[NV], double*
     out[i] = s;
   }
   __syncthreads();
+}
+
+// R_new = exp([w]x) R (fp64; the camera update of the reduced-system solve kernels)
+__device__ inline void so3_exp_left(const double w[3], const double* R, double* Rn) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  double A, B;
+  if (th2 < 1e-8) {
+    A = 1.0 - th2 / 6.0;
+    B = 0.5 - th2 / 24.0;
+  } else {
+    const double th = sqrt(th2);
+    A = sin(th) / th;
+    B = (1.0 - cos(th)) / th2;
+  }
+  // E = I + A [w]x + B [w]x^2
+  const double wx = w[0], wy = w[1], wz = w[2];
+  double E[9];
+  E[0] = 1.0 - B * (wy * wy + wz * wz);
+  E[1] = -A * wz + B * wx * wy;
+  E[2] = A * wy + B * wx * wz;
+  E[3] = A * wz + B * wx * wy;
+  E[4] = 1.0 - B * (wx * wx + wz * wz);
+  E[5] = -A * wx + B * wy * wz;
+  E[6] = -A * wy + B * wx * wz;
+  E[7] = A * wx + B * wy * wz;
+  E[8] = 1.0 - B * (wx * wx + wy * wy);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Rn[3 * r + c] = E[3 * r] * R[c] + E[3 * r + 1] * R[3 + c] + E[3 * r + 2] * R[6 + c];
+}
+
+// ---- shared by the warp-cooperative linearisation kernels (ska_ba_wide.cu, ska_ba_calib.cu)
+constexpr int kFlush = 16;
+constexpr int kYStride = 100;  // 96 rows + 4: column stride = 4 banks mod 32
+
+constexpr int largest_div(int n, int cap) {
+  int best = 1;
+  for (int d = 1; d <= n; ++d)
+    if (n % d == 0 && d <= cap) best = d;
+  return best;
+}
+
+// lane i ends up with the sum over the warp of v[i] (i < 32); v is destroyed
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
 }
 
 // Observation addressing for both layouts: frame-major (T,C,J,.) is the reference's

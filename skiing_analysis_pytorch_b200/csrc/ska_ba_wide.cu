@@ -39,16 +39,6 @@ struct BaKernelArgsW {
   double* partials;
 };
 
-constexpr int kFlush = 16;
-constexpr int kYStride = 100;  // 96 rows + 4: column stride = 4 banks mod 32
-
-constexpr int largest_div(int n, int cap) {
-  int best = 1;
-  for (int d = 1; d <= n; ++d)
-    if (n % d == 0 && d <= cap) best = d;
-  return best;
-}
-
 #ifndef SKA_BA_WIDE_WARPS
 #define SKA_BA_WIDE_WARPS 12  // 384 threads x <= 168 registers = the whole register file, one CTA per SM
 #endif
@@ -64,21 +54,6 @@ struct Wide {
   static constexpr int warp_floats = n * kYStride;
   static constexpr size_t smem = (size_t)W * warp_floats * sizeof(float) + (size_t)size * sizeof(double) + C * sizeof(CamF);
 };
-
-// lane i ends up with the sum over the warp of v[i] (i < 32); v is destroyed
-__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < o; ++i) {
-      const float send = up ? v[i] : v[i + o];
-      const float keep = up ? v[i + o] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-  return v[0];
-}
 
 template <int C>
 __global__ void __launch_bounds__(32 * Wide<C>::W, 1) ba_linearize_wide_kernel(const BaKernelArgsW a) {

@@ -281,5 +281,36 @@ int ska_ba_control_f64(const SkaBaProblem* p, void* stream) {
   return ba_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, stream);
 }
 
+int32_t ska_ba_calib_red_doubles(int32_t C) { return C == 2 ? ba_calib_red_size(C) : 0; }
+
+size_t ska_ba_calib_workspace_bytes(int32_t C) {
+  if (C != 2) return 0;
+  return (size_t)ba_max_grid() * (size_t)ba_calib_red_size(C) * sizeof(double);
+}
+
+int ska_ba_calib_linearize_f32(const SkaBaProblem* p, void* stream) {
+  const int rc = check_problem(p, true);
+  if (rc != SKA_OK) return rc;
+  return ba_calib_linearize(*p, (cudaStream_t)stream);
+}
+
+int ska_ba_calib_solve_f64(const SkaBaProblem* p, uint64_t free_mask, const double* d_prior, void* stream) {
+  const int rc = check_problem(p, false);
+  if (rc != SKA_OK) return rc;
+  return ba_calib_solve(p->C, free_mask, p->d_red, d_prior, p->d_cams, p->d_ctrl, p->d_delta, stream);
+}
+
+int ska_ba_calib_backsub_f32(const SkaBaProblem* p, void* stream) {
+  const int rc = check_problem(p, true);
+  if (rc != SKA_OK) return rc;
+  return ba_calib_backsub(*p, (cudaStream_t)stream);
+}
+
+int ska_ba_calib_control_f64(const SkaBaProblem* p, void* stream) {
+  const int rc = check_problem(p, false);
+  if (rc != SKA_OK) return rc;
+  return ba_calib_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, stream);
+}
+
 #pragma GCC visibility pop
 }  // extern "C"

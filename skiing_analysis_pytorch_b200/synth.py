@@ -138,6 +138,43 @@ def perturb_cameras(R, t, seed: int = 1, rot_sigma: float = 0.01, trans_sigma: f
     return R2, t2
 
 
+CALIB_THETA_PERTURB = np.array([1.01, 0.99, 4.0, -3.0, 0.05, -0.02, 1e-3, -1e-3, 0.01])
+CALIB_PRIOR_RHO = np.array([1e-4, 1e-4, 1e-4, 1e-4, 1.0, 1.0, 1.0, 1.0, 1.0])
+
+
+def theta_from_K(K, dist=None):
+    """K (C,3,3) zero skew (+ optional [k1 k2 p1 p2 k3]) -> (C,9) intrinsic vectors [fx fy cx cy k1 k2 p1 p2 k3]."""
+    K = np.asarray(K, float)
+    th = np.zeros((K.shape[0], 9))
+    th[:, 0], th[:, 1], th[:, 2], th[:, 3] = K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2]
+    if dist is not None:
+        th[:, 4:] = np.broadcast_to(np.asarray(dist, float), (K.shape[0], 5))
+    return th
+
+
+def perturb_intrinsics(K):
+    """Initial intrinsics of the calibrating-BA test / bench problems: (C,9) [fx fy cx cy k1 k2 p1 p2 k3] with
+    fx * 1.01, fy * 0.99, (cx, cy) + (4, -3) px and a small non-zero distortion vector, sign alternating per camera.
+    The synthetic observations are pinhole under K, so the optimiser has ~1 % focal error, a few px of principal-point
+    error and the distortion to remove.  CALIB_PRIOR_RHO is the matching prior precision (100 px / unit-coefficient sigma)."""
+    th = theta_from_K(K)
+    for c in range(len(th)):
+        sg = 1.0 if c % 2 == 0 else -1.0
+        th[c, 0] *= 1.0 + sg * (CALIB_THETA_PERTURB[0] - 1.0)
+        th[c, 1] *= 1.0 + sg * (CALIB_THETA_PERTURB[1] - 1.0)
+        th[c, 2:4] += sg * CALIB_THETA_PERTURB[2:4]
+        th[c, 4:] = sg * CALIB_THETA_PERTURB[4:]
+    return th
+
+
+def theta_to_K_dist(th):
+    """(C,9) intrinsic vectors -> K (C,3,3), dist (C,5)."""
+    th = np.asarray(th, float)
+    K = np.zeros((len(th), 3, 3))
+    K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = th[:, 0], th[:, 1], th[:, 2], th[:, 3], 1.0
+    return K, th[:, 4:].copy()
+
+
 def make_clip_device(rig_name: str, T: int, J: int, device, seed: int = 0, noise_px: float = 1.0, layout: str = "TCJ2",
                      chunk_frames: int = 65536):
     """Same statistical model as make_clip but generated on the GPU with torch (synthetic-data

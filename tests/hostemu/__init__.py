@@ -44,3 +44,26 @@ def triangulate(cams, V, kpts_vm, conf_vm=None, flags=0, centre=None):
     if rc != 0:
         raise RuntimeError(f"hostemu rc={rc}")
     return X, err, st
+
+
+def calib_obs(cam24, X, uv):
+    """One camera (24 doubles: R t theta pad), X (N,3) f32, uv (N,2) f32 -> au, av (N,3), bu, bv (N,17), clamped (N,),
+    err2 (N,) exactly as the calibrating-BA kernels compute them (ska_ba_calib.cuh)."""
+    lib = C.CDLL(str(build()))
+    X = np.ascontiguousarray(X, np.float32)
+    uv = np.ascontiguousarray(uv, np.float32)
+    cam = np.ascontiguousarray(cam24, np.float64)
+    N = X.shape[0]
+    au, av = np.zeros((N, 3), np.float32), np.zeros((N, 3), np.float32)
+    bu, bv = np.zeros((N, 17), np.float32), np.zeros((N, 17), np.float32)
+    cl, e2 = np.zeros(N, np.uint8), np.zeros(N, np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.hostemu_calib_obs(p(cam), p(X), p(uv), C.c_int64(N), p(au), p(av), p(bu), p(bv), p(cl), p(e2))
+    if rc != 0:
+        raise RuntimeError(f"hostemu rc={rc}")
+    return au, av, bu, bv, cl, e2
+
+
+def calib_tri_maps():
+    lib = C.CDLL(str(build()))
+    return lib.hostemu_calib_tri, lib.hostemu_calib_tri_row, lib.hostemu_calib_tri_col

@@ -238,3 +238,35 @@ extern "C" void hostemu_project_loss(const double* R, const double* t, const dou
     project_loss_adjoint<double>(K, o, g[2 * i], g[2 * i + 1], gXc + 3 * i, gK + 6 * i);
   }
 }
+
+// ---- calibrating BA: one observation's linearisation rows (ska_ba_calib.cuh) -------------------------------
+#include "../../skiing_analysis_pytorch_b200/csrc/ska_ba_calib.cuh"
+
+extern "C" int hostemu_calib_obs(const double* cam24, const float* X, const float* uv, int64_t N, float* au, float* av, float* bu,
+                                 float* bv, uint8_t* clamped, float* err2) {
+  CamC c;
+  for (int i = 0; i < 9; ++i) c.R[i] = (float)cam24[i];
+  for (int i = 0; i < 3; ++i) c.t[i] = (float)cam24[9 + i];
+  c.fx = (float)cam24[12]; c.fy = (float)cam24[13]; c.cx = (float)cam24[14]; c.cy = (float)cam24[15];
+  c.k1 = (float)cam24[16]; c.k2 = (float)cam24[17]; c.p1 = (float)cam24[18]; c.p2 = (float)cam24[19]; c.k3 = (float)cam24[20];
+  for (int64_t i = 0; i < N; ++i) {
+    ObsCalib o;
+    calib_obs(c, X + 3 * i, uv[2 * i], uv[2 * i + 1], o);
+    for (int k = 0; k < 3; ++k) {
+      au[3 * i + k] = o.au[k];
+      av[3 * i + k] = o.av[k];
+    }
+    for (int k = 0; k < kCalibRow; ++k) {
+      bu[kCalibRow * i + k] = o.bu[k];
+      bv[kCalibRow * i + k] = o.bv[k];
+    }
+    clamped[i] = o.clamped ? 1 : 0;
+    bool cl;
+    err2[i] = calib_err2(c, X + 3 * i, uv[2 * i], uv[2 * i + 1], cl);
+  }
+  return 0;
+}
+
+extern "C" int hostemu_calib_tri(int r, int s) { return calib_tri(r, s); }
+extern "C" int hostemu_calib_tri_row(int q) { return calib_tri_row(q); }
+extern "C" int hostemu_calib_tri_col(int q) { return calib_tri_col(q); }

@@ -211,3 +211,36 @@ def test_hostemu_view_pair_form_matches_oracle(rig, T, J, use_conf, dist):
     assert (st == 0).all()
     X1, e1, _ = hostemu.triangulate(cams, V, k, c, flags=0)
     assert (np.linalg.norm(X - X1, axis=1) / np.linalg.norm(X1, axis=1)).max() < 1e-6   # same sums in a different order
+
+
+def test_hostemu_calib_observation_rows_match_oracle():
+    """The calibrating-BA per-observation arithmetic (ska_ba_calib.cuh, fp32) against oracle/lm_calib.py (fp64):
+    residual, point rows, all 15 camera-parameter rows, trial-cost error."""
+    from oracle import lm_calib as lc
+
+    clip, R0, t0, th, X0 = lc.make_problem("2b", 8, 17)
+    X = X0.reshape(-1, 3)
+    x = clip.x_fm.astype(float).transpose(0, 2, 1, 3).reshape(-1, 2, 2)
+    e, A, B, cl = lc.residual_blocks(X, R0, t0, th, x)
+    for c in range(2):
+        cam = np.zeros(24)
+        cam[:9], cam[9:12], cam[12:21] = R0[c].ravel(), t0[c], th[c]
+        au, av, bu, bv, clamped, e2 = hostemu.calib_obs(cam, X, x[:, c])
+        assert not clamped.any() and not cl.any()
+        # the residual is a difference of ~1e3 px numbers in fp32: 1e-3 px absolute
+        np.testing.assert_allclose(bu[:, 15], e[:, c, 0], atol=2e-3)
+        np.testing.assert_allclose(bv[:, 15], e[:, c, 1], atol=2e-3)
+        np.testing.assert_allclose(e2, (e[:, c] ** 2).sum(-1), rtol=1e-3, atol=1e-3)
+        for got, ref in ((au, A[:, c, 0]), (av, A[:, c, 1]), (bu[:, :15], B[:, c, 0]), (bv[:, :15], B[:, c, 1])):
+            scale = np.abs(ref).max(0)
+            np.testing.assert_allclose(got / np.where(scale > 0, scale, 1), ref / np.where(scale > 0, scale, 1), atol=3e-5)
+
+
+def test_hostemu_calib_triangle_index_maps():
+    tri, row, col = hostemu.calib_tri_maps()
+    q = 0
+    for r in range(17):
+        for s in range(r, 17):
+            assert tri(r, s) == q and row(q) == r and col(q) == s
+            q += 1
+    assert q == 153

@@ -26,7 +26,13 @@ def main():
     kv = d["x2d"].permute(1, 0, 2, 3).contiguous()
     X0 = api.triangulate_reproject(kv, d["K"], R0, t0, want=("X",)).X
     del kv
-    s = ba.BundleAdjuster(d["x2d"], d["conf"], d["K"], R0, t0, X0, max_iters=iters + 8)
+    if "--calib" in sys.argv:  # config 3 with free intrinsics + distortion (15 parameters per camera)
+        K_init, dist_init = synth.theta_to_K_dist(synth.perturb_intrinsics(d["K"]))
+        X0 = api.triangulate_reproject(d["x2d"].permute(1, 0, 2, 3).contiguous(), K_init, R0, t0, want=("X",)).X
+        s = ba.CalibratingBundleAdjuster(d["x2d"], d["conf"], K_init, R0, t0, X0, dist=dist_init, prior_rho=synth.CALIB_PRIOR_RHO,
+                                         prior_theta=synth.theta_from_K(d["K"]), max_iters=iters + 8)
+    else:
+        s = ba.BundleAdjuster(d["x2d"], d["conf"], d["K"], R0, t0, X0, max_iters=iters + 8)
     s.run(3, graph=graph)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
