@@ -13,6 +13,8 @@ tests only ever read the .npz files.  Golden sets:
   G3  bundle_adjustment.loss.project_points / reprojection_loss for every accepted shape, f32+f64
   G4  camera_smooth / baseline_reg / bone_length / pose_temporal scalars
   G7  triangulation.postprocess.post_triage_sequence / post_triage_single / smooth_skeleton (row N2)
+  G8  fuse.main_raw / fuse.confidence / fuse.fuse: rigid alignment, weak-perspective and cross-view confidences,
+      softmax fusion, adaptive EMA (row N3)
   G6  LM history of oracle/lm.py on BASELINE configs 3 and 5 at reduced T, with the REFERENCE's
       reprojection_loss evaluated at the initial and final state of each solve (pins the cost the
       LM minimises; the trajectory itself has no reference implementation - "parity unpinned")
@@ -216,8 +218,65 @@ def g7():
     np.savez_compressed(OUT / "g7_post_triage.npz", **out)
 
 
+def g8():
+    """fuse/main_raw.py's per-frame pipeline + fuse/fuse.py's EMA, run through the reference's own dict-based functions
+    (row N3): _align_right_to_left, weakpersp_reproj_confidence, crossview_consistency_confidence, fuse_frame_3d,
+    temporal_smooth_ema (adaptive and fixed alpha)."""
+    mr = ref_import.load("fuse.main_raw")
+    cf = ref_import.load("fuse.confidence")
+    ff = ref_import.load("fuse.fuse")
+    T, J = 60, 70
+    d = synth.make_fusion_clip(T, J, seed=3, nan_frac=0.05)
+    ids = list(range(J))
+    to_dict = lambda A: {j: A[j].copy() for j in ids}                 # loaders keep every joint id (NaN rows included)
+    fused = np.full((T, J, 3), np.nan)
+    ql, qr, aligned = np.zeros((T, J)), np.zeros((T, J)), np.full((T, J, 3), np.nan)
+    c1l_all, c2_all = np.zeros((T, J)), np.zeros((T, J))
+    seq = []
+    for t in range(T):
+        Xl, Xr, Ul, Ur = (to_dict(d[k][t]) for k in ("Xl", "Xr", "Ul", "Ur"))
+        Xa = mr._align_right_to_left(Xl, Xr, ids)
+        c1l, _, _, _ = cf.weakpersp_reproj_confidence(Xl, Ul, sigma_px=12.0)
+        c1r, _, _, _ = cf.weakpersp_reproj_confidence(Xr, Ur, sigma_px=12.0)
+        c2, _, _, _, _ = cf.crossview_consistency_confidence(
+            Xl, Xr, root_idx=mr.IDX_PELVIS, left_hip_idx=mr.IDX_LHIP, right_hip_idx=mr.IDX_RHIP, left_shoulder_idx=mr.IDX_LSHO,
+            right_shoulder_idx=mr.IDX_RSHO, sigma_3d=0.08, scale_mode="hip")
+        ql[t], qr[t] = np.sqrt(c1l * c2), np.sqrt(c1r * c2)
+        c1l_all[t], c2_all[t] = c1l, c2
+        fd = ff.fuse_frame_3d(Xl, Xa, ql[t], qr[t], ids)
+        seq.append(fd)
+        for j in ids:
+            if j in Xa:
+                aligned[t, j] = Xa[j]
+            if j in fd:
+                fused[t, j] = fd[j]
+    # a second sequence with 25 % of the joints missing (runs of NaN: the hold / reset branches of fuse.py:400-404)
+    rng = np.random.default_rng(8)
+    sparse = fused.copy()
+    sparse[rng.random((T, J)) < 0.25] = np.nan
+    sparse[10:14, :8] = np.nan
+    seq_sparse = [{j: sparse[t, j].copy() for j in ids if np.isfinite(sparse[t, j]).all()} for t in range(T)]
+
+    def ema(src=None, **kw):
+        out = ff.temporal_smooth_ema(seq if src is None else src, ids, **kw)
+        Y = np.full((T, J, 3), np.nan)
+        for t in range(T):
+            for j, v in out[t].items():
+                Y[t, j] = v
+        return Y
+    np.savez_compressed(
+        OUT / "g8_fusion.npz", Xl=d["Xl"], Xr=d["Xr"], Ul=d["Ul"], Ur=d["Ur"], fused=fused, q_l=ql, q_r=qr, aligned=aligned,
+        conf1_l=c1l_all, conf2=c2_all, ema_adaptive=ema(alpha=0.7, adaptive=True, alpha_min=0.45, alpha_max=0.92, speed_gain=0.25),
+        ema_fixed=ema(alpha=0.7, adaptive=False), fused_sparse=sparse,
+        ema_sparse=ema(seq_sparse, alpha=0.7, adaptive=True, alpha_min=0.45, alpha_max=0.92, speed_gain=0.25), ema_gain=ema(alpha=0.6, adaptive=True, alpha_min=0.3, alpha_max=0.95, speed_gain=2.0))
+    print("g8 written: missing fused joints", int(np.isnan(fused[..., 0]).sum()), "of", T * J)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    if "--only-g8" in sys.argv:
+        return g8()
+    g8()
     g7()
     g1()
     g2()

@@ -216,3 +216,31 @@ def make_clip_device(rig_name: str, T: int, J: int, device, seed: int = 0, noise
             x2d[:, a:b] = obs.permute(1, 0, 2, 3)
             conf[:, a:b] = cf.permute(1, 0, 2)
     return dict(x2d=x2d, conf=conf, X=X, R=R, t=t, K=K)
+
+
+def make_fusion_clip(T: int, J: int = 70, seed: int = 0, nan_frac: float = 0.03, outlier_frac: float = 0.05, dtype=np.float64):
+    """Two monocular 3D estimates of the same skeleton (what SAM-3D-Body gives per view: `pred_keypoints_3d` in each
+    camera's own frame + `pred_keypoints_2d`; fuse/main_raw.py:192-197) for the fusion path.
+    Xl / Xr (T,J,3): the ground truth in the left / right camera frame of rig '2b' + N(0, 2 cm) + a few 30 cm outliers;
+    Ul / Ur (T,J,2): pinhole pixels + N(0, 2 px); a fraction of joints is missing (NaN rows) in either view - except the
+    five key joints of the canonical frame, which only go missing in whole frames (1 %).  Returns dict of arrays."""
+    rng = np.random.default_rng(seed)
+    R, t = rig("2b")
+    X = skeleton_clip(T, J, rng)
+    out = {}
+    for name, v in (("l", 0), ("r", 1)):
+        Xc = X @ R[v].T + t[v]
+        U = pinhole(X, R[v], t[v], K_CALIB) + rng.normal(0.0, 2.0, (T, J, 2))
+        Xn = Xc + rng.normal(0.0, 0.02, Xc.shape)
+        o = rng.random((T, J)) < outlier_frac
+        Xn[o] += rng.normal(0.0, 0.3, (int(o.sum()), 3))
+        m3 = rng.random((T, J)) < nan_frac
+        m2 = rng.random((T, J)) < nan_frac
+        key = [k for k in (14, 11, 12, 5, 6) if k < J]
+        m3[:, key] = False
+        whole = rng.random(T) < 0.01
+        m3[np.ix_(whole, key)] = True
+        Xn[m3] = np.nan
+        U[m2] = np.nan
+        out["X" + name], out["U" + name] = Xn.astype(dtype), U.astype(dtype)
+    return out

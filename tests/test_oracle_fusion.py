@@ -1,0 +1,52 @@
+"""The fusion oracle (oracle/fusion.py, array form) against golden G8 = outputs of the reference's own dict-based
+fuse/main_raw.py, fuse/confidence.py and fuse/fuse.py.  Same LAPACK calls in the same order: 1e-12."""
+import numpy as np
+import pytest
+
+from oracle import fusion as F
+
+
+def test_fuse_clip_matches_reference(golden):
+    g = golden("g8_fusion.npz")
+    fused, ql, qr, Xa = F.fuse_clip(g["Xl"], g["Xr"], g["Ul"], g["Ur"])
+    np.testing.assert_allclose(Xa, g["aligned"], rtol=1e-12, atol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(ql, g["q_l"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(qr, g["q_r"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(fused, g["fused"], rtol=1e-12, atol=1e-12, equal_nan=True)
+    assert np.isnan(g["fused"]).any() and (g["q_l"] > 0.5).any() and (g["q_l"] < 0.1).any()
+    c1, _ = F.weakpersp_reproj_confidence(g["Xl"][5], g["Ul"][5])
+    c2, _ = F.crossview_consistency_confidence(g["Xl"][5], g["Xr"][5])
+    np.testing.assert_allclose(c1, g["conf1_l"][5], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(c2, g["conf2"][5], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("key,kw", [
+    ("ema_adaptive", dict(alpha=0.7, adaptive=True, alpha_min=0.45, alpha_max=0.92, speed_gain=0.25)),
+    ("ema_fixed", dict(alpha=0.7, adaptive=False)),
+    ("ema_gain", dict(alpha=0.6, adaptive=True, alpha_min=0.3, alpha_max=0.95, speed_gain=2.0)),
+])
+def test_ema_matches_reference(golden, key, kw):
+    g = golden("g8_fusion.npz")
+    Y = F.temporal_smooth_ema(g["fused"], **kw)
+    np.testing.assert_allclose(Y, g[key], rtol=1e-13, atol=1e-13, equal_nan=True)
+
+
+def test_ema_hold_and_reset_branches_match_reference(golden):
+    g = golden("g8_fusion.npz")
+    Y = F.temporal_smooth_ema(g["fused_sparse"], alpha=0.7, adaptive=True, alpha_min=0.45, alpha_max=0.92, speed_gain=0.25)
+    np.testing.assert_allclose(Y, g["ema_sparse"], rtol=1e-13, atol=1e-13, equal_nan=True)
+    assert np.isnan(g["fused_sparse"][..., 0]).mean() > 0.2 and np.isnan(g["ema_sparse"][..., 0]).mean() < 0.05
+
+
+def test_reference_errors_and_fallbacks():
+    d = np.full((70, 3), np.nan)
+    with pytest.raises(ValueError):
+        F.weakpersp_reproj_confidence(d, np.zeros((70, 2)))
+    X = np.random.default_rng(0).normal(size=(70, 3))
+    Xr = X.copy()
+    Xr[2:] = np.nan  # fewer than 3 common joints: right view returned unchanged (main_raw.py:83-84)
+    np.testing.assert_array_equal(F.align_right_to_left(X, Xr), Xr)
+    Xk = X.copy()
+    Xk[14] = np.nan  # a key joint missing: canonicalisation undefined -> confidence 0 everywhere (confidence.py:150-153)
+    c, dist = F.crossview_consistency_confidence(Xk, X)
+    assert (c == 0).all() and np.isnan(dist).all()
