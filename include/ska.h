@@ -305,6 +305,41 @@ size_t ska_savgol_workspace_bytes(int64_t T, int32_t S);
 int ska_savgol_f32(const float* d_X, int64_t T, int32_t S, int32_t win, int32_t poly, float* d_out, void* d_workspace,
                    size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Two-view 3D-3D fusion of monocular pose estimates + adaptive EMA smoothing, whole clip per call.
+ * Replaces the per-frame numpy of the reference's `fuse` pipeline (fuse/main_raw.py:199-250):
+ *   _align_right_to_left (Kabsch, main_raw.py:48-95) -> weakpersp_reproj_confidence per view (fuse/confidence.py:9-108)
+ *   -> crossview_consistency_confidence (confidence.py:118-224) -> q = sqrt(conf1 * conf2) -> fuse_frame_3d
+ *   (softmax2 weights, fuse/fuse.py:87-94, 289-326); then temporal_smooth_ema (fuse/fuse.py:329-412).
+ * All arrays are fp64 device arrays (the reference computes in numpy float64); a missing joint is a NaN row.
+ * ska_fuse_frames_f64: d_Xl, d_Xr (T,J,3) per-view 3D in each view's own frame; d_Ul, d_Ur (T,J,2) pixels; J <= 96.
+ *   d_fused (T,J,3); nullable d_ql, d_qr (T,J), d_aligned (T,J,3) = right view in the left frame, d_status (T,) bit set:
+ *   SKA_FUSE_NO_ALIGN (fewer than 3 common joints: right view used unaligned, main_raw.py:83-84),
+ *   SKA_FUSE_FIT_LEFT_FAILED / _RIGHT_FAILED (weak-perspective fit impossible: the reference raises ValueError,
+ *   confidence.py:31-32,52-53; the frame's outputs are NaN).
+ * ska_ema_f64: d_X (T,J,3) -> d_Y (T,J,3) (may not alias); d_alpha_joint (J,) per-joint base alpha (fuse.py:362-376);
+ *   adaptive != 0: alpha_t = clip(alpha_joint + speed_gain |x_t - y_{t-1}|, alpha_min, alpha_max), else the fixed `alpha`.
+ *   Frames are processed in chunks of `chunk` frames, each replaying `halo` finite samples before its start; halo < 0
+ *   (or chunk >= T) runs the exact sequential scan.  The recurrence contracts by rho = max(1 - alpha_min,
+ *   |1 + alpha_min - 2 alpha_max|) per step, so halo >= log(1e-18) / log(rho) reproduces the sequential result to below
+ *   fp64 rounding. */
+typedef struct SkaFuseParams {
+  double sigma_px;     /* 12.0  (main_raw.py:133) */
+  double sigma_3d;     /* 0.08  (main_raw.py:134) */
+  int32_t scale_mode;  /* 0 = "hip", 1 = "torso" (confidence.py:170-175) */
+  int32_t min_points;  /* 8     (confidence.py:12) */
+  int32_t root, lhip, rhip, lsho, rsho; /* 14, 11, 12, 5, 6 (main_raw.py:18-22) */
+  int32_t pad_;        /* 0; bit 0 set = always take the Jacobi SVD path of the rigid alignment (test hook) */
+} SkaFuseParams;
+#define SKA_FUSE_NO_ALIGN 1
+#define SKA_FUSE_FIT_LEFT_FAILED 2
+#define SKA_FUSE_FIT_RIGHT_FAILED 4
+int ska_fuse_frames_f64(const double* d_Xl, const double* d_Xr, const double* d_Ul, const double* d_Ur, int64_t T, int32_t J,
+                        const SkaFuseParams* prm, double* d_fused, double* d_ql, double* d_qr, double* d_aligned,
+                        uint8_t* d_status, void* stream);
+int ska_ema_f64(const double* d_X, int64_t T, int32_t J, const double* d_alpha_joint, int32_t adaptive, double alpha,
+                double alpha_min, double alpha_max, double speed_gain, int64_t chunk, int32_t halo, double* d_Y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

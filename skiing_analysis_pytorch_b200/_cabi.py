@@ -62,6 +62,25 @@ class SkaBaProblem(C.Structure):
     ]
 
 
+class SkaFuseParams(C.Structure):
+    _fields_ = [
+        ("sigma_px", C.c_double),
+        ("sigma_3d", C.c_double),
+        ("scale_mode", C.c_int32),
+        ("min_points", C.c_int32),
+        ("root", C.c_int32),
+        ("lhip", C.c_int32),
+        ("rhip", C.c_int32),
+        ("lsho", C.c_int32),
+        ("rsho", C.c_int32),
+        ("pad_", C.c_int32),
+    ]
+
+
+FUSE_NO_ALIGN, FUSE_FIT_LEFT_FAILED, FUSE_FIT_RIGHT_FAILED = 1, 2, 4
+FUSE_MAX_JOINTS = 96
+
+
 def red_layout(n_cams: int) -> dict:
     """Offsets inside the packed reduced system d_red (include/ska.h)."""
     nc = n_cams - 1

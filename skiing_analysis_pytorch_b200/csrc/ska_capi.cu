@@ -312,5 +312,30 @@ int ska_ba_calib_control_f64(const SkaBaProblem* p, void* stream) {
   return ba_calib_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, stream);
 }
 
+int ska_fuse_frames_f64(const double* d_Xl, const double* d_Xr, const double* d_Ul, const double* d_Ur, int64_t T, int32_t J,
+                        const SkaFuseParams* prm, double* d_fused, double* d_ql, double* d_qr, double* d_aligned,
+                        uint8_t* d_status, void* stream) {
+  if (prm == nullptr) return set_error(SKA_EINVAL, "prm must not be NULL");
+  if (T < 0 || J < 1 || J > 96) return set_error(SKA_EINVAL, "T must be >= 0 and 1 <= J <= 96");
+  if (T > 0 && (d_Xl == nullptr || d_Xr == nullptr || d_Ul == nullptr || d_Ur == nullptr || d_fused == nullptr))
+    return set_error(SKA_EINVAL, "d_Xl, d_Xr, d_Ul, d_Ur and d_fused must not be NULL");
+  const int32_t key[5] = {prm->root, prm->lhip, prm->rhip, prm->lsho, prm->rsho};
+  for (int k = 0; k < 5; ++k)
+    if (key[k] < 0 || key[k] >= J) return set_error(SKA_EINVAL, "key joint index outside 0..J-1");
+  if (prm->scale_mode != 0 && prm->scale_mode != 1) return set_error(SKA_EINVAL, "scale_mode must be 0 (hip) or 1 (torso)");
+  if (prm->min_points < 1) return set_error(SKA_EINVAL, "min_points must be >= 1");
+  return fuse_frames(d_Xl, d_Xr, d_Ul, d_Ur, T, J, *prm, d_fused, d_ql, d_qr, d_aligned, d_status, (cudaStream_t)stream);
+}
+
+int ska_ema_f64(const double* d_X, int64_t T, int32_t J, const double* d_alpha_joint, int32_t adaptive, double alpha,
+                double alpha_min, double alpha_max, double speed_gain, int64_t chunk, int32_t halo, double* d_Y, void* stream) {
+  if (T < 0 || J < 1) return set_error(SKA_EINVAL, "T must be >= 0 and J >= 1");
+  if (T > 0 && (d_X == nullptr || d_Y == nullptr || d_alpha_joint == nullptr))
+    return set_error(SKA_EINVAL, "d_X, d_Y and d_alpha_joint must not be NULL");
+  if (d_X == d_Y && T > 0) return set_error(SKA_EINVAL, "d_Y may not alias d_X");
+  if (!(alpha_min <= alpha_max)) return set_error(SKA_EINVAL, "alpha_min must be <= alpha_max");
+  return ema_smooth(d_X, T, J, d_alpha_joint, adaptive, alpha, alpha_min, alpha_max, speed_gain, chunk, halo, d_Y, (cudaStream_t)stream);
+}
+
 #pragma GCC visibility pop
 }  // extern "C"
