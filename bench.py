@@ -371,6 +371,61 @@ def run_tri_8view(a, dev, world, barrier, dist):
                          "note": "fp32-pipe bound: ~800 FMA-pipe cycles per 32 points = the HBM roofline time"}}
 
 
+def run_fusion(a, dev, world, barrier, dist):
+    """Row N3: two-view 3D fusion + adaptive EMA of 1M frames x 70 joints per GPU (fp64 like the reference's numpy);
+    frames shard by range with no collective (the EMA chunks replay their own halo).  Extra object `fusion`."""
+    import torch
+
+    from skiing_analysis_pytorch_b200 import fusion, synth
+
+    T, J = 1_000_000, 70
+    small = synth.make_fusion_clip(2000, J, seed=0)
+    reps = (T + 1999) // 2000
+    d = {k: torch.from_numpy(v).to(dev).repeat(reps, 1, 1)[:T].contiguous() for k, v in small.items()}
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / n
+
+    ms_f = timed(lambda: fusion.fuse_clip(d["Xl"], d["Xr"], d["Ul"], d["Ur"], want=(), strict=False), 5)
+    fused = fusion.fuse_clip(d["Xl"], d["Xr"], d["Ul"], d["Ur"], want=(), strict=False).fused
+    ms_e = timed(lambda: fusion.temporal_smooth_ema(fused), 5)
+    peak, _ = hbm_peak()
+    b_f, b_e = T * J * 104, T * J * 48
+    out = {"workload": "1M frames x 70 joints per GPU: Kabsch alignment + weak-perspective / cross-view confidences + softmax fusion, then adaptive EMA (fp64)",
+           "fuse_ms": ms_f, "ema_ms": ms_e, "value": world * T / ((ms_f + ms_e) * 1e-3), "unit": "frames/s",
+           "roofline_fuse": {"bound": "hbm", "achieved": b_f / ms_f / 1e6, "peak": peak, "unit": "GB/s", "frac": b_f / ms_f / 1e6 / peak,
+                             "bytes_per_joint": 104, "note": "fp64-pipe / latency bound (per-frame 3x3 polar iteration, 42 warp reductions): DESIGN.md 3.6"},
+           "roofline_ema": {"bound": "hbm", "achieved": b_e / ms_e / 1e6, "peak": peak, "unit": "GB/s", "frac": b_e / ms_e / 1e6 / peak,
+                            "bytes_per_joint": 48, "note": "chunks of 512 frames replay a 70-sample halo (+14 % reads)"}}
+    del d, fused
+    torch.cuda.empty_cache()
+    return out
+
+
+def fusion_cpu_rate(frames=600):
+    """The reference's per-frame numpy fusion + EMA (array form, oracle/fusion.py) on one core."""
+    from oracle import fusion as F
+    from skiing_analysis_pytorch_b200 import synth
+
+    d = synth.make_fusion_clip(frames, 70, seed=0)
+    t0 = time.perf_counter()
+    fz, *_ = F.fuse_clip(d["Xl"], d["Xr"], d["Ul"], d["Ur"])
+    F.temporal_smooth_ema(fz)
+    return frames / (time.perf_counter() - t0)
+
+
 def run_ours(a, out_fd=1):
     import torch
     import torch.distributed as dist
@@ -511,6 +566,11 @@ def run_ours(a, out_fd=1):
     if not a.no_extra:
         line["tri_8view"] = run_tri_8view(a, dev, world, barrier, dist)
         torch.cuda.empty_cache()
+    if not a.no_extra:
+        line["fusion"] = run_fusion(a, dev, world, barrier, dist)
+        if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
+            line["fusion"]["cpu_baseline"] = {"value": fusion_cpu_rate(), "unit": "frames/s", "cores": 1, "kind": "port",
+                                              "sample": "600 frames x 70 joints through the reference's per-frame numpy path (oracle/fusion.py)"}
     if not a.no_ba:
         line["ba"] = run_ba(a, dev, world, rank, barrier, dist)
         line["gpu_launches_ba_per_iter"] = 6

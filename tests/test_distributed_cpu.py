@@ -75,6 +75,54 @@ def test_sharded_lm_over_gloo_matches_single_process_oracle(tmp_path, world, rig
     assert sum(int(o["b"]) - int(o["a"]) for o in outs) == T
 
 
+def _calib_worker(rank, world, port, T, J, iters, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    from oracle import lm_calib as lc
+    from skiing_analysis_pytorch_b200.ba import frame_shard
+    from tests.oracle_engine import OracleCalibratingBundleAdjuster
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        clip, R0, t0, th, X0 = lc.make_problem("2b", T, J)
+        a, b = frame_shard(T, world, rank)
+        ba = OracleCalibratingBundleAdjuster(clip.x_fm[a:b], clip.conf_fm[a:b], th, R0, t0, X0[a:b], max_iters=iters,
+                                             prior_theta=lc.intr_from_K(clip.K), prior_rho=lc.PRIOR_RHO)
+        ba.run(iters)
+        np.savez(Path(out_dir) / f"rank{rank}.npz", th=ba.th, R=ba.R,
+                 hist=np.array([[h["cost"], h["trial_cost"], h["lam"], float(h["accepted"])] for h in ba.history]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_calibrating_lm_over_gloo_matches_single_process_oracle(tmp_path, world):
+    """The calibrating BA's payload (n = 15 C - 6 reduced system + two 17 x 17 camera blocks, include/ska.h) is a plain
+    sum over frames: frame-sharded ranks all-reducing it reproduce oracle/lm_calib.py's single-process trajectory."""
+    from oracle import lm_calib as lc
+
+    T, J, iters = 31, 17, 6
+    mp.spawn(_calib_worker, args=(world, _free_port(), T, J, iters, str(tmp_path)), nprocs=world, join=True)
+    clip, R0, t0, th, X0 = lc.make_problem("2b", T, J)
+    R, t, th1, X, hist = lc.run_lm(X0, R0, t0, th, clip.x_fm, clip.conf_fm, num_iters=iters, prior_theta=lc.intr_from_K(clip.K),
+                                   prior_rho=lc.PRIOR_RHO)
+    ref = np.array([[h["cost"], h["trial_cost"], h["lam"], float(h["accepted"])] for h in hist])
+    outs = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    for o in outs:
+        np.testing.assert_allclose(o["hist"][:, :2], ref[:, :2], rtol=1e-8)
+        decisive = np.abs(ref[:, 0] - ref[:, 1]) > 1e-8 * ref[:, 0]
+        n_ok = len(decisive) if decisive.all() else int(np.argmin(decisive))
+        assert n_ok >= 3
+        np.testing.assert_array_equal(o["hist"][:n_ok, 3], ref[:n_ok, 3])
+        if n_ok == len(decisive):
+            np.testing.assert_allclose(o["th"], th1, rtol=1e-6, atol=1e-6)
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o["hist"], outs[0]["hist"])
+        np.testing.assert_array_equal(o["th"], outs[0]["th"])
+
+
 def test_frame_shard_partitions_the_clip():
     from skiing_analysis_pytorch_b200.ba import frame_shard
 
