@@ -340,6 +340,27 @@ int ska_fuse_frames_f64(const double* d_Xl, const double* d_Xr, const double* d_
 int ska_ema_f64(const double* d_X, int64_t T, int32_t J, const double* d_alpha_joint, int32_t adaptive, double alpha,
                 double alpha_min, double alpha_max, double speed_gain, int64_t chunk, int32_t halo, double* d_Y, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * First-order (Adam) form of the regularised bundle adjustment: the update kernels.  The objective
+ *   w_reproj * reprojection_loss + w_smooth * camera_smooth_loss + w_baseline * baseline_reg_loss
+ *   + w_bone_length * bone_length_loss + w_pose_temporal * pose_temporal_loss      (bundle_adjustment/loss.py:90-155)
+ * with the weights, `lr` and `num_iters` of configs/vggt.yaml:43-52 and per-frame cameras (vggt/multi_view_process.py:546-564)
+ * is evaluated, value and analytic gradient, by the loss entry points above; these three apply the step
+ * (specification: oracle/first_order.py).
+ *   ska_adam_step_*: torch.optim.Adam's update on n elements: m <- m + (1-beta1)(g-m); v <- beta2 v + (1-beta2) g^2;
+ *       step = step_size * m / (sqrt(v) * inv_sqrt_bc2 + eps), step_size = lr / (1 - beta1^k), inv_sqrt_bc2 = 1 / sqrt(1 - beta2^k);
+ *       d_p (nullable) <- d_p - step; d_step_out (nullable) <- step.
+ *   ska_so3_tangent_grad_*: n rotations (row-major 3x3) and dL/dR -> gradient w.r.t. the left tangent of R = exp([w]x) R.
+ *   ska_so3_retract_*: R <- exp([-step]x) R. */
+int ska_adam_step_f32(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, double step_size, double beta1, double beta2,
+                      double eps, double inv_sqrt_bc2, float* d_step_out, void* stream);
+int ska_adam_step_f64(double* d_p, const double* d_g, double* d_m, double* d_v, int64_t n, double step_size, double beta1, double beta2,
+                      double eps, double inv_sqrt_bc2, double* d_step_out, void* stream);
+int ska_so3_tangent_grad_f32(const float* d_R, const float* d_gR, int64_t n, float* d_gw, void* stream);
+int ska_so3_tangent_grad_f64(const double* d_R, const double* d_gR, int64_t n, double* d_gw, void* stream);
+int ska_so3_retract_f32(float* d_R, const float* d_step, int64_t n, void* stream);
+int ska_so3_retract_f64(double* d_R, const double* d_step, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ tests only ever read the .npz files.  Golden sets:
   G7  triangulation.postprocess.post_triage_sequence / post_triage_single / smooth_skeleton (row N2)
   G8  fuse.main_raw / fuse.confidence / fuse.fuse: rigid alignment, weak-perspective and cross-view confidences,
       softmax fusion, adaptive EMA (row N3)
+  G9  oracle/first_order.py (Adam on the full configured objective) driven by the reference's bundle_adjustment/loss.py
   G6  LM history of oracle/lm.py on BASELINE configs 3 and 5 at reduced T, with the REFERENCE's
       reprojection_loss evaluated at the initial and final state of each solve (pins the cost the
       LM minimises; the trajectory itself has no reference implementation - "parity unpinned")
@@ -272,10 +273,43 @@ def g8():
     print("g8 written: missing fused joints", int(np.isnan(fused[..., 0]).sum()), "of", T * J)
 
 
+def first_order_problem(T=24, J=17, seed=0):
+    """Per-frame cameras as vggt/multi_view_process.py:546-551 passes them: the perturbed rig of oracle/lm.py plus a small
+    per-frame jitter (so camera_smooth / baseline_reg have something to do)."""
+    from oracle import lm
+
+    clip, R0, t0, X0 = lm.make_problem("2b", T, J, seed)
+    rng = np.random.default_rng(seed + 7)
+    R = np.stack([[synth.so3_exp(rng.normal(0.0, 2e-3, 3)) @ R0[c] for c in range(2)] for _ in range(T)])
+    t = np.broadcast_to(t0[None], (T, 2, 3)) + rng.normal(0.0, 0.01, (T, 2, 3))
+    return clip, R, t, X0
+
+
+def g9():
+    """Adam on the reference's full configured objective (oracle/first_order.py) with the loss VALUES computed by the
+    reference's own bundle_adjustment/loss.py (row N1, first-order form)."""
+    import torch
+
+    from oracle import first_order as FO
+
+    L = ref_import.load("bundle_adjustment.loss")
+    clip, R, t, X0 = first_order_problem()
+    out = dict(R0=R, t0=t, X0=X0, K=clip.K, x2d=clip.x_fm, conf=clip.conf_fm)
+    for mode in FO.MODES:
+        Ro, to, Xo, hist = FO.run_adam(L, clip.K, R, t, X0, clip.x_fm, clip.conf_fm, num_iters=25, lr=1e-2, mode=mode)
+        out[f"{mode}_hist"] = np.array([[h["loss"]] + [h[k] for k in FO.TERMS] for h in hist])
+        out[f"{mode}_R"], out[f"{mode}_t"], out[f"{mode}_X"] = Ro.numpy(), to.numpy(), Xo.numpy()
+    np.savez_compressed(OUT / "g9_first_order.npz", **out)
+    print("g9 written:", {m: (out[f"{m}_hist"][0, 0], out[f"{m}_hist"][-1, 0]) for m in FO.MODES})
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     if "--only-g8" in sys.argv:
         return g8()
+    if "--only-g9" in sys.argv:
+        return g9()
+    g9()
     g8()
     g7()
     g1()

@@ -86,6 +86,15 @@ int flag_counts(const uint8_t* flags, int64_t T, int J, int32_t* out, cudaStream
 size_t savgol_workspace_bytes(int64_t T, int S);
 int savgol(const float* X, int64_t T, int S, int win, int poly, float* out, void* ws, size_t ws_bytes, cudaStream_t s);
 
+// first-order optimiser updates (ska_optim.cu)
+template <typename S>
+int adam_step(S* p, const S* g, S* m, S* v, int64_t n, double step_size, double b1, double b2, double eps, double inv_sqrt_bc2, S* step_out,
+              cudaStream_t s);
+template <typename S>
+int so3_tangent_grad(const S* R, const S* gR, int64_t n, S* gw, cudaStream_t s);
+template <typename S>
+int so3_retract(S* R, const S* step, int64_t n, cudaStream_t s);
+
 // two-view 3D fusion + EMA (ska_fuse.cu)
 int fuse_frames(const double* Xl, const double* Xr, const double* Ul, const double* Ur, int64_t T, int J, const SkaFuseParams& prm,
                 double* fused, double* ql, double* qr, double* aligned, uint8_t* status, cudaStream_t s);
