@@ -329,7 +329,8 @@ typedef struct SkaFuseParams {
   int32_t scale_mode;  /* 0 = "hip", 1 = "torso" (confidence.py:170-175) */
   int32_t min_points;  /* 8     (confidence.py:12) */
   int32_t root, lhip, rhip, lsho, rsho; /* 14, 11, 12, 5, 6 (main_raw.py:18-22) */
-  int32_t pad_;        /* 0; bit 0 set = always take the Jacobi SVD path of the rigid alignment (test hook) */
+  int32_t pad_;        /* flags: bit 0 = always take the Jacobi SVD path of the rigid alignment (test hook);
+                          bit 1 = skip the rigid alignment (views already in one frame: fuse/main_unity.py:96-132) */
 } SkaFuseParams;
 #define SKA_FUSE_NO_ALIGN 1
 #define SKA_FUSE_FIT_LEFT_FAILED 2

@@ -195,13 +195,14 @@ def temporal_smooth_ema(X, target_ids=None, alpha=0.7, adaptive=True, alpha_min=
     return Y
 
 
-def fuse_clip(Xl, Xr, Ul, Ur, sigma_px=12.0, sigma_3d=0.08, scale_mode="hip"):
-    """The per-frame pipeline of fuse/main_raw.py:199-250 on (T,J,.) arrays.
+def fuse_clip(Xl, Xr, Ul, Ur, sigma_px=12.0, sigma_3d=0.08, scale_mode="hip", align=True):
+    """The per-frame pipeline of fuse/main_raw.py:199-250 on (T,J,.) arrays; align=False is fuse/main_unity.py:96-132
+    (both views already share a coordinate system: no rigid alignment).
     Returns fused (T,J,3), q_l (T,J), q_r (T,J), Xr_aligned (T,J,3)."""
     T, J, _ = Xl.shape
     fused, ql, qr, Xa = (np.full((T, J, 3), np.nan), np.zeros((T, J)), np.zeros((T, J)), np.full((T, J, 3), np.nan))
     for t in range(T):
-        Xa[t] = align_right_to_left(Xl[t], Xr[t])
+        Xa[t] = align_right_to_left(Xl[t], Xr[t]) if align else Xr[t]
         c1l, _ = weakpersp_reproj_confidence(Xl[t], Ul[t], sigma_px)
         c1r, _ = weakpersp_reproj_confidence(Xr[t], Ur[t], sigma_px)
         c2, _ = crossview_consistency_confidence(Xl[t], Xr[t], sigma_3d, scale_mode)

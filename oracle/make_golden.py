@@ -265,8 +265,29 @@ def g8():
             for j, v in out[t].items():
                 Y[t, j] = v
         return Y
+    # fuse/main_unity.py:_fuse_pair (:96-132): the same pipeline WITHOUT the rigid alignment on the 15 Unity target joints
+    # (the key indices 14, 11, 12, 5, 6 are then POSITIONS in the 15-joint array, as the reference uses them)
+    mu = ref_import.load("fuse.main_unity")
+    du = synth.make_fusion_clip(40, 15, seed=5, nan_frac=0.04)
+    du["Xr"] = du["Xl"] + np.random.default_rng(6).normal(0.0, 0.03, du["Xl"].shape)   # both views in one coordinate system
+    mk = lambda A: {jid: A[k] for k, jid in enumerate(mu.TARGET_IDS)}
+    seq_a = [{"p2d": mk(du["Ul"][t]), "p3d": mk(du["Xl"][t])} for t in range(40)]
+    seq_b = [{"p2d": mk(du["Ur"][t]), "p3d": mk(du["Xr"][t])} for t in range(40)]
+    fu = mu._fuse_pair(seq_a, seq_b, sigma_px=12.0, sigma_3d=0.08)
+    unity = np.full((40, 15, 3), np.nan)
+    for t in range(40):
+        for k, jid in enumerate(mu.TARGET_IDS):
+            if jid in fu[t]:
+                unity[t, k] = fu[t][jid]
+    su = ff.temporal_smooth_ema(fu, mu.TARGET_IDS, alpha=0.7, adaptive=True, alpha_min=0.45, alpha_max=0.92, speed_gain=0.25)
+    unity_s = np.full((40, 15, 3), np.nan)
+    for t in range(40):
+        for k, jid in enumerate(mu.TARGET_IDS):
+            if jid in su[t]:
+                unity_s[t, k] = su[t][jid]
     np.savez_compressed(
-        OUT / "g8_fusion.npz", Xl=d["Xl"], Xr=d["Xr"], Ul=d["Ul"], Ur=d["Ur"], fused=fused, q_l=ql, q_r=qr, aligned=aligned,
+        OUT / "g8_fusion.npz", unity_Xl=du["Xl"], unity_Xr=du["Xr"], unity_Ul=du["Ul"], unity_Ur=du["Ur"], unity_fused=unity,
+        unity_smooth=unity_s, unity_ids=np.array(mu.TARGET_IDS), Xl=d["Xl"], Xr=d["Xr"], Ul=d["Ul"], Ur=d["Ur"], fused=fused, q_l=ql, q_r=qr, aligned=aligned,
         conf1_l=c1l_all, conf2=c2_all, ema_adaptive=ema(alpha=0.7, adaptive=True, alpha_min=0.45, alpha_max=0.92, speed_gain=0.25),
         ema_fixed=ema(alpha=0.7, adaptive=False), fused_sparse=sparse,
         ema_sparse=ema(seq_sparse, alpha=0.7, adaptive=True, alpha_min=0.45, alpha_max=0.92, speed_gain=0.25), ema_gain=ema(alpha=0.6, adaptive=True, alpha_min=0.3, alpha_max=0.95, speed_gain=2.0))

@@ -349,7 +349,9 @@ __global__ void __launch_bounds__(128, SKA_FUSE_MINB) fuse_frames_kernel(const F
   for (int k = 0; k < kFuseJPL; ++k)
 #pragma unroll
     for (int d = 0; d < 3; ++d) Xa[k][d] = Xr[k][d];
-  if (cnt >= 3.0) {
+  if ((a.prm.pad_ & 2) != 0) {
+    // flags bit 1: the views already share a coordinate system (fuse/main_unity.py:96-132): no rigid alignment
+  } else if (cnt >= 3.0) {
     double mr[3], ml[3], H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int d = 0; d < 3; ++d) {

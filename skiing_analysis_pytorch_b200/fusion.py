@@ -52,13 +52,15 @@ def _f64_cuda(x, name, last):
 
 def fuse_clip(Xl, Xr, Ul, Ur, *, sigma_px: float = 12.0, sigma_3d: float = 0.08, scale_mode: str = "hip", min_points: int = 8,
               key_joints=(IDX_PELVIS, IDX_LHIP, IDX_RHIP, IDX_LSHO, IDX_RSHO), want=("q", "aligned"), strict: bool = True,
-              force_jacobi: bool = False) -> FusedClip:
+              force_jacobi: bool = False, align: bool = True) -> FusedClip:
     """Fuse two per-view 3D skeleton sequences.  Xl, Xr (T,J,3) in each view's own frame, Ul, Ur (T,J,2) pixels.
     strict=True raises ValueError if the weak-perspective fit of any frame is impossible (fewer than `min_points`
     joints with finite 3D and 2D, or degenerate 3D), as the reference does (fuse/confidence.py:31-32, 52-53) - this
     reads the status back (one synchronisation); strict=False leaves those frames NaN and reports them in `status`.
     force_jacobi=True runs the one-sided Jacobi SVD for every frame's rigid alignment (the kernel otherwise takes a Newton
-    polar-decomposition fast path when the cross-covariance is well conditioned and not reflected) - a test hook."""
+    polar-decomposition fast path when the cross-covariance is well conditioned and not reflected) - a test hook.
+    align=False skips the rigid alignment: the two views already share a coordinate system, as in the reference's Unity
+    pipeline (fuse/main_unity.py:96-132, 15 target joints whose key indices are positions in that array)."""
     Xl = _f64_cuda(Xl, "Xl", 3)
     T, J, _ = Xl.shape
     Xr, Ul, Ur = _f64_cuda(Xr, "Xr", 3), _f64_cuda(Ul, "Ul", 2), _f64_cuda(Ur, "Ur", 2)
@@ -74,7 +76,7 @@ def fuse_clip(Xl, Xr, Ul, Ur, *, sigma_px: float = 12.0, sigma_3d: float = 0.08,
     dev = Xl.device
     prm = _cabi.SkaFuseParams(sigma_px=float(sigma_px), sigma_3d=float(sigma_3d), scale_mode=0 if scale_mode == "hip" else 1,
                               min_points=int(min_points), root=int(key_joints[0]), lhip=int(key_joints[1]), rhip=int(key_joints[2]),
-                              lsho=int(key_joints[3]), rsho=int(key_joints[4]), pad_=1 if force_jacobi else 0)
+                              lsho=int(key_joints[3]), rsho=int(key_joints[4]), pad_=(1 if force_jacobi else 0) | (0 if align else 2))
     f64 = dict(dtype=torch.float64, device=dev)
     fused = torch.empty((T, J, 3), **f64)
     ql = torch.empty((T, J), **f64) if "q" in want else None

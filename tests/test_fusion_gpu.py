@@ -28,6 +28,16 @@ def test_fuse_clip_matches_reference_golden(cuda, golden):
     assert int(r.status.sum()) == 0
 
 
+def test_unity_pipeline_matches_reference_golden(cuda, golden):
+    """fuse/main_unity.py: no rigid alignment, 15 target joints, the Unity joint ids select the EMA's alpha classes."""
+    g = golden("g8_fusion.npz")
+    r = fusion.fuse_clip(*_dev(cuda, g["unity_Xl"], g["unity_Xr"], g["unity_Ul"], g["unity_Ur"]), align=False)
+    np.testing.assert_allclose(r.fused.cpu().numpy(), g["unity_fused"], rtol=TOL, atol=TOL, equal_nan=True)
+    assert int(r.status.sum()) == 0
+    Y = fusion.temporal_smooth_ema(r.fused, [int(i) for i in g["unity_ids"]], exact=True).cpu().numpy()
+    np.testing.assert_allclose(Y, g["unity_smooth"], rtol=TOL, atol=TOL, equal_nan=True)
+
+
 @pytest.mark.parametrize("J,scale_mode", [(70, "hip"), (70, "torso"), (17, "hip"), (33, "hip"), (96, "torso")])
 def test_fuse_clip_matches_oracle(cuda, J, scale_mode):
     d = synth.make_fusion_clip(257, J, seed=J, nan_frac=0.08)

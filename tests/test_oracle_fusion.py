@@ -38,6 +38,16 @@ def test_ema_hold_and_reset_branches_match_reference(golden):
     assert np.isnan(g["fused_sparse"][..., 0]).mean() > 0.2 and np.isnan(g["ema_sparse"][..., 0]).mean() < 0.05
 
 
+def test_unity_pipeline_without_alignment_matches_reference(golden):
+    """fuse/main_unity.py:_fuse_pair (no rigid alignment, 15 target joints, key indices as array positions) + EMA with
+    the Unity joint ids selecting the per-joint alpha classes."""
+    g = golden("g8_fusion.npz")
+    fused, _, _, _ = F.fuse_clip(g["unity_Xl"], g["unity_Xr"], g["unity_Ul"], g["unity_Ur"], align=False)
+    np.testing.assert_allclose(fused, g["unity_fused"], rtol=1e-12, atol=1e-12, equal_nan=True)
+    Y = F.temporal_smooth_ema(fused, list(g["unity_ids"]))
+    np.testing.assert_allclose(Y, g["unity_smooth"], rtol=1e-13, atol=1e-13, equal_nan=True)
+
+
 def test_reference_errors_and_fallbacks():
     d = np.full((70, 3), np.nan)
     with pytest.raises(ValueError):
