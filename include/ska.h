@@ -248,6 +248,8 @@ int ska_ba_control_f64(const SkaBaProblem* p, void* stream);
  * (triangulation/reproject.py:77-78, bundle_adjustment/reproject.py:147-148) + loss.py's depth clamp (:67):
  *   x = X_c.x/Z, y = X_c.y/Z, r2 = x^2 + y^2, rad = 1 + k1 r2 + k2 r2^2 + k3 r2^3
  *   u = fx (x rad + 2 p1 x y + p2 (r2 + 2 x^2)) + cx,   v = fy (y rad + p1 (r2 + 2 y^2) + 2 p2 x y) + cy
+ * Observations with depth < 1e-6 (loss.py:67's clamp threshold) are EXCLUDED (zero weight, counted): the polynomial
+ * distortion of a clamped projection overflows fp32.
  * 15 parameters per camera: [d_omega(3), d_t(3), fx, fy, cx, cy, k1, k2, p1, p2, k3]; camera 0's extrinsics are the gauge.
  * Cost = loss.py's confidence-weighted mean squared error under that projection
  *        + sum_c sum_k rho_ck (theta_ck - theta0_ck)^2   (optional Gaussian prior on the 9 intrinsics; d_prior).

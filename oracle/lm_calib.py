@@ -12,7 +12,8 @@ PARITY STATUS: "parity unpinned" for the LM trajectory, exactly like oracle/lm.p
     trajectory (and therefore the reference's ``reprojection_loss`` values, golden G3/G6) to rounding.
 
 Model (per camera c, 15 parameters [d_omega(3), d_t(3), fx, fy, cx, cy, k1, k2, p1, p2, k3]):
-  X_c = R X + t;  Z = max(z, 1e-6) (loss.py:67, zero z-derivative while active);  x = X_c.x/Z, y = X_c.y/Z
+  X_c = R X + t;  x = X_c.x/z, y = X_c.y/z; an observation with z < 1e-6 (loss.py:67's clamp threshold: the point is at /
+  behind the camera plane) is EXCLUDED - zero residual and Jacobians, counted in n_clamped
   r2 = x^2 + y^2;  rad = 1 + k1 r2 + k2 r2^2 + k3 r2^3
   x" = x rad + 2 p1 x y + p2 (r2 + 2 x^2);  y" = y rad + p1 (r2 + 2 y^2) + 2 p2 x y
   u = fx x" + cx;  v = fy y" + cy
@@ -110,12 +111,16 @@ def residual_blocks(X, R, t, th, x2d):
     Bu = np.stack([xd, zero, one, zero, fx * x * r2, fx * x * r4, fx * 2 * x * y, fx * (r2 + 2 * x * x), fx * x * r6], -1)
     Bv = np.stack([zero, yd, zero, one, fy * y * r2, fy * y * r4, fy * (r2 + 2 * y * y), fy * 2 * x * y, fy * y * r6], -1)
     B = np.concatenate([Bw, Jx, np.stack([Bu, Bv], -2)], -1)
-    return e, A, B, clamped
+    # a depth-clamped observation is EXCLUDED (zero residual and Jacobians, still counted): the polynomial distortion of a
+    # clamped projection (|x| ~ 1e6) is meaningless and overflows fp32 - see csrc/ska_ba_calib.cuh
+    keep = ~clamped
+    return np.where(keep[..., None], e, 0.0), np.where(keep[..., None, None], A, 0.0), np.where(keep[..., None, None], B, 0.0), clamped
 
 
 def cost_only(X, R, t, th, x2d, w):
     uv, clamped = project(X, R, t, th)
-    return float((w[..., None] * (uv - x2d) ** 2).sum()), int(clamped.sum())
+    d = np.where(clamped[..., None], 0.0, uv - x2d)  # excluded observations
+    return float((w[..., None] * d**2).sum()), int(clamped.sum())
 
 
 def prior_cost(th, th0, rho):

@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(32 * Calib<C>::W, 1) ba_calib_linearize_kernel
     for (int c = 0; c < C; ++c) {
       ObsCalib o;
       calib_obs(s_cam[c], Xp, u[c], v[c], o);
+      cw[c] = o.clamped ? 0.f : cw[c];  // a depth-clamped observation is excluded (ska_ba_calib.cuh)
       pb_add(pb, cw[c], o.au, o.av, o.bu[15], o.bv[15]);
     }
     const Chol3 f = chol3_damped(pb, lam);
@@ -334,14 +335,14 @@ __global__ void __launch_bounds__(kBaBlock, 2) ba_calib_backsub_kernel(const Cal
     for (int c = 0; c < C; ++c) {
       ObsCalib o;
       calib_obs(s_cam[c], Xp, u[c], v[c], o);
-      pb_add(pb, cw[c], o.au, o.av, o.bu[15], o.bv[15]);
+      const float w = o.clamped ? 0.f : cw[c];  // excluded observation
+      pb_add(pb, w, o.au, o.av, o.bu[15], o.bv[15]);
       float lu = o.bu[15], lv = o.bv[15];
 #pragma unroll
       for (int r = (c == 0 ? 6 : 0); r < kCalibP; ++r) {
         lu = fmaf(o.bu[r], s_delta[c][r], lu);
         lv = fmaf(o.bv[r], s_delta[c][r], lv);
       }
-      const float w = cw[c];
       r0 = fmaf(w * o.au[0], lu, fmaf(w * o.av[0], lv, r0));
       r1 = fmaf(w * o.au[1], lu, fmaf(w * o.av[1], lv, r1));
       r2 = fmaf(w * o.au[2], lu, fmaf(w * o.av[2], lv, r2));

@@ -6,7 +6,8 @@
 // Projection = cv2.projectPoints' 5-coefficient model, the one the reference reprojects with
 // (triangulation/reproject.py:77-78, bundle_adjustment/reproject.py:147-148), with loss.py's depth clamp
 // (bundle_adjustment/loss.py:67):
-//   X_c = R X + t;  Z = max(z, 1e-6);  x = X_c.x / Z, y = X_c.y / Z;  r2 = x^2 + y^2
+//   X_c = R X + t;  x = X_c.x / z, y = X_c.y / z;  r2 = x^2 + y^2   (observations with z < 1e-6 - loss.py:67's clamp
+//   threshold - are excluded and counted: a polynomial distortion of a clamped projection is meaningless)
 //   rad = 1 + k1 r2 + k2 r2^2 + k3 r2^3
 //   x" = x rad + 2 p1 x y + p2 (r2 + 2 x^2);   y" = y rad + p1 (r2 + 2 y^2) + 2 p2 x y
 //   u = fx x" + cx;  v = fy y" + cy
@@ -76,10 +77,17 @@ SKA_HD void calib_obs(const CamC& c, const float X[3], float uo, float vo, ObsCa
   const float p0 = fmaf(c.R[0], X[0], fmaf(c.R[1], X[1], c.R[2] * X[2]));
   const float p1 = fmaf(c.R[3], X[0], fmaf(c.R[4], X[1], c.R[5] * X[2]));
   const float p2 = fmaf(c.R[6], X[0], fmaf(c.R[7], X[1], c.R[8] * X[2]));
-  const float xc = p0 + c.t[0], yc = p1 + c.t[1], zc = p2 + c.t[2];
+  float xc = p0 + c.t[0], yc = p1 + c.t[1], zc = p2 + c.t[2];
   o.clamped = zc < kCalibZMin;
-  const float iz = calib_rcp(fmaxf(zc, kCalibZMin));
-  const float live = o.clamped ? 0.0f : 1.0f;  // d/dz vanishes while the clamp is active (autograd of loss.py:67)
+  // A depth-clamped observation (the point is at / behind the camera plane) is EXCLUDED from the calibrating problem:
+  // the caller gives it zero weight (oracle/lm_calib.py does the same).  loss.py's clamp would put it at |x| ~ 1e6,
+  // where the r^6 distortion term overflows fp32 and 0 * inf would poison every sum; evaluating the row at the optical
+  // axis instead keeps all of its entries finite.
+  xc = o.clamped ? 0.0f : xc;
+  yc = o.clamped ? 0.0f : yc;
+  zc = o.clamped ? 1.0f : zc;
+  const float iz = calib_rcp(zc);
+  const float live = 1.0f;
   const float x = xc * iz, y = yc * iz;
   const float xx = x * x, yy = y * y, xy = x * y;
   const float r2 = xx + yy, r4 = r2 * r2, r6 = r4 * r2;
@@ -119,13 +127,14 @@ SKA_HD void calib_obs(const CamC& c, const float X[3], float uo, float vo, ObsCa
   o.bv[16] = 0.0f;
 }
 
-// squared pixel error only (trial cost)
+// squared pixel error only (trial cost); 0 for a depth-clamped (excluded) observation
 SKA_HD float calib_err2(const CamC& c, const float X[3], float uo, float vo, bool& clamped) {
   const float xc = fmaf(c.R[0], X[0], fmaf(c.R[1], X[1], fmaf(c.R[2], X[2], c.t[0])));
   const float yc = fmaf(c.R[3], X[0], fmaf(c.R[4], X[1], fmaf(c.R[5], X[2], c.t[1])));
   const float zc = fmaf(c.R[6], X[0], fmaf(c.R[7], X[1], fmaf(c.R[8], X[2], c.t[2])));
   clamped = zc < kCalibZMin;
-  const float iz = calib_rcp(fmaxf(zc, kCalibZMin));
+  if (clamped) return 0.0f;
+  const float iz = calib_rcp(zc);
   const float x = xc * iz, y = yc * iz;
   const float xx = x * x, yy = y * y, xy = x * y, r2 = xx + yy;
   const float rad = fmaf(r2, fmaf(r2, fmaf(r2, c.k3, c.k2), c.k1), 1.0f);

@@ -172,6 +172,25 @@ def test_unobserved_and_ragged(cuda):
     _check_history(h, ref, 4)
 
 
+def test_clamped_points_are_counted_and_harmless(cuda):
+    """A point behind camera 1 hits loss.py's depth clamp: counted per camera in slot 153 of the camera blocks, zero
+    z-derivative, and the first trial's costs still match the oracle."""
+    clip, R0, t0, th, X0 = lc.make_problem("2b", 40, 17)
+    K, dist = _K_dist(th)
+    X0 = X0.copy()
+    X0[3, 5] = [0.0, 0.0, -5.0]
+    X0[9, 2] = [30.0, 0.0, 10.0]
+    x, c, X = _dev(clip, X0, cuda)
+    s = ba.CalibratingBundleAdjuster(x, c, K, R0, t0, X, dist=dist, prior_rho=lc.PRIOR_RHO)
+    s.run(2)
+    ref = lc.run_lm(X0.astype(np.float32).astype(float), R0, t0, th, clip.x_fm, clip.conf_fm, num_iters=2, prior_theta=th,
+                    prior_rho=lc.PRIOR_RHO)[4]
+    h = s.history
+    assert h[0]["n_clamped"] == ref[0]["n_clamped"] >= 2
+    assert abs(h[0]["cost"] - ref[0]["cost"]) <= 1e-4 * ref[0]["cost"]
+    assert all(np.isfinite(r["trial_cost"]) for r in h)
+
+
 def test_unsupported_camera_count(cuda):
     clip, R0, t0, X0 = lm.make_problem("3", 20, 17)
     x, c, X = _dev(clip, X0, cuda)
