@@ -26,6 +26,20 @@ def main():
     kv = d["x2d"].permute(1, 0, 2, 3).contiguous()
     X0 = api.triangulate_reproject(kv, d["K"], R0, t0, want=("X",)).X
     del kv
+    if "--adam" in sys.argv:  # first-order form of the regularised objective with per-frame cameras (row N1)
+        Rf = torch.tensor(R0, device=dev)[None].expand(T, C, 3, 3).contiguous()
+        tf = torch.tensor(t0, device=dev)[None].expand(T, C, 3).contiguous()
+        dt = torch.float64 if "--f64" in sys.argv else torch.float32
+        for mode in ba.MODES:
+            args = (torch.tensor(d["K"]), Rf.to(dt), tf.to(dt), X0.to(dt), d["x2d"], d["conf"])
+            ba.run_local_ba(*args, num_iters=3, lr=1e-2, mode=mode, optimizer="adam")
+            torch.cuda.synchronize()
+            t0_ = time.perf_counter()
+            _, _, _, h = ba.run_local_ba(*args, num_iters=iters, lr=1e-2, mode=mode, optimizer="adam")
+            torch.cuda.synchronize()
+            ms = 1e3 * (time.perf_counter() - t0_) / iters
+            print(f"{name} adam {mode:10s} {str(dt)[6:]}: T={T} J={J} C={C}  {ms:.3f} ms/iter (wall, incl. Python)  loss {h[0]['loss']:.4f} -> {h[-1]['loss']:.4f}")
+        return
     if "--calib" in sys.argv:  # config 3 with free intrinsics + distortion (15 parameters per camera)
         K_init, dist_init = synth.theta_to_K_dist(synth.perturb_intrinsics(d["K"]))
         X0 = api.triangulate_reproject(d["x2d"].permute(1, 0, 2, 3).contiguous(), K_init, R0, t0, want=("X",)).X

@@ -1,8 +1,10 @@
+# One gpurun call that produces the round's evidence: GPU tests, smoke, the default bench, the ncu launch list of a short
+# bench run and ncu --set full captures of the dominant kernels.  Usage: gpurun --timeout 2400 -- 'bash tools/gpu_round_check.sh TAG'
+TAG=${1:-r1}
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/gpu_tests_r1z.log; cat gpurun_out/gpu_tests_r1z.log
-timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -6 | tee gpurun_out/smoke_r1z.log
-timeout 600 python bench.py > gpurun_out/bench_r1z.json 2> gpurun_out/bench_r1z.err; tail -c 600 gpurun_out/bench_r1z.err; head -c 300 gpurun_out/bench_r1z.json
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:ba_calib_linearize -s 2 -c 1 -o gpurun_out/prof_ba_calib_r1z -f python tools/ba_bench.py c3 100000 3 --calib > gpurun_out/ncu_ba_calib_r1z.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:fuse_frames -s 2 -c 1 -o gpurun_out/prof_fuse_r1z -f python tools/fusion_bench.py 200000 > gpurun_out/ncu_fuse_r1z.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:ema_kernel -s 2 -c 1 -o gpurun_out/prof_ema_r1z -f python tools/fusion_bench.py 1000000 > gpurun_out/ncu_ema_r1z.log 2>&1
-ls -la gpurun_out/*r1z*
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/gpu_tests_$TAG.log; cat gpurun_out/gpu_tests_$TAG.log
+timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -6 | tee gpurun_out/smoke_$TAG.log
+timeout 600 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -c 600 gpurun_out/bench_$TAG.err; head -c 300 gpurun_out/bench_$TAG.json
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; head -c 400 gpurun_out/bench_ref_$TAG.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 3 --warmup 3 --ba-iters 6 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
+ls -la gpurun_out/*$TAG*
