@@ -15,6 +15,8 @@ tests only ever read the .npz files.  Golden sets:
   G7  triangulation.postprocess.post_triage_sequence / post_triage_single / smooth_skeleton (row N2)
   G8  fuse.main_raw / fuse.confidence / fuse.fuse: rigid alignment, weak-perspective and cross-view confidences,
       softmax fusion, adaptive EMA (row N3)
+  G10 on-disk schemas (row N4): .pt keypoint dicts, SAM-3D-Body npz, fuse / triangulation writers - fixture files under
+      tests/golden/io/ and the reference loaders' outputs for them
   G9  oracle/first_order.py (Adam on the full configured objective) driven by the reference's bundle_adjustment/loss.py
   G6  LM history of oracle/lm.py on BASELINE configs 3 and 5 at reduced T, with the REFERENCE's
       reprojection_loss evaluated at the initial and final state of each solve (pins the cost the
@@ -324,8 +326,76 @@ def g9():
     print("g9 written:", {m: (out[f"{m}_hist"][0, 0], out[f"{m}_hist"][-1, 0]) for m in FO.MODES})
 
 
+def g10():
+    """On-disk schemas either side of the path (row N4): fixture files written in the reference's formats - by the
+    reference's own writers where it has one - and what the reference's own loaders return for them."""
+    import json
+    import shutil
+
+    import torch
+    import torchvision.io
+
+    if not hasattr(torchvision.io, "read_video"):  # removed in torchvision 0.26; triangulation/load.py:9 imports it
+        torchvision.io.read_video = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("no video decoding in the golden generator"))
+    io_dir = OUT / "io"
+    if io_dir.exists():
+        shutil.rmtree(io_dir)
+    io_dir.mkdir(parents=True)
+    rng = np.random.default_rng(10)
+    T, K = 9, 17
+    H, W = 1080, 1920
+    out = {}
+    # ---- .pt dicts in the schema of prepare_dataset/process/preprocess.py:157-181
+    tl = ref_import.load("triangulation.load")
+    for side in ("left", "right"):
+        px = np.concatenate([rng.uniform(0, W, (T, K, 1)), rng.uniform(0, H, (T, K, 1)), rng.uniform(0.2, 1, (T, K, 1))], -1).astype(np.float32)
+        nrm = px.copy()
+        nrm[..., 0] /= W
+        nrm[..., 1] /= H
+        pt = {"img_shape": (H, W), "none_index": [],
+              "YOLO": {"bbox": torch.zeros(T, 4), "keypoints": torch.from_numpy(nrm), "keypoints_score": torch.from_numpy(rng.uniform(0, 1, (T, K)).astype(np.float32))},
+              "detectron2": {"bbox": torch.tensor(rng.uniform(0, 1000, (T, 4)).astype(np.float32)), "keypoints": torch.from_numpy(px)}}
+        torch.save(pt, io_dir / f"{side}.pt")
+        xy, sc, _ = tl.load_keypoints_from_yolo_pt(str(io_dir / f"{side}.pt"))
+        out[f"{side}_yolo_xy"], out[f"{side}_yolo_score"] = xy, sc
+        xy, sc, *_ = tl.load_kpt_and_bbox_from_d2_pt(str(io_dir / f"{side}.pt"))
+        out[f"{side}_d2_xy"], out[f"{side}_d2_score"] = xy, sc
+    # ---- SAM-3D-Body outputs: one npz with the frame list (left), a directory of per-frame files (right, one frame longer)
+    lr = ref_import.load("fuse.load.load_raw")
+    d = synth.make_fusion_clip(7, 70, seed=12, dtype=np.float32)
+    frames_l = [{"pred_keypoints_2d": d["Ul"][t], "pred_keypoints_3d": d["Xl"][t], "pred_cam_t": np.zeros(3, np.float32), "focal_length": np.float32(1100)} for t in range(6)]
+    np.savez(io_dir / "osmo_2_sam_3d_body_outputs.npz", outputs=np.array(frames_l, dtype=object))
+    (io_dir / "right").mkdir()
+    for t in range(7):
+        fr = {"pred_keypoints_2d": d["Ur"][t], "pred_keypoints_3d": d["Xr"][t], "pred_cam_t": np.zeros(3, np.float32), "focal_length": np.float32(1100)}
+        np.savez(io_dir / "right" / f"frame_{t:04d}_sam_3d_body_outputs.npz", outputs=np.array([fr], dtype=object))
+    res = lr.load_raw({"sam_l": str(io_dir / "osmo_2_sam_3d_body_outputs.npz"), "sam_r": str(io_dir / "right")})
+    arr = lambda key, dim: np.stack([np.stack([np.asarray(res[t][key]["pred"][j], np.float64) for j in range(70)]) for t in sorted(res)])
+    out.update(sam_Xl=arr("L_3D", 3), sam_Xr=arr("R_3D", 3), sam_Ul=arr("L_2D", 2), sam_Ur=arr("R_2D", 2))
+    # ---- writers: the reference's own files
+    fs = ref_import.load("fuse.save")
+    seq = out["sam_Xl"].copy()
+    seq[2, 5] = np.nan
+    seq_dicts = [{j: seq[t, j] for j in range(70) if np.isfinite(seq[t, j]).all()} for t in range(len(seq))]
+    fs.save_smoothed_results(seq_dicts, list(range(70)), str(io_dir / "ref_out" / "person_smoothed.npy"))
+    out["seq_to_save"] = seq
+    ts = ref_import.load("triangulation.save")
+    X = rng.normal(size=(3, 17, 3)).astype(np.float32)
+    Rr = [np.eye(3) * (1 + i) for i in range(3)]
+    Tt = [np.arange(3.0).reshape(3, 1) + i for i in range(3)]
+    vp = {"left": "/data/left.mp4", "right": Path("/data/right.mp4")}
+    for fmt in ("npy", "csv", "json"):
+        for i in range(3):
+            ts.save_3d_joints(X[i], str(io_dir / "ref_out" / "joints"), 40 + i, Rr[i], Tt[i], vp, fmt=fmt)
+    out.update(joints_X=X, joints_R=np.stack(Rr), joints_T=np.stack(Tt))
+    np.savez_compressed(OUT / "g10_io.npz", **out)
+    print("g10 written:", sorted(p.name for p in (io_dir / "ref_out" / "joints").iterdir())[:4], "...")
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    if "--only-g10" in sys.argv:
+        return g10()
     if "--only-g8" in sys.argv:
         return g8()
     if "--only-g9" in sys.argv:
