@@ -352,13 +352,14 @@ int ska_ema_f64(const double* d_X, int64_t T, int32_t J, const double* d_alpha_j
  * (specification: oracle/first_order.py).
  *   ska_adam_step_*: torch.optim.Adam's update on n elements: m <- m + (1-beta1)(g-m); v <- beta2 v + (1-beta2) g^2;
  *       step = step_size * m / (sqrt(v) * inv_sqrt_bc2 + eps), step_size = lr / (1 - beta1^k), inv_sqrt_bc2 = 1 / sqrt(1 - beta2^k);
- *       d_p (nullable) <- d_p - step; d_step_out (nullable) <- step.
+ *       d_p (nullable) <- d_p - step; d_step_out (nullable) <- step.  d_scalars (nullable): device [2] = {step_size,
+ *       inv_sqrt_bc2} overriding the by-value arguments, so a captured CUDA graph of one iteration replays for every k.
  *   ska_so3_tangent_grad_*: n rotations (row-major 3x3) and dL/dR -> gradient w.r.t. the left tangent of R = exp([w]x) R.
  *   ska_so3_retract_*: R <- exp([-step]x) R. */
 int ska_adam_step_f32(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, double step_size, double beta1, double beta2,
-                      double eps, double inv_sqrt_bc2, float* d_step_out, void* stream);
+                      double eps, double inv_sqrt_bc2, float* d_step_out, const double* d_scalars, void* stream);
 int ska_adam_step_f64(double* d_p, const double* d_g, double* d_m, double* d_v, int64_t n, double step_size, double beta1, double beta2,
-                      double eps, double inv_sqrt_bc2, double* d_step_out, void* stream);
+                      double eps, double inv_sqrt_bc2, double* d_step_out, const double* d_scalars, void* stream);
 int ska_so3_tangent_grad_f32(const float* d_R, const float* d_gR, int64_t n, float* d_gw, void* stream);
 int ska_so3_tangent_grad_f64(const double* d_R, const double* d_gR, int64_t n, double* d_gw, void* stream);
 int ska_so3_retract_f32(float* d_R, const float* d_step, int64_t n, void* stream);

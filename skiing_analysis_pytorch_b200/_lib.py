@@ -81,7 +81,7 @@ for _sfx in ("f32", "f64"):
     )
     _SIGS[f"ska_camera_centre_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _vp, _vp])
     _SIGS[f"ska_camera_smooth_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, C.c_size_t, _vp])
-    _SIGS[f"ska_adam_step_{_sfx}"] = (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp])
+    _SIGS[f"ska_adam_step_{_sfx}"] = (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp])
     _SIGS[f"ska_so3_tangent_grad_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _vp, _vp])
     _SIGS[f"ska_so3_retract_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _vp])
     _SIGS[f"ska_baseline_reg_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp])

@@ -381,14 +381,20 @@ FIRST_ORDER_TERMS = ("reproj", "smooth", "baseline", "bone_length", "pose_tempor
 
 
 class _DeviceAdam:
-    """torch.optim.Adam's update applied by libska (ska_adam_step_*): state and parameters stay on the device."""
+    """torch.optim.Adam's update applied by libska (ska_adam_step_*): state and parameters stay on the device.  The
+    per-iteration scalars lr / (1 - b1^k) and 1 / sqrt(1 - b2^k) live in device memory (`scal`, refreshed by `begin`
+    from the device-side iteration counter `k`), so one captured CUDA graph of an iteration replays for every k."""
 
-    def __init__(self, lr, betas=(0.9, 0.999), eps=1e-8):
-        self.lr, self.b1, self.b2, self.eps, self.k, self.state = float(lr), betas[0], betas[1], float(eps), 0, {}
+    def __init__(self, lr, dev, betas=(0.9, 0.999), eps=1e-8):
+        self.lr, self.b1, self.b2, self.eps, self.state = float(lr), betas[0], betas[1], float(eps), {}
         self.lib = _lib.load()
+        self.k = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.scal = torch.zeros(2, dtype=torch.float64, device=dev)
 
     def begin(self):
-        self.k += 1
+        self.k += 1.0
+        self.scal[0:1] = self.lr / (1.0 - torch.pow(self.b1, self.k))
+        self.scal[1:2] = torch.rsqrt(1.0 - torch.pow(self.b2, self.k))
 
     def apply(self, name, p, g, step_out=None):
         """p <- p - step (p may be None: only step_out is written)."""
@@ -396,16 +402,14 @@ class _DeviceAdam:
         m, v = self.state.setdefault(name, (torch.zeros_like(ref), torch.zeros_like(ref)))
         g = g.contiguous()
         sfx = "f32" if ref.dtype == torch.float32 else "f64"
-        step_size = self.lr / (1.0 - self.b1**self.k)
-        inv_sqrt_bc2 = 1.0 / (1.0 - self.b2**self.k) ** 0.5
         ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
         with torch.cuda.device(ref.device):
-            _lib.check(getattr(self.lib, f"ska_adam_step_{sfx}")(ptr(p), ptr(g), ptr(m), ptr(v), ref.numel(), step_size, self.b1, self.b2,
-                                                                 self.eps, inv_sqrt_bc2, ptr(step_out), _stream_ptr(ref.device)))
+            _lib.check(getattr(self.lib, f"ska_adam_step_{sfx}")(ptr(p), ptr(g), ptr(m), ptr(v), ref.numel(), 0.0, self.b1, self.b2, self.eps,
+                                                                 1.0, ptr(step_out), ptr(self.scal), _stream_ptr(ref.device)))
 
 
 def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch, x2d_torch, conf2d_torch, num_iters=200, lr=1e-3,
-                             device="cuda", mode="pose_only", weights=None):
+                             device="cuda", mode="pose_only", weights=None, graph=True):
     """First-order (Adam) minimisation of the reference's full configured objective (SURVEY row N1, first-order form;
     specification oracle/first_order.py):
         w_reproj reprojection_loss + w_smooth camera_smooth_loss + w_baseline baseline_reg_loss
@@ -414,7 +418,9 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
     the call site passes them (vggt/multi_view_process.py:546-564).  mode: "pose_only" (X), "pose_cam_t" (X, t), "full"
     (X, t and R; rotations move on SO(3) through the left tangent).  Every loss value and analytic gradient comes from the
     loss kernels (losses.py -> libska), the updates from ska_adam_step_* / ska_so3_*; computed in X3d_init's dtype
-    (float32 / float64) like loss.py:27-32.  Returns (R_opt, t_opt, X_opt, history) with one history row per iteration:
+    (float32 / float64) like loss.py:27-32.  graph=True captures one iteration (~20 launches: the loop is launch-bound)
+    in a CUDA graph and replays it; nothing synchronises with the host until the history is read back.
+    Returns (R_opt, t_opt, X_opt, history) with one history row per iteration:
     {iter, loss, reproj, smooth, baseline, bone_length, pose_temporal} (values before that iteration's step)."""
     from . import losses
 
@@ -423,6 +429,8 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("run_local_ba runs on a CUDA device: this package has no CPU path")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
     w = dict(FIRST_ORDER_WEIGHTS, **(weights or {}))
     dt = X3d_init_torch.dtype if X3d_init_torch.dtype in (torch.float32, torch.float64) else torch.float32
     to = lambda a: a.detach().to(dev, dt).contiguous().clone()
@@ -432,16 +440,19 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
     K, x2d, conf = to(K_torch), to(x2d_torch), to(conf2d_torch)
     lib = _lib.load()
     sfx = "f32" if dt == torch.float32 else "f64"
-    opt = _DeviceAdam(lr)
+    num_iters = int(num_iters)
+    opt = _DeviceAdam(lr, dev)
     n_rot = R.shape[0] * R.shape[1]
     gw = torch.empty((n_rot, 3), dtype=dt, device=dev)
     sw = torch.empty((n_rot, 3), dtype=dt, device=dev)
-    hist = torch.zeros((int(num_iters), 1 + len(FIRST_ORDER_TERMS)), dtype=torch.float64, device=dev)
+    hist = torch.zeros((max(num_iters, 1), 1 + len(FIRST_ORDER_TERMS)), dtype=torch.float64, device=dev)
+    row = torch.zeros((1, 1 + len(FIRST_ORDER_TERMS)), dtype=torch.float64, device=dev)
     ptr = lambda a: C.c_void_p(a.data_ptr())
-    for it in range(int(num_iters)):
-        Xv = X.requires_grad_(True)
-        tv = t.requires_grad_(mode != "pose_only")
-        Rv = R.requires_grad_(mode == "full")
+
+    def iteration():
+        Xv = X.detach().requires_grad_(True)                    # views of the static buffers: the updates below are in place
+        tv = t.detach().requires_grad_(mode != "pose_only")
+        Rv = R.detach().requires_grad_(mode == "full")
         terms = {}
         if w["reproj"]:
             terms["reproj"] = losses.reprojection_loss(Xv, Rv, tv, K, x2d, conf, w=w["reproj"])
@@ -455,32 +466,48 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
             terms["pose_temporal"] = losses.pose_temporal_loss(Xv, w=w["pose_temporal"])
         total = sum(terms.values())
         total.backward()
-        hist[it, 0] = total.detach()
+        row.zero_()
+        row[0, 0:1] = total.detach().to(torch.float64)
         for k, name in enumerate(FIRST_ORDER_TERMS):
             if name in terms:
-                hist[it, 1 + k] = terms[name].detach()
-        gX, gt, gR = X.grad, t.grad, R.grad
-        X, t, R = X.detach(), t.detach(), R.detach()
-        X.grad = t.grad = R.grad = None
+                row[0, 1 + k: 2 + k] = terms[name].detach().to(torch.float64)
+        hist.index_copy_(0, opt.k.to(torch.int64), row)       # row k (the counter is incremented by begin() below)
         opt.begin()
-        opt.apply("X", X, gX)
+        opt.apply("X", X, Xv.grad)
         if mode != "pose_only":
-            opt.apply("t", t, gt if gt is not None else torch.zeros_like(t))
+            opt.apply("t", t, tv.grad if tv.grad is not None else torch.zeros_like(t))
         if mode == "full":
-            gRc = (gR if gR is not None else torch.zeros_like(R)).contiguous()
+            gRc = (Rv.grad if Rv.grad is not None else torch.zeros_like(R)).contiguous()
             with torch.cuda.device(dev):
                 _lib.check(getattr(lib, f"ska_so3_tangent_grad_{sfx}")(ptr(R), ptr(gRc), n_rot, ptr(gw), _stream_ptr(dev)))
             opt.apply("w", None, gw, step_out=sw)
             with torch.cuda.device(dev):
                 _lib.check(getattr(lib, f"ska_so3_retract_{sfx}")(ptr(R), ptr(sw), n_rot, _stream_ptr(dev)))
-    h = hist.cpu().numpy()
+
+    done = 0
+    if graph and num_iters >= 4:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            iteration()                                          # warm-up outside capture: a real iteration (k = 1)
+            done = 1
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                iteration()                                      # capture does not execute
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for _ in range(num_iters - done):
+            g.replay()
+    else:
+        for _ in range(num_iters):
+            iteration()
+    h = hist[:num_iters].cpu().numpy()
     history = [dict(iter=i, loss=float(r[0]), **{n: float(r[1 + k]) for k, n in enumerate(FIRST_ORDER_TERMS)}) for i, r in enumerate(h)]
     od = R_init_torch.dtype
     return R.to(od), t.to(t_init_torch.dtype), X.to(X3d_init_torch.dtype), history
 
 
 def run_local_ba(K_torch, R_init_torch, t_init_torch, X3d_init_torch, x2d_torch, conf2d_torch, num_iters=200, lr=1e-3,
-                 device="cuda", mode="pose_only", optimizer="lm", weights=None):
+                 device="cuda", mode="pose_only", optimizer="lm", weights=None, graph=True):
     """The optimiser the reference calls but never defines (vggt/multi_view_process.py:553-564;
     argument shapes :546-551).  Returns (R_opt (T,C,3,3), t_opt (T,C,3), X_opt (T,J,3), history).
 
@@ -493,7 +520,7 @@ def run_local_ba(K_torch, R_init_torch, t_init_torch, X3d_init_torch, x2d_torch,
     (reprojection + the four regularisers of loss.py, weights of configs/vggt.yaml) with per-frame free cameras."""
     if optimizer == "adam":
         return run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch, x2d_torch, conf2d_torch, num_iters, lr,
-                                        device, mode, weights)
+                                        device, mode, weights, graph)
     if optimizer != "lm":
         raise ValueError(f"optimizer must be 'lm' or 'adam', got {optimizer!r}")
     dev = torch.device(device)

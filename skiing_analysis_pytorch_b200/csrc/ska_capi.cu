@@ -339,10 +339,11 @@ int ska_ema_f64(const double* d_X, int64_t T, int32_t J, const double* d_alpha_j
 
 #define SKA_OPTIM_ENTRY(SFX, S)                                                                                                   \
   int ska_adam_step_##SFX(S* d_p, const S* d_g, S* d_m, S* d_v, int64_t n, double step_size, double beta1, double beta2, double eps,  \
-                          double inv_sqrt_bc2, S* d_step_out, void* stream) {                                                      \
+                          double inv_sqrt_bc2, S* d_step_out, const double* d_scalars, void* stream) {                             \
     if (n < 0 || (n > 0 && (d_g == nullptr || d_m == nullptr || d_v == nullptr || (d_p == nullptr && d_step_out == nullptr))))      \
       return set_error(SKA_EINVAL, "d_g, d_m, d_v and one of d_p / d_step_out must not be NULL; n >= 0");                          \
-    return adam_step<S>(d_p, d_g, d_m, d_v, n, step_size, beta1, beta2, eps, inv_sqrt_bc2, d_step_out, (cudaStream_t)stream);       \
+    return adam_step<S>(d_p, d_g, d_m, d_v, n, step_size, beta1, beta2, eps, inv_sqrt_bc2, d_step_out, d_scalars,                   \
+                        (cudaStream_t)stream);                                                                                      \
   }                                                                                                                                 \
   int ska_so3_tangent_grad_##SFX(const S* d_R, const S* d_gR, int64_t n, S* d_gw, void* stream) {                                   \
     if (n < 0 || (n > 0 && (d_R == nullptr || d_gR == nullptr || d_gw == nullptr)))                                                 \

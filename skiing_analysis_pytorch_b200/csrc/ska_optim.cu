@@ -4,7 +4,9 @@
 // the optimiser it never defines is `lr`, `num_iters` and one weight per loss term (configs/vggt.yaml:43-52;
 // call site vggt/multi_view_process.py:553-564).  Three element-wise kernels, templated on the caller's dtype:
 //   adam_kernel         torch.optim.Adam's update: m <- m + (1-b1)(g-m); v <- b2 v + (1-b2) g^2;
-//                       step = step_size * m / (sqrt(v) * inv_sqrt_bc2 + eps); p <- p - step (and / or step_out <- step)
+//                       step = step_size * m / (sqrt(v) * inv_sqrt_bc2 + eps); p <- p - step (and / or step_out <- step);
+//                       step_size / inv_sqrt_bc2 optionally come from device memory so that one captured CUDA graph of an
+//                       iteration can be replayed for every k
 //   so3_tangent_grad    g_omega = (B21 - B12, B02 - B20, B10 - B01), B = (dL/dR) R^T   (left perturbation R = exp([w]x) R)
 //   so3_retract         R <- exp([-step]x) R   (Rodrigues in fp64, series below |w|^2 < 1e-16)
 #include <cuda_runtime.h>
@@ -17,7 +19,11 @@ namespace ska {
 template <typename S>
 __global__ void __launch_bounds__(256) adam_kernel(S* __restrict__ p, const S* __restrict__ g, S* __restrict__ m, S* __restrict__ v,
                                                    int64_t n, double step_size, double b1, double b2, double eps, double inv_sqrt_bc2,
-                                                   S* __restrict__ step_out) {
+                                                   S* __restrict__ step_out, const double* __restrict__ scalars) {
+  if (scalars != nullptr) {  // per-iteration scalars from device memory: lets a captured CUDA graph be replayed for every k
+    step_size = scalars[0];
+    inv_sqrt_bc2 = scalars[1];
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const double gi = (double)g[i];
@@ -90,9 +96,9 @@ static int grid_of(int64_t n) {
 
 template <typename S>
 int adam_step(S* p, const S* g, S* m, S* v, int64_t n, double step_size, double b1, double b2, double eps, double inv_sqrt_bc2, S* step_out,
-              cudaStream_t s) {
+              const double* scalars, cudaStream_t s) {
   if (n == 0) return SKA_OK;
-  adam_kernel<S><<<grid_of(n), 256, 0, s>>>(p, g, m, v, n, step_size, b1, b2, eps, inv_sqrt_bc2, step_out);
+  adam_kernel<S><<<grid_of(n), 256, 0, s>>>(p, g, m, v, n, step_size, b1, b2, eps, inv_sqrt_bc2, step_out, scalars);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }
@@ -111,8 +117,8 @@ int so3_retract(S* R, const S* step, int64_t n, cudaStream_t s) {
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }
 
-template int adam_step<float>(float*, const float*, float*, float*, int64_t, double, double, double, double, double, float*, cudaStream_t);
-template int adam_step<double>(double*, const double*, double*, double*, int64_t, double, double, double, double, double, double*, cudaStream_t);
+template int adam_step<float>(float*, const float*, float*, float*, int64_t, double, double, double, double, double, float*, const double*, cudaStream_t);
+template int adam_step<double>(double*, const double*, double*, double*, int64_t, double, double, double, double, double, double*, const double*, cudaStream_t);
 template int so3_tangent_grad<float>(const float*, const float*, int64_t, float*, cudaStream_t);
 template int so3_tangent_grad<double>(const double*, const double*, int64_t, double*, cudaStream_t);
 template int so3_retract<float>(float*, const float*, int64_t, cudaStream_t);

@@ -32,13 +32,14 @@ def main():
         dt = torch.float64 if "--f64" in sys.argv else torch.float32
         for mode in ba.MODES:
             args = (torch.tensor(d["K"]), Rf.to(dt), tf.to(dt), X0.to(dt), d["x2d"], d["conf"])
-            ba.run_local_ba(*args, num_iters=3, lr=1e-2, mode=mode, optimizer="adam")
+            use_graph = "--no-graph" not in sys.argv
+            ba.run_local_ba(*args, num_iters=5, lr=1e-2, mode=mode, optimizer="adam", graph=use_graph)
             torch.cuda.synchronize()
             t0_ = time.perf_counter()
-            _, _, _, h = ba.run_local_ba(*args, num_iters=iters, lr=1e-2, mode=mode, optimizer="adam")
+            _, _, _, h = ba.run_local_ba(*args, num_iters=iters, lr=1e-2, mode=mode, optimizer="adam", graph=use_graph)
             torch.cuda.synchronize()
             ms = 1e3 * (time.perf_counter() - t0_) / iters
-            print(f"{name} adam {mode:10s} {str(dt)[6:]}: T={T} J={J} C={C}  {ms:.3f} ms/iter (wall, incl. Python)  loss {h[0]['loss']:.4f} -> {h[-1]['loss']:.4f}")
+            print(f"{name} adam {mode:10s} {str(dt)[6:]}: T={T} J={J} C={C}  {ms:.3f} ms/iter (wall incl. set-up, graph={use_graph})  loss {h[0]['loss']:.4f} -> {h[-1]['loss']:.4f}")
         return
     if "--calib" in sys.argv:  # config 3 with free intrinsics + distortion (15 parameters per camera)
         K_init, dist_init = synth.theta_to_K_dist(synth.perturb_intrinsics(d["K"]))
