@@ -318,7 +318,9 @@ int ska_savgol_f32(const float* d_X, int64_t T, int32_t S, int32_t win, int32_t 
  *   d_fused (T,J,3); nullable d_ql, d_qr (T,J), d_aligned (T,J,3) = right view in the left frame, d_status (T,) bit set:
  *   SKA_FUSE_NO_ALIGN (fewer than 3 common joints: right view used unaligned, main_raw.py:83-84),
  *   SKA_FUSE_FIT_LEFT_FAILED / _RIGHT_FAILED (weak-perspective fit impossible: the reference raises ValueError,
- *   confidence.py:31-32,52-53; the frame's outputs are NaN).
+ *   confidence.py:31-32,52-53; the frame's outputs are NaN).  d_workspace >= ska_fuse_workspace_bytes(T) (56 doubles per
+ *   frame: the frame's raw moments, then its alignment / fit / canonical-frame parameters), 8-byte aligned; three launches:
+ *   moments (warp per frame) -> parameters (thread per frame) -> fusion (thread per joint).
  * ska_ema_f64: d_X (T,J,3) -> d_Y (T,J,3) (may not alias); d_alpha_joint (J,) per-joint base alpha (fuse.py:362-376);
  *   adaptive != 0: alpha_t = clip(alpha_joint + speed_gain |x_t - y_{t-1}|, alpha_min, alpha_max), else the fixed `alpha`.
  *   Frames are processed in chunks of `chunk` frames, each replaying `halo` finite samples before its start; halo < 0
@@ -332,14 +334,16 @@ typedef struct SkaFuseParams {
   int32_t min_points;  /* 8     (confidence.py:12) */
   int32_t root, lhip, rhip, lsho, rsho; /* 14, 11, 12, 5, 6 (main_raw.py:18-22) */
   int32_t pad_;        /* flags: bit 0 = always take the Jacobi SVD path of the rigid alignment (test hook);
-                          bit 1 = skip the rigid alignment (views already in one frame: fuse/main_unity.py:96-132) */
+                          bit 1 = skip the rigid alignment (views already in one frame: fuse/main_unity.py:96-132);
+                          bit 2 = run the single warp-per-frame kernel (no workspace) instead of the three-stage path (A/B testing) */
 } SkaFuseParams;
 #define SKA_FUSE_NO_ALIGN 1
 #define SKA_FUSE_FIT_LEFT_FAILED 2
 #define SKA_FUSE_FIT_RIGHT_FAILED 4
+size_t ska_fuse_workspace_bytes(int64_t T);
 int ska_fuse_frames_f64(const double* d_Xl, const double* d_Xr, const double* d_Ul, const double* d_Ur, int64_t T, int32_t J,
                         const SkaFuseParams* prm, double* d_fused, double* d_ql, double* d_qr, double* d_aligned,
-                        uint8_t* d_status, void* stream);
+                        uint8_t* d_status, void* d_workspace, size_t ws_bytes, void* stream);
 int ska_ema_f64(const double* d_X, int64_t T, int32_t J, const double* d_alpha_joint, int32_t adaptive, double alpha,
                 double alpha_min, double alpha_max, double speed_gain, int64_t chunk, int32_t halo, double* d_Y, void* stream);
 

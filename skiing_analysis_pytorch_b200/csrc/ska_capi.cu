@@ -312,9 +312,11 @@ int ska_ba_calib_control_f64(const SkaBaProblem* p, void* stream) {
   return ba_calib_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, stream);
 }
 
+size_t ska_fuse_workspace_bytes(int64_t T) { return fuse_workspace_bytes(T); }
+
 int ska_fuse_frames_f64(const double* d_Xl, const double* d_Xr, const double* d_Ul, const double* d_Ur, int64_t T, int32_t J,
                         const SkaFuseParams* prm, double* d_fused, double* d_ql, double* d_qr, double* d_aligned,
-                        uint8_t* d_status, void* stream) {
+                        uint8_t* d_status, void* d_workspace, size_t ws_bytes, void* stream) {
   if (prm == nullptr) return set_error(SKA_EINVAL, "prm must not be NULL");
   if (T < 0 || J < 1 || J > 96) return set_error(SKA_EINVAL, "T must be >= 0 and 1 <= J <= 96");
   if (T > 0 && (d_Xl == nullptr || d_Xr == nullptr || d_Ul == nullptr || d_Ur == nullptr || d_fused == nullptr))
@@ -324,7 +326,8 @@ int ska_fuse_frames_f64(const double* d_Xl, const double* d_Xr, const double* d_
     if (key[k] < 0 || key[k] >= J) return set_error(SKA_EINVAL, "key joint index outside 0..J-1");
   if (prm->scale_mode != 0 && prm->scale_mode != 1) return set_error(SKA_EINVAL, "scale_mode must be 0 (hip) or 1 (torso)");
   if (prm->min_points < 1) return set_error(SKA_EINVAL, "min_points must be >= 1");
-  return fuse_frames(d_Xl, d_Xr, d_Ul, d_Ur, T, J, *prm, d_fused, d_ql, d_qr, d_aligned, d_status, (cudaStream_t)stream);
+  return fuse_frames(d_Xl, d_Xr, d_Ul, d_Ur, T, J, *prm, d_fused, d_ql, d_qr, d_aligned, d_status, d_workspace, ws_bytes,
+                     (cudaStream_t)stream);
 }
 
 int ska_ema_f64(const double* d_X, int64_t T, int32_t J, const double* d_alpha_joint, int32_t adaptive, double alpha,

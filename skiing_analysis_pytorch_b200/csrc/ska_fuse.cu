@@ -443,6 +443,303 @@ __global__ void __launch_bounds__(128, SKA_FUSE_MINB) fuse_frames_kernel(const F
 }
 
 // ------------------------------------------------------------------------------------------------
+// Product path: the same arithmetic as fuse_frames_kernel with the FRAME-LEVEL work de-duplicated and every stage at its
+// own register budget.  In the warp-per-frame kernel above every lane repeats the frame's 3x3 polar / SVD iteration, the
+// two weak-perspective fits and the two canonical frames (~2 600 of its 4 840 warp instructions per frame), at 12 warps
+// per SM.  Three launches over a caller-provided workspace of kFuseRow doubles per frame:
+//   fuse_moments_kernel  warp per frame: the 42 raw moments (counts, sums, second moments) of the frame's joints,
+//                        fixed-order butterfly sums;
+//   fuse_params_kernel   thread per frame: moments -> rigid alignment, both weak-perspective fits, both canonical frames
+//                        (32 frames' factorisations side by side in a warp instead of one repeated 32 times); the 53
+//                        parameters overwrite the frame's row;
+//   fuse_joints_kernel   thread per (frame, joint): confidences, softmax fusion, stores - fully coalesced, ~70 registers.
+// Centred second moments come from raw ones (sum x y^T - n mx my^T): coordinates are O(10) with O(0.3) spread, so the
+// cancellation costs < 3 of fp64's 16 digits - far inside the 1e-9 parity tolerance.
+constexpr int kFuseRow = 56;   // doubles per frame in the workspace (42 moments, then 53 parameters)
+constexpr int kMomK = 0, kMomL = 16, kMomR = 29, kMomN = 42;
+
+struct FitWP {  // weak-perspective map of one view: uhat = s X M + t
+  double M[3][2], s, t[2];
+  bool ok;
+};
+
+// moments m[0..12] = cnt, sum X (3), sum U (2), sum X_a U_b (6, a-major), sum |X|^2
+__device__ __forceinline__ FitWP fit_from_moments(const double* m, int min_points) {
+  FitWP f;
+  f.ok = false;
+  f.s = 0.0;
+  f.t[0] = f.t[1] = 0.0;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) f.M[d][0] = f.M[d][1] = 0.0;
+  const double n = m[0];
+  if (n < (double)min_points) return f;
+  const double in = 1.0 / n;
+  const double muX[3] = {m[1] * in, m[2] * in, m[3] * in}, muU[2] = {m[4] * in, m[5] * in};
+  double c1[3], c2[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    c1[d] = m[6 + 2 * d] - n * muX[d] * muU[0];
+    c2[d] = m[7 + 2 * d] - n * muX[d] * muU[1];
+  }
+  const double den = m[12] - n * (muX[0] * muX[0] + muX[1] * muX[1] + muX[2] * muX[2]);
+  if (!(den >= 1e-12)) return f;
+  double v1[2] = {1.0, 0.0}, v2[2] = {0.0, 1.0};
+  hestenes_rotate<2>(c1, c2, v1, v2);
+  const double s1 = sqrt(c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2]);
+  const double s2 = sqrt(c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2]);
+  const double r1 = s1 > 0.0 ? 1.0 / s1 : 0.0, r2 = s2 > 0.0 ? 1.0 / s2 : 0.0;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    f.M[d][0] = c1[d] * r1 * v1[0] + c2[d] * r2 * v2[0];
+    f.M[d][1] = c1[d] * r1 * v1[1] + c2[d] * r2 * v2[1];
+  }
+  f.s = (s1 + s2) / den;
+  f.t[0] = muU[0] - f.s * (muX[0] * f.M[0][0] + muX[1] * f.M[1][0] + muX[2] * f.M[2][0]);
+  f.t[1] = muU[1] - f.s * (muX[0] * f.M[0][1] + muX[1] * f.M[1][1] + muX[2] * f.M[2][1]);
+  f.ok = true;
+  return f;
+}
+
+struct FuseArgs3 {
+  FuseArgs a;
+  double* ws;  // [T][kFuseRow]
+};
+
+__global__ void __launch_bounds__(256) fuse_moments_kernel(const FuseArgs3 g) {
+  const FuseArgs& a = g.a;
+  const int lane = threadIdx.x & 31;
+  const int64_t frame = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (frame >= a.T) return;
+  const int J = a.J;
+  double* row = g.ws + frame * kFuseRow;
+  const double* Xlf = a.Xl + frame * J * 3;
+  const double* Xrf = a.Xr + frame * J * 3;
+  const double* Ulf = a.Ul + frame * J * 2;
+  const double* Urf = a.Ur + frame * J * 2;
+  double m[kMomN];
+#pragma unroll
+  for (int q = 0; q < kMomN; ++q) m[q] = 0.0;
+#pragma unroll
+  for (int k = 0; k < kFuseJPL; ++k) {
+    const int j = lane + 32 * k;
+    if (j >= J) continue;
+    double xl[3], xr[3], ul[2], ur[2];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      xl[d] = Xlf[3 * j + d];
+      xr[d] = Xrf[3 * j + d];
+    }
+    ul[0] = Ulf[2 * j];
+    ul[1] = Ulf[2 * j + 1];
+    ur[0] = Urf[2 * j];
+    ur[1] = Urf[2 * j + 1];
+    const bool fl = fin3(xl), fr = fin3(xr);
+    if (fl && fr) {
+      m[kMomK] += 1.0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        m[kMomK + 1 + d] += xr[d];
+        m[kMomK + 4 + d] += xl[d];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) m[kMomK + 7 + 3 * d + e] += xr[d] * xl[e];
+      }
+    }
+    if (fl && fin2(ul)) {
+      m[kMomL] += 1.0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        m[kMomL + 1 + d] += xl[d];
+        m[kMomL + 6 + 2 * d] += xl[d] * ul[0];
+        m[kMomL + 7 + 2 * d] += xl[d] * ul[1];
+        m[kMomL + 12] += xl[d] * xl[d];
+      }
+      m[kMomL + 4] += ul[0];
+      m[kMomL + 5] += ul[1];
+    }
+    if (fr && fin2(ur)) {
+      m[kMomR] += 1.0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        m[kMomR + 1 + d] += xr[d];
+        m[kMomR + 6 + 2 * d] += xr[d] * ur[0];
+        m[kMomR + 7 + 2 * d] += xr[d] * ur[1];
+        m[kMomR + 12] += xr[d] * xr[d];
+      }
+      m[kMomR + 4] += ur[0];
+      m[kMomR + 5] += ur[1];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kMomN; ++q) {
+    const double v = wsum(m[q]);
+    if (lane == 0) row[q] = v;
+  }
+}
+
+__global__ void __launch_bounds__(64) fuse_params_kernel(const FuseArgs3 g) {
+  const FuseArgs& a = g.a;
+  const int64_t frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (frame >= a.T) return;
+  const int J = a.J;
+  double* out = g.ws + frame * kFuseRow;
+  double m[kMomN];
+#pragma unroll
+  for (int q = 0; q < kMomN; ++q) m[q] = out[q];
+  uint8_t st = 0;
+  // rigid alignment right -> left (main_raw.py:48-95); flags bit 1: views already share a frame (main_unity.py:96-132)
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tr[3] = {0, 0, 0};
+  bool aligned = false;
+  if ((a.prm.pad_ & 2) == 0) {
+    const double n = m[kMomK];
+    if (n >= 3.0) {
+      const double in = 1.0 / n;
+      double mr[3], ml[3], H[9];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        mr[d] = m[kMomK + 1 + d] * in;
+        ml[d] = m[kMomK + 4 + d] * in;
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int e = 0; e < 3; ++e) H[3 * d + e] = m[kMomK + 7 + 3 * d + e] - n * mr[d] * ml[e];
+      if ((a.prm.pad_ & 1) || !polar_rotation(H, R)) kabsch_rotation(H, R);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) tr[r] = ml[r] - (R[3 * r] * mr[0] + R[3 * r + 1] * mr[1] + R[3 * r + 2] * mr[2]);
+      aligned = true;
+    } else {
+      st |= SKA_FUSE_NO_ALIGN;
+    }
+  }
+  const FitWP fl = fit_from_moments(m + kMomL, a.prm.min_points), fr = fit_from_moments(m + kMomR, a.prm.min_points);
+  if (!fl.ok) st |= SKA_FUSE_FIT_LEFT_FAILED;
+  if (!fr.ok) st |= SKA_FUSE_FIT_RIGHT_FAILED;
+  const Canon ca = canonical_frame(a.Xl + frame * J * 3, a.prm), cb = canonical_frame(a.Xr + frame * J * 3, a.prm);
+  int o = 0;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) out[o++] = R[q];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) out[o++] = tr[q];
+  const FitWP* fits[2] = {&fl, &fr};
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      out[o++] = fits[v]->s * fits[v]->M[d][0];  // s folded into the map
+      out[o++] = fits[v]->s * fits[v]->M[d][1];
+    }
+    out[o++] = fits[v]->t[0];
+    out[o++] = fits[v]->t[1];
+  }
+  const Canon* cans[2] = {&ca, &cb};
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const double is = cans[v]->ok ? 1.0 / cans[v]->s : 0.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) out[o++] = cans[v]->R[r][c] * is;  // scale folded into the rotation rows
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[o++] = cans[v]->root[c];
+  }
+  out[o++] = (double)(st | (aligned ? 8 : 0) | (ca.ok && cb.ok ? 16 : 0));  // 28 + 24 + 1 = 53 doubles
+  if (a.status != nullptr) a.status[frame] = st;
+}
+
+__global__ void __launch_bounds__(256) fuse_joints_kernel(const FuseArgs3 g) {
+  const FuseArgs& a = g.a;
+  const int J = a.J;
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= a.T * J) return;
+  const int64_t frame = o / J;
+  const int j = (int)(o - frame * J);
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  const double sig = a.prm.sigma_px > 1e-12 ? a.prm.sigma_px : 1e-12;
+  const double inv2s = 1.0 / (2.0 * sig * sig);
+  const double sig3 = a.prm.sigma_3d > 1e-12 ? a.prm.sigma_3d : 1e-12;
+  const double inv2s3 = 1.0 / (2.0 * sig3 * sig3);
+  const double* P = g.ws + frame * kFuseRow;
+  const int flags = (int)P[52];
+  const bool fit_failed = (flags & (SKA_FUSE_FIT_LEFT_FAILED | SKA_FUSE_FIT_RIGHT_FAILED)) != 0;
+  const bool aligned = (flags & 8) != 0, canon_ok = (flags & 16) != 0;
+  const bool fit_l = !(flags & SKA_FUSE_FIT_LEFT_FAILED), fit_r = !(flags & SKA_FUSE_FIT_RIGHT_FAILED);
+  const double* Xlf = a.Xl + frame * J * 3;
+  const double* Xrf = a.Xr + frame * J * 3;
+  const double* Ulf = a.Ul + frame * J * 2;
+  const double* Urf = a.Ur + frame * J * 2;
+  double xl[3], xr[3], ul[2], ur[2];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    xl[d] = Xlf[3 * j + d];
+    xr[d] = Xrf[3 * j + d];
+  }
+  ul[0] = Ulf[2 * j];
+  ul[1] = Ulf[2 * j + 1];
+  ur[0] = Urf[2 * j];
+  ur[1] = Urf[2 * j + 1];
+  const bool okl = fin3(xl), okr_raw = fin3(xr);
+  // right view in the left frame
+  double xa[3] = {xr[0], xr[1], xr[2]};
+  if (aligned && okl && okr_raw) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) xa[r] = (P[3 * r] * xr[0] + P[3 * r + 1] * xr[1] + P[3 * r + 2] * xr[2]) + P[9 + r];
+  }
+  // weak-perspective residual exponents (confidence.py:62-108); < 0 = confidence 0
+  double a1l = -1.0, a1r = -1.0;
+  if (fit_l) {
+    const double* W = P + 12;
+    const double d0 = (xl[0] * W[0] + xl[1] * W[2] + xl[2] * W[4]) + W[6] - ul[0];
+    const double d1 = (xl[0] * W[1] + xl[1] * W[3] + xl[2] * W[5]) + W[7] - ul[1];
+    const double e2 = d0 * d0 + d1 * d1;
+    if (isfinite(e2)) a1l = e2 * inv2s;
+  }
+  if (fit_r) {
+    const double* W = P + 20;
+    const double d0 = (xr[0] * W[0] + xr[1] * W[2] + xr[2] * W[4]) + W[6] - ur[0];
+    const double d1 = (xr[0] * W[1] + xr[1] * W[3] + xr[2] * W[5]) + W[7] - ur[1];
+    const double e2 = d0 * d0 + d1 * d1;
+    if (isfinite(e2)) a1r = e2 * inv2s;
+  }
+  // cross-view distance in the canonical frames (confidence.py:183-224), RAW right view
+  double b2 = -1.0;
+  if (canon_ok) {
+    const double* A = P + 28;
+    const double* B = P + 40;
+    double d2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double pa = A[3 * r] * (xl[0] - A[9]) + A[3 * r + 1] * (xl[1] - A[10]) + A[3 * r + 2] * (xl[2] - A[11]);
+      const double pb = B[3 * r] * (xr[0] - B[9]) + B[3 * r + 1] * (xr[1] - B[10]) + B[3 * r + 2] * (xr[2] - B[11]);
+      d2 += (pa - pb) * (pa - pb);
+    }
+    if (isfinite(d2)) b2 = d2 * inv2s3;
+  }
+  const double ql = (a1l >= 0.0 && b2 >= 0.0) ? exp(-0.5 * (a1l + b2)) : 0.0;
+  const double qr = (a1r >= 0.0 && b2 >= 0.0) ? exp(-0.5 * (a1r + b2)) : 0.0;
+  const double eo = exp(-fabs(ql - qr));
+  const double ea = ql >= qr ? 1.0 : eo, eb = ql >= qr ? eo : 1.0;
+  const double iss = 1.0 / (ea + eb + kFuseEps);
+  const double wl = ea * iss, wr = eb * iss;
+  const double iw = 1.0 / (wl + wr + kFuseEps);
+  const bool okr = fin3(xa);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    double fv;
+    if (okl && okr) fv = (wl * xl[d] + wr * xa[d]) * iw;
+    else if (okl) fv = xl[d];
+    else if (okr) fv = xa[d];
+    else fv = nan;
+    a.fused[3 * o + d] = fit_failed ? nan : fv;  // the reference raises ValueError for such a frame
+  }
+  if (a.ql != nullptr) a.ql[o] = fit_failed ? nan : ql;
+  if (a.qr != nullptr) a.qr[o] = fit_failed ? nan : qr;
+  if (a.aligned != nullptr) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) a.aligned[3 * o + d] = okr ? xa[d] : nan;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct EmaArgs {
   const double* X;
   double* Y;
@@ -557,12 +854,25 @@ __global__ void __launch_bounds__(128) ema_kernel(const EmaArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+size_t fuse_workspace_bytes(int64_t T) { return (size_t)(T > 0 ? T : 0) * kFuseRow * sizeof(double); }
+
 int fuse_frames(const double* Xl, const double* Xr, const double* Ul, const double* Ur, int64_t T, int J, const SkaFuseParams& prm,
-                double* fused, double* ql, double* qr, double* aligned, uint8_t* status, cudaStream_t s) {
+                double* fused, double* ql, double* qr, double* aligned, uint8_t* status, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (T == 0) return SKA_OK;
   FuseArgs a{Xl, Xr, Ul, Ur, T, J, prm, fused, ql, qr, aligned, status};
   const int wpb = 4;
-  const int64_t grid = (T + wpb - 1) / wpb;
+  if ((prm.pad_ & 4) == 0) {  // product path: moments -> per-frame parameters -> per-joint fusion
+    if (ws == nullptr || ws_bytes < (size_t)T * kFuseRow * sizeof(double))
+      return set_error(SKA_EWORKSPACE, "workspace too small (see ska_fuse_workspace_bytes)");
+    if ((T * (int64_t)J + 255) / 256 > 0x7fffffffLL) return set_error(SKA_EINVAL, "too many joints for one launch; shard the clip");
+    const FuseArgs3 g{a, (double*)ws};
+    fuse_moments_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(g);
+    fuse_params_kernel<<<(unsigned)((T + 63) / 64), 64, 0, s>>>(g);
+    fuse_joints_kernel<<<(unsigned)((T * (int64_t)J + 255) / 256), 256, 0, s>>>(g);
+    const cudaError_t ce = cudaGetLastError();
+    return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
+  }
+  const int64_t grid = (T + wpb - 1) / wpb;  // flags bit 2: the warp-per-frame kernel (A/B testing)
   if (grid > 0x7fffffffLL) return set_error(SKA_EINVAL, "too many frames for one launch; shard the clip");
   fuse_frames_kernel<<<(unsigned)grid, 32 * wpb, 0, s>>>(a);
   const cudaError_t ce = cudaGetLastError();

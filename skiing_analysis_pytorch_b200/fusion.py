@@ -52,13 +52,14 @@ def _f64_cuda(x, name, last):
 
 def fuse_clip(Xl, Xr, Ul, Ur, *, sigma_px: float = 12.0, sigma_3d: float = 0.08, scale_mode: str = "hip", min_points: int = 8,
               key_joints=(IDX_PELVIS, IDX_LHIP, IDX_RHIP, IDX_LSHO, IDX_RSHO), want=("q", "aligned"), strict: bool = True,
-              force_jacobi: bool = False, align: bool = True) -> FusedClip:
+              force_jacobi: bool = False, align: bool = True, per_frame_kernel: bool = False) -> FusedClip:
     """Fuse two per-view 3D skeleton sequences.  Xl, Xr (T,J,3) in each view's own frame, Ul, Ur (T,J,2) pixels.
     strict=True raises ValueError if the weak-perspective fit of any frame is impossible (fewer than `min_points`
     joints with finite 3D and 2D, or degenerate 3D), as the reference does (fuse/confidence.py:31-32, 52-53) - this
     reads the status back (one synchronisation); strict=False leaves those frames NaN and reports them in `status`.
     force_jacobi=True runs the one-sided Jacobi SVD for every frame's rigid alignment (the kernel otherwise takes a Newton
     polar-decomposition fast path when the cross-covariance is well conditioned and not reflected) - a test hook.
+    per_frame_kernel=True runs the single warp-per-frame kernel instead of the three-stage path (A/B testing).
     align=False skips the rigid alignment: the two views already share a coordinate system, as in the reference's Unity
     pipeline (fuse/main_unity.py:96-132, 15 target joints whose key indices are positions in that array)."""
     Xl = _f64_cuda(Xl, "Xl", 3)
@@ -76,7 +77,7 @@ def fuse_clip(Xl, Xr, Ul, Ur, *, sigma_px: float = 12.0, sigma_3d: float = 0.08,
     dev = Xl.device
     prm = _cabi.SkaFuseParams(sigma_px=float(sigma_px), sigma_3d=float(sigma_3d), scale_mode=0 if scale_mode == "hip" else 1,
                               min_points=int(min_points), root=int(key_joints[0]), lhip=int(key_joints[1]), rhip=int(key_joints[2]),
-                              lsho=int(key_joints[3]), rsho=int(key_joints[4]), pad_=(1 if force_jacobi else 0) | (0 if align else 2))
+                              lsho=int(key_joints[3]), rsho=int(key_joints[4]), pad_=(1 if force_jacobi else 0) | (0 if align else 2) | (4 if per_frame_kernel else 0))
     f64 = dict(dtype=torch.float64, device=dev)
     fused = torch.empty((T, J, 3), **f64)
     ql = torch.empty((T, J), **f64) if "q" in want else None
@@ -85,9 +86,11 @@ def fuse_clip(Xl, Xr, Ul, Ur, *, sigma_px: float = 12.0, sigma_3d: float = 0.08,
     status = torch.zeros((T,), dtype=torch.uint8, device=dev)
     p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
     lib = _lib.load()
+    ws_bytes = 0 if per_frame_kernel else int(lib.ska_fuse_workspace_bytes(T))
+    ws = torch.empty(max(ws_bytes, 8) // 8, dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.ska_fuse_frames_f64(p(Xl), p(Xr), p(Ul), p(Ur), T, J, C.byref(prm), p(fused), p(ql), p(qr), p(al), p(status),
-                                           _stream(dev)))
+                                           p(ws), ws_bytes, _stream(dev)))
     if strict and T:
         bad = (status & (_cabi.FUSE_FIT_LEFT_FAILED | _cabi.FUSE_FIT_RIGHT_FAILED)) != 0
         if bool(bad.any()):

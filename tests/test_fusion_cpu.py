@@ -45,11 +45,13 @@ def test_c_abi_argument_errors_without_gpu():
     lib = _lib.load()
     prm = _cabi.SkaFuseParams(12.0, 0.08, 0, 8, 14, 11, 12, 5, 6, 0)
     fake = C.c_void_p(4096)
-    call = lambda J=70, T=1, p=prm, x=fake: lib.ska_fuse_frames_f64(x, fake, fake, fake, T, J, C.byref(p) if p else None, fake, None, None, None, None, None)
+    call = lambda J=70, T=1, p=prm, x=fake: lib.ska_fuse_frames_f64(x, fake, fake, fake, T, J, C.byref(p) if p else None, fake, None, None, None, None, None, 0, None)
     assert call(J=97) == -1 and call(J=0) == -1 and call(T=-1) == -1 and call(x=None) == -1 and call(p=None) == -1
     assert call(J=12) == -1  # key joint 14 outside a 12-joint skeleton
     bad = _cabi.SkaFuseParams(12.0, 0.08, 2, 8, 14, 11, 12, 5, 6, 0)
     assert call(p=bad) == -1
+    assert call() == -4   # valid arguments but no workspace: SKA_EWORKSPACE before any CUDA call
+    assert lib.ska_fuse_workspace_bytes(1000) == 1000 * 56 * 8 and lib.ska_fuse_workspace_bytes(0) == 0
     ema = lambda **k: lib.ska_ema_f64(k.get("x", fake), k.get("T", 4), k.get("J", 3), fake, 1, 0.7, k.get("amin", 0.45), 0.92, 0.25, 512, 70,
                                       k.get("y", C.c_void_p(8192)), None)
     assert ema(x=None) == -1 and ema(J=0) == -1 and ema(amin=0.95) == -1 and ema(y=fake) == -1

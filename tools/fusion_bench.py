@@ -32,12 +32,14 @@ def main():
     reps = (T + 1999) // 2000
     d = {k: torch.from_numpy(v).to(dev).repeat(reps, 1, 1)[:T].contiguous() for k, v in small.items()}
     ms_fuse = timed(lambda: fusion.fuse_clip(d["Xl"], d["Xr"], d["Ul"], d["Ur"], want=(), strict=False))
+    ms_old = timed(lambda: fusion.fuse_clip(d["Xl"], d["Xr"], d["Ul"], d["Ur"], want=(), strict=False, per_frame_kernel=True), n=3)
     fused = fusion.fuse_clip(d["Xl"], d["Xr"], d["Ul"], d["Ur"], want=(), strict=False).fused
     ms_ema = timed(lambda: fusion.temporal_smooth_ema(fused))
     ms_seq = timed(lambda: fusion.temporal_smooth_ema(fused, exact=True), n=2) if T <= 200_000 else float("nan")
     b_fuse = T * J * (24 + 24 + 16 + 16 + 24)
     halo = fusion.ema_halo(0.7, True, 0.45, 0.92)
     b_ema = T * J * 48
+    print(f"fuse_frames (warp-per-frame kernel): {ms_old:.3f} ms")
     print(f"fuse_frames: T={T} J={J}  {ms_fuse:.3f} ms  {T / ms_fuse * 1e3:.3e} frames/s  alg {b_fuse / 1e9:.2f} GB -> {b_fuse / ms_fuse / 1e6:.0f} GB/s")
     print(f"ema (chunk 512, halo {halo}): {ms_ema:.3f} ms  {T / ms_ema * 1e3:.3e} frames/s  alg {b_ema / 1e9:.2f} GB -> {b_ema / ms_ema / 1e6:.0f} GB/s"
           f"   sequential scan: {ms_seq:.1f} ms")
