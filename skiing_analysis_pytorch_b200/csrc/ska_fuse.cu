@@ -505,24 +505,28 @@ struct FuseArgs3 {
   double* ws;  // [T][kFuseRow]
 };
 
+// kLPF lanes share a frame (32 / kLPF frames per warp): the butterfly sums need log2(kLPF) steps instead of 5 and run for
+// all of the warp's frames at once - with 8 lanes per frame the 42 reductions cost 95 warp instructions per frame
+// instead of 630 (measured: 2.49 -> see profiles/README.md).
+constexpr int kLPF = 8;
+
 __global__ void __launch_bounds__(256) fuse_moments_kernel(const FuseArgs3 g) {
   const FuseArgs& a = g.a;
-  const int lane = threadIdx.x & 31;
-  const int64_t frame = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (frame >= a.T) return;
+  const int lane = threadIdx.x & 31, sub = lane & (kLPF - 1);
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t frame = warp_global * (32 / kLPF) + (lane / kLPF);
+  const bool live = frame < a.T;   // no early return: the shuffles below are warp-wide
+  const int64_t fr = live ? frame : a.T - 1;
   const int J = a.J;
-  double* row = g.ws + frame * kFuseRow;
-  const double* Xlf = a.Xl + frame * J * 3;
-  const double* Xrf = a.Xr + frame * J * 3;
-  const double* Ulf = a.Ul + frame * J * 2;
-  const double* Urf = a.Ur + frame * J * 2;
+  const double* Xlf = a.Xl + fr * J * 3;
+  const double* Xrf = a.Xr + fr * J * 3;
+  const double* Ulf = a.Ul + fr * J * 2;
+  const double* Urf = a.Ur + fr * J * 2;
   double m[kMomN];
 #pragma unroll
   for (int q = 0; q < kMomN; ++q) m[q] = 0.0;
-#pragma unroll
-  for (int k = 0; k < kFuseJPL; ++k) {
-    const int j = lane + 32 * k;
-    if (j >= J) continue;
+#pragma unroll 1
+  for (int j = sub; j < J; j += kLPF) {
     double xl[3], xr[3], ul[2], ur[2];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -533,8 +537,8 @@ __global__ void __launch_bounds__(256) fuse_moments_kernel(const FuseArgs3 g) {
     ul[1] = Ulf[2 * j + 1];
     ur[0] = Urf[2 * j];
     ur[1] = Urf[2 * j + 1];
-    const bool fl = fin3(xl), fr = fin3(xr);
-    if (fl && fr) {
+    const bool fl = fin3(xl), fr_ = fin3(xr);
+    if (fl && fr_) {
       m[kMomK] += 1.0;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
@@ -556,7 +560,7 @@ __global__ void __launch_bounds__(256) fuse_moments_kernel(const FuseArgs3 g) {
       m[kMomL + 4] += ul[0];
       m[kMomL + 5] += ul[1];
     }
-    if (fr && fin2(ur)) {
+    if (fr_ && fin2(ur)) {
       m[kMomR] += 1.0;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
@@ -569,10 +573,13 @@ __global__ void __launch_bounds__(256) fuse_moments_kernel(const FuseArgs3 g) {
       m[kMomR + 5] += ur[1];
     }
   }
+  double* row = g.ws + fr * kFuseRow;
 #pragma unroll
   for (int q = 0; q < kMomN; ++q) {
-    const double v = wsum(m[q]);
-    if (lane == 0) row[q] = v;
+    double v = m[q];
+#pragma unroll
+    for (int o = kLPF / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);  // fixed order within the frame's lanes
+    if (live && sub == 0) row[q] = v;
   }
 }
 
@@ -866,7 +873,10 @@ int fuse_frames(const double* Xl, const double* Xr, const double* Ul, const doub
       return set_error(SKA_EWORKSPACE, "workspace too small (see ska_fuse_workspace_bytes)");
     if ((T * (int64_t)J + 255) / 256 > 0x7fffffffLL) return set_error(SKA_EINVAL, "too many joints for one launch; shard the clip");
     const FuseArgs3 g{a, (double*)ws};
-    fuse_moments_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(g);
+    {
+      const int64_t fpb = 8 * (32 / kLPF);  // frames per 256-thread block
+      fuse_moments_kernel<<<(unsigned)((T + fpb - 1) / fpb), 256, 0, s>>>(g);
+    }
     fuse_params_kernel<<<(unsigned)((T + 63) / 64), 64, 0, s>>>(g);
     fuse_joints_kernel<<<(unsigned)((T * (int64_t)J + 255) / 256), 256, 0, s>>>(g);
     const cudaError_t ce = cudaGetLastError();
