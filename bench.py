@@ -263,6 +263,56 @@ def ba_cpu_iteration_rate(frames=1500, joints=17, rig="2b", iters=3):
     return iters / (time.perf_counter() - t0_)
 
 
+def run_first_order(a, dev, rank, n_gpus):
+    """Row N1 (first-order form): Adam iterations/s on the reference's full configured objective (configs/vggt.yaml:43-52)
+    with per-frame cameras at config-3 size, one iteration replayed from a CUDA graph; beside it the same iteration
+    (forward + backward of the five loss terms, all host threads) of the torch restatement on the CPU."""
+    import torch
+
+    from skiing_analysis_pytorch_b200 import ba, synth
+
+    T, J = 100_000, 17
+    d = synth.make_clip_device("2b", T, J, dev, seed=100 + rank)
+    R0, t0 = synth.perturb_cameras(d["R"], d["t"], seed=1)
+    R = torch.tensor(R0, device=dev, dtype=torch.float32)[None].expand(T, 2, 3, 3).contiguous()
+    t = torch.tensor(t0, device=dev, dtype=torch.float32)[None].expand(T, 2, 3).contiguous()
+    X0 = (d["X"] + 0.05 * torch.randn(T, J, 3, dtype=torch.float64, device=dev)).float()
+    args = (torch.tensor(d["K"], dtype=torch.float32), R, t, X0, d["x2d"], d["conf"])
+    ba.run_local_ba(*args, num_iters=8, lr=1e-2, mode="full", optimizer="adam")  # warm-up
+    torch.cuda.synchronize()
+    iters = 200
+    t0_ = time.perf_counter()
+    _, _, _, h = ba.run_local_ba(*args, num_iters=iters, lr=1e-2, mode="full", optimizer="adam")
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0_) / iters
+    out = {"metric": "ba_first_order_iterations_per_sec", "value": 1e3 / ms, "unit": "iters/s", "ms_per_iter": ms, "frames": T, "joints": J,
+           "cameras": 2, "mode": "full", "objective": "reproj + camera_smooth + baseline_reg + bone_length + pose_temporal (configs/vggt.yaml weights)",
+           "timing": "wall clock around 200 iterations incl. graph capture (device work only: nothing synchronises inside)",
+           "loss_first": h[0]["loss"], "loss_last": h[-1]["loss"]}
+    if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
+        from oracle import first_order as FO
+        from oracle import torch_ref as TR
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        Tc = 20_000
+        c = lambda x: x[:Tc].detach().double().cpu()
+        Xc, Rc, tc = c(X0).requires_grad_(True), c(R).requires_grad_(True), c(t).requires_grad_(True)
+        Kc, xc, cc = torch.tensor(d["K"]), c(d["x2d"]), c(d["conf"])
+        best = 1e9
+        for _ in range(3):
+            for v in (Xc, Rc, tc):
+                v.grad = None
+            t1 = time.perf_counter()
+            FO.total_loss(TR.ReferenceNames, Xc, Rc, tc, Kc, xc, cc, FO.DEFAULT_WEIGHTS)[0].backward()
+            best = min(best, time.perf_counter() - t1)
+        out["cpu_baseline"] = {"value": 1.0 / (best * T / Tc), "unit": "iters/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"forward + backward of the five loss terms (torch restatement of loss.py, float64, all host threads) on "
+                                         f"{Tc} of the {T} frames, scaled linearly"}
+    del d, R, t, X0
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ba(a, dev, world, rank, barrier, dist):
     """BA LM iterations/s (second half of BASELINE's metric).  Strong scaling: the clip's frames are
     split over the ranks; per LM trial the packed reduced camera system and the 3 trial scalars are
@@ -574,6 +624,8 @@ def run_ours(a, out_fd=1):
     if not a.no_ba:
         line["ba"] = run_ba(a, dev, world, rank, barrier, dist)
         line["gpu_launches_ba_per_iter"] = 6
+        if n_gpus == 1:
+            line["ba"]["first_order"] = run_first_order(a, dev, rank, n_gpus)
         if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
             r = ba_cpu_iteration_rate()
             line["ba"]["cpu_baseline"] = {

@@ -287,7 +287,7 @@ int ska_ba_calib_control_f64(const SkaBaProblem* p, void* stream);
  *   A joint is kept iff depth > 0 in both cameras (:47-52), 0.5 (e1 + e2) is finite and <= err_thresh_px (:112)
  *   and both confidences >= conf_thr (:108-110).  Outputs: d_Xclean (T,J,3) = X or NaN (:115-116);
  *   d_em (T,J) mean pixel error, nullable; d_flags (T,J) nullable: SKA_TRIAGE_POS | _ERR | _CONF | _KEEP.
- * ska_frame_flag_counts_u8: d_counts (T,4) int32 = per-frame count of each of the four flag bits
+ * ska_frame_flag_counts_u8: d_counts (T,4) int32, 16-byte aligned = per-frame count of each of the four flag bits
  *   (pos_depth_ratio, kept_ratio, kept_count of :118-124; rmse / median of d_em via ska_frame_stats_f32, V = 1).
  * ska_savgol_f32: Savitzky-Golay (scipy.signal.savgol_filter, mode="interp") along T for each of the S = J*3
  *   series of d_X (T,S), over the series' FINITE samples only (compacted in time, filtered, scattered back;

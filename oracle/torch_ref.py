@@ -1,6 +1,7 @@
-"""Plain-PyTorch restatement of bundle_adjustment/loss.py used ONLY by the tests as the autograd
-reference for the CUDA value+gradient kernels (values themselves are pinned by the reference's own
-outputs in tests/golden/g3_g4_loss.npz).  Works on any device; the tests run it in float64."""
+"""Plain-PyTorch restatement of bundle_adjustment/loss.py:17-155 - TEST INFRASTRUCTURE (see oracle/__init__.py): the
+autograd reference for the CUDA value+gradient kernels (values themselves are pinned by the reference's own outputs in
+tests/golden/g3_g4_loss.npz and, through oracle/first_order.py, golden G9) and the CPU baseline of bench.py's first-order
+bundle-adjustment leg.  Works on any device; the tests run it in float64."""
 import torch
 
 BONES = [(11, 13), (13, 15), (12, 14), (14, 16), (5, 7), (7, 9), (6, 8), (8, 10), (5, 6), (11, 12), (5, 11), (6, 12)]
@@ -53,3 +54,13 @@ def bone_length(X, ref, w):
 
 def pose_temporal(X, w):
     return w * ((X[1:] - X[:-1]) ** 2).mean()
+
+
+class ReferenceNames:
+    """This module under the reference's function names and signatures (bundle_adjustment/loss.py:90-155), the interface
+    oracle/first_order.py expects."""
+    reprojection_loss = staticmethod(reprojection_loss)
+    camera_smooth_loss = staticmethod(lambda R, t, w: camera_smooth(R, t, w))
+    baseline_reg_loss = staticmethod(lambda R, t, w: baseline_reg(R, t, w))
+    bone_length_loss = staticmethod(lambda X, ref, w: bone_length(X, ref, w))
+    pose_temporal_loss = staticmethod(lambda X, w: pose_temporal(X, w))

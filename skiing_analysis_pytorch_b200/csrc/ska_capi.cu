@@ -210,6 +210,7 @@ int ska_frame_flag_counts_u8(const uint8_t* d_flags, int64_t T, int32_t J, int32
   if (T < 0 || J < 1) return set_error(SKA_EINVAL, "T >= 0, J >= 1");
   if (T == 0) return SKA_OK;
   if (d_flags == nullptr || d_counts == nullptr) return set_error(SKA_EINVAL, "d_flags and d_counts must not be NULL");
+  if (reinterpret_cast<uintptr_t>(d_counts) % 16 != 0) return set_error(SKA_EALIGN, "d_counts must be 16-byte aligned");
   return flag_counts(d_flags, T, J, d_counts, (cudaStream_t)stream);
 }
 

@@ -134,37 +134,26 @@ int post_triage(const SkaCamera* cams, const float* X, const float* kpts, const 
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }
 
-// per-frame counts of the four flag bits: one warp per frame
+// per-frame counts of the four flag bits: THREAD per frame (a frame's J flag bytes are contiguous; a warp-per-frame
+// shuffle reduction of 17 bytes cost 113 warp instructions per frame, this costs ~3)
 __global__ void __launch_bounds__(128) flag_counts_kernel(const uint8_t* __restrict__ flags, int64_t T, int J, int32_t* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t t = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
+  const uint8_t* f = flags + t * J;
   int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-  for (int j = lane; j < J; j += 32) {
-    const unsigned f = flags[t * J + j];
-    c0 += f & 1u;
-    c1 += (f >> 1) & 1u;
-    c2 += (f >> 2) & 1u;
-    c3 += (f >> 3) & 1u;
+  for (int j = 0; j < J; ++j) {
+    const unsigned b = f[j];
+    c0 += b & 1u;
+    c1 += (b >> 1) & 1u;
+    c2 += (b >> 2) & 1u;
+    c3 += (b >> 3) & 1u;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-    c2 += __shfl_xor_sync(0xffffffffu, c2, o);
-    c3 += __shfl_xor_sync(0xffffffffu, c3, o);
-  }
-  if (lane == 0) {
-    out[4 * t] = c0;
-    out[4 * t + 1] = c1;
-    out[4 * t + 2] = c2;
-    out[4 * t + 3] = c3;
-  }
+  *reinterpret_cast<int4*>(out + 4 * t) = make_int4(c0, c1, c2, c3);
 }
 
 int flag_counts(const uint8_t* flags, int64_t T, int J, int32_t* out, cudaStream_t s) {
   if (T == 0) return SKA_OK;
-  flag_counts_kernel<<<(unsigned)((T + 3) / 4), 128, 0, s>>>(flags, T, J, out);
+  flag_counts_kernel<<<(unsigned)((T + 127) / 128), 128, 0, s>>>(flags, T, J, out);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }

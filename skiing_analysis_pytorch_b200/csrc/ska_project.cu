@@ -177,12 +177,66 @@ __global__ void __launch_bounds__(32 * kStatsWarps) frame_stats_kernel(const flo
   }
 }
 
+// Small skeletons (J <= JM <= 32: COCO-17 is the common case): THREAD per (frame, view) row, the row in registers, ranks
+// by J^2 register compares.  The warp-per-row kernel above spends 435 warp instructions on a 17-joint row (15 idle lanes,
+// shared-memory rank loop); this one ~27 per row, and a warp's 32 rows are one contiguous 32 * J * 4-byte read.
+template <int JM>
+__global__ void __launch_bounds__(128) frame_stats_small_kernel(const float* __restrict__ err, int64_t T, int V, int J, int64_t e_sT,
+                                                                int64_t e_sV, float* __restrict__ out) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // = t * V + v
+  if (row >= T * V) return;
+  const int64_t t = row / V;
+  const int v = (int)(row - t * V);
+  const float* e = err + t * e_sT + (int64_t)v * e_sV;
+  float x[JM];
+  double s1 = 0.0, s2 = 0.0;
+  float mx = -INFINITY;
+  int n = 0;
+#pragma unroll
+  for (int j = 0; j < JM; ++j) {
+    x[j] = (j < J) ? e[j] : NAN;
+    if (x[j] == x[j]) {
+      s1 += (double)x[j];
+      s2 += (double)x[j] * (double)x[j];
+      mx = fmaxf(mx, x[j]);
+      ++n;
+    }
+  }
+  const int r_lo = (n - 1) / 2, r_hi = n / 2;
+  float a_lo = 0.f, a_hi = 0.f;
+#pragma unroll
+  for (int j = 0; j < JM; ++j) {
+    int rank = 0;
+#pragma unroll
+    for (int k = 0; k < JM; ++k) rank += (x[k] < x[j] || (x[k] == x[j] && k < j)) ? 1 : 0;  // NaN compares false: never counted
+    const bool ok = x[j] == x[j];
+    a_lo = (ok && rank == r_lo) ? x[j] : a_lo;
+    a_hi = (ok && rank == r_hi) ? x[j] : a_hi;
+  }
+  float* o = out + row * 4;
+  if (n == 0) {
+    o[0] = o[1] = o[2] = o[3] = NAN;
+  } else {
+    o[0] = (float)sqrt(s2 / n);
+    o[1] = (float)(s1 / n);
+    o[2] = (a_lo == a_hi) ? a_lo : 0.5f * a_lo + 0.5f * a_hi;
+    o[3] = mx;
+  }
+}
+
 int frame_stats(const float* err, int64_t T, int J, int V, int layout, float* out, cudaStream_t s) {
   if (J > kStatsMaxJ) return set_error(SKA_EUNSUPPORTED, "frame statistics support J <= 1024");
   const bool fm = layout == SKA_LAYOUT_FRAME_MAJOR;
   const int64_t e_sT = fm ? (int64_t)J * V : J, e_sV = fm ? J : T * (int64_t)J;
   const int64_t rows = T * V;
   if (rows == 0) return SKA_OK;
+  if (J <= 32) {
+    const unsigned grid = (unsigned)((rows + 127) / 128);
+    if (J <= 17) frame_stats_small_kernel<17><<<grid, 128, 0, s>>>(err, T, V, J, e_sT, e_sV, out);
+    else frame_stats_small_kernel<32><<<grid, 128, 0, s>>>(err, T, V, J, e_sT, e_sV, out);
+    const cudaError_t ce = cudaGetLastError();
+    return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
+  }
   const size_t smem = (size_t)kStatsWarps * J * sizeof(float);
   frame_stats_kernel<<<(unsigned)((rows + kStatsWarps - 1) / kStatsWarps), 32 * kStatsWarps, smem, s>>>(err, T, V, J, e_sT, e_sV, out);
   const cudaError_t ce = cudaGetLastError();

@@ -1,6 +1,6 @@
 """Edge cases of the standalone entry points on the GPU: empty / single-frame / single-joint inputs,
 zero confidences, NaN propagation - compared with what the reference's expressions give (evaluated with
-the plain torch restatement, tests/torch_ref.py)."""
+the plain torch restatement, oracle/torch_ref.py)."""
 import math
 
 import numpy as np
@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from skiing_analysis_pytorch_b200 import api, ba, losses as L, synth
-from tests import torch_ref as TR
+from oracle import torch_ref as TR
 
 pytestmark = pytest.mark.gpu
 
@@ -59,6 +59,26 @@ def test_reprojection_and_stats_edges(cuda):
     p, _ = api.reproject_points(Xz, synth.K_CALIB, np.eye(3)[None], np.zeros((1, 3)), None)
     assert torch.isfinite(p).all()
     assert p[0, 0, 0, 0].item() == pytest.approx(synth.K_CALIB[0, 0] * 1.0 + synth.K_CALIB[0, 2], rel=1e-6)
+
+
+@pytest.mark.parametrize("J", [1, 5, 16, 17, 18, 25, 32, 33, 70])
+def test_frame_stats_all_kernel_paths_match_numpy(cuda, J):
+    """J <= 17 and J <= 32 run the thread-per-row register kernels, larger skeletons the warp-per-row kernel: all three
+    must give numpy's nan-aware rmse / mean / median / max (triangulation/reproject.py:254-261), ties and NaNs included."""
+    rng = np.random.default_rng(J)
+    e = rng.uniform(0, 5, (2, 300, J)).astype(np.float32)
+    e[rng.random(e.shape) < 0.2] = np.nan
+    e[0, 7] = np.nan                      # an empty row
+    e[1, 9] = 1.25                        # all ties
+    if J >= 5:
+        e[0, 11, :4] = 2.0                # partial ties around the median
+    st = api.frame_stats(torch.from_numpy(e).to(cuda)).cpu().numpy()  # (T,V,4)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = np.stack([np.sqrt(np.nanmean(e.astype(np.float64) ** 2, -1)), np.nanmean(e.astype(np.float64), -1),
+                        np.nanmedian(e.astype(np.float64), -1), np.nanmax(e, -1)], -1).transpose(1, 0, 2)
+    np.testing.assert_allclose(st, ref, rtol=2e-7, atol=0, equal_nan=True)
 
 
 def test_ba_with_unobserved_points_and_frozen_cameras(cuda):

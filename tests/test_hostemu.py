@@ -118,7 +118,7 @@ def test_hostemu_loss_projection_and_adjoint_match_autograd():
 
     import torch
 
-    from tests import torch_ref as TR
+    from oracle import torch_ref as TR
 
     lib = C.CDLL(str(hostemu.build()))
     rng = np.random.default_rng(1)

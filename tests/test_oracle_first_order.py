@@ -1,5 +1,5 @@
 """The first-order regularised BA oracle (oracle/first_order.py, row N1): golden G9 was produced with the REFERENCE's own
-bundle_adjustment/loss.py as the loss module; here the portable torch restatement (tests/torch_ref.py) must walk the same
+bundle_adjustment/loss.py as the loss module; here the portable torch restatement (oracle/torch_ref.py) must walk the same
 trajectory, the tangent-space rotation gradient must equal autograd through the exponential map, and the Adam step must
 be torch.optim.Adam's."""
 import numpy as np
@@ -7,16 +7,10 @@ import pytest
 import torch
 
 from oracle import first_order as FO
-from tests import torch_ref as TR
+from oracle import torch_ref as TR
 
 
-class RefNames:
-    """tests/torch_ref.py under the reference's function names (bundle_adjustment/loss.py:90-155)."""
-    reprojection_loss = staticmethod(TR.reprojection_loss)
-    camera_smooth_loss = staticmethod(lambda R, t, w: TR.camera_smooth(R, t, w))
-    baseline_reg_loss = staticmethod(lambda R, t, w: TR.baseline_reg(R, t, w))
-    bone_length_loss = staticmethod(lambda X, ref, w: TR.bone_length(X, ref, w))
-    pose_temporal_loss = staticmethod(lambda X, w: TR.pose_temporal(X, w))
+RefNames = TR.ReferenceNames
 
 
 @pytest.mark.parametrize("mode", FO.MODES)
