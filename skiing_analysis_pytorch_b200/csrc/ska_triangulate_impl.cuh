@@ -449,6 +449,126 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
   int st = 0;
   uint32_t par = 0;
   float* sx = sX[warp];
+#ifdef SKA_WS_PIPE
+  // Software-pipelined form (experiment): the SOLVE of tile i+1 (rows, normal matrix, LDL^T, secular step: one long
+  // dependent chain) and the SCORING of tile i (two views x two coordinates: wide and independent) sit in ONE basic
+  // block, so the scheduler can fill the solve chain's latency with scoring work of the previous tile.  Per-point
+  // arithmetic and its order are unchanged (fast_stage / score_views): results are bit-identical.  A tile that is not
+  // entirely on the certified fast path is finished at once by the general tri_points<>.
+  if constexpr (!STREAM && LEAN) {
+    F2 pY[3], pra[V], prb[V], pu[V], pv[V];
+    uint32_t p_wt = 0;
+    bool p_valid = false;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) pY[m] = mk2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < V; ++k) pra[k] = prb[k] = pu[k] = pv[k] = mk2(0.f, 1.f);
+    auto flush = [&](const F2 (&Y)[3], const F2 (&ra)[V], const F2 (&rb)[V], const F2 (&uu)[V], const F2 (&vv)[V], uint32_t twt, bool valid) {
+      F2 dut[V], dvt[V];
+      score_views<V, DIST, F2>(prm.cam, Y[0], Y[1], Y[2], ra, rb, uu, vv, dut, dvt);
+      if (valid) {
+        const uint32_t j0 = twt * kWarpPts + 2u * lane;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float e0 = sqrt_fast(fmaf(dut[k].x, dut[k].x, dvt[k].x * dvt[k].x));
+          const float e1 = sqrt_fast(fmaf(dut[k].y, dut[k].y, dvt[k].y * dvt[k].y));
+          __stcs(reinterpret_cast<float2*>(prm.err + (int64_t)k * prm.c_sV + j0), make_float2(e0, e1));
+        }
+        sx[lane * 6 + 0] = Y[0].x + prm.c[0];
+        sx[lane * 6 + 1] = Y[1].x + prm.c[1];
+        sx[lane * 6 + 2] = Y[2].x + prm.c[2];
+        sx[lane * 6 + 3] = Y[0].y + prm.c[0];
+        sx[lane * 6 + 4] = Y[1].y + prm.c[1];
+        sx[lane * 6 + 5] = Y[2].y + prm.c[2];
+        __syncwarp();
+        float* gx = prm.X + (int64_t)twt * (kWarpPts * 3);
+        __stcs(reinterpret_cast<float4*>(gx) + lane, reinterpret_cast<const float4*>(sx)[lane]);
+        if (lane < 16) __stcs(reinterpret_cast<float4*>(gx) + 32 + lane, reinterpret_cast<const float4*>(sx)[32 + lane]);
+        __syncwarp();
+      }
+    };
+    for (; wt < n_wt; wt += stride) {
+      mbar_wait(&sFull[warp][st], par);
+      const float* stage = sK + ((size_t)warp * kStages + st) * Cf::kStageFloats;
+      const uint32_t i0 = wt * kWarpPts + 2u * lane;
+      F2 ut[V], vt[V], wtt[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float4 q = *reinterpret_cast<const float4*>(stage + k * Cf::kViewFloats + 4 * lane);
+        ut[k] = mk2(q.x, q.z);
+        vt[k] = mk2(q.y, q.w);
+        if (CONF) {
+          float2 c = make_float2(1.f, 1.f);
+          if (prm.conf != nullptr) c = __ldcs(reinterpret_cast<const float2*>(prm.conf + (int64_t)k * prm.c_sV + i0));
+          wtt[k] = prm.weight_sqrt ? mk2(c.x, c.y) : mk2(c.x * c.x, c.y * c.y);
+        } else {
+          wtt[k] = mk2(1.f, 1.f);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sEmpty[warp][st]);
+      if (++st == kStages) {
+        st = 0;
+        par ^= 1u;
+      }
+      // ---- solve(new) and score(pending) in one basic block
+      F2 a[V][4], b[V][4], ra[V], rb[V];
+      Sym4T<F2> M;
+      FastStage<F2> fs;
+      fast_stage<V, CONF, 1, F2>(prm.cam, prm.c[0], prm.c[1], prm.c[2], ut, vt, wtt, a, b, M, ra, rb, fs);
+      flush(pY, pra, prb, pu, pv, p_wt, p_valid);
+      const bool fin = fabsf(M.m33.x) <= 3.0e38f && fabsf(M.m33.y) <= 3.0e38f;
+      const bool fast = mall(fs.conv) && mall(fs.ok) && mall(fs.well) && fin;
+      if (__all_sync(0xffffffffu, fast)) {
+        pY[0] = fs.y0;
+        pY[1] = fs.y1;
+        pY[2] = fs.y2;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          pra[k] = ra[k];
+          prb[k] = rb[k];
+          pu[k] = ut[k];
+          pv[k] = vt[k];
+        }
+        p_wt = wt;
+        p_valid = true;
+      } else {  // rare: the general path finishes this tile now
+        p_valid = false;
+        float u[PTS][V], v[PTS][V], w2[PTS][V], du[PTS][V], dv[PTS][V], X[PTS][3];
+        uint8_t stt[PTS];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          u[0][k] = ut[k].x; u[1][k] = ut[k].y; v[0][k] = vt[k].x; v[1][k] = vt[k].y;
+          w2[0][k] = wtt[k].x; w2[1][k] = wtt[k].y;
+        }
+        PointSource src;
+        src.kpts = prm.kpts + 2 * (int64_t)i0;
+        src.conf = (prm.conf != nullptr) ? prm.conf + i0 : nullptr;
+        src.k_sV = prm.k_sV;
+        src.c_sV = prm.c_sV;
+        src.weight_sqrt = prm.weight_sqrt;
+        tri_points<V, PTS, CONF, DIST, kSolverSecular>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], u, v, w2, src, X, du, dv, stt);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float e0 = sqrt_fast(fmaf(du[0][k], du[0][k], dv[0][k] * dv[0][k]));
+          const float e1 = sqrt_fast(fmaf(du[1][k], du[1][k], dv[1][k] * dv[1][k]));
+          __stcs(reinterpret_cast<float2*>(prm.err + (int64_t)k * prm.c_sV + i0), make_float2(e0, e1));
+        }
+#pragma unroll
+        for (int pp = 0; pp < PTS; ++pp)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) sx[(lane * PTS + pp) * 3 + k] = X[pp][k];
+        __syncwarp();
+        float* gx = prm.X + (int64_t)wt * (kWarpPts * 3);
+        __stcs(reinterpret_cast<float4*>(gx) + lane, reinterpret_cast<const float4*>(sx)[lane]);
+        if (lane < 16) __stcs(reinterpret_cast<float4*>(gx) + 32 + lane, reinterpret_cast<const float4*>(sx)[32 + lane]);
+        __syncwarp();
+      }
+    }
+    flush(pY, pra, prb, pu, pv, p_wt, p_valid);
+    return;
+  }
+#endif
   for (; wt < n_wt; wt += stride) {
     mbar_wait(&sFull[warp][st], par);
     const float* stage = sK + ((size_t)warp * kStages + st) * Cf::kStageFloats;
