@@ -464,6 +464,60 @@ def run_fusion(a, dev, world, barrier, dist):
     return out
 
 
+def run_post(a, dev, world, barrier, dist):
+    """Row N2: post-triangulation triage (+ per-frame report) and Savitzky-Golay smoothing of 1M frames x 17 joints per GPU."""
+    import torch
+
+    from skiing_analysis_pytorch_b200 import api, post, synth
+
+    T, J = 1_000_000, 17
+    d = synth.make_clip_device("2b", T, J, dev, seed=21, layout="CTJ2")
+    X = api.triangulate_reproject(d["x2d"], d["K"], d["R"], d["t"], want=("X",)).X
+    K, R, t = d["K"][0], d["R"][1], d["t"][1]
+
+    def timed(fn, n=5):
+        for _ in range(3):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / n
+
+    ms_plain = timed(lambda: post.post_triage(X, d["x2d"], K, K, R, t))
+    ms_und = timed(lambda: post.post_triage(X, d["x2d"], K, K, R, t, dist1=synth.DIST_CALIB, dist2=synth.DIST_CALIB, conf=d["conf"]))
+    ms_sg = timed(lambda: post.smooth_skeleton(X, 9, 2))
+    peak, _ = hbm_peak()
+    N = T * J
+    out = {"workload": "1M frames x 17 joints per GPU: triage (pinhole reprojection, depth / error / confidence gates, per-frame report) and Savitzky-Golay smoothing",
+           "triage_ms": ms_plain, "triage_undistort_conf_ms": ms_und, "savgol_ms": ms_sg, "value": world * N / (ms_plain * 1e-3), "unit": "joints/s",
+           "roofline": {"bound": "hbm", "achieved": N * 45 / ms_plain / 1e6, "peak": peak, "unit": "GB/s", "frac": N * 45 / ms_plain / 1e6 / peak,
+                        "bytes_per_joint": 45, "note": "fp64 arithmetic like the reference's numpy (identical accept / reject decisions)"}}
+    del d, X
+    torch.cuda.empty_cache()
+    return out
+
+
+def post_cpu_rate(frames=300):
+    """The reference's per-frame numpy triage (array form, oracle/postprocess.py) on one core."""
+    from oracle import geometry as G
+    from oracle import postprocess as PP
+    from skiing_analysis_pytorch_b200 import synth
+
+    clip = synth.make_clip("2b", frames, 17, seed=0)
+    P = np.stack([G.make_P(clip.K[v], clip.R[v], clip.t[v]) for v in range(2)])
+    X = G.dlt_triangulate(P, clip.x_vm.reshape(2, -1, 2)).reshape(frames, 17, 3).astype(np.float32)
+    t0 = time.perf_counter()
+    PP.post_triage_sequence(X, clip.x_vm[0], clip.x_vm[1], clip.K[0], clip.K[1], clip.R[1], clip.t[1])
+    return frames * 17 / (time.perf_counter() - t0)
+
+
 def fusion_cpu_rate(frames=600):
     """The reference's per-frame numpy fusion + EMA (array form, oracle/fusion.py) on one core."""
     from oracle import fusion as F
@@ -621,6 +675,14 @@ def run_ours(a, out_fd=1):
         if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
             line["fusion"]["cpu_baseline"] = {"value": fusion_cpu_rate(), "unit": "frames/s", "cores": 1, "kind": "port",
                                               "sample": "600 frames x 70 joints through the reference's per-frame numpy path (oracle/fusion.py)"}
+    if not a.no_extra:
+        line["post"] = run_post(a, dev, world, barrier, dist)
+        if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
+            try:
+                line["post"]["cpu_baseline"] = {"value": post_cpu_rate(), "unit": "joints/s", "cores": 1, "kind": "port",
+                                                "sample": "300 frames x 17 joints through the reference's per-frame numpy triage (oracle/postprocess.py)"}
+            except Exception as e:  # the CPU leg is a reported baseline, never the thing measured
+                line["post"]["cpu_baseline"] = {"unavailable": repr(e)[:200]}
     if not a.no_ba:
         line["ba"] = run_ba(a, dev, world, rank, barrier, dist)
         line["gpu_launches_ba_per_iter"] = 6
