@@ -364,6 +364,21 @@ int ska_adam_step_f32(float* d_p, const float* d_g, float* d_m, float* d_v, int6
                       double eps, double inv_sqrt_bc2, float* d_step_out, const double* d_scalars, void* stream);
 int ska_adam_step_f64(double* d_p, const double* d_g, double* d_m, double* d_v, int64_t n, double step_size, double beta1, double beta2,
                       double eps, double inv_sqrt_bc2, double* d_step_out, const double* d_scalars, void* stream);
+/* the same update with the gradient given as up to three UNSCALED terms, g = s0 g0 + s1 g1 + s2 g2 (d_g1 / d_g2 nullable):
+ * the loss entry points return gradients of their raw sums, the weights / counts are folded in here; step_size and
+ * inv_sqrt_bc2 always come from d_scalars. */
+int ska_adam_step_terms_f32(float* d_p, const float* d_g0, double s0, const float* d_g1, double s1, const float* d_g2, double s2,
+                            float* d_m, float* d_v, int64_t n, double beta1, double beta2, double eps, float* d_step_out,
+                            const double* d_scalars, void* stream);
+int ska_adam_step_terms_f64(double* d_p, const double* d_g0, double s0, const double* d_g1, double s1, const double* d_g2, double s2,
+                            double* d_m, double* d_v, int64_t n, double beta1, double beta2, double eps, double* d_step_out,
+                            const double* d_scalars, void* stream);
+/* scalar bookkeeping of one first-order iteration in one launch: d_hist[k] (6 doubles per row, nullable, max_rows rows) =
+ * [total, coef5[0] * sums5[0][0] / (d_den[0] + 1e-6) (d_den NULL: no division), coef5[q] * sums5[q][0] for q = 1..4] where
+ * sums5 / coef5 are HOST arrays of 5 device pointers (NULL = term off) / 5 coefficients in the order reproj, smooth,
+ * baseline, bone_length, pose_temporal; then d_k[0] <- k + 1 and d_scal = {lr / (1 - beta1^k), 1 / sqrt(1 - beta2^k)}. */
+int ska_first_order_record_f64(double* d_k, double* d_scal, double* d_hist, int64_t max_rows, const double* const* sums5,
+                               const double* d_den, const double* coef5, double lr, double beta1, double beta2, void* stream);
 int ska_so3_tangent_grad_f32(const float* d_R, const float* d_gR, int64_t n, float* d_gw, void* stream);
 int ska_so3_tangent_grad_f64(const double* d_R, const double* d_gR, int64_t n, double* d_gw, void* stream);
 int ska_so3_retract_f32(float* d_R, const float* d_step, int64_t n, void* stream);

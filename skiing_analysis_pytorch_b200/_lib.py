@@ -71,6 +71,8 @@ _SIGS = {
     "ska_ema_f64": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64,
                               C.c_int32, _vp, _vp]),
 }
+_SIGS["ska_first_order_record_f64"] = (C.c_int, [_vp, _vp, _vp, C.c_int64, C.POINTER(C.c_void_p), _vp, C.POINTER(C.c_double), C.c_double,
+                                                 C.c_double, C.c_double, _vp])
 for _sfx in ("f32", "f64"):
     _i64, _i32 = C.c_int64, C.c_int32
     _SIGS[f"ska_project_points_{_sfx}"] = (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp])
@@ -84,6 +86,8 @@ for _sfx in ("f32", "f64"):
     _SIGS[f"ska_camera_centre_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _vp, _vp])
     _SIGS[f"ska_camera_smooth_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, C.c_size_t, _vp])
     _SIGS[f"ska_adam_step_{_sfx}"] = (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp])
+    _SIGS[f"ska_adam_step_terms_{_sfx}"] = (C.c_int, [_vp, _vp, C.c_double, _vp, C.c_double, _vp, C.c_double, _vp, _vp, _i64, C.c_double, C.c_double,
+                                                      C.c_double, _vp, _vp, _vp])
     _SIGS[f"ska_so3_tangent_grad_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _vp, _vp])
     _SIGS[f"ska_so3_retract_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _vp])
     _SIGS[f"ska_baseline_reg_{_sfx}"] = (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp])

@@ -409,7 +409,7 @@ class _DeviceAdam:
 
 
 def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch, x2d_torch, conf2d_torch, num_iters=200, lr=1e-3,
-                             device="cuda", mode="pose_only", weights=None, graph=True):
+                             device="cuda", mode="pose_only", weights=None, graph=True, fused=True):
     """First-order (Adam) minimisation of the reference's full configured objective (SURVEY row N1, first-order form;
     specification oracle/first_order.py):
         w_reproj reprojection_loss + w_smooth camera_smooth_loss + w_baseline baseline_reg_loss
@@ -418,8 +418,11 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
     the call site passes them (vggt/multi_view_process.py:546-564).  mode: "pose_only" (X), "pose_cam_t" (X, t), "full"
     (X, t and R; rotations move on SO(3) through the left tangent).  Every loss value and analytic gradient comes from the
     loss kernels (losses.py -> libska), the updates from ska_adam_step_* / ska_so3_*; computed in X3d_init's dtype
-    (float32 / float64) like loss.py:27-32.  graph=True captures one iteration (~20 launches: the loop is launch-bound)
-    in a CUDA graph and replays it; nothing synchronises with the host until the history is read back.
+    (float32 / float64) like loss.py:27-32.  graph=True captures one iteration in a CUDA graph and replays it; nothing
+    synchronises with the host until the history is read back.  fused=True (default) calls the loss entry points
+    directly and folds every weight / count into the multi-term Adam kernel (ska_adam_step_terms_*): ~35 launches per
+    iteration and no element-wise torch arithmetic; fused=False goes through the autograd wrappers of losses.py (the
+    same kernels plus ~100 small torch kernels of gradient scaling / accumulation) - kept as the cross-check.
     Returns (R_opt, t_opt, X_opt, history) with one history row per iteration:
     {iter, loss, reproj, smooth, baseline, bone_length, pose_temporal} (values before that iteration's step)."""
     from . import losses
@@ -449,7 +452,100 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
     row = torch.zeros((1, 1 + len(FIRST_ORDER_TERMS)), dtype=torch.float64, device=dev)
     ptr = lambda a: C.c_void_p(a.data_ptr())
 
+    # ---------------------------------------------------------------- fused form: raw kernels, weights folded into Adam
+    Tn, Jn, Cn = X.shape[0], X.shape[1], R.shape[1]
+    keep = [k for k, (i, j) in enumerate(losses.BONES) if i < Jn and j < Jn]
+    nb = len(keep)
+    use = dict(reproj=bool(w["reproj"]), smooth=bool(w["smooth"]) and Tn > 1, baseline=bool(w["baseline"]) and Cn >= 2,
+               bone_length=bool(w["bone_length"]) and nb > 0, pose_temporal=bool(w["pose_temporal"]) and Tn > 1)
+    cam_free, rot_free = mode != "pose_only", mode == "full"
+    f64d = dict(dtype=torch.float64, device=dev)
+    if fused:
+        bi = (C.c_int32 * max(nb, 1))(*[losses.BONES[k][0] for k in keep])
+        bj = (C.c_int32 * max(nb, 1))(*[losses.BONES[k][1] for k in keep])
+        with torch.cuda.device(dev):
+            ws_bytes = max(int(lib.ska_loss_workspace_bytes(Cn)), int(lib.ska_reg_workspace_bytes()), 1 << 20)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        like = lambda a, on: torch.zeros_like(a) if on else None
+        gX_r, gX_b, gX_t = like(X, use["reproj"]), like(X, use["bone_length"]), like(X, use["pose_temporal"])
+        gR_r, gR_s, gR_b = like(R, use["reproj"] and rot_free), like(R, use["smooth"] and cam_free), like(R, use["baseline"] and cam_free)
+        gt_r, gt_s, gt_b = like(t, use["reproj"] and cam_free), like(t, use["smooth"] and cam_free), like(t, use["baseline"] and cam_free)
+        s_r, s_t, s_s, s_bl = torch.zeros(4, **f64d), torch.zeros(1, **f64d), torch.zeros(1, **f64d), torch.zeros(1, **f64d)
+        s_b0, s_b1, s_m = torch.zeros(_cabi.MAX_BONES, **f64d), torch.zeros(_cabi.MAX_BONES, **f64d), torch.zeros(1, **f64d)
+        gw3 = [torch.empty((n_rot, 3), dtype=dt, device=dev) for _ in range(3)] if rot_free else None
+        P = lambda a: None if a is None else C.c_void_p(a.data_ptr())
+        fn = lambda name: getattr(lib, f"{name}_{sfx}")
+        strm = lambda: _stream_ptr(dev)
+
+        def eval_terms():
+            with torch.cuda.device(dev):
+                if use["reproj"]:
+                    _lib.check(fn("ska_reprojection_loss")(P(X), Tn, Jn, Cn, P(R), Cn * 9, P(t), Cn * 3, P(K), 0, P(x2d), P(conf), P(s_r), P(gX_r),
+                                                          P(gR_r), P(gt_r), None, P(ws), ws_bytes, strm()))
+                if use["pose_temporal"]:
+                    _lib.check(fn("ska_pose_temporal")(P(X), Tn, Jn, P(s_t), P(gX_t), P(ws), ws_bytes, strm()))
+                if use["bone_length"]:
+                    _lib.check(fn("ska_bone_length")(P(X), Tn, Jn, bi, bj, nb, None, P(s_b0), None, P(ws), ws_bytes, strm()))
+                    s_b0.div_(Tn)  # per-bone mean length over the clip: the (detached) reference of loss.py:141-146
+                    _lib.check(fn("ska_bone_length")(P(X), Tn, Jn, bi, bj, nb, P(s_b0), P(s_b1), P(gX_b), P(ws), ws_bytes, strm()))
+                if use["smooth"]:
+                    _lib.check(fn("ska_camera_smooth")(P(R), P(t), Tn, Cn, P(s_s), P(gR_s), P(gt_s), P(ws), ws_bytes, strm()))
+                if use["baseline"]:
+                    _lib.check(fn("ska_baseline_reg")(P(R), P(t), Tn, Cn, None, P(s_m), None, None, P(ws), ws_bytes, strm()))
+                    s_m.div_(Tn)
+                    _lib.check(fn("ska_baseline_reg")(P(R), P(t), Tn, Cn, P(s_m), P(s_bl), P(gR_b), P(gt_b), P(ws), ws_bytes, strm()))
+
+        eval_terms()  # set-up evaluation: the sum of confidences (constant over the solve) fixes the reprojection scale
+        sum_conf = float(s_r[1].item()) if use["reproj"] else 1.0
+        c_r = w["reproj"] / (sum_conf + 1e-6)
+        c_t = w["pose_temporal"] / max((Tn - 1) * Jn * 3, 1)
+        c_b = w["bone_length"] / max(Tn * nb, 1)
+        c_s = w["smooth"] / max((Tn - 1) * Cn * 3, 1)
+        c_bl = w["baseline"] / max(Tn, 1)
+
+        def terms3(cands):
+            live = [(g, sc) for g, sc in cands if g is not None]
+            while len(live) < 3:
+                live.append((None, 0.0))
+            return live
+
+        def adam_terms(name, p, cands, step_out=None):
+            (g0, a0), (g1, a1), (g2, a2) = terms3(cands)
+            ref = p if p is not None else step_out
+            if g0 is None:
+                return
+            m, v = opt.state.setdefault(name, (torch.zeros_like(ref), torch.zeros_like(ref)))
+            with torch.cuda.device(dev):
+                _lib.check(fn("ska_adam_step_terms")(P(p), P(g0), a0, P(g1), a1, P(g2), a2, P(m), P(v), ref.numel(), opt.b1, opt.b2, opt.eps,
+                                                    P(step_out), P(opt.scal), strm()))
+
+        order = ("reproj", "smooth", "baseline", "bone_length", "pose_temporal")   # FIRST_ORDER_TERMS
+        sums5 = (C.c_void_p * 5)(*[(src.data_ptr() if use[name] else None) for name, src in zip(order, (s_r, s_s, s_bl, s_b1, s_t))])
+        coef5 = (C.c_double * 5)(w["reproj"], c_s, c_bl, c_b, c_t)
+
+        def fused_iteration():
+            eval_terms()
+            with torch.cuda.device(dev):   # history row k, k <- k + 1, Adam scalars of step k: one single-thread launch
+                _lib.check(lib.ska_first_order_record_f64(P(opt.k), P(opt.scal), P(hist), hist.shape[0], sums5, P(s_r[1:2]) if use["reproj"] else None,
+                                                          coef5, opt.lr, opt.b1, opt.b2, strm()))
+            adam_terms("X", X, [(gX_r, 2.0 * c_r), (gX_b, c_b), (gX_t, c_t)])
+            if cam_free:
+                adam_terms("t", t, [(gt_r, 2.0 * c_r), (gt_s, c_s), (gt_b, c_bl)])
+            if rot_free:
+                cands = []
+                with torch.cuda.device(dev):
+                    for buf, (gRk, sc) in zip(gw3, ((gR_r, 2.0 * c_r), (gR_s, c_s), (gR_b, c_bl))):
+                        if gRk is not None:
+                            _lib.check(fn("ska_so3_tangent_grad")(P(R), P(gRk), n_rot, P(buf), strm()))  # linear in dL/dR
+                            cands.append((buf, sc))
+                adam_terms("w", None, cands, step_out=sw)
+                if cands:
+                    with torch.cuda.device(dev):
+                        _lib.check(fn("ska_so3_retract")(P(R), P(sw), n_rot, strm()))
+
     def iteration():
+        if fused:
+            return fused_iteration()
         Xv = X.detach().requires_grad_(True)                    # views of the static buffers: the updates below are in place
         tv = t.detach().requires_grad_(mode != "pose_only")
         Rv = R.detach().requires_grad_(mode == "full")
@@ -507,7 +603,7 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
 
 
 def run_local_ba(K_torch, R_init_torch, t_init_torch, X3d_init_torch, x2d_torch, conf2d_torch, num_iters=200, lr=1e-3,
-                 device="cuda", mode="pose_only", optimizer="lm", weights=None, graph=True):
+                 device="cuda", mode="pose_only", optimizer="lm", weights=None, graph=True, fused=True):
     """The optimiser the reference calls but never defines (vggt/multi_view_process.py:553-564;
     argument shapes :546-551).  Returns (R_opt (T,C,3,3), t_opt (T,C,3), X_opt (T,J,3), history).
 
@@ -520,7 +616,7 @@ def run_local_ba(K_torch, R_init_torch, t_init_torch, X3d_init_torch, x2d_torch,
     (reprojection + the four regularisers of loss.py, weights of configs/vggt.yaml) with per-frame free cameras."""
     if optimizer == "adam":
         return run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch, x2d_torch, conf2d_torch, num_iters, lr,
-                                        device, mode, weights, graph)
+                                        device, mode, weights, graph, fused)
     if optimizer != "lm":
         raise ValueError(f"optimizer must be 'lm' or 'adam', got {optimizer!r}")
     dev = torch.device(device)

@@ -341,12 +341,28 @@ int ska_ema_f64(const double* d_X, int64_t T, int32_t J, const double* d_alpha_j
   return ema_smooth(d_X, T, J, d_alpha_joint, adaptive, alpha, alpha_min, alpha_max, speed_gain, chunk, halo, d_Y, (cudaStream_t)stream);
 }
 
+int ska_first_order_record_f64(double* d_k, double* d_scal, double* d_hist, int64_t max_rows, const double* const* sums5,
+                               const double* d_den, const double* coef5, double lr, double beta1, double beta2, void* stream) {
+  if (d_k == nullptr || d_scal == nullptr || sums5 == nullptr || coef5 == nullptr || max_rows < 0)
+    return set_error(SKA_EINVAL, "d_k, d_scal, sums5 and coef5 must not be NULL; max_rows >= 0");
+  return first_order_record(d_k, d_scal, d_hist, max_rows, sums5, d_den, coef5, lr, beta1, beta2, (cudaStream_t)stream);
+}
+
 #define SKA_OPTIM_ENTRY(SFX, S)                                                                                                   \
   int ska_adam_step_##SFX(S* d_p, const S* d_g, S* d_m, S* d_v, int64_t n, double step_size, double beta1, double beta2, double eps,  \
                           double inv_sqrt_bc2, S* d_step_out, const double* d_scalars, void* stream) {                             \
     if (n < 0 || (n > 0 && (d_g == nullptr || d_m == nullptr || d_v == nullptr || (d_p == nullptr && d_step_out == nullptr))))      \
       return set_error(SKA_EINVAL, "d_g, d_m, d_v and one of d_p / d_step_out must not be NULL; n >= 0");                          \
-    return adam_step<S>(d_p, d_g, d_m, d_v, n, step_size, beta1, beta2, eps, inv_sqrt_bc2, d_step_out, d_scalars,                   \
+    return adam_step<S>(d_p, d_g, d_m, d_v, n, step_size, beta1, beta2, eps, inv_sqrt_bc2, d_step_out, d_scalars, nullptr, nullptr, \
+                        1.0, 0.0, 0.0, (cudaStream_t)stream);                                                                       \
+  }                                                                                                                                 \
+  int ska_adam_step_terms_##SFX(S* d_p, const S* d_g0, double s0, const S* d_g1, double s1, const S* d_g2, double s2, S* d_m,       \
+                                S* d_v, int64_t n, double beta1, double beta2, double eps, S* d_step_out, const double* d_scalars,  \
+                                void* stream) {                                                                                     \
+    if (n < 0 || (n > 0 && (d_g0 == nullptr || d_m == nullptr || d_v == nullptr || d_scalars == nullptr ||                         \
+                            (d_p == nullptr && d_step_out == nullptr))))                                                            \
+      return set_error(SKA_EINVAL, "d_g0, d_m, d_v, d_scalars and one of d_p / d_step_out must not be NULL; n >= 0");             \
+    return adam_step<S>(d_p, d_g0, d_m, d_v, n, 0.0, beta1, beta2, eps, 1.0, d_step_out, d_scalars, d_g1, d_g2, s0, s1, s2,         \
                         (cudaStream_t)stream);                                                                                      \
   }                                                                                                                                 \
   int ska_so3_tangent_grad_##SFX(const S* d_R, const S* d_gR, int64_t n, S* d_gw, void* stream) {                                   \

@@ -89,7 +89,9 @@ int savgol(const float* X, int64_t T, int S, int win, int poly, float* out, void
 // first-order optimiser updates (ska_optim.cu)
 template <typename S>
 int adam_step(S* p, const S* g, S* m, S* v, int64_t n, double step_size, double b1, double b2, double eps, double inv_sqrt_bc2, S* step_out,
-              const double* scalars, cudaStream_t s);
+              const double* scalars, const S* g1, const S* g2, double s0, double s1, double s2, cudaStream_t s);
+int first_order_record(double* k, double* scal, double* hist, int64_t max_rows, const double* const* sums, const double* den,
+                       const double* coef, double lr, double b1, double b2, cudaStream_t s);
 template <typename S>
 int so3_tangent_grad(const S* R, const S* gR, int64_t n, S* gw, cudaStream_t s);
 template <typename S>

@@ -100,6 +100,7 @@ int pose_temporal(const S* X, int64_t T, int J, double* sum, S* gX, void* ws, si
   // one partial per block in the workspace: keep the block count within it by lengthening the chunks of long clips
   const int64_t max_blocks = (int64_t)(reg_workspace_bytes() / sizeof(double));
   int64_t chunk = kPtChunk;
+  while (chunk > 8 && (T + chunk - 1) / chunk * M < 300000) chunk /= 2;  // short clips: enough threads to fill the GPU
   while (((T + chunk - 1) / chunk * M + kLB - 1) / kLB > max_blocks) chunk *= 2;
   const int64_t threads = (T + chunk - 1) / chunk * M;
   const int grid = (int)((threads + kLB - 1) / kLB < 1 ? 1 : (threads + kLB - 1) / kLB);

@@ -16,8 +16,18 @@
 
 namespace ska {
 
+// up to three gradient terms g = s0 g0 + s1 g1 + s2 g2 (the loss kernels return UNSCALED gradients of their raw sums: the
+// weights / counts are applied here instead of in separate element-wise passes)
 template <typename S>
-__global__ void __launch_bounds__(256) adam_kernel(S* __restrict__ p, const S* __restrict__ g, S* __restrict__ m, S* __restrict__ v,
+struct GradTerms {
+  const S* g0;
+  const S* g1;
+  const S* g2;
+  double s0, s1, s2;
+};
+
+template <typename S>
+__global__ void __launch_bounds__(256) adam_kernel(S* __restrict__ p, const GradTerms<S> gt, S* __restrict__ m, S* __restrict__ v,
                                                    int64_t n, double step_size, double b1, double b2, double eps, double inv_sqrt_bc2,
                                                    S* __restrict__ step_out, const double* __restrict__ scalars) {
   if (scalars != nullptr) {  // per-iteration scalars from device memory: lets a captured CUDA graph be replayed for every k
@@ -26,7 +36,9 @@ __global__ void __launch_bounds__(256) adam_kernel(S* __restrict__ p, const S* _
   }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double gi = (double)g[i];
+    double gi = gt.s0 * (double)gt.g0[i];
+    if (gt.g1 != nullptr) gi += gt.s1 * (double)gt.g1[i];
+    if (gt.g2 != nullptr) gi += gt.s2 * (double)gt.g2[i];
     const double mi = (double)m[i] + (1.0 - b1) * (gi - (double)m[i]);
     const double vi = b2 * (double)v[i] + (1.0 - b2) * gi * gi;
     m[i] = (S)mi;
@@ -88,6 +100,51 @@ __global__ void __launch_bounds__(256) so3_retract_kernel(S* __restrict__ R, con
     for (int c = 0; c < 3; ++c) R[9 * i + 3 * a + c] = (S)(E[3 * a] * r[c] + E[3 * a + 1] * r[3 + c] + E[3 * a + 2] * r[6 + c]);
 }
 
+// Scalar bookkeeping of one first-order iteration in ONE thread (instead of ~20 one-element torch kernels):
+// record: hist[k] = [total, c0 s0 / (den + 1e-6) (den == nullptr: c0 s0), c1 s1, c2 s2, c3 s3, c4 s4] for the five loss terms
+// (a NULL sum pointer = term switched off), then k <- k + 1 and the Adam scalars of step k:
+// scal = {lr / (1 - b1^k), 1 / sqrt(1 - b2^k)}.
+struct RecordArgs {
+  const double* s[5];
+  const double* den;
+  double c[5];
+};
+__global__ void first_order_record_kernel(double* __restrict__ k, double* __restrict__ scal, double* __restrict__ hist, int64_t max_rows,
+                                          const RecordArgs a, double lr, double b1, double b2) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const int64_t it = (int64_t)k[0];
+  double tot = 0.0, term[5];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    term[q] = 0.0;
+    if (a.s[q] != nullptr) term[q] = (q == 0 && a.den != nullptr) ? a.c[q] * a.s[q][0] / (a.den[0] + 1e-6) : a.c[q] * a.s[q][0];
+    tot += term[q];
+  }
+  if (hist != nullptr && it < max_rows) {
+    double* h = hist + it * 6;
+    h[0] = tot;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) h[1 + q] = term[q];
+  }
+  const double kk = (double)(it + 1);
+  k[0] = kk;
+  scal[0] = lr / (1.0 - pow(b1, kk));
+  scal[1] = rsqrt(1.0 - pow(b2, kk));
+}
+
+int first_order_record(double* k, double* scal, double* hist, int64_t max_rows, const double* const* sums, const double* den,
+                       const double* coef, double lr, double b1, double b2, cudaStream_t s) {
+  RecordArgs a;
+  for (int q = 0; q < 5; ++q) {
+    a.s[q] = sums[q];
+    a.c[q] = coef[q];
+  }
+  a.den = den;
+  first_order_record_kernel<<<1, 32, 0, s>>>(k, scal, hist, max_rows, a, lr, b1, b2);
+  const cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
+}
+
 static int grid_of(int64_t n) {
   int64_t g = (n + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
@@ -96,9 +153,10 @@ static int grid_of(int64_t n) {
 
 template <typename S>
 int adam_step(S* p, const S* g, S* m, S* v, int64_t n, double step_size, double b1, double b2, double eps, double inv_sqrt_bc2, S* step_out,
-              const double* scalars, cudaStream_t s) {
+              const double* scalars, const S* g1, const S* g2, double s0, double s1, double s2, cudaStream_t s) {
   if (n == 0) return SKA_OK;
-  adam_kernel<S><<<grid_of(n), 256, 0, s>>>(p, g, m, v, n, step_size, b1, b2, eps, inv_sqrt_bc2, step_out, scalars);
+  const GradTerms<S> gt{g, g1, g2, s0, s1, s2};
+  adam_kernel<S><<<grid_of(n), 256, 0, s>>>(p, gt, m, v, n, step_size, b1, b2, eps, inv_sqrt_bc2, step_out, scalars);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }
@@ -117,8 +175,10 @@ int so3_retract(S* R, const S* step, int64_t n, cudaStream_t s) {
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }
 
-template int adam_step<float>(float*, const float*, float*, float*, int64_t, double, double, double, double, double, float*, const double*, cudaStream_t);
-template int adam_step<double>(double*, const double*, double*, double*, int64_t, double, double, double, double, double, double*, const double*, cudaStream_t);
+template int adam_step<float>(float*, const float*, float*, float*, int64_t, double, double, double, double, double, float*, const double*, const float*,
+                              const float*, double, double, double, cudaStream_t);
+template int adam_step<double>(double*, const double*, double*, double*, int64_t, double, double, double, double, double, double*, const double*,
+                               const double*, const double*, double, double, double, cudaStream_t);
 template int so3_tangent_grad<float>(const float*, const float*, int64_t, float*, cudaStream_t);
 template int so3_tangent_grad<double>(const double*, const double*, int64_t, double*, cudaStream_t);
 template int so3_retract<float>(float*, const float*, int64_t, cudaStream_t);

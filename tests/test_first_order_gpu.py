@@ -38,6 +38,20 @@ def test_graph_replay_equals_eager(cuda, golden):
     assert torch.equal(a[2], b[2]) and torch.equal(a[0], b[0])
 
 
+@pytest.mark.parametrize("mode", ba.MODES)
+def test_fused_iteration_equals_autograd_iteration(cuda, golden, mode):
+    """The product iteration (raw loss kernels, weights folded into the multi-term Adam kernel) against the same
+    optimiser driven through the autograd wrappers of losses.py."""
+    g = golden("g9_first_order.npz")
+    a = ba.run_local_ba(**_args(g, torch.float64), num_iters=20, lr=1e-2, device="cuda", mode=mode, optimizer="adam", fused=True)
+    b = ba.run_local_ba(**_args(g, torch.float64), num_iters=20, lr=1e-2, device="cuda", mode=mode, optimizer="adam", fused=False, graph=False)
+    np.testing.assert_allclose([h["loss"] for h in a[3]], [h["loss"] for h in b[3]], rtol=1e-10)
+    for k in TERMS:
+        np.testing.assert_allclose([h[k] for h in a[3]], [h[k] for h in b[3]], rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(a[2].cpu().numpy(), b[2].cpu().numpy(), atol=1e-10)
+    np.testing.assert_allclose(a[0].cpu().numpy(), b[0].cpu().numpy(), atol=1e-11)
+
+
 def test_f32_trajectory_within_tolerance(cuda, golden):
     g = golden("g9_first_order.npz")
     R, t, X, hist = ba.run_local_ba(**_args(g, torch.float32), num_iters=12, lr=1e-2, device="cuda", mode="pose_cam_t", optimizer="adam")

@@ -33,6 +33,9 @@ def main():
         for mode in ba.MODES:
             args = (torch.tensor(d["K"]), Rf.to(dt), tf.to(dt), X0.to(dt), d["x2d"], d["conf"])
             use_graph = "--no-graph" not in sys.argv
+            only = [a.split("=")[1] for a in sys.argv if a.startswith("--mode=")]
+            if only and mode not in only:
+                continue
             ba.run_local_ba(*args, num_iters=5, lr=1e-2, mode=mode, optimizer="adam", graph=use_graph)
             torch.cuda.synchronize()
             t0_ = time.perf_counter()
