@@ -46,7 +46,7 @@ static int small_grid(int64_t n) {
   return g < 1 ? 1 : g;
 }
 
-size_t reg_workspace_bytes() { return (size_t)(ba_max_grid() / 4) * SKA_MAX_BONES * sizeof(double); }
+size_t reg_workspace_bytes() { return (size_t)ba_max_grid() * SKA_MAX_BONES * sizeof(double); }  // one partial row per block
 
 #define SKA_LAUNCH_CHECK()                                                     \
   do {                                                                         \
@@ -156,6 +156,88 @@ __global__ void __launch_bounds__(kLB) bone_length_kernel(const S* __restrict__ 
   block_sum_store<SKA_MAX_BONES>(acc, scratch, partials + (int64_t)blockIdx.x * SKA_MAX_BONES);
 }
 
+// Staged form: a block of FB threads owns FB consecutive frames; their rows (one contiguous run in global memory) are
+// copied into shared memory coalesced, every thread works on its frame's row there (gradient accumulation included - the
+// direct kernel above read-modify-writes its gradient row in GLOBAL memory, 12 bones x 6 entries per frame), and the
+// gradient rows leave coalesced.  Same arithmetic in the same order per frame: bit-identical results.  Row stride is odd
+// (3J | 1): the FB threads of a warp hit distinct banks.
+template <typename S>
+__global__ void __launch_bounds__(128) bone_length_staged_kernel(const S* __restrict__ X, int64_t T, int J, const Bones bones,
+                                                                const double* __restrict__ ref, S* __restrict__ gX,
+                                                                double* __restrict__ partials) {
+  extern __shared__ __align__(16) unsigned char bl_smem[];
+  __shared__ double scratch[4 * SKA_MAX_BONES];
+  const int FB = blockDim.x, M = 3 * J, RS = M | 1;
+  S* xs = reinterpret_cast<S*>(bl_smem);
+  S* gs = xs + (size_t)FB * RS;
+  double acc[SKA_MAX_BONES];
+#pragma unroll
+  for (int b = 0; b < SKA_MAX_BONES; ++b) acc[b] = 0.0;
+  const bool want_g = gX != nullptr && ref != nullptr;
+  for (int64_t f0 = (int64_t)blockIdx.x * FB; f0 < T; f0 += (int64_t)gridDim.x * FB) {
+    const int nv = (int)((T - f0) < FB ? (T - f0) : FB);
+    const int64_t base = f0 * M;
+    {
+      int f = 0, k = threadIdx.x;
+      while (k >= M) {
+        k -= M;
+        ++f;
+      }
+      for (int e = threadIdx.x; e < nv * M; e += FB) {
+        xs[f * RS + k] = X[base + e];
+        if (want_g) gs[f * RS + k] = S(0);
+        k += FB;
+        while (k >= M) {
+          k -= M;
+          ++f;
+        }
+      }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nv) {
+      const S* x = xs + threadIdx.x * RS;
+      S* g = gs + threadIdx.x * RS;
+#pragma unroll
+      for (int b = 0; b < SKA_MAX_BONES; ++b) {
+        if (b < bones.n) {
+          const int i = bones.i[b], j = bones.j[b];
+          const S d0 = x[3 * i] - x[3 * j], d1 = x[3 * i + 1] - x[3 * j + 1], d2 = x[3 * i + 2] - x[3 * j + 2];
+          const double len = sqrt((double)d0 * d0 + (double)d1 * d1 + (double)d2 * d2);
+          if (ref == nullptr) {
+            acc[b] += len;
+          } else {
+            const double r = len - ref[b];
+            acc[0] += r * r;
+            if (want_g && len > 0.0) {  // torch.norm's subgradient at 0 is 0
+              const double fq = 2.0 * r / len;
+              g[3 * i] += (S)(fq * d0); g[3 * i + 1] += (S)(fq * d1); g[3 * i + 2] += (S)(fq * d2);
+              g[3 * j] -= (S)(fq * d0); g[3 * j + 1] -= (S)(fq * d1); g[3 * j + 2] -= (S)(fq * d2);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (gX != nullptr) {
+      int f = 0, k = threadIdx.x;
+      while (k >= M) {
+        k -= M;
+        ++f;
+      }
+      for (int e = threadIdx.x; e < nv * M; e += FB) {
+        gX[base + e] = want_g ? gs[f * RS + k] : S(0);
+        k += FB;
+        while (k >= M) {
+          k -= M;
+          ++f;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  block_sum_store<SKA_MAX_BONES>(acc, scratch, partials + (int64_t)blockIdx.x * SKA_MAX_BONES);
+}
+
 template <typename S>
 int bone_length(const S* X, int64_t T, int J, const int32_t* bi, const int32_t* bj, int nb, const double* ref, double* sums,
                 S* gX, void* ws, size_t ws_bytes, cudaStream_t s) {
@@ -167,6 +249,27 @@ int bone_length(const S* X, int64_t T, int J, const int32_t* bi, const int32_t* 
     b.i[k] = k < nb ? bi[k] : 0;
     b.j[k] = k < nb ? bj[k] : 0;
     if (k < nb && (bi[k] < 0 || bi[k] >= J || bj[k] < 0 || bj[k] >= J)) return set_error(SKA_EINVAL, "bone index out of range");
+  }
+  // gradient pass: staged kernel when FB rows of x and g fit in shared memory (J <= ~140 in fp32); the direct kernel otherwise
+  const int RS = (3 * J) | 1;
+  int FB = 128;
+  while (FB > 32 && (size_t)2 * FB * RS * sizeof(S) > 96 * 1024) FB /= 2;
+  const size_t smem = (size_t)2 * FB * RS * sizeof(S);
+  if (gX != nullptr && ref != nullptr && smem <= 200 * 1024) {  // forward-only passes: the direct kernel's row reads are already L1-coalesced (measured faster)
+    static size_t attr_bytes[64] = {};
+    int dev = 0;
+    if (smem > 48 * 1024 && cudaGetDevice(&dev) == cudaSuccess && dev < 64 && attr_bytes[dev] < smem) {  // idempotent; benign race
+      const cudaError_t ca = cudaFuncSetAttribute(bone_length_staged_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (ca != cudaSuccess) return set_error((int)ca, cudaGetErrorString(ca));
+      attr_bytes[dev] = smem;
+    }
+    const int64_t need = (T + FB - 1) / FB;
+    int grid = ba_max_grid();  // one partial row per block in the workspace (reg_workspace_bytes)
+    if (grid > need) grid = (int)need;
+    if (grid < 1) grid = 1;
+    bone_length_staged_kernel<S><<<grid, FB, smem, s>>>(X, T, J, b, ref, gX, (double*)ws);
+    SKA_LAUNCH_CHECK();
+    return launch_reduce((const double*)ws, grid, SKA_MAX_BONES, sums, s);
   }
   const int grid = small_grid(T);
   bone_length_kernel<S><<<grid, kLB, 0, s>>>(X, T, J, b, ref, gX, (double*)ws);
