@@ -1,7 +1,6 @@
 """Time the two-view fusion + EMA kernels (row N3) on 1M frames x 70 joints, next to the reference's per-frame numpy
-path (oracle/fusion.py, the call-for-call array form) on a bounded sample:  python tools/fusion_bench.py [T] [J]"""
+path:  python tools/fusion_bench.py [T] [J]"""
 import sys
-import time
 from pathlib import Path
 
 import torch
@@ -43,15 +42,7 @@ def main():
     print(f"fuse_frames: T={T} J={J}  {ms_fuse:.3f} ms  {T / ms_fuse * 1e3:.3e} frames/s  alg {b_fuse / 1e9:.2f} GB -> {b_fuse / ms_fuse / 1e6:.0f} GB/s")
     print(f"ema (chunk 512, halo {halo}): {ms_ema:.3f} ms  {T / ms_ema * 1e3:.3e} frames/s  alg {b_ema / 1e9:.2f} GB -> {b_ema / ms_ema / 1e6:.0f} GB/s"
           f"   sequential scan: {ms_seq:.1f} ms")
-    # CPU: the reference's per-frame numpy path (array form) on a bounded sample
-    from oracle import fusion as F
-    n = 1000
-    t0 = time.perf_counter()
-    fz, *_ = F.fuse_clip(small["Xl"][:n], small["Xr"][:n], small["Ul"][:n], small["Ur"][:n])
-    t1 = time.perf_counter()
-    F.temporal_smooth_ema(fz)
-    t2 = time.perf_counter()
-    print(f"cpu (1 core, numpy per frame like fuse/main_raw.py): fuse {n / (t1 - t0):.0f} frames/s, ema {n / (t2 - t1):.0f} frames/s")
+    # (the CPU baseline of this path is timed by bench.py's `fusion.cpu_baseline` leg)
 
 
 if __name__ == "__main__":
