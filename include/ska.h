@@ -344,6 +344,20 @@ size_t ska_fuse_workspace_bytes(int64_t T);
 int ska_fuse_frames_f64(const double* d_Xl, const double* d_Xr, const double* d_Ul, const double* d_Ur, int64_t T, int32_t J,
                         const SkaFuseParams* prm, double* d_fused, double* d_ql, double* d_qr, double* d_aligned,
                         uint8_t* d_status, void* d_workspace, size_t ws_bytes, void* stream);
+/* ska_rigid_fuse_f64: rigid_transform_3D of bundle_adjustment/fuse/fuse.py:96-232 (== fuse/side/fuse/fuse.py,
+ *   front_side/side/fuse/fuse.py; called at bundle_adjustment/run.py:225) for a whole clip.  d_L (target / left), d_R
+ *   (source / right) (T,J,3) fp64, NaN rows = missing.  Per frame: Umeyama alignment s R x + t of the right view onto the
+ *   left from the joints torso5 (HOST array of 5 indices; fuse.py:27-31 uses 69, 9, 10, 5, 6) exactly as
+ *   estimate_rigid_umeyama does (fuse_check.py:26-78: cross-covariance / N, det-fixed rotation, s = sum(S) / (var + 1e-12)
+ *   when allow_scale, else 1), then per joint (fuse.py:55-93): one view missing -> the other; both present and farther
+ *   apart than tau (d_tau_j (J,) if not NULL, else the scalar) -> the view with the larger weight (left on ties); else the
+ *   weighted mean / (wL + wR + 1e-9).  d_wL / d_wR nullable (weights 1): (T,J) with w_frame_stride = J or (J,) with 0.
+ *   Outputs: d_fused (T,J,3); d_Rts (T,13) = R (9, row-major), t (3), s; nullable d_diag (T,4) = LR_before, Fused_vs_L,
+ *   Fused_vs_R, gain (plain means over the joints: NaN if one is missing, like the reference); nullable d_status (T,):
+ *   1 = fewer than 3 usable torso joints (the reference raises ValueError; that frame's d_Rts is NaN). */
+int ska_rigid_fuse_f64(const double* d_L, const double* d_R, int64_t T, int32_t J, const int32_t* torso5, double tau,
+                       const double* d_tau_j, int32_t allow_scale, const double* d_wL, const double* d_wR, int64_t w_frame_stride,
+                       double* d_fused, double* d_Rts, double* d_diag, uint8_t* d_status, void* stream);
 int ska_ema_f64(const double* d_X, int64_t T, int32_t J, const double* d_alpha_joint, int32_t adaptive, double alpha,
                 double alpha_min, double alpha_max, double speed_gain, int64_t chunk, int32_t halo, double* d_Y, void* stream);
 

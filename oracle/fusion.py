@@ -209,3 +209,68 @@ def fuse_clip(Xl, Xr, Ul, Ur, sigma_px=12.0, sigma_3d=0.08, scale_mode="hip", al
         ql[t], qr[t] = np.sqrt(c1l * c2), np.sqrt(c1r * c2)
         fused[t] = fuse_frame_3d(Xl[t], Xa[t], ql[t], qr[t])
     return fused, ql, qr, Xa
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the second fusion path of the reference: bundle_adjustment/fuse/fuse.py (== fuse/side/fuse/fuse.py ==
+# front_side/side/fuse/fuse.py), called per frame by bundle_adjustment/run.py:225, fuse/side/run.py:81,
+# front_side/side/run.py:81
+TORSO_IDX = (69, 9, 10, 5, 6)  # NECK, L_HIP, R_HIP, L_SHO, R_SHO (bundle_adjustment/fuse/fuse.py:27-31)
+
+
+def estimate_rigid_umeyama(target, source, allow_scale=False):
+    """bundle_adjustment/fuse/fuse_check.py:26-78 -> R, t, s with s R source + t ~ target."""
+    mask = _finite_rows(target) & _finite_rows(source)
+    target, source = target[mask], source[mask]
+    N = target.shape[0]
+    if N < 3:
+        raise ValueError("need at least 3 corresponding points")
+    tm, sm = target.mean(0), source.mean(0)
+    tc, sc = target - tm, source - sm
+    H = (sc.T @ tc) / N
+    U, S, Vt = np.linalg.svd(H)
+    R = Vt.T @ U.T
+    if np.linalg.det(R) < 0:
+        Vt[-1, :] *= -1
+        R = Vt.T @ U.T
+    s = S.sum() / ((sc**2).sum() / N + 1e-12) if allow_scale else 1.0
+    return R, tm - s * (R @ sm), float(s)
+
+
+def fuse_two(L, R_align, tau, wL, wR):
+    """bundle_adjustment/fuse/fuse.py:55-93: per joint - one view missing: the other; both present and farther apart than
+    tau: the more confident view (left on ties); else the confidence-weighted mean."""
+    out = np.full_like(L, np.nan)
+    okl, okr = _finite_rows(L), _finite_rows(R_align)
+    out[okl & ~okr] = L[okl & ~okr]
+    out[okr & ~okl] = R_align[okr & ~okl]
+    both = okl & okr
+    d = np.linalg.norm(L - R_align, axis=1)
+    far = both & (d > tau)
+    pickL = far & (wL >= wR)
+    out[pickL] = L[pickL]
+    out[far & ~pickL] = R_align[far & ~pickL]
+    near = both & ~far
+    out[near] = (wL[near, None] * L[near] + wR[near, None] * R_align[near]) / (wL[near, None] + wR[near, None] + 1e-9)
+    return out
+
+
+def rigid_transform_3D(target, source, tau=0.08, allow_scale=False, wL=None, wR=None):
+    """bundle_adjustment/fuse/fuse.py:96-232 on (T,J,3) arrays -> fused (T,J,3), Rhat (T,3,3), that (T,3), s (T,),
+    diag (T,4) = [LR_before, Fused_vs_L, Fused_vs_R, gain] (plain means: NaN if any joint is missing, like the reference)."""
+    L, R = np.asarray(target, float), np.asarray(source, float)
+    T, J, _ = L.shape
+    ex = lambda w: np.ones((T, J)) if w is None else np.broadcast_to(np.asarray(w, float), (T, J))
+    wLs, wRs = ex(wL), ex(wR)
+    tauv = np.broadcast_to(np.asarray(tau, float), (J,))
+    fused, Rh, th, sh, diag = np.empty_like(L), np.empty((T, 3, 3)), np.empty((T, 3)), np.empty(T), np.empty((T, 4))
+    idx = list(TORSO_IDX)
+    for t in range(T):
+        Rh[t], th[t], sh[t] = estimate_rigid_umeyama(L[t][idx], R[t][idx], allow_scale)
+        Ra = sh[t] * (Rh[t] @ R[t].T).T + th[t]
+        fused[t] = fuse_two(L[t], Ra, tauv, wLs[t], wRs[t])
+        lr = np.linalg.norm(L[t] - R[t], axis=-1).mean()
+        fl = np.linalg.norm(fused[t] - L[t], axis=-1).mean()
+        fr = np.linalg.norm(fused[t] - R[t], axis=-1).mean()
+        diag[t] = [lr, fl, fr, lr - 0.5 * (fl + fr)]
+    return fused, Rh, th, sh, diag

@@ -17,6 +17,7 @@ tests only ever read the .npz files.  Golden sets:
       softmax fusion, adaptive EMA (row N3)
   G10 on-disk schemas (row N4): .pt keypoint dicts, SAM-3D-Body npz, fuse / triangulation writers - fixture files under
       tests/golden/io/ and the reference loaders' outputs for them
+  G11 bundle_adjustment/fuse/fuse.py rigid_transform_3D (Umeyama on the torso joints + threshold fusion, row N3)
   G9  oracle/first_order.py (Adam on the full configured objective) driven by the reference's bundle_adjustment/loss.py
   G6  LM history of oracle/lm.py on BASELINE configs 3 and 5 at reduced T, with the REFERENCE's
       reprojection_loss evaluated at the initial and final state of each solve (pins the cost the
@@ -392,8 +393,39 @@ def g10():
     print("g10 written:", sorted(p.name for p in (io_dir / "ref_out" / "joints").iterdir())[:4], "...")
 
 
+def g11():
+    """bundle_adjustment/fuse/fuse.py:rigid_transform_3D (Umeyama alignment on the 5 torso joints + threshold fusion),
+    the fusion the bundle_adjustment / fuse.side / front_side.side pipelines call (second half of row N3)."""
+    bf = ref_import.load("bundle_adjustment.fuse.fuse")
+    T, J = 40, 70
+    d = synth.make_fusion_clip(T, J, seed=21, nan_frac=0.05)
+    L, R = d["Xl"].copy(), d["Xr"].copy()
+    full = synth.make_fusion_clip(12, J, seed=23, nan_frac=0.0)   # 12 complete frames: finite diagnostics (plain means)
+    L[:12], R[:12] = full["Xl"], full["Xr"]
+    rng = np.random.default_rng(22)
+    wL, wR = rng.uniform(0.2, 1.0, (T, J)), rng.uniform(0.2, 1.0, (T, J))
+    out = dict(L=L, R=R, wL=wL, wR=wR)
+    for name, kw in (("plain", dict()), ("weighted", dict(wL=wL, wR=wR, tau=0.05)), ("scaled", dict(allow_scale=True, wL=wL[0], wR=wR[0]))):
+        ok = np.array([np.isfinite(L[t][list(bf.TORSO_IDX)]).all(1).__and__(np.isfinite(R[t][list(bf.TORSO_IDX)]).all(1)).sum() >= 3 for t in range(T)])
+        fused, diag = bf.rigid_transform_3D(L[ok], R[ok], return_diagnostics=True, **kw)
+        out[f"{name}_ok"] = ok
+        out[f"{name}_fused"] = fused
+        out[f"{name}_R"] = np.stack([p["R"] for p in diag["per_frame"]])
+        out[f"{name}_t"] = np.stack([p["t"] for p in diag["per_frame"]])
+        out[f"{name}_s"] = np.array([p["s"] for p in diag["per_frame"]])
+        out[f"{name}_diag"] = np.array([[p["LR_before"], p["Fused_vs_L"], p["Fused_vs_R"], p["gain"]] for p in diag["per_frame"]])
+        out[f"{name}_mean_gain"] = diag["mean_gain"]
+        out[f"{name}_bad"] = np.array(diag["bad_frames"], dtype=np.int64)
+    f1, d1 = bf.rigid_transform_3D(L[0], R[0])   # single frame (J,3) in, (J,3) out
+    out["single_fused"] = f1
+    np.savez_compressed(OUT / "g11_rigid_fuse.npz", **out)
+    print("g11 written: frames ok", int(out["plain_ok"].sum()), "of", T, "mean gain", out["plain_mean_gain"])
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    if "--only-g11" in sys.argv:
+        return g11()
     if "--only-g10" in sys.argv:
         return g10()
     if "--only-g8" in sys.argv:

@@ -68,6 +68,8 @@ _SIGS = {
     "ska_fuse_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "ska_fuse_frames_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.POINTER(_cabi.SkaFuseParams), _vp, _vp, _vp, _vp, _vp, _vp,
                                        C.c_size_t, _vp]),
+    "ska_rigid_fuse_f64": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_double, _vp, C.c_int32, _vp, _vp, C.c_int64, _vp, _vp,
+                                     _vp, _vp, _vp]),
     "ska_ema_f64": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64,
                               C.c_int32, _vp, _vp]),
 }

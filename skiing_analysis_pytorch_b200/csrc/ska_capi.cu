@@ -331,6 +331,19 @@ int ska_fuse_frames_f64(const double* d_Xl, const double* d_Xr, const double* d_
                      (cudaStream_t)stream);
 }
 
+int ska_rigid_fuse_f64(const double* d_L, const double* d_R, int64_t T, int32_t J, const int32_t* torso5, double tau,
+                       const double* d_tau_j, int32_t allow_scale, const double* d_wL, const double* d_wR, int64_t w_frame_stride,
+                       double* d_fused, double* d_Rts, double* d_diag, uint8_t* d_status, void* stream) {
+  if (T < 0 || J < 1 || torso5 == nullptr) return set_error(SKA_EINVAL, "T >= 0, J >= 1, torso5 must not be NULL");
+  for (int k = 0; k < 5; ++k)
+    if (torso5[k] < 0 || torso5[k] >= J) return set_error(SKA_EINVAL, "torso joint index outside 0..J-1");
+  if (T > 0 && (d_L == nullptr || d_R == nullptr || d_fused == nullptr || d_Rts == nullptr))
+    return set_error(SKA_EINVAL, "d_L, d_R, d_fused and d_Rts must not be NULL");
+  if (w_frame_stride != 0 && w_frame_stride != J) return set_error(SKA_EINVAL, "w_frame_stride must be 0 (per-joint weights) or J (per-frame)");
+  return rigid_fuse(d_L, d_R, T, J, torso5, tau, d_tau_j, allow_scale, d_wL, d_wR, w_frame_stride, d_fused, d_Rts, d_diag, d_status,
+                    (cudaStream_t)stream);
+}
+
 int ska_ema_f64(const double* d_X, int64_t T, int32_t J, const double* d_alpha_joint, int32_t adaptive, double alpha,
                 double alpha_min, double alpha_max, double speed_gain, int64_t chunk, int32_t halo, double* d_Y, void* stream) {
   if (T < 0 || J < 1) return set_error(SKA_EINVAL, "T must be >= 0 and J >= 1");

@@ -70,7 +70,7 @@ __device__ __forceinline__ void cross3(const double* a, const double* b, double*
 }
 
 // Rotation of the Kabsch problem for H = src_c^T dst_c (row-major 3x3): R = V diag(1, 1, det) U^T  (main_raw.py:58-65)
-__device__ void kabsch_rotation(const double H[9], double R[9]) {
+__device__ void kabsch_rotation(const double H[9], double R[9], double* sum_sv = nullptr) {
   double a[3][3], v[3][3];  // columns
 #pragma unroll
   for (int c = 0; c < 3; ++c)
@@ -89,6 +89,7 @@ __device__ void kabsch_rotation(const double H[9], double R[9]) {
   double s[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) s[c] = sqrt(a[c][0] * a[c][0] + a[c][1] * a[c][1] + a[c][2] * a[c][2]);
+  if (sum_sv != nullptr) *sum_sv = s[0] + s[1] + s[2];
   // the two largest singular values (order between them is irrelevant for the sum of outer products)
   int i0 = 0, i1 = 1, i2 = 2;
   if (s[i2] > s[i0]) { const int q = i0; i0 = i2; i2 = q; }
@@ -113,7 +114,7 @@ __device__ void kabsch_rotation(const double H[9], double R[9]) {
 // (no reflection to repair), and Newton's iteration X <- (X + X^-T) / 2 reaches it quadratically - six iterations of ~80
 // fp64 operations for a body-shaped point set instead of ~5 Jacobi sweeps with two roots and two divisions per rotation.
 // Returns false (caller runs kabsch_rotation) for a reflected or nearly planar / collinear cross-covariance.
-__device__ __forceinline__ bool polar_rotation(const double H[9], double R[9]) {
+__device__ __forceinline__ bool polar_rotation(const double H[9], double R[9], double* sum_sv = nullptr) {
   double f = 0.0;
 #pragma unroll
   for (int q = 0; q < 9; ++q) f += H[q] * H[q];
@@ -148,6 +149,12 @@ __device__ __forceinline__ bool polar_rotation(const double H[9], double R[9]) {
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) R[3 * r + c] = X[3 * c + r];
+  if (sum_sv != nullptr) {  // H = Q P with P = Q^T H symmetric positive definite: trace(P) = sum of singular values
+    double tr = 0.0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) tr += X[q] * H[q];
+    *sum_sv = tr;
+  }
   return true;
 }
 
@@ -763,6 +770,197 @@ __global__ void __launch_bounds__(256) fuse_joints_kernel(const FuseArgs3 g) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) a.aligned[3 * o + d] = okr ? xa[d] : nan;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rigid_transform_3D of bundle_adjustment/fuse/fuse.py:96-232 (the fusion the bundle_adjustment / fuse.side /
+// front_side.side pipelines call) for a whole clip: Umeyama alignment of the right view onto the left from the five torso
+// joints (fuse_check.py:26-78: cross-covariance / N, SVD with det fix, optional scale sum(S) / var), threshold fusion per
+// joint (fuse.py:55-93) and the per-frame diagnostics (plain means, NaN when a joint is missing - like the reference).
+//   rigid_params_kernel  thread per frame -> [R (9) | t (3) | s] and status
+//   rigid_fuse_kernel    kLPF lanes per frame: aligned right view, fused joints, the three mean distances
+struct RigidArgs {
+  const double* L;
+  const double* R;
+  int64_t T;
+  int32_t J;
+  int32_t torso[5];
+  int32_t allow_scale;
+  double tau;
+  const double* tau_j;  // nullable (J,)
+  const double* wL;     // nullable, (T,J) or (J,) with w_sT = 0
+  const double* wR;
+  int64_t w_sT;
+  double* fused;
+  double* Rts;          // (T,13)
+  double* diag;         // nullable (T,4)
+  uint8_t* status;      // nullable
+};
+
+__global__ void __launch_bounds__(64) rigid_params_kernel(const RigidArgs a) {
+  const int64_t frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (frame >= a.T) return;
+  const double* Lf = a.L + frame * a.J * 3;
+  const double* Rf = a.R + frame * a.J * 3;
+  double tl[5][3], sr[5][3];
+  bool ok[5];
+  double n = 0.0, tm[3] = {0, 0, 0}, sm[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      tl[k][d] = Lf[3 * a.torso[k] + d];
+      sr[k][d] = Rf[3 * a.torso[k] + d];
+    }
+    ok[k] = fin3(tl[k]) && fin3(sr[k]);
+    if (ok[k]) {
+      n += 1.0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        tm[d] += tl[k][d];
+        sm[d] += sr[k][d];
+      }
+    }
+  }
+  double* out = a.Rts + frame * 13;
+  if (n < 3.0) {  // the reference raises ValueError (fuse_check.py:43-44)
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int q = 0; q < 13; ++q) out[q] = nan;
+    if (a.status != nullptr) a.status[frame] = 1;
+    return;
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    tm[d] /= n;
+    sm[d] /= n;
+  }
+  double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, var = 0.0;
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+    if (ok[k]) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double sc = sr[k][r] - sm[r];
+        var += sc * sc;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) H[3 * r + c] += sc * (tl[k][c] - tm[c]);
+      }
+    }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) H[q] /= n;
+  double Rm[9], sumS = 0.0;
+  if (!polar_rotation(H, Rm, &sumS)) kabsch_rotation(H, Rm, &sumS);
+  const double s = a.allow_scale ? sumS / (var / n + 1e-12) : 1.0;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) out[q] = Rm[q];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) out[9 + r] = tm[r] - s * (Rm[3 * r] * sm[0] + Rm[3 * r + 1] * sm[1] + Rm[3 * r + 2] * sm[2]);
+  out[12] = s;
+  if (a.status != nullptr) a.status[frame] = 0;
+}
+
+__global__ void __launch_bounds__(256) rigid_fuse_kernel(const RigidArgs a) {
+  const int lane = threadIdx.x & 31, sub = lane & (kLPF - 1);
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t frame = warp_global * (32 / kLPF) + (lane / kLPF);
+  const bool live = frame < a.T;
+  const int64_t fr = live ? frame : a.T - 1;
+  const int J = a.J;
+  const double* Lf = a.L + fr * J * 3;
+  const double* Rf = a.R + fr * J * 3;
+  const double* P = a.Rts + fr * 13;
+  double Rm[9], tv[3];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) Rm[q] = P[q];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) tv[q] = P[9 + q];
+  const double s = P[12];
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  double d_lr = 0.0, d_fl = 0.0, d_fr = 0.0;
+#pragma unroll 1
+  for (int j = sub; j < J; j += kLPF) {
+    double l[3], r[3], ra[3], f[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      l[d] = Lf[3 * j + d];
+      r[d] = Rf[3 * j + d];
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) ra[q] = s * (Rm[3 * q] * r[0] + Rm[3 * q + 1] * r[1] + Rm[3 * q + 2] * r[2]) + tv[q];
+    const bool okl = fin3(l), okr = fin3(ra);
+    const double wl = a.wL != nullptr ? a.wL[fr * a.w_sT + j] : 1.0, wr = a.wR != nullptr ? a.wR[fr * a.w_sT + j] : 1.0;
+    const double tau = a.tau_j != nullptr ? a.tau_j[j] : a.tau;
+    if (okl && okr) {
+      const double e0 = l[0] - ra[0], e1 = l[1] - ra[1], e2 = l[2] - ra[2];
+      const double dist = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
+      if (dist > tau) {
+        const bool pick_l = wl >= wr;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) f[d] = pick_l ? l[d] : ra[d];
+      } else {
+        const double iw = wl + wr + 1e-9;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) f[d] = (wl * l[d] + wr * ra[d]) / iw;
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) f[d] = okl ? l[d] : (okr ? ra[d] : nan);
+    }
+    if (live) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) a.fused[(fr * J + j) * 3 + d] = f[d];
+    }
+    // diagnostics against the RAW right view (fuse.py:205-208): plain means, NaN propagates
+    {
+      const double a0 = l[0] - r[0], a1 = l[1] - r[1], a2 = l[2] - r[2];
+      const double b0 = f[0] - l[0], b1 = f[1] - l[1], b2 = f[2] - l[2];
+      const double c0 = f[0] - r[0], c1 = f[1] - r[1], c2 = f[2] - r[2];
+      d_lr += sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+      d_fl += sqrt(b0 * b0 + b1 * b1 + b2 * b2);
+      d_fr += sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+    }
+  }
+#pragma unroll
+  for (int o = kLPF / 2; o > 0; o >>= 1) {
+    d_lr += __shfl_xor_sync(0xffffffffu, d_lr, o);
+    d_fl += __shfl_xor_sync(0xffffffffu, d_fl, o);
+    d_fr += __shfl_xor_sync(0xffffffffu, d_fr, o);
+  }
+  if (live && sub == 0 && a.diag != nullptr) {
+    const double lr = d_lr / J, fl = d_fl / J, frr = d_fr / J;
+    double* o = a.diag + fr * 4;
+    o[0] = lr;
+    o[1] = fl;
+    o[2] = frr;
+    o[3] = lr - 0.5 * (fl + frr);
+  }
+}
+
+int rigid_fuse(const double* L, const double* R, int64_t T, int J, const int32_t* torso5, double tau, const double* tau_j, int allow_scale,
+               const double* wL, const double* wR, int64_t w_sT, double* fused, double* Rts, double* diag, uint8_t* status,
+               cudaStream_t s) {
+  if (T == 0) return SKA_OK;
+  RigidArgs a;
+  a.L = L;
+  a.R = R;
+  a.T = T;
+  a.J = J;
+  for (int k = 0; k < 5; ++k) a.torso[k] = torso5[k];
+  a.allow_scale = allow_scale;
+  a.tau = tau;
+  a.tau_j = tau_j;
+  a.wL = wL;
+  a.wR = wR;
+  a.w_sT = w_sT;
+  a.fused = fused;
+  a.Rts = Rts;
+  a.diag = diag;
+  a.status = status;
+  rigid_params_kernel<<<(unsigned)((T + 63) / 64), 64, 0, s>>>(a);
+  const int64_t fpb = 8 * (32 / kLPF);
+  rigid_fuse_kernel<<<(unsigned)((T + fpb - 1) / fpb), 256, 0, s>>>(a);
+  const cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }
 
 // ------------------------------------------------------------------------------------------------

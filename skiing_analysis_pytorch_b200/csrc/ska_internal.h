@@ -101,6 +101,9 @@ int so3_retract(S* R, const S* step, int64_t n, cudaStream_t s);
 size_t fuse_workspace_bytes(int64_t T);
 int fuse_frames(const double* Xl, const double* Xr, const double* Ul, const double* Ur, int64_t T, int J, const SkaFuseParams& prm,
                 double* fused, double* ql, double* qr, double* aligned, uint8_t* status, void* ws, size_t ws_bytes, cudaStream_t s);
+int rigid_fuse(const double* L, const double* R, int64_t T, int J, const int32_t* torso5, double tau, const double* tau_j, int allow_scale,
+               const double* wL, const double* wR, int64_t w_sT, double* fused, double* Rts, double* diag, uint8_t* status,
+               cudaStream_t s);
 int ema_smooth(const double* X, int64_t T, int J, const double* alpha_joint, int adaptive, double alpha, double alpha_min,
                double alpha_max, double speed_gain, int64_t chunk, int halo, double* Y, cudaStream_t s);
 

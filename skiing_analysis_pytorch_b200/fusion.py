@@ -190,3 +190,100 @@ def fuse_person(all_frame_results, *, sigma_px: float = 12.0, sigma_3d: float = 
     res = fuse_clip(get("L_3D", 3), get("R_3D", 3), get("L_2D", 2), get("R_2D", 2), sigma_px=sigma_px, sigma_3d=sigma_3d, want=())
     smooth = temporal_smooth_ema(res.fused, ids, alpha, adaptive_smooth, smooth_alpha_min, smooth_alpha_max, smooth_speed_gain)
     return array_to_dicts(res.fused.cpu().numpy(), ids), array_to_dicts(smooth.cpu().numpy(), ids), ids
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rigid_transform_3D: the fusion of bundle_adjustment/fuse/fuse.py (== fuse/side/fuse/fuse.py, front_side/side/fuse/fuse.py)
+NECK, L_HIP, R_HIP, L_SHO, R_SHO = 69, 9, 10, 5, 6          # bundle_adjustment/fuse/fuse.py:27-29
+TORSO_IDX = [NECK, L_HIP, R_HIP, L_SHO, R_SHO]             # :31
+
+
+class RigidFusedClip(NamedTuple):
+    fused: torch.Tensor   # (T,J,3) float64
+    R: torch.Tensor       # (T,3,3) right -> left rotation
+    t: torch.Tensor       # (T,3)
+    s: torch.Tensor       # (T,) scale (1 unless allow_scale)
+    diag: torch.Tensor    # (T,4): LR_before, Fused_vs_L, Fused_vs_R, gain
+    status: torch.Tensor  # (T,) uint8: 1 = fewer than 3 usable torso joints
+
+
+def rigid_fuse_clip(target, source, *, tau=0.08, allow_scale: bool = False, wL=None, wR=None, torso_idx=TORSO_IDX,
+                    strict: bool = True) -> RigidFusedClip:
+    """Clip-level form of rigid_transform_3D (bundle_adjustment/fuse/fuse.py:96-232): target / source (T,J,3) CUDA
+    tensors (left / right view), tau scalar or (J,), wL / wR None, scalar, (J,) or (T,J).  One launch pair for the clip."""
+    L = _f64_cuda(target, "target", 3)
+    T, J, _ = L.shape
+    R = _f64_cuda(source, "source", 3)
+    if tuple(R.shape) != (T, J, 3):
+        raise ValueError(f"source must be ({T},{J},3), got {tuple(R.shape)}")   # the reference asserts equal shapes (:128)
+    if max(torso_idx) >= J:
+        raise ValueError(f"torso index {max(torso_idx)} outside a {J}-joint skeleton")  # assertion at fuse.py:131-133
+    dev = L.device
+    f64 = dict(dtype=torch.float64, device=dev)
+
+    def weights(w):
+        if w is None:
+            return None, 0
+        w = torch.as_tensor(w, **f64)
+        if w.dim() == 0:
+            return w.expand(J).contiguous(), 0
+        if w.dim() == 1:
+            if w.shape[0] != J:
+                raise ValueError("wL/wR shape must be (J,), (T,J) or a scalar")
+            return w.contiguous(), 0
+        if tuple(w.shape) != (T, J):
+            raise ValueError("wL/wR shape must be (J,), (T,J) or a scalar")
+        return w.contiguous(), J
+
+    (wl, sl), (wr, sr) = weights(wL), weights(wR)
+    if sl != sr:  # one per-frame, one per-joint: expand the per-joint one
+        if sl == 0 and wl is not None:
+            wl, sl = wl[None].expand(T, J).contiguous(), J
+        if sr == 0 and wr is not None:
+            wr, sr = wr[None].expand(T, J).contiguous(), J
+    stride = max(sl, sr)
+    tau_t = torch.as_tensor(tau, **f64)
+    tau_j = tau_t.contiguous() if tau_t.dim() == 1 else None
+    if tau_j is not None and tau_j.shape[0] != J:
+        raise ValueError("tau must be a scalar or (J,)")
+    fused = torch.empty((T, J, 3), **f64)
+    Rts = torch.empty((T, 13), **f64)
+    diag = torch.empty((T, 4), **f64)
+    status = torch.zeros((T,), dtype=torch.uint8, device=dev)
+    torso = (C.c_int32 * 5)(*[int(k) for k in torso_idx])
+    p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.ska_rigid_fuse_f64(p(L), p(R), T, J, torso, float(tau_t) if tau_j is None else 0.0, p(tau_j), 1 if allow_scale else 0,
+                                          p(wl), p(wr), stride, p(fused), p(Rts), p(diag), p(status), _stream(dev)))
+    if strict and T and bool((status != 0).any()):
+        raise ValueError(f"frame {int(torch.nonzero(status)[0])}: at least 3 non-collinear corresponding torso points are needed")
+    return RigidFusedClip(fused, Rts[:, :9].reshape(T, 3, 3), Rts[:, 9:12], Rts[:, 12], diag, status)
+
+
+def rigid_transform_3D(target, source, tau=0.08, allow_scale=False, wL=None, wR=None, return_diagnostics=True, verbose=False,
+                       device="cuda"):
+    """Signature and return structure of the reference's rigid_transform_3D (bundle_adjustment/fuse/fuse.py:96-105):
+    numpy (J,3) or (T,J,3) in, (fused like the input, diag dict or None) out - with the whole sequence in one launch."""
+    Ln, Rn = np.asarray(target, dtype=float), np.asarray(source, dtype=float)
+    single = Ln.ndim == 2
+    if single:
+        Ln, Rn = Ln[None], Rn[None]
+    assert Ln.shape == Rn.shape and Ln.shape[-1] == 3
+    T, J, _ = Ln.shape
+    assert max(TORSO_IDX) < J, f"max(TORSO_IDX)={max(TORSO_IDX)}, J={J}"
+    r = rigid_fuse_clip(torch.from_numpy(Ln).to(device), torch.from_numpy(Rn).to(device), tau=tau, allow_scale=allow_scale, wL=wL, wR=wR)
+    fused = r.fused.cpu().numpy()
+    out = fused[0] if single else fused
+    if not return_diagnostics:
+        return out, None
+    d, Rh, th, sh = r.diag.cpu().numpy(), r.R.cpu().numpy(), r.t.cpu().numpy(), r.s.cpu().numpy()
+    per = [{"frame": t, "LR_before": float(d[t, 0]), "Fused_vs_L": float(d[t, 1]), "Fused_vs_R": float(d[t, 2]), "gain": float(d[t, 3]),
+            "s": float(sh[t]), "R": Rh[t].copy(), "t": th[t].copy()} for t in range(T)]
+    gains = d[:, 3]
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mean_gain = float(np.nanmean(gains)) if T else float("nan")
+    return out, {"per_frame": per, "mean_gain": mean_gain, "bad_frames": [int(t) for t in np.nonzero(gains < 0)[0]]}

@@ -214,3 +214,59 @@ def test_full_size_properties(cuda):
     Ye = fusion.temporal_smooth_ema(a.fused, exact=True)
     Yc = fusion.temporal_smooth_ema(a.fused)
     assert float(((Ye - Yc).abs() / Ye.abs().clamp_min(1.0)).max()) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["plain", "weighted", "scaled"])
+def test_rigid_transform_3d_matches_reference_golden(cuda, golden, name):
+    """bundle_adjustment/fuse/fuse.py:rigid_transform_3D through ska_rigid_fuse_f64 against golden G11 (the reference's own
+    outputs): fused joints, per-frame R / t / s and the diagnostics."""
+    g = golden("g11_rigid_fuse.npz")
+    ok = g[f"{name}_ok"]
+    kw = {"plain": {}, "weighted": dict(wL=g["wL"][ok], wR=g["wR"][ok], tau=0.05), "scaled": dict(allow_scale=True, wL=g["wL"][0], wR=g["wR"][0])}[name]
+    L, R = _dev(cuda, g["L"][ok], g["R"][ok])
+    r = fusion.rigid_fuse_clip(L, R, **kw)
+    np.testing.assert_allclose(r.fused.cpu().numpy(), g[f"{name}_fused"], rtol=TOL, atol=TOL, equal_nan=True)
+    np.testing.assert_allclose(r.R.cpu().numpy(), g[f"{name}_R"], atol=TOL)
+    np.testing.assert_allclose(r.t.cpu().numpy(), g[f"{name}_t"], atol=TOL)
+    np.testing.assert_allclose(r.s.cpu().numpy(), g[f"{name}_s"], rtol=TOL)
+    np.testing.assert_allclose(r.diag.cpu().numpy(), g[f"{name}_diag"], rtol=TOL, atol=TOL, equal_nan=True)
+    # the reference's own signature: numpy in, (fused, diag dict) out; single frame (J,3) too
+    fused, diag = fusion.rigid_transform_3D(g["L"][ok], g["R"][ok], **kw)
+    np.testing.assert_allclose(fused, g[f"{name}_fused"], rtol=TOL, atol=TOL, equal_nan=True)
+    assert abs(diag["mean_gain"] - float(g[f"{name}_mean_gain"])) < 1e-9 and diag["bad_frames"] == list(g[f"{name}_bad"])
+    assert set(diag["per_frame"][0]) == {"frame", "LR_before", "Fused_vs_L", "Fused_vs_R", "gain", "s", "R", "t"}
+    if name == "plain":
+        f1, d1 = fusion.rigid_transform_3D(g["L"][0], g["R"][0])
+        np.testing.assert_allclose(f1, g["single_fused"], rtol=TOL, atol=TOL, equal_nan=True)
+        assert f1.shape == (70, 3) and len(d1["per_frame"]) == 1
+        assert fusion.rigid_transform_3D(g["L"][0], g["R"][0], return_diagnostics=False)[1] is None
+
+
+def test_rigid_fuse_edges_and_oracle(cuda):
+    d = synth.make_fusion_clip(500, 70, seed=31, nan_frac=0.04)
+    full = synth.make_fusion_clip(500, 70, seed=31, nan_frac=0.0)
+    L, R = d["Xl"], d["Xr"]
+    L[:, fusion.TORSO_IDX[:4]], R[:, fusion.TORSO_IDX[:4]] = full["Xl"][:, fusion.TORSO_IDX[:4]], full["Xr"][:, fusion.TORSO_IDX[:4]]  # >= 3 torso joints everywhere
+    R[100:150] = R[100:150] * np.array([1.0, 1.0, -1.0])   # mirrored right view: the reflection fix of fuse_check.py:57-62
+    tau = np.linspace(0.02, 0.3, 70)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fo, Ro, to, so, do = F.rigid_transform_3D(L, R, tau=tau, allow_scale=True)
+    r = fusion.rigid_fuse_clip(*_dev(cuda, L, R), tau=tau, allow_scale=True)
+    np.testing.assert_allclose(r.fused.cpu().numpy(), fo, rtol=TOL, atol=TOL, equal_nan=True)
+    np.testing.assert_allclose(r.R.cpu().numpy(), Ro, atol=TOL)
+    np.testing.assert_allclose(r.s.cpu().numpy(), so, rtol=TOL)
+    np.testing.assert_allclose(r.diag.cpu().numpy(), do, rtol=TOL, atol=TOL, equal_nan=True)
+    bad = L.copy()
+    bad[7, [69, 9, 10]] = np.nan
+    with pytest.raises(ValueError):
+        fusion.rigid_fuse_clip(*_dev(cuda, bad, R))
+    st = fusion.rigid_fuse_clip(*_dev(cuda, bad, R), strict=False).status.cpu().numpy()
+    assert st[7] == 1 and st.sum() == 1
+    with pytest.raises(ValueError):
+        fusion.rigid_fuse_clip(*_dev(cuda, L[:, :60], R[:, :60]))
+    with pytest.raises(ValueError):
+        fusion.rigid_fuse_clip(*_dev(cuda, L, R), wL=np.ones(5))
+    e = fusion.rigid_fuse_clip(*_dev(cuda, L[:0], R[:0]))
+    assert e.fused.shape == (0, 70, 3)

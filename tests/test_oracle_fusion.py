@@ -60,3 +60,28 @@ def test_reference_errors_and_fallbacks():
     Xk[14] = np.nan  # a key joint missing: canonicalisation undefined -> confidence 0 everywhere (confidence.py:150-153)
     c, dist = F.crossview_consistency_confidence(Xk, X)
     assert (c == 0).all() and np.isnan(dist).all()
+
+
+@pytest.mark.parametrize("name", ["plain", "weighted", "scaled"])
+def test_rigid_transform_3d_matches_reference(golden, name):
+    """bundle_adjustment/fuse/fuse.py:rigid_transform_3D (Umeyama on the torso joints + threshold fusion + diagnostics)."""
+    import warnings
+
+    g = golden("g11_rigid_fuse.npz")
+    ok = g[f"{name}_ok"]
+    kw = {"plain": {}, "weighted": dict(wL=g["wL"][ok], wR=g["wR"][ok], tau=0.05), "scaled": dict(allow_scale=True, wL=g["wL"][0], wR=g["wR"][0])}[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fused, Rh, th, sh, dg = F.rigid_transform_3D(g["L"][ok], g["R"][ok], **kw)
+    np.testing.assert_allclose(fused, g[f"{name}_fused"], rtol=1e-12, atol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(Rh, g[f"{name}_R"], atol=1e-12)
+    np.testing.assert_allclose(th, g[f"{name}_t"], atol=1e-12)
+    np.testing.assert_allclose(sh, g[f"{name}_s"], rtol=1e-12)
+    np.testing.assert_allclose(dg, g[f"{name}_diag"], rtol=1e-12, atol=1e-14, equal_nan=True)
+    assert np.isfinite(g[f"{name}_diag"][:12]).all() and np.isnan(g[f"{name}_diag"][12:]).any()
+    if name == "scaled":
+        assert np.abs(sh - 1.0).max() > 1e-4
+    with pytest.raises(ValueError):
+        bad = g["L"][:1].copy()
+        bad[0, [69, 9, 10]] = np.nan
+        F.rigid_transform_3D(bad, g["R"][:1])
