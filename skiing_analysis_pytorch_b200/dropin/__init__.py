@@ -33,6 +33,9 @@ MODULE_MAP = {
     "vggt.reproject": "reproject_world",
     "front_side.side.reproject": "reproject_world",
     "fuse.side.reproject": "reproject_world",
+    "bundle_adjustment.fuse.fuse": "rigid_fuse",
+    "fuse.side.fuse.fuse": "rigid_fuse",
+    "front_side.side.fuse.fuse": "rigid_fuse",
 }
 
 

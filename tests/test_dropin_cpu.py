@@ -52,9 +52,14 @@ for _m in ("bundle_adjustment.reproject", "vggt.reproject", "front_side.side.rep
     EXPECTED[_m] = EXPECTED["triangulation.reproject"]
 
 
+for _m in ("bundle_adjustment.fuse.fuse", "fuse.side.fuse.fuse", "front_side.side.fuse.fuse"):
+    EXPECTED[_m] = {"rigid_transform_3D": ["target", "source", "tau", "allow_scale", "wL", "wR", "return_diagnostics", "verbose"]}
+
+
 def test_install_registers_reference_module_names():
     saved = {k: sys.modules.get(k) for k in list(dropin.MODULE_MAP) + ["triangulation", "bundle_adjustment", "vggt", "front_side",
-                                                                        "front_side.side", "fuse", "fuse.side"]}
+                                                                        "front_side.side", "fuse", "fuse.side", "bundle_adjustment.fuse", "fuse.side.fuse",
+                                                                        "front_side.side.fuse"]}
     try:
         mods = dropin.install()
         assert set(mods) == set(dropin.MODULE_MAP)

@@ -236,6 +236,11 @@ def test_rigid_transform_3d_matches_reference_golden(cuda, golden, name):
     assert abs(diag["mean_gain"] - float(g[f"{name}_mean_gain"])) < 1e-9 and diag["bad_frames"] == list(g[f"{name}_bad"])
     assert set(diag["per_frame"][0]) == {"frame", "LR_before", "Fused_vs_L", "Fused_vs_R", "gain", "s", "R", "t"}
     if name == "plain":
+        from skiing_analysis_pytorch_b200 import dropin
+
+        fs, _ = dropin.shim("front_side.side.fuse.fuse").rigid_transform_3D(target=g["L"][0], source=g["R"][0], wL=None, wR=None,
+                                                                          return_diagnostics=True)  # the call of front_side/side/run.py:81
+        np.testing.assert_allclose(fs, g["single_fused"], rtol=TOL, atol=TOL, equal_nan=True)
         f1, d1 = fusion.rigid_transform_3D(g["L"][0], g["R"][0])
         np.testing.assert_allclose(f1, g["single_fused"], rtol=TOL, atol=TOL, equal_nan=True)
         assert f1.shape == (70, 3) and len(d1["per_frame"]) == 1
