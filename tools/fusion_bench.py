@@ -35,10 +35,12 @@ def main():
     fused = fusion.fuse_clip(d["Xl"], d["Xr"], d["Ul"], d["Ur"], want=(), strict=False).fused
     ms_ema = timed(lambda: fusion.temporal_smooth_ema(fused))
     ms_seq = timed(lambda: fusion.temporal_smooth_ema(fused, exact=True), n=2) if T <= 200_000 else float("nan")
+    ms_rigid = timed(lambda: fusion.rigid_fuse_clip(d["Xl"], d["Xr"], strict=False)) if J >= 70 else float("nan")
     b_fuse = T * J * (24 + 24 + 16 + 16 + 24)
     halo = fusion.ema_halo(0.7, True, 0.45, 0.92)
     b_ema = T * J * 48
     print(f"fuse_frames (warp-per-frame kernel): {ms_old:.3f} ms")
+    print(f"rigid_fuse (rigid_transform_3D): {ms_rigid:.3f} ms  alg {T * J * 72 / 1e9:.2f} GB -> {T * J * 72 / ms_rigid / 1e6:.0f} GB/s")
     print(f"fuse_frames: T={T} J={J}  {ms_fuse:.3f} ms  {T / ms_fuse * 1e3:.3e} frames/s  alg {b_fuse / 1e9:.2f} GB -> {b_fuse / ms_fuse / 1e6:.0f} GB/s")
     print(f"ema (chunk 512, halo {halo}): {ms_ema:.3f} ms  {T / ms_ema * 1e3:.3e} frames/s  alg {b_ema / 1e9:.2f} GB -> {b_ema / ms_ema / 1e6:.0f} GB/s"
           f"   sequential scan: {ms_seq:.1f} ms")
