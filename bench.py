@@ -458,10 +458,13 @@ def run_fusion(a, dev, world, barrier, dist):
     ms_f = timed(lambda: fusion.fuse_clip(d["Xl"], d["Xr"], d["Ul"], d["Ur"], want=(), strict=False), 5)
     fused = fusion.fuse_clip(d["Xl"], d["Xr"], d["Ul"], d["Ur"], want=(), strict=False).fused
     ms_e = timed(lambda: fusion.temporal_smooth_ema(fused), 5)
+    ms_r = timed(lambda: fusion.rigid_fuse_clip(d["Xl"], d["Xr"], strict=False), 5)
     peak, _ = hbm_peak()
-    b_f, b_e = T * J * 104, T * J * 48
+    b_f, b_e, b_r = T * J * 104, T * J * 48, T * J * 72
     out = {"workload": "1M frames x 70 joints per GPU: Kabsch alignment + weak-perspective / cross-view confidences + softmax fusion, then adaptive EMA (fp64)",
-           "fuse_ms": ms_f, "ema_ms": ms_e, "value": world * T / ((ms_f + ms_e) * 1e-3), "unit": "frames/s",
+           "fuse_ms": ms_f, "ema_ms": ms_e, "rigid_transform_3d_ms": ms_r, "value": world * T / ((ms_f + ms_e) * 1e-3), "unit": "frames/s",
+           "roofline_rigid_transform_3d": {"bound": "hbm", "achieved": b_r / ms_r / 1e6, "peak": peak, "unit": "GB/s", "frac": b_r / ms_r / 1e6 / peak,
+                                           "bytes_per_joint": 72, "note": "bundle_adjustment/fuse/fuse.py rigid_transform_3D: Umeyama on the torso joints + threshold fusion"},
            "roofline_fuse": {"bound": "hbm", "achieved": b_f / ms_f / 1e6, "peak": peak, "unit": "GB/s", "frac": b_f / ms_f / 1e6 / peak,
                              "bytes_per_joint": 104, "note": "three launches (moments, per-frame parameters, per-joint fusion) read the inputs twice + a 448 B/frame workspace: ~190 B/joint of DRAM traffic against 104 algorithmic; the moments and fusion stages run at 55-65 % of HBM on their own traffic: DESIGN.md 3.6"},
            "roofline_ema": {"bound": "hbm", "achieved": b_e / ms_e / 1e6, "peak": peak, "unit": "GB/s", "frac": b_e / ms_e / 1e6 / peak,
