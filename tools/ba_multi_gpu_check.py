@@ -44,6 +44,27 @@ def main():
                   f"cost {hr[0]['cost']:.5f} -> {ref.cost:.5f} | sharded {s.cost:.5f}; R dev {np.abs(s.R - ref.R).max():.2e}")
             ok = ok and dev_cost < 1e-4 and dev_trial < 1e-4 and all(same)
         del s
+    # the calibrating BA (15 parameters per camera) sharded by frames: same check against the single-GPU trajectory
+    d = synth.make_clip_device("2b", 20_000, 17, dev, seed=7)
+    R0, t0 = synth.perturb_cameras(d["R"], d["t"], seed=1)
+    K_init, dist_init = synth.theta_to_K_dist(synth.perturb_intrinsics(d["K"]))
+    X0 = api.triangulate_reproject(d["x2d"].permute(1, 0, 2, 3).contiguous(), K_init, R0, t0, want=("X",)).X
+    kw = dict(dist=dist_init, prior_rho=synth.CALIB_PRIOR_RHO, prior_theta=synth.theta_from_K(d["K"]), max_iters=12)
+    a, b = ba.frame_shard(20_000, world, rank)
+    s = ba.CalibratingBundleAdjuster(d["x2d"][a:b].contiguous(), d["conf"][a:b].contiguous(), K_init, R0, t0, X0[a:b].contiguous(),
+                                     group=dist.group.WORLD, **kw)
+    s.run(10)
+    h = s.history
+    if rank == 0:
+        ref = ba.CalibratingBundleAdjuster(d["x2d"], d["conf"], K_init, R0, t0, X0, local_only=True, **kw)
+        ref.run(10)
+        hr = ref.history
+        dev_cost = max(abs(x["cost"] - y["cost"]) / y["cost"] for x, y in zip(h, hr))
+        same = [x["accepted"] == y["accepted"] for x, y in zip(h, hr) if abs(y["cost"] - y["trial_cost"]) > 1e-3 * y["cost"]]
+        print(f"calibrating BA: world={world} cost dev {dev_cost:.2e} decisions equal {all(same)} cost {hr[0]['cost']:.5f} -> {ref.cost:.5f} "
+              f"| sharded {s.cost:.5f}; theta dev {np.abs(s.theta - ref.theta).max():.2e}")
+        ok = ok and dev_cost < 1e-4 and all(same)
+    del s
     # every rank holds the same cameras / decisions
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.broadcast(flag, 0)
