@@ -285,20 +285,20 @@ SKA_HD void jacobi4_smallest(T a[4][4], T vec[4], int sweeps) {
 // PRISM adds the thin-prism terms s1..s4.
 template <bool PRISM, typename T, typename CamT>
 SKA_HD void distort_delta(const CamT& c, T x, T y, T& dx, T& dy) {
-  const T xx = vmul(x, x), xy = vmul(x, y), yy = vmul(y, y);
-  const T r2 = vadd(yy, xx);
+  // dx = x (rad-1) + 2 p1 x y + p2 (r2 + 2 x^2) = x s + p2 r2,  dy = y s + p1 r2  with  s = (rad-1) + 2 p1 y + 2 p2 x
+  const T r2 = vfma(y, y, vmul(x, x));
   const T num = vmul(r2, vfma(r2, vfma(r2, c.dk[2], c.dk[1]), c.dk[0]));
   const T den = vfma(r2, vfma(r2, vfma(r2, c.kd[2], c.kd[1]), c.kd[0]), 1.0f);
-  const T radm1 = vmul(num, rcp_fast(den));
-  T tx = vmul(vfma(xx, 2.0f, r2), c.p2);
-  T ty = vmul(vfma(yy, 2.0f, r2), c.p1);
+  const T s = vfma(x, c.tp2, vfma(y, c.tp1, vmul(num, rcp_fast(den))));
+  T tx = vmul(r2, c.p2);
+  T ty = vmul(r2, c.p1);
   if (PRISM) {
     const T r4 = vmul(r2, r2);
     tx = vfma(r2, c.s[0], vfma(r4, c.s[1], tx));
     ty = vfma(r2, c.s[2], vfma(r4, c.s[3], ty));
   }
-  dx = vfma(x, radm1, vfma(xy, c.tp1, tx));
-  dy = vfma(y, radm1, vfma(xy, c.tp2, ty));
+  dx = vfma(x, s, tx);
+  dy = vfma(y, s, ty);
 }
 
 SKA_HD void distort64(const double* d /*12*/, double x, double y, double& xd, double& yd) {

@@ -155,12 +155,25 @@ struct FastStage {
   typename Vec<T>::Mask conv, well, ok;
 };
 
-// rows -> normal matrix -> LDL^T at lam = 0 -> inhomogeneous least-squares point -> first-order
-// secular step with the SAME factorisation -> certificate.  a, b, M, ra, rb are kept for the caller
-// (scoring reuses the residuals; the rare general path needs the rows and M).
+// fp32 error allowance of the Rayleigh numerator formed from the normal matrix (below): its terms are bounded by
+// m33 and carry the rounding of ~2V accumulations + 3 FMAs each
+template <int V>
+struct LamEps {
+  static constexpr float value = (2.0f * V + 8.0f) * 6e-8f;
+};
+
+// rows -> normal matrix -> LDL^T at lam = 0 -> inhomogeneous least-squares point Y0 -> first-order secular step
+// with the SAME factorisation -> certificate.  The rows a, b and M are kept for the caller (residuals at the
+// final point; the rare general path).
+//
+// The Rayleigh quotient at Y0 comes from the normal matrix: [Y0;1]^T M [Y0;1] = m33 + m3.Y0 (since M33 Y0 = -m3).
+// In CENTRED coordinates m33 = sum (row . [0;1])^2 is only (|Y|/sigma)^2 ~ 1e4 times the quotient, so the fp32
+// cancellation costs ~1e-3 of lam - irrelevant for a correction that is itself < 3.2e-5 of |X| - and the
+// certificate uses the upper bound lam_c = (num + eps m33) / den, which keeps it rigorous.  (Evaluating the
+// quotient from the row residuals, as the general path does, costs 9 more FMAs per view.)
 template <int V, bool CONF, int LO, typename T>
 SKA_HD void fast_stage(const CamDev* __restrict__ cam, const float cx, const float cy, const float cz, const T* u, const T* v,
-                       const T* w2, T (*a)[4], T (*b)[4], Sym4T<T>& M, T* ra, T* rb, FastStage<T>& o) {
+                       const T* w2, T (*a)[4], T (*b)[4], Sym4T<T>& M, FastStage<T>& o) {
   sym4_zero(M);
 #pragma unroll
   for (int k = 0; k < V; ++k) {
@@ -175,20 +188,25 @@ SKA_HD void fast_stage(const CamDev* __restrict__ cam, const float cx, const flo
   }
   // lam = 0: the inhomogeneous least-squares point
   const Ldl3T<T> f0 = ldl3(M.m00, M.m01, M.m02, M.m11, M.m12, M.m22);
-  T y0, y1, y2, den;
+  T y0, y1, y2;
   ldl3_solve(f0, vneg(M.m03), vneg(M.m13), vneg(M.m23), y0, y1, y2);
-  const T lam = rayleigh<V, CONF, T>(a, b, w2, y0, y1, y2, cx, cy, cz, ra, rb, den);
+  const T num = vfma(M.m03, y0, vfma(M.m13, y1, vfma(M.m23, y2, M.m33)));
+  const T X0 = vadd(y0, cx), X1 = vadd(y1, cy), X2 = vadd(y2, cz);
+  const T den = vfma(X0, X0, vfma(X1, X1, vfma(X2, X2, 1.0f)));
+  const T rden = rcp_fast(den);
+  const T lam = vmul(num, rden);
+  const T lam_c = vmul(vfma(M.m33, LamEps<V>::value, num), rden);
   // first-order step of the secular equation with the SAME factorisation:
   //   Y(lam) - Y(0) = lam (M33 - lam I)^-1 (c + Y0) = lam z + O(lam^2),  z = M33^-1 (c + Y0)
   T z0, z1, z2;
-  ldl3_solve(f0, vadd(y0, cx), vadd(y1, cy), vadd(y2, cz), z0, z1, z2);
+  ldl3_solve(f0, X0, X1, X2, z0, z1, z2);
   const T d0 = vmul(lam, z0), d1 = vmul(lam, z1), d2 = vmul(lam, z2);
   const T step2 = vfma(d0, d0, vfma(d1, d1, vmul(d2, d2)));
   // certificate: lam * trace(M33^-1) < 1e-3 => lam < 1e-3 lambda_min(M33): M33 - lam I is positive
   // definite (Cauchy interlacing: this is the smallest eigenpair) and the dropped second-order
   // term is < 1e-3 of a step that is itself < 3.2e-5 relative.
   const T itr = ldl3_inv_trace(f0);
-  o.conv = mand(mand(f0.pos, vlt(vmul(lam, itr), kFastLamTr)), vle(step2, vmul(den, kFastTol2)));
+  o.conv = mand(mand(f0.pos, vlt(vmul(lam_c, itr), kFastLamTr)), vle(step2, vmul(den, kFastTol2)));
   // conditioning gate: trace(M33) trace(M33^-1) bounds cond(M33); beyond kCondMax (rays nearly
   // parallel, point near infinity) fp32 cannot hold the north-star tolerance -> fp64 path
   o.well = vle(vmul(vadd(vadd(M.m00, M.m11), M.m22), itr), kCondMax);
@@ -198,11 +216,15 @@ SKA_HD void fast_stage(const CamDev* __restrict__ cam, const float cx, const flo
   o.lam = lam;
   o.step2 = step2;
   o.ok = f0.pos;
-  // row residuals at the corrected point: r(Y0 + d) = r(Y0) + a[0:3] . d
+}
+
+// row residuals (a . [Y;1], b . [Y;1]) of every view at the point Y
+template <int V, typename T>
+SKA_HD void row_residuals(const T (*a)[4], const T (*b)[4], T Y0, T Y1, T Y2, T* ra, T* rb) {
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    ra[k] = vfma(a[k][0], d0, vfma(a[k][1], d1, vfma(a[k][2], d2, ra[k])));
-    rb[k] = vfma(b[k][0], d0, vfma(b[k][1], d1, vfma(b[k][2], d2, rb[k])));
+    ra[k] = vfma(a[k][0], Y0, vfma(a[k][1], Y1, vfma(a[k][2], Y2, a[k][3])));
+    rb[k] = vfma(b[k][0], Y0, vfma(b[k][1], Y1, vfma(b[k][2], Y2, b[k][3])));
   }
 }
 
@@ -213,9 +235,12 @@ SKA_HD float pix_norm(float u, float s, float o) { return fmaf(u, s, o); }
 SKA_HD F2 pix_norm(F2 u, float s, float o) { return mk2(fmaf(u.x, s, o), fmaf(u.y, s, o)); }  // scalar: see dlt_rows_pts
 
 // u, v: the observed pixel (DIST == 1 derives the normalised coordinates from it).
+// c: the view's projection rows; ck: the camera whose intrinsics / distortion apply (the view's own, or view 0's
+// when the caller knows that all views share them - the constant loads then fold across views).
 template <int DIST, typename T>
-SKA_HD void score_view(const CamDev& c, T Y0, T Y1, T Y2, T ra, T rb, T u, T v, T& eu, T& ev) {
-  const T z = vadd(vfma(c.Ph[8], Y0, vfma(c.Ph[9], Y1, vfma(c.Ph[10], Y2, c.Ph[11]))), c.Pl[11]);
+SKA_HD void score_view(const CamDev& c, const CamDev& ck, T Y0, T Y1, T Y2, T ra, T rb, T u, T v, T& eu, T& ev) {
+  // depth: the hi part alone is good to 6e-8 relative, which is all a divisor of a ~1 px quantity needs
+  const T z = vfma(c.Ph[8], Y0, vfma(c.Ph[9], Y1, vfma(c.Ph[10], Y2, c.Ph[11])));
   const T iz = rcp_fast(z);
   eu = vmul(vneg(ra), iz);
   ev = vmul(vneg(rb), iz);
@@ -225,25 +250,25 @@ SKA_HD void score_view(const CamDev& c, T Y0, T Y1, T Y2, T ra, T rb, T u, T v, 
       // zero skew: the pinhole reprojection is u + eu, so x = (u + eu - cx) / fx - two FMAs per coordinate
       // instead of a second 3x4 row product (the cancellation u - cx costs 6e-8 in x: nothing after the
       // distortion polynomial's ~0.1 sensitivity)
-      x = vfma(eu, c.ifx, pix_norm(u, c.ifx, c.ncx));
-      y = vfma(ev, c.ify, pix_norm(v, c.ify, c.ncy));
+      x = vfma(eu, ck.ifx, pix_norm(u, ck.ifx, ck.ncx));
+      y = vfma(ev, ck.ify, pix_norm(v, ck.ify, ck.ncy));
     } else {
       x = vmul(vfma(c.Rxy[0], Y0, vfma(c.Rxy[1], Y1, vfma(c.Rxy[2], Y2, c.txy[0]))), iz);
       y = vmul(vfma(c.Rxy[3], Y0, vfma(c.Rxy[4], Y1, vfma(c.Rxy[5], Y2, c.txy[1]))), iz);
     }
     T dx, dy;
-    distort_delta<(DIST >= 2)>(c, x, y, dx, dy);
-    eu = vfma(dx, c.fx, eu);
-    ev = vfma(dy, c.fy, ev);
-    if (DIST >= 2) eu = vfma(y, -c.skew, eu);
+    distort_delta<(DIST >= 2)>(ck, x, y, dx, dy);
+    eu = vfma(dx, ck.fx, eu);
+    ev = vfma(dy, ck.fy, ev);
+    if (DIST >= 2) eu = vfma(y, -ck.skew, eu);
   }
 }
 
-template <int V, int DIST, typename T>
+template <int V, int DIST, bool SAMEK, typename T>
 SKA_HD void score_views(const CamDev* __restrict__ cam, T Y0, T Y1, T Y2, const T* ra, const T* rb, const T* u, const T* v,
                         T* du, T* dv) {
 #pragma unroll
-  for (int k = 0; k < V; ++k) score_view<DIST, T>(cam[k], Y0, Y1, Y2, ra[k], rb[k], u[k], v[k], du[k], dv[k]);
+  for (int k = 0; k < V; ++k) score_view<DIST, T>(cam[k], cam[SAMEK ? 0 : k], Y0, Y1, Y2, ra[k], rb[k], u[k], v[k], du[k], dv[k]);
 }
 
 template <bool PACK>
@@ -259,16 +284,13 @@ struct PointVec<true> {
 // FFMA of the hot path becomes an FFMA2; any other PTS runs them one by one in scalar fp32.
 // u,v,w2: [PTS][V] pixel coordinates and squared row weights (w2 unused if !CONF).
 // LO: see dlt_rows.  DIST: 0 pinhole scoring, 1 rational+tangential, 2 + thin prism + skew.
+// SAMEK: every view shares view 0's intrinsics / distortion (checked by the caller).
 // Outputs: X (un-centred), du/dv = reprojected minus observed pixel per view, status.
-template <int V, int PTS, bool CONF, int DIST, uint32_t SOLVER, int LO = 1>
+template <int V, int PTS, bool CONF, int DIST, uint32_t SOLVER, int LO = 1, bool SAMEK = false>
 SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], const float cx, const float cy,
                        const float cz, const float (*u)[V], const float (*v)[V], const float (*w2)[V],
                        const PointSource& src, float (*X)[3], float (*du)[V], float (*dv)[V], uint8_t* status) {
-#ifdef SKA_NO_PACK  // measurement variant (tools/variants.py): two points per thread in scalar fp32
-  constexpr bool PACK = (PTS == 2) && (V < 0);  // value-dependent false
-#else
   constexpr bool PACK = (PTS == 2);
-#endif
   using T = typename PointVec<PACK>::type;
   constexpr int NG = PACK ? 1 : PTS;   // lockstep groups
   // ---- gather the inputs of each group
@@ -287,14 +309,13 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
         wt[g][k] = CONF ? w2[g][k] : 1.f;
       }
     }
-  T a[NG][V][4], b[NG][V][4], ra[NG][V], rb[NG][V];
+  T a[NG][V][4], b[NG][V][4];
   Sym4T<T> M[NG];
   float Y[PTS][3];
-  bool need64[PTS], have_res[PTS];
+  bool need64[PTS];
 #pragma unroll
   for (int p = 0; p < PTS; ++p) {
     need64[p] = (SOLVER == kSolverJacobi64);
-    have_res[p] = false;
     status[p] = 0;
   }
   if (SOLVER == kSolverSecular) {
@@ -302,7 +323,7 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
     bool all_fast = true;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      fast_stage<V, CONF, LO, T>(cam, cx, cy, cz, ut[g], vt[g], wt[g], a[g], b[g], M[g], ra[g], rb[g], fs[g]);
+      fast_stage<V, CONF, LO, T>(cam, cx, cy, cz, ut[g], vt[g], wt[g], a[g], b[g], M[g], fs[g]);
       all_fast = all_fast && mall(fs[g].conv);
     }
     SecularState s[PTS];
@@ -318,11 +339,10 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
       s[p].ok = pick(fs[g].ok, i);
       conv[p] = pick(fs[g].conv, i);
       well[p] = pick(fs[g].well, i);
-      have_res[p] = true;
     }
     if (!SKA_WARP_ALL(all_fast)) {
       // general path (rare): full secular iteration per point in scalar fp32 (refactorise at every
-      // lam), quadratically convergent
+      // lam, Rayleigh quotient from the row residuals), quadratically convergent
 #pragma unroll 1
       for (int it = 0; it < kSecularMaxIter; ++it) {
         bool done = true;
@@ -343,7 +363,6 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
             const float lam = rayleigh<V, CONF, float>(as, bs, ws, s[p].y0, s[p].y1, s[p].y2, cx, cy, cz, r1, r2, den);
             const Sym4 Ms = PACK ? (i == 0 ? sym4_lane<0>(M[g]) : sym4_lane<1>(M[g])) : sym4_lane<0>(M[g]);
             conv[p] = secular_step(Ms, cx, cy, cz, lam, s[p]);
-            have_res[p] = false;
           }
           // a lane that lost positive-definiteness can never certify: do not wait for it
           done = done && (conv[p] || !s[p].ok);
@@ -368,7 +387,7 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
       sym4_zero(M[g]);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        dlt_rows<LO>(cam[k], ut[g][k], vt[g][k], a[g][k], b[g][k]);
+        dlt_rows_pts<LO>(cam[k], ut[g][k], vt[g][k], a[g][k], b[g][k]);
         sym4_rank1(M[g], a[g][k], wt[g][k]);
         sym4_rank1(M[g], b[g][k], wt[g][k]);
       }
@@ -396,14 +415,13 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
           Y[p][0] = (float)(Xd.x - (double)cx);
           Y[p][1] = (float)(Xd.y - (double)cy);
           Y[p][2] = (float)(Xd.z - (double)cz);
-          have_res[p] = false;
           if (SOLVER == kSolverSecular) status[p] = 1;
         }
       }
     }
   }
 
-  // ---- un-centre, flag non-finite results, score every view
+  // ---- un-centre, flag non-finite results, residuals at the final point, score every view
 #pragma unroll
   for (int p = 0; p < PTS; ++p) {
     X[p][0] = Y[p][0] + cx;
@@ -414,27 +432,16 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     T Yt[3];
-    bool have = true;
     if constexpr (PACK) {
 #pragma unroll
       for (int m = 0; m < 3; ++m) Yt[m] = mk2(Y[0][m], Y[1][m]);
-      have = have_res[0] && have_res[1];
     } else {
 #pragma unroll
       for (int m = 0; m < 3; ++m) Yt[m] = Y[g][m];
-      have = have_res[g];
     }
-    if (!have) {  // the iterate moved after the fast stage: residuals from the rows; a partner of a
-                  // packed pair that kept its fast-stage point keeps its fast-stage residuals
-      const typename Vec<T>::Mask keep = Vec<T>::mask(PACK ? have_res[0] : false, PACK ? have_res[PTS - 1] : false);
-#pragma unroll
-      for (int k = 0; k < V; ++k) {
-        ra[g][k] = vsel(keep, ra[g][k], vfma(a[g][k][0], Yt[0], vfma(a[g][k][1], Yt[1], vfma(a[g][k][2], Yt[2], a[g][k][3]))));
-        rb[g][k] = vsel(keep, rb[g][k], vfma(b[g][k][0], Yt[0], vfma(b[g][k][1], Yt[1], vfma(b[g][k][2], Yt[2], b[g][k][3]))));
-      }
-    }
-    T dut[V], dvt[V];
-    score_views<V, DIST, T>(cam, Yt[0], Yt[1], Yt[2], ra[g], rb[g], ut[g], vt[g], dut, dvt);
+    T ra[V], rb[V], dut[V], dvt[V];
+    row_residuals<V, T>(a[g], b[g], Yt[0], Yt[1], Yt[2], ra, rb);
+    score_views<V, DIST, SAMEK, T>(cam, Yt[0], Yt[1], Yt[2], ra, rb, ut[g], vt[g], dut, dvt);
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       if constexpr (PACK) {
@@ -451,217 +458,66 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Streaming form of the same arithmetic for many views (V >= 5): nothing per view is kept in
-// registers.  The observations are re-read through `obs(k, u, v, w2)` (shared memory in the
-// kernel) and the DLT rows are recomputed in each of three passes over the views
-//   pass 1  rows -> normal matrix M
-//   pass 2  rows -> Rayleigh quotient at the inhomogeneous least-squares point
-//   pass 3  rows -> residuals at the final point -> scoring -> emit(k, u, v, du, dv)
-// which costs 24 more FMAs per view than tri_points<> but needs ~90 registers for ANY V, so an
-// 8-view point pair fits the packed (F2) path and three times as many warps stay resident.
-// T = float (one point) or F2 (two points in lockstep); src addresses the thread's first point in
-// global memory for the fp64 fallback (second point: +2 floats / +1 float).
-template <int V, bool CONF, int DIST, typename T, typename Obs, typename Emit, int LO = 1>
-SKA_HD void tri_points_stream(const CamDev* __restrict__ cam, const double (*P64)[12], const float cx, const float cy,
-                              const float cz, const Obs& obs, const PointSource& src, float (*X)[3], uint8_t* status,
-                              Emit& emit) {
-  constexpr int NP = Vec<T>::N;
-#ifndef SKA_STREAM_UNROLL
-#define SKA_STREAM_UNROLL 1
-#endif
-  // the view loops stay ROLLED for many views: unrolled, the scheduler interleaves all V views' rows
-  // (8 views x 8 row entries x 2 registers) and spills; rolled, one view is live at a time
-  constexpr int kU = (V >= 5 && NP == 2) ? SKA_STREAM_UNROLL : V;  // scalar form: unrolled (coefficients stay constant-bank operands)
-  Sym4T<T> M;
-  sym4_zero(M);
-#pragma unroll kU
-  for (int k = 0; k < V; ++k) {
-    T u, v, w2, a[4], b[4];
-    obs(k, u, v, w2);
-    dlt_rows<LO>(cam[k], u, v, a, b);
-    if (CONF) {
-      sym4_rank1(M, a, w2);
-      sym4_rank1(M, b, w2);
-    } else {
-      sym4_rank1_unit(M, a);
-      sym4_rank1_unit(M, b);
-    }
-  }
-  const Ldl3T<T> f0 = ldl3(M.m00, M.m01, M.m02, M.m11, M.m12, M.m22);
-  T y0, y1, y2;
-  ldl3_solve(f0, vneg(M.m03), vneg(M.m13), vneg(M.m23), y0, y1, y2);
-  T num = Vec<T>::splat(0.f);
-#pragma unroll kU
-  for (int k = 0; k < V; ++k) {
-    T u, v, w2, a[4], b[4];
-    obs(k, u, v, w2);
-    dlt_rows<LO>(cam[k], u, v, a, b);
-    const T ra = vfma(a[0], y0, vfma(a[1], y1, vfma(a[2], y2, a[3])));
-    const T rb = vfma(b[0], y0, vfma(b[1], y1, vfma(b[2], y2, b[3])));
-    const T rr = vfma(ra, ra, vmul(rb, rb));
-    num = CONF ? vfma(w2, rr, num) : vadd(num, rr);
-  }
-  const T X0 = vadd(y0, cx), X1 = vadd(y1, cy), X2 = vadd(y2, cz);
-  const T den = vfma(X0, X0, vfma(X1, X1, vfma(X2, X2, 1.0f)));
-  const T lam = vmul(num, rcp_fast(den));
-  T z0, z1, z2;
-  ldl3_solve(f0, X0, X1, X2, z0, z1, z2);
-  const T d0 = vmul(lam, z0), d1 = vmul(lam, z1), d2 = vmul(lam, z2);
-  const T step2 = vfma(d0, d0, vfma(d1, d1, vmul(d2, d2)));
-  const T itr = ldl3_inv_trace(f0);
-  const typename Vec<T>::Mask fast = mand(mand(f0.pos, vlt(vmul(lam, itr), kFastLamTr)), vle(step2, vmul(den, kFastTol2)));
-  const typename Vec<T>::Mask wellm = vle(vmul(vadd(vadd(M.m00, M.m11), M.m22), itr), kCondMax);
-  const T Yf0 = vadd(y0, d0), Yf1 = vadd(y1, d1), Yf2 = vadd(y2, d2);
-
-  SecularState s[NP];
-  bool conv[NP], well[NP], need64[NP];
-  float Y[NP][3];
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    s[p].y0 = pick(Yf0, p);
-    s[p].y1 = pick(Yf1, p);
-    s[p].y2 = pick(Yf2, p);
-    s[p].lam = pick(lam, p);
-    s[p].step2 = pick(step2, p);
-    s[p].ok = pick(f0.pos, p);
-    conv[p] = pick(fast, p);
-    well[p] = pick(wellm, p);
-    status[p] = 0;
-  }
-  if (!SKA_WARP_ALL(mall(fast))) {
-    // general path (rare): full secular iteration per point in scalar fp32
-#pragma unroll 1
-    for (int it = 0; it < kSecularMaxIter; ++it) {
-      bool done = true;
-#pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        if (!conv[p]) {
-          float nm = 0.f;
-#pragma unroll 1
-          for (int k = 0; k < V; ++k) {
-            T u, v, w2;
-            obs(k, u, v, w2);
-            float a[4], b[4];
-            dlt_rows<LO>(cam[k], pick(u, p), pick(v, p), a, b);
-            const float ra = fmaf(a[0], s[p].y0, fmaf(a[1], s[p].y1, fmaf(a[2], s[p].y2, a[3])));
-            const float rb = fmaf(b[0], s[p].y0, fmaf(b[1], s[p].y1, fmaf(b[2], s[p].y2, b[3])));
-            const float rr = fmaf(ra, ra, rb * rb);
-            nm = CONF ? fmaf(pick(w2, p), rr, nm) : nm + rr;
-          }
-          const float Xa = s[p].y0 + cx, Xb = s[p].y1 + cy, Xc = s[p].y2 + cz;
-          const float lm = nm * rcp_fast(fmaf(Xa, Xa, fmaf(Xb, Xb, fmaf(Xc, Xc, 1.0f))));
-          const Sym4 Ms = (p == 0) ? sym4_lane<0>(M) : sym4_lane<1>(M);
-          conv[p] = secular_step(Ms, cx, cy, cz, lm, s[p]);
-        }
-        done = done && (conv[p] || !s[p].ok);
-      }
-      if (SKA_WARP_ALL(done)) break;
-    }
-  }
-  bool any64 = false;
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    Y[p][0] = s[p].y0;
-    Y[p][1] = s[p].y1;
-    Y[p][2] = s[p].y2;
-    const bool finite_in = fabsf(pick(M.m33, p)) <= 3.0e38f;  // false for NaN / inf inputs
-    need64[p] = !(conv[p] && s[p].ok && well[p]) && finite_in;
-    if (!finite_in) status[p] = 2;
-    any64 = any64 || need64[p];
-  }
-  if (SKA_WARP_ANY(any64)) {
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      if (need64[p]) {
-        const Vec3d Xd = solve_jacobi64<V>(P64, src.kpts + 2 * p, src.conf ? src.conf + p : nullptr, src.k_sV, src.c_sV,
-                                           src.weight_sqrt);
-        Y[p][0] = (float)(Xd.x - (double)cx);
-        Y[p][1] = (float)(Xd.y - (double)cy);
-        Y[p][2] = (float)(Xd.z - (double)cz);
-        status[p] = 1;
-      }
-    }
-  }
-  T Yt[3];
-#pragma unroll
-  for (int m = 0; m < 3; ++m) {
-    if constexpr (NP == 2) Yt[m] = mk2(Y[0][m], Y[NP - 1][m]);
-    else Yt[m] = Y[0][m];
-  }
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    X[p][0] = Y[p][0] + cx;
-    X[p][1] = Y[p][1] + cy;
-    X[p][2] = Y[p][2] + cz;
-    if (!(fabsf(X[p][0]) <= 3.0e38f && fabsf(X[p][1]) <= 3.0e38f && fabsf(X[p][2]) <= 3.0e38f)) status[p] = 2;
-  }
-#pragma unroll kU
-  for (int k = 0; k < V; ++k) {
-    T u, v, w2, a[4], b[4], eu, ev;
-    obs(k, u, v, w2);
-    dlt_rows<LO>(cam[k], u, v, a, b);
-    const T ra = vfma(a[0], Yt[0], vfma(a[1], Yt[1], vfma(a[2], Yt[2], a[3])));
-    const T rb = vfma(b[0], Yt[0], vfma(b[1], Yt[1], vfma(b[2], Yt[2], b[3])));
-    score_view<DIST, T>(cam[k], Yt[0], Yt[1], Yt[2], ra, rb, u, v, eu, ev);
-    emit(k, u, v, eu, ev);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // View-pair form for many views (even V >= 4): ONE point per call, the per-view work - DLT rows, normal-matrix
-// accumulation, Rayleigh residuals, residual update, scoring - packed over PAIRS OF VIEWS (F2 = views 2i, 2i+1)
+// accumulation, final residuals, scoring - packed over PAIRS OF VIEWS (F2 = views 2i, 2i+1)
 // with interleaved camera constants (CamPairDev); the 3x3 solve, the secular step and the certificate are scalar.
 // Same arithmetic per view as tri_points<V, 1, ...> (each packed half is the scalar IEEE operation); sums over the
 // views are formed as (even views) + (odd views), so results agree with the scalar form to rounding, not bit for bit.
 // The rare general path and the fp64 fallback reuse the scalar per-view code on `cam`.
-template <int V, bool CONF, int DIST, int LO = 1>
+// RECOMP: the rows are formed a second time for the final residuals instead of being kept in registers between the
+// normal-matrix pass and the scoring pass (12 more packed operations per view pair, 16 fewer live registers per view
+// pair: at 8 views the difference between 8 and 12+ resident warps per SM).
+#if defined(__CUDA_ARCH__)
+#define SKA_OPAQUE(x) asm volatile("" : "+f"(x))
+#else
+#define SKA_OPAQUE(x) (void)(x)
+#endif
+template <int V, bool CONF, int DIST, bool RECOMP = false, int LO = 1>
 SKA_HD void tri_point_vp(const CamPairDev* __restrict__ camp, const CamDev* __restrict__ cam, const double (*P64)[12],
                          const float cx, const float cy, const float cz, const float* u, const float* v, const float* w2,
                          const PointSource& src, float* X, float* du, float* dv, uint8_t& status) {
   static_assert(V % 2 == 0 && DIST <= 1 && LO == 1, "view-pair form: even V, no skew / thin prism");
   constexpr int H = V / 2;
-  F2 a[H][4], b[H][4], ra[H], rb[H], u2[H], v2[H], w22[H];
+  constexpr int HK = RECOMP ? 1 : H;  // rows kept: all pairs, or one transient pair
+  F2 a[HK][4], b[HK][4], u2[H], v2[H];
   Sym4T<F2> M2;
   sym4_zero(M2);
 #pragma unroll
   for (int i = 0; i < H; ++i) {
     u2[i] = mk2(u[2 * i], u[2 * i + 1]);
     v2[i] = mk2(v[2 * i], v[2 * i + 1]);
-    w22[i] = CONF ? mk2(w2[2 * i], w2[2 * i + 1]) : mk2(1.f, 1.f);
-    dlt_rows_vp(camp[i], u2[i], v2[i], a[i], b[i]);
+    const F2 w22 = CONF ? mk2(w2[2 * i], w2[2 * i + 1]) : mk2(1.f, 1.f);
+    F2(&ai)[4] = a[RECOMP ? 0 : i];
+    F2(&bi)[4] = b[RECOMP ? 0 : i];
+    dlt_rows_vp(camp[i], u2[i], v2[i], ai, bi);
     if (CONF) {
-      sym4_rank1(M2, a[i], w22[i]);
-      sym4_rank1(M2, b[i], w22[i]);
+      sym4_rank1(M2, ai, w22);
+      sym4_rank1(M2, bi, w22);
     } else {
-      sym4_rank1_unit(M2, a[i]);
-      sym4_rank1_unit(M2, b[i]);
+      sym4_rank1_unit(M2, ai);
+      sym4_rank1_unit(M2, bi);
     }
   }
   Sym4 M;
   M.m00 = M2.m00.x + M2.m00.y; M.m01 = M2.m01.x + M2.m01.y; M.m02 = M2.m02.x + M2.m02.y; M.m03 = M2.m03.x + M2.m03.y;
   M.m11 = M2.m11.x + M2.m11.y; M.m12 = M2.m12.x + M2.m12.y; M.m13 = M2.m13.x + M2.m13.y;
   M.m22 = M2.m22.x + M2.m22.y; M.m23 = M2.m23.x + M2.m23.y; M.m33 = M2.m33.x + M2.m33.y;
-  // lam = 0: the inhomogeneous least-squares point
+  // lam = 0: the inhomogeneous least-squares point; Rayleigh numerator from the normal matrix (see fast_stage)
   const Ldl3 f0 = ldl3(M.m00, M.m01, M.m02, M.m11, M.m12, M.m22);
   float y0, y1, y2;
   ldl3_solve(f0, -M.m03, -M.m13, -M.m23, y0, y1, y2);
-  F2 num2 = mk2(0.f, 0.f);
-#pragma unroll
-  for (int i = 0; i < H; ++i) {
-    ra[i] = vfma(a[i][0], y0, vfma(a[i][1], y1, vfma(a[i][2], y2, a[i][3])));
-    rb[i] = vfma(b[i][0], y0, vfma(b[i][1], y1, vfma(b[i][2], y2, b[i][3])));
-    const F2 rr = vfma(ra[i], ra[i], vmul(rb[i], rb[i]));
-    num2 = CONF ? vfma(w22[i], rr, num2) : vadd(num2, rr);
-  }
+  const float num = fmaf(M.m03, y0, fmaf(M.m13, y1, fmaf(M.m23, y2, M.m33)));
   const float X0 = y0 + cx, X1 = y1 + cy, X2 = y2 + cz;
   const float den = fmaf(X0, X0, fmaf(X1, X1, fmaf(X2, X2, 1.0f)));
-  const float lam = (num2.x + num2.y) * rcp_fast(den);
+  const float rden = rcp_fast(den);
+  const float lam = num * rden;
+  const float lam_c = fmaf(M.m33, LamEps<V>::value, num) * rden;
   float z0, z1, z2;
   ldl3_solve(f0, X0, X1, X2, z0, z1, z2);
   const float d0 = lam * z0, d1 = lam * z1, d2 = lam * z2;
   const float step2 = fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
   const float itr = ldl3_inv_trace(f0);
-  bool conv = f0.pos && (lam * itr < kFastLamTr) && (step2 <= kFastTol2 * den);
+  bool conv = f0.pos && (lam_c * itr < kFastLamTr) && (step2 <= kFastTol2 * den);
   const bool well = (M.m00 + M.m11 + M.m22) * itr <= kCondMax;
   SecularState s;
   s.y0 = y0 + d0;
@@ -670,12 +526,6 @@ SKA_HD void tri_point_vp(const CamPairDev* __restrict__ camp, const CamDev* __re
   s.lam = lam;
   s.step2 = step2;
   s.ok = f0.pos;
-  bool have_res = true;
-#pragma unroll
-  for (int i = 0; i < H; ++i) {  // r(Y0 + d) = r(Y0) + a[0:3] . d
-    ra[i] = vfma(a[i][0], d0, vfma(a[i][1], d1, vfma(a[i][2], d2, ra[i])));
-    rb[i] = vfma(b[i][0], d0, vfma(b[i][1], d1, vfma(b[i][2], d2, rb[i])));
-  }
   status = 0;
   if (!SKA_WARP_ALL(conv)) {
     // general path (rare): full secular iteration in scalar fp32 on the scalar cameras
@@ -695,7 +545,6 @@ SKA_HD void tri_point_vp(const CamPairDev* __restrict__ camp, const CamDev* __re
         const float Xa = s.y0 + cx, Xb = s.y1 + cy, Xc = s.y2 + cz;
         const float lm = nm * rcp_fast(fmaf(Xa, Xa, fmaf(Xb, Xb, fmaf(Xc, Xc, 1.0f))));
         conv = secular_step(M, cx, cy, cz, lm, s);
-        have_res = false;
       }
       if (SKA_WARP_ALL(conv || !s.ok)) break;
     }
@@ -710,7 +559,6 @@ SKA_HD void tri_point_vp(const CamPairDev* __restrict__ camp, const CamDev* __re
       Y[0] = (float)(Xd.x - (double)cx);
       Y[1] = (float)(Xd.y - (double)cy);
       Y[2] = (float)(Xd.z - (double)cz);
-      have_res = false;
       status = 1;
     }
   }
@@ -720,14 +568,21 @@ SKA_HD void tri_point_vp(const CamPairDev* __restrict__ camp, const CamDev* __re
   if (!(fabsf(X[0]) <= 3.0e38f && fabsf(X[1]) <= 3.0e38f && fabsf(X[2]) <= 3.0e38f)) status = 2;
 #pragma unroll
   for (int i = 0; i < H; ++i) {
-    if (!have_res) {
-      ra[i] = vfma(a[i][0], Y[0], vfma(a[i][1], Y[1], vfma(a[i][2], Y[2], a[i][3])));
-      rb[i] = vfma(b[i][0], Y[0], vfma(b[i][1], Y[1], vfma(b[i][2], Y[2], b[i][3])));
-    }
     const CamPairDev& c = camp[i];
-    const F2 z = vadd(vfma(c.Ph[8], Y[0], vfma(c.Ph[9], Y[1], vfma(c.Ph[10], Y[2], c.Ph[11]))), c.Pl3[2]);
+    F2(&ai)[4] = a[RECOMP ? 0 : i];
+    F2(&bi)[4] = b[RECOMP ? 0 : i];
+    if (RECOMP) {
+      SKA_OPAQUE(u2[i].x);  // a new value as far as the compiler knows: the rows are recomputed, not kept
+      SKA_OPAQUE(u2[i].y);
+      SKA_OPAQUE(v2[i].x);
+      SKA_OPAQUE(v2[i].y);
+      dlt_rows_vp(c, u2[i], v2[i], ai, bi);
+    }
+    const F2 ra = vfma(ai[0], Y[0], vfma(ai[1], Y[1], vfma(ai[2], Y[2], ai[3])));
+    const F2 rb = vfma(bi[0], Y[0], vfma(bi[1], Y[1], vfma(bi[2], Y[2], bi[3])));
+    const F2 z = vfma(c.Ph[8], Y[0], vfma(c.Ph[9], Y[1], vfma(c.Ph[10], Y[2], c.Ph[11])));
     const F2 iz = rcp_fast(z);
-    F2 eu = vmul(vneg(ra[i]), iz), ev = vmul(vneg(rb[i]), iz);
+    F2 eu = vmul(vneg(ra), iz), ev = vmul(vneg(rb), iz);
     if (DIST) {
       const F2 x = vfma(eu, c.ifx, vfma(u2[i], c.ifx, c.ncx));
       const F2 y = vfma(ev, c.ify, vfma(v2[i], c.ify, c.ncy));

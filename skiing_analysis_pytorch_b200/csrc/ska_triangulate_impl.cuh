@@ -43,6 +43,9 @@ struct TriParams {
   uint8_t* status;
 };
 
+#ifndef SKA_VP_RECOMP
+#define SKA_VP_RECOMP 1  // view-pair form: form the rows a second time for the final residuals (fewer live registers)
+#endif
 #ifndef SKA_KBLOCK
 #define SKA_KBLOCK 256
 #endif
@@ -153,14 +156,10 @@ __global__ void __launch_bounds__(kBlock, MINB) tri_kernel(const __grid_constant
 
     float X[PTS][3], du[PTS][V], dv[PTS][V];
     uint8_t st[PTS];
-#ifndef SKA_NO_VP
     constexpr bool kVP = (PTS == 1) && (V >= 4) && (V % 2 == 0) && (DIST <= 1) && (SOLVER == kSolverSecular);
-#else
-    constexpr bool kVP = false;
-#endif
     if constexpr (kVP) {
       // many views: one point per thread, per-view work packed over pairs of views
-      tri_point_vp<V, CONF, DIST>(prm.camp, prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], cur.u[0], cur.v[0], w2[0], src, X[0],
+      tri_point_vp<V, CONF, DIST, (SKA_VP_RECOMP != 0)>(prm.camp, prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], cur.u[0], cur.v[0], w2[0], src, X[0],
                                   du[0], dv[0], st[0]);
     } else {
       tri_points<V, PTS, CONF, DIST, SOLVER>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], cur.u, cur.v, w2, src, X, du, dv, st);
@@ -234,14 +233,28 @@ __global__ void __launch_bounds__(kBlock, MINB) tri_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
-// PTS = 2 hot path with bulk-asynchronous input staging (the TMA engine's 1-D form):
-// every warp owns tiles of 64 consecutive points; lane 0 arms an mbarrier and issues ONE
-// cp.async.bulk per view (512 contiguous bytes of keypoints) for the NEXT tile into the other half
-// of a per-warp double buffer, then the warp waits on the current half, reads its two points with
-// one 128-bit shared load per view and computes them as one packed (FFMA2) pair.  Compared with the
-// register prefetch of tri_kernel this keeps the next tile out of the register file (no spills at
-// 128 registers with the packed arithmetic) and removes the per-lane global loads and their address
-// arithmetic from the instruction stream.  Warps never meet at a CTA barrier.
+// Hot path (view-major layout, V <= 4, whole 64-point tiles): tri_kernel_cta.
+//
+// CTA = NW consumer warps + 1 producer warp, one CTA per SM, persistent.  The clip is cut into GROUPS of NW
+// consecutive 64-point tiles; CTA b handles groups b, b + grid, ...  For one group the producer thread issues ONE
+// bulk-asynchronous copy (TMA 1-D, cp.async.bulk) per view - NW x 512 contiguous bytes of keypoints, plus NW x 256
+// bytes of confidences - into a ring of STAGES shared-memory stages; a `full` mbarrier per stage carries the byte
+// count, an `empty` mbarrier collects one arrival per consumer warp.  Consumer warp w owns tile w of the group: it
+// waits on `full`, reads its lane's two points with one 128-bit shared load per view, releases the stage and runs
+// the two points as ONE packed (F2 -> FFMA2) computation.  Consumers issue no global loads and no load addressing;
+// the producer costs ~2 instructions per tile (the first form of this kernel fed every consumer warp from its own
+// producer lane: 22 serialised single-lane copies per group, ~40 issue slots per tile).
+//
+// The arithmetic per pair is fast_stage<> (normal matrix, one LDL^T, secular step, certificate) -> ONE warp vote ->
+// final row residuals -> scoring.  A warp in which any point fails the certificate (rare: near-degenerate geometry,
+// non-finite input) finishes its tile in tri_pair_cold (noinline: general secular iteration + fp64 Jacobi), so the
+// hot loop carries none of that state.  X leaves through a per-warp staging buffer as 128-bit stores, the per-view
+// error as 64-bit stores.
+#ifdef SKA_PLAIN_STORES  // measurement variant: default-policy stores instead of st.global.cs
+#define SKA_ST(p, v) (*(p) = (v))
+#else
+#define SKA_ST(p, v) __stcs((p), (v))
+#endif
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -266,176 +279,117 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Warp-specialised form.  CTA = NW consumer warps + 1 producer warp.  Every consumer warp owns a
-// ring of kStages 1 KB*V/2 buffers with a full / empty mbarrier pair per stage; lane w of the producer
-// warp feeds consumer warp w: wait(empty) -> expect_tx -> one bulk copy per view (64 points = 512
-// contiguous bytes).  Consumers therefore execute no global loads, no load addressing and no
-// tail logic at all (the host gives this kernel whole 64-point tiles only; the < 64-point tail
-// goes to tri_kernel in a second launch).
-#ifndef SKA_WS_WARPS
-#define SKA_WS_WARPS 11  // consumer warps per CTA: (11 + 1) * 32 = 384 threads x <= 168 registers (158 used, no spills); 15 x 128 spills and is 3 % slower
+#ifndef SKA_CTA_WARPS
+#define SKA_CTA_WARPS 15  // consumer warps: (15 + 1) warps x 128 registers = the whole register file (registers are granted per
+                          // warp in units of 512, so 14 warps could have 144 each, 12 warps 168); measured: 15 x 128 > 11 x 168
 #endif
-#ifndef SKA_WS_MINB
-#define SKA_WS_MINB 1
+#ifndef SKA_CTA_STAGES
+#define SKA_CTA_STAGES 4
 #endif
-#ifndef SKA_WS_STAGES
-#define SKA_WS_STAGES 4
-#endif
-#ifndef SKA_WS_STREAM_STAGES
-#define SKA_WS_STREAM_STAGES 3
+#ifndef SKA_CTA_MAXREG
+#define SKA_CTA_MAXREG 128
 #endif
 constexpr int kWarpPts = 64;  // points per warp tile (2 per lane)
+constexpr int kColdCap = 32;  // per-warp list of tiles deferred to the cold loop
 
-// STREAM = false: the warp copies its pair into registers, releases the stage and runs tri_points<>
-//                 (rows kept in registers; V <= 4).
-// STREAM = true : tri_points_stream<> re-reads the observations from the stage in each of its three
-//                 passes (nothing per view in registers; V >= 5), confidences are staged by the
-//                 producer as well, and the stage is released after the last pass.
-#ifdef SKA_STREAM_THREE_PASS
-constexpr bool kStreamThreePass = true;   // measurement variant: tri_points_stream instead of tri_point_vp
-#else
-constexpr bool kStreamThreePass = false;
-#endif
-
-template <int V, bool CONF, bool STREAM>
-struct WsCfg {
-  static constexpr int kStages = STREAM ? SKA_WS_STREAM_STAGES : (V <= 4 ? SKA_WS_STAGES : 3);  // a warp finishes a tile in ~1.2 us: the ring must cover HBM + TMA latency
-  static constexpr bool kStageConf = STREAM && CONF;
-  static constexpr int kViewFloats = kWarpPts * 2 + (kStageConf ? kWarpPts : 0);  // keypoints (+ confidences) of one view
-  static constexpr int kStageFloats = V * kViewFloats;
-};
-
-template <int V, int NW, bool CONF, bool STREAM>
-struct WsSmem {  // dynamic shared-memory layout of tri_kernel_ws
-  using Cf = WsCfg<V, CONF, STREAM>;
-  static constexpr size_t oX = (size_t)NW * Cf::kStages * Cf::kStageFloats * sizeof(float);
+template <int V, int NW, bool CONF, int STAGES>
+struct CtaSmem {  // dynamic shared-memory layout of tri_kernel_cta
+  static constexpr int kViewK = NW * kWarpPts * 2;           // floats of one view's keypoints in a stage
+  static constexpr int kViewC = CONF ? NW * kWarpPts : 0;    // ... confidences
+  static constexpr int kKptFloats = V * kViewK;
+  static constexpr int kStageFloats = kKptFloats + V * kViewC;
+  static constexpr size_t oX = (size_t)STAGES * kStageFloats * sizeof(float);
   static constexpr size_t oFull = oX + (size_t)NW * kWarpPts * 3 * sizeof(float);
-  static constexpr size_t oEmpty = oFull + (size_t)NW * Cf::kStages * sizeof(uint64_t);
-  static constexpr size_t bytes = oEmpty + (size_t)NW * Cf::kStages * sizeof(uint64_t);
+  static constexpr size_t oEmpty = oFull + (size_t)STAGES * sizeof(uint64_t);
+  static constexpr size_t oCold = oEmpty + (size_t)STAGES * sizeof(uint64_t);
+  static constexpr size_t bytes = oCold + (size_t)NW * kColdCap * sizeof(uint32_t);
 };
 
-// observations of the lane's point pair, read from the warp's stage (tri_points_stream)
-template <bool CONF>
-struct StageObs {
-  const float* stage;  // [V][kViewFloats]
-  int view_floats, lane;
-  uint32_t weight_sqrt;
-  __device__ __forceinline__ void operator()(int k, F2& u, F2& v, F2& w2) const {
-    // volatile asm loads: each pass must RE-READ the stage - a plain load would let the compiler keep the
-    // observations (and the rows derived from them) live across the three passes, which is exactly the
-    // register footprint the streaming form exists to avoid
-    const float* p = stage + k * view_floats;
-    float4 q;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(smem_u32(p + 4 * lane)));
-    u = mk2(q.x, q.z);
-    v = mk2(q.y, q.w);
-    if (CONF) {
-      float2 c;
-      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(c.x), "=f"(c.y) : "r"(smem_u32(p + kWarpPts * 2 + 2 * lane)));
-      w2 = weight_sqrt ? mk2(c.x, c.y) : mk2(c.x * c.x, c.y * c.y);
-    } else {
-      w2 = mk2(1.f, 1.f);
-    }
+// The rare tile: general secular iteration / fp64 fallback for the lane's pair (the general tri_points<>), results
+// written where the hot path writes them.  Runs in the deferred cold loop of tri_kernel_cta, outside the hot loop.
+template <int V, bool CONF, int DIST, bool SAMEK>
+__device__ __forceinline__ void tri_pair_cold(const TriParams<V>& prm, uint32_t i0, float* sx6) {
+  constexpr int PTS = 2;
+  float u[PTS][V], v[PTS][V], w2[PTS][V], du[PTS][V], dv[PTS][V], X[PTS][3];
+  uint8_t stt[PTS];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {  // the stage was handed back: the pair is read again from global memory
+    const float4 q = *reinterpret_cast<const float4*>(prm.kpts + (int64_t)k * prm.k_sV + 2 * (int64_t)i0);
+    u[0][k] = q.x; v[0][k] = q.y; u[1][k] = q.z; v[1][k] = q.w;
+    float2 cf = make_float2(1.f, 1.f);
+    if (CONF) cf = *reinterpret_cast<const float2*>(prm.conf + (int64_t)k * prm.c_sV + i0);
+    w2[0][k] = CONF ? (prm.weight_sqrt ? cf.x : cf.x * cf.x) : 1.0f;
+    w2[1][k] = CONF ? (prm.weight_sqrt ? cf.y : cf.y * cf.y) : 1.0f;
   }
-};
-
-// scalar (one point at a time) counterparts: sub = 0 / 1 selects the lane's first / second point
-template <bool CONF>
-struct StageObs1 {
-  const float* stage;
-  int view_floats, lane, sub;
-  uint32_t weight_sqrt;
-  __device__ __forceinline__ void operator()(int k, float& u, float& v, float& w2) const {
-    const float* p = stage + k * view_floats;
-    float2 q;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(q.x), "=f"(q.y) : "r"(smem_u32(p + 4 * lane + 2 * sub)));
-    u = q.x;
-    v = q.y;
-    if (CONF) {
-      float c;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c) : "r"(smem_u32(p + kWarpPts * 2 + 2 * lane + sub)));
-      w2 = weight_sqrt ? c : c * c;
-    } else {
-      w2 = 1.f;
-    }
-  }
-};
-
-template <int V>
-struct StreamEmit1 {
-  const TriParams<V>& prm;
-  uint32_t i;  // the point's index
-  __device__ __forceinline__ void operator()(int k, float u, float v, float du, float dv) const {
-    if (prm.err != nullptr) __stcs(prm.err + (int64_t)k * prm.c_sV + i, sqrt_fast(fmaf(du, du, dv * dv)));
-    if (prm.proj != nullptr)
-      __stcs(reinterpret_cast<float2*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)i), make_float2(u + du, v + dv));
-  }
-};
-
-template <int V>
-struct StreamEmit {  // per-view outputs of tri_points_stream, written as they are produced
-  const TriParams<V>& prm;
-  uint32_t i0;
-  __device__ __forceinline__ void operator()(int k, F2 u, F2 v, F2 du, F2 dv) const {
+  PointSource src;
+  src.kpts = prm.kpts + 2 * (int64_t)i0;
+  src.conf = (CONF && prm.conf != nullptr) ? prm.conf + i0 : nullptr;
+  src.k_sV = prm.k_sV;
+  src.c_sV = prm.c_sV;
+  src.weight_sqrt = prm.weight_sqrt;
+  tri_points<V, PTS, CONF, DIST, kSolverSecular, 1, SAMEK>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], u, v, w2, src, X, du, dv, stt);
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
     if (prm.err != nullptr) {
-      const float e0 = sqrt_fast(fmaf(du.x, du.x, dv.x * dv.x)), e1 = sqrt_fast(fmaf(du.y, du.y, dv.y * dv.y));
+      const float e0 = sqrt_fast(fmaf(du[0][k], du[0][k], dv[0][k] * dv[0][k]));
+      const float e1 = sqrt_fast(fmaf(du[1][k], du[1][k], dv[1][k] * dv[1][k]));
       __stcs(reinterpret_cast<float2*>(prm.err + (int64_t)k * prm.c_sV + i0), make_float2(e0, e1));
     }
     if (prm.proj != nullptr)
       __stcs(reinterpret_cast<float4*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)i0),
-             make_float4(u.x + du.x, v.x + dv.x, u.y + du.y, v.y + dv.y));
+             make_float4(u[0][k] + du[0][k], v[0][k] + dv[0][k], u[1][k] + du[1][k], v[1][k] + dv[1][k]));
   }
-};
+  if (prm.status != nullptr) *reinterpret_cast<uchar2*>(prm.status + i0) = make_uchar2(stt[0], stt[1]);
+#pragma unroll
+  for (int p = 0; p < PTS; ++p)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sx6[p * 3 + k] = X[p][k];
+}
 
-// LEAN: the common output set (X and err, no proj / status, 16-byte aligned X) compiled without the per-tile
-// pointer tests of the general form.
-template <int V, bool CONF, int DIST, int NW, int MINB, bool STREAM, bool LEAN>
-__global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __grid_constant__ TriParams<V> prm) {
-  constexpr int PTS = 2;
-  using Cf = WsCfg<V, CONF, STREAM>;
-  using L = WsSmem<V, NW, CONF, STREAM>;
-  constexpr int kStages = Cf::kStages;
-  extern __shared__ __align__(128) unsigned char ws_smem[];
-  float* sK = reinterpret_cast<float*>(ws_smem);  // [NW][kStages][V][kViewFloats]
-  float(*sX)[kWarpPts * 3] = reinterpret_cast<float(*)[kWarpPts * 3]>(ws_smem + L::oX);
-  uint64_t(*sFull)[kStages] = reinterpret_cast<uint64_t(*)[kStages]>(ws_smem + L::oFull);
-  uint64_t(*sEmpty)[kStages] = reinterpret_cast<uint64_t(*)[kStages]>(ws_smem + L::oEmpty);
+// LEAN: the common output set (X and err, no proj / status, 16-byte aligned X) compiled without pointer tests.
+template <int V, bool CONF, int DIST, int NW, int STAGES, bool SAMEK, bool LEAN>
+__global__ void __maxnreg__(SKA_CTA_MAXREG) tri_kernel_cta(const __grid_constant__ TriParams<V> prm) {
+  using L = CtaSmem<V, NW, CONF, STAGES>;
+  extern __shared__ __align__(128) unsigned char cta_smem[];
+  float* sK = reinterpret_cast<float*>(cta_smem);  // [STAGES][ V x NW x 128 kpts | V x NW x 64 conf ]
+  float(*sX)[kWarpPts * 3] = reinterpret_cast<float(*)[kWarpPts * 3]>(cta_smem + L::oX);
+  uint64_t* sFull = reinterpret_cast<uint64_t*>(cta_smem + L::oFull);
+  uint64_t* sEmpty = reinterpret_cast<uint64_t*>(cta_smem + L::oEmpty);
+  uint32_t(*sCold)[kColdCap] = reinterpret_cast<uint32_t(*)[kColdCap]>(cta_smem + L::oCold);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t n_wt = (uint32_t)prm.n_tiles;  // whole 64-point tiles
-  const uint32_t stride = gridDim.x * NW;
-  if (threadIdx.x < NW * kStages) {
-    mbar_init(&sFull[0][0] + threadIdx.x, 1);
-    mbar_init(&sEmpty[0][0] + threadIdx.x, 1);
+  const uint32_t n_wt = (uint32_t)prm.n_tiles;             // whole 64-point tiles
+  const uint32_t n_groups = (n_wt + NW - 1) / NW;
+  if (threadIdx.x < STAGES) {
+    mbar_init(sFull + threadIdx.x, 1);
+    mbar_init(sEmpty + threadIdx.x, NW);
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();  // the only CTA-wide barrier: barrier initialisation
 
   if (warp == NW) {
-    // ---------------------------------------------------------------- producer warp
-    if (lane < NW) {
-      const int w = lane;
-      uint32_t wt = blockIdx.x * NW + w;
+    // ---------------------------------------------------------------- producer: one thread
+    if (lane == 0) {
       int st = 0;
       uint32_t round = 0;  // how many times the ring wrapped
-      for (; wt < n_wt; wt += stride) {
-        if (round > 0) mbar_wait(&sEmpty[w][st], (round - 1) & 1u);  // consumers released this stage
-        float* stage = sK + ((size_t)w * kStages + st) * Cf::kStageFloats;
-        mbar_expect_tx(&sFull[w][st], (uint32_t)(Cf::kStageFloats * sizeof(float)));
+      for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        if (round > 0) mbar_wait(sEmpty + st, (round - 1) & 1u);  // every consumer warp released this stage
+        const uint32_t t0 = g * NW;
+        const uint32_t nt = (n_wt - t0 < (uint32_t)NW) ? (n_wt - t0) : (uint32_t)NW;
+        float* stage = sK + (size_t)st * L::kStageFloats;
+        mbar_expect_tx(sFull + st, (uint32_t)V * nt * (uint32_t)(kWarpPts * (CONF ? 12 : 8)));
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-          bulk_g2s(stage + k * Cf::kViewFloats, prm.kpts + (int64_t)k * prm.k_sV + (int64_t)wt * (kWarpPts * 2), kWarpPts * 8,
-                   &sFull[w][st]);
-          if (Cf::kStageConf)
-            bulk_g2s(stage + k * Cf::kViewFloats + kWarpPts * 2, prm.conf + (int64_t)k * prm.c_sV + (int64_t)wt * kWarpPts,
-                     kWarpPts * 4, &sFull[w][st]);
+          bulk_g2s(stage + k * L::kViewK, prm.kpts + (int64_t)k * prm.k_sV + (int64_t)t0 * (kWarpPts * 2), nt * (kWarpPts * 8), sFull + st);
+          if (CONF)
+            bulk_g2s(stage + L::kKptFloats + k * L::kViewC, prm.conf + (int64_t)k * prm.c_sV + (int64_t)t0 * kWarpPts, nt * (kWarpPts * 4),
+                     sFull + st);
         }
-        if (++st == kStages) {
+        if (++st == STAGES) {
           st = 0;
           ++round;
         }
@@ -445,301 +399,162 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) tri_kernel_ws(const __gri
   }
 
   // ------------------------------------------------------------------ consumer warps
-  uint32_t wt = blockIdx.x * NW + warp;
   int st = 0;
   uint32_t par = 0;
   float* sx = sX[warp];
-#ifdef SKA_WS_PIPE
-  // Software-pipelined form (experiment): the SOLVE of tile i+1 (rows, normal matrix, LDL^T, secular step: one long
-  // dependent chain) and the SCORING of tile i (two views x two coordinates: wide and independent) sit in ONE basic
-  // block, so the scheduler can fill the solve chain's latency with scoring work of the previous tile.  Per-point
-  // arithmetic and its order are unchanged (fast_stage / score_views): results are bit-identical.  A tile that is not
-  // entirely on the certified fast path is finished at once by the general tri_points<>.
-  if constexpr (!STREAM && LEAN) {
-    F2 pY[3], pra[V], prb[V], pu[V], pv[V];
-    uint32_t p_wt = 0;
-    bool p_valid = false;
-#pragma unroll
-    for (int m = 0; m < 3; ++m) pY[m] = mk2(0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < V; ++k) pra[k] = prb[k] = pu[k] = pv[k] = mk2(0.f, 1.f);
-    auto flush = [&](const F2 (&Y)[3], const F2 (&ra)[V], const F2 (&rb)[V], const F2 (&uu)[V], const F2 (&vv)[V], uint32_t twt, bool valid) {
-      F2 dut[V], dvt[V];
-      score_views<V, DIST, F2>(prm.cam, Y[0], Y[1], Y[2], ra, rb, uu, vv, dut, dvt);
-      if (valid) {
-        const uint32_t j0 = twt * kWarpPts + 2u * lane;
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          const float e0 = sqrt_fast(fmaf(dut[k].x, dut[k].x, dvt[k].x * dvt[k].x));
-          const float e1 = sqrt_fast(fmaf(dut[k].y, dut[k].y, dvt[k].y * dvt[k].y));
-          __stcs(reinterpret_cast<float2*>(prm.err + (int64_t)k * prm.c_sV + j0), make_float2(e0, e1));
-        }
-        sx[lane * 6 + 0] = Y[0].x + prm.c[0];
-        sx[lane * 6 + 1] = Y[1].x + prm.c[1];
-        sx[lane * 6 + 2] = Y[2].x + prm.c[2];
-        sx[lane * 6 + 3] = Y[0].y + prm.c[0];
-        sx[lane * 6 + 4] = Y[1].y + prm.c[1];
-        sx[lane * 6 + 5] = Y[2].y + prm.c[2];
-        __syncwarp();
-        float* gx = prm.X + (int64_t)twt * (kWarpPts * 3);
-        __stcs(reinterpret_cast<float4*>(gx) + lane, reinterpret_cast<const float4*>(sx)[lane]);
-        if (lane < 16) __stcs(reinterpret_cast<float4*>(gx) + 32 + lane, reinterpret_cast<const float4*>(sx)[32 + lane]);
-        __syncwarp();
+  uint32_t* cold = sCold[warp];  // tiles of this warp that failed the certificate vote, finished after the hot loop
+  const float cx = prm.c[0], cy = prm.c[1], cz = prm.c[2];
+  uint32_t g = blockIdx.x;
+  for (;;) {
+    uint32_t n_cold = 0;
+    // ---- hot loop: certified tiles only
+    for (; g < n_groups && n_cold < (uint32_t)kColdCap; g += gridDim.x) {
+      const uint32_t wt = g * NW + warp;
+      if (wt >= n_wt) {  // last, partial group: nothing follows for this CTA
+        g = n_groups;
+        break;
       }
-    };
-    for (; wt < n_wt; wt += stride) {
-      mbar_wait(&sFull[warp][st], par);
-      const float* stage = sK + ((size_t)warp * kStages + st) * Cf::kStageFloats;
+      mbar_wait(sFull + st, par);
+      const float* stage = sK + (size_t)st * L::kStageFloats;
       const uint32_t i0 = wt * kWarpPts + 2u * lane;
-      F2 ut[V], vt[V], wtt[V];
+      F2 ut[V], vt[V], w2[V];
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const float4 q = *reinterpret_cast<const float4*>(stage + k * Cf::kViewFloats + 4 * lane);
+        const float4 q = *reinterpret_cast<const float4*>(stage + k * L::kViewK + warp * (kWarpPts * 2) + 4 * lane);
         ut[k] = mk2(q.x, q.z);
         vt[k] = mk2(q.y, q.w);
         if (CONF) {
-          float2 c = make_float2(1.f, 1.f);
-          if (prm.conf != nullptr) c = __ldcs(reinterpret_cast<const float2*>(prm.conf + (int64_t)k * prm.c_sV + i0));
-          wtt[k] = prm.weight_sqrt ? mk2(c.x, c.y) : mk2(c.x * c.x, c.y * c.y);
+          const float2 cf = *reinterpret_cast<const float2*>(stage + L::kKptFloats + k * L::kViewC + warp * kWarpPts + 2 * lane);
+          w2[k] = prm.weight_sqrt ? mk2(cf.x, cf.y) : mk2(cf.x * cf.x, cf.y * cf.y);
         } else {
-          wtt[k] = mk2(1.f, 1.f);
+          w2[k] = mk2(1.f, 1.f);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sEmpty[warp][st]);
-      if (++st == kStages) {
+      __syncwarp();                               // every lane holds its pair in registers
+      if (lane == 0) mbar_arrive(sEmpty + st);    // hand the stage back to the producer
+      if (++st == STAGES) {
         st = 0;
         par ^= 1u;
       }
-      // ---- solve(new) and score(pending) in one basic block
-      F2 a[V][4], b[V][4], ra[V], rb[V];
+      F2 a[V][4], b[V][4];
       Sym4T<F2> M;
       FastStage<F2> fs;
-      fast_stage<V, CONF, 1, F2>(prm.cam, prm.c[0], prm.c[1], prm.c[2], ut, vt, wtt, a, b, M, ra, rb, fs);
-      flush(pY, pra, prb, pu, pv, p_wt, p_valid);
-      const bool fin = fabsf(M.m33.x) <= 3.0e38f && fabsf(M.m33.y) <= 3.0e38f;
-      const bool fast = mall(fs.conv) && mall(fs.ok) && mall(fs.well) && fin;
-      if (__all_sync(0xffffffffu, fast)) {
-        pY[0] = fs.y0;
-        pY[1] = fs.y1;
-        pY[2] = fs.y2;
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          pra[k] = ra[k];
-          prb[k] = rb[k];
-          pu[k] = ut[k];
-          pv[k] = vt[k];
-        }
-        p_wt = wt;
-        p_valid = true;
-      } else {  // rare: the general path finishes this tile now
-        p_valid = false;
-        float u[PTS][V], v[PTS][V], w2[PTS][V], du[PTS][V], dv[PTS][V], X[PTS][3];
-        uint8_t stt[PTS];
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          u[0][k] = ut[k].x; u[1][k] = ut[k].y; v[0][k] = vt[k].x; v[1][k] = vt[k].y;
-          w2[0][k] = wtt[k].x; w2[1][k] = wtt[k].y;
-        }
-        PointSource src;
-        src.kpts = prm.kpts + 2 * (int64_t)i0;
-        src.conf = (prm.conf != nullptr) ? prm.conf + i0 : nullptr;
-        src.k_sV = prm.k_sV;
-        src.c_sV = prm.c_sV;
-        src.weight_sqrt = prm.weight_sqrt;
-        tri_points<V, PTS, CONF, DIST, kSolverSecular>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], u, v, w2, src, X, du, dv, stt);
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          const float e0 = sqrt_fast(fmaf(du[0][k], du[0][k], dv[0][k] * dv[0][k]));
-          const float e1 = sqrt_fast(fmaf(du[1][k], du[1][k], dv[1][k] * dv[1][k]));
-          __stcs(reinterpret_cast<float2*>(prm.err + (int64_t)k * prm.c_sV + i0), make_float2(e0, e1));
-        }
-#pragma unroll
-        for (int pp = 0; pp < PTS; ++pp)
-#pragma unroll
-          for (int k = 0; k < 3; ++k) sx[(lane * PTS + pp) * 3 + k] = X[pp][k];
-        __syncwarp();
-        float* gx = prm.X + (int64_t)wt * (kWarpPts * 3);
-        __stcs(reinterpret_cast<float4*>(gx) + lane, reinterpret_cast<const float4*>(sx)[lane]);
-        if (lane < 16) __stcs(reinterpret_cast<float4*>(gx) + 32 + lane, reinterpret_cast<const float4*>(sx)[32 + lane]);
-        __syncwarp();
+      fast_stage<V, CONF, 1, F2>(prm.cam, cx, cy, cz, ut, vt, w2, a, b, M, fs);
+      // conv is false for non-finite inputs as well (every comparison with NaN fails): one vote decides the tile
+      const bool good = mall(fs.conv) && mall(fs.well);
+      if (!__all_sync(0xffffffffu, good)) {
+        if (lane == 0) cold[n_cold] = wt;
+        ++n_cold;
+        continue;
       }
-    }
-    flush(pY, pra, prb, pu, pv, p_wt, p_valid);
-    return;
-  }
-#endif
-  for (; wt < n_wt; wt += stride) {
-    mbar_wait(&sFull[warp][st], par);
-    const float* stage = sK + ((size_t)warp * kStages + st) * Cf::kStageFloats;
-    const uint32_t i0 = wt * kWarpPts + 2u * lane;
-    PointSource src;
-    src.kpts = prm.kpts + 2 * (int64_t)i0;
-    src.conf = (prm.conf != nullptr) ? prm.conf + i0 : nullptr;
-    src.k_sV = prm.k_sV;
-    src.c_sV = prm.c_sV;
-    src.weight_sqrt = prm.weight_sqrt;
-    float X[PTS][3];
-    uint8_t stt[PTS];
-    if constexpr (STREAM && V % 2 == 0 && V >= 4 && DIST <= 1 && !kStreamThreePass) {
-      // many views: the lane's two points one after the other, each with its per-view work packed over pairs of
-      // views (tri_point_vp); observations come from the stage right when they are needed - no prefetch registers,
-      // no global-load addressing in the consumer
-#pragma unroll 1
-      for (int sub = 0; sub < 2; ++sub) {
-        float u[V], v[V], w2[V], du[V], dv[V], Xp[3];
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          const float* p = stage + k * Cf::kViewFloats;
-          const float2 q = *reinterpret_cast<const float2*>(p + 4 * lane + 2 * sub);
-          u[k] = q.x;
-          v[k] = q.y;
-          if (CONF) {
-            const float c = p[kWarpPts * 2 + 2 * lane + sub];
-            w2[k] = prm.weight_sqrt ? c : c * c;
-          } else {
-            w2[k] = 1.0f;
-          }
-        }
-        PointSource s1 = src;
-        s1.kpts += 2 * sub;
-        if (s1.conf != nullptr) s1.conf += sub;
-        uint8_t st1;
-        tri_point_vp<V, CONF, DIST>(prm.camp, prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], u, v, w2, s1, Xp, du, dv, st1);
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          if (prm.err != nullptr) __stcs(prm.err + (int64_t)k * prm.c_sV + i0 + sub, sqrt_fast(fmaf(du[k], du[k], dv[k] * dv[k])));
-          if (prm.proj != nullptr)
-            __stcs(reinterpret_cast<float2*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)(i0 + sub)), make_float2(u[k] + du[k], v[k] + dv[k]));
-        }
-        if (prm.status != nullptr) prm.status[i0 + sub] = st1;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) sx[(lane * PTS + sub) * 3 + k] = Xp[k];
-      }
-      __syncwarp();                                  // both points done with the stage
-      if (lane == 0) mbar_arrive(&sEmpty[warp][st]);
-    } else if constexpr (STREAM) {
-#ifdef SKA_STREAM_SCALAR
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {  // the lane's two points one after the other, scalar fp32, view loops unrolled
-        StageObs1<CONF> obs{stage, Cf::kViewFloats, lane, sub, prm.weight_sqrt};
-        StreamEmit1<V> emit{prm, i0 + sub};
-        PointSource s1 = src;
-        s1.kpts += 2 * sub;
-        if (s1.conf != nullptr) s1.conf += sub;
-        tri_points_stream<V, CONF, DIST, float>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], obs, s1, X + sub, stt + sub, emit);
-      }
-#else
-      StageObs<CONF> obs{stage, Cf::kViewFloats, lane, prm.weight_sqrt};
-      StreamEmit<V> emit{prm, i0};
-      tri_points_stream<V, CONF, DIST, F2>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], obs, src, X, stt, emit);
-#endif
-      __syncwarp();                                  // every lane finished its last pass over the stage
-      if (lane == 0) mbar_arrive(&sEmpty[warp][st]);  // hand it back to the producer
-    } else {
-      float u[PTS][V], v[PTS][V], w2[PTS][V], du[PTS][V], dv[PTS][V];
-#pragma unroll
-      for (int k = 0; k < V; ++k) {
-        const float4 q = *reinterpret_cast<const float4*>(stage + k * Cf::kViewFloats + 4 * lane);
-        u[0][k] = q.x; v[0][k] = q.y; u[1][k] = q.z; v[1][k] = q.w;
-        if (CONF) {
-          float2 c = make_float2(1.f, 1.f);
-          if (prm.conf != nullptr) c = __ldcs(reinterpret_cast<const float2*>(prm.conf + (int64_t)k * prm.c_sV + i0));
-          w2[0][k] = prm.weight_sqrt ? c.x : c.x * c.x;
-          w2[1][k] = prm.weight_sqrt ? c.y : c.y * c.y;
-        } else {
-          w2[0][k] = w2[1][k] = 1.0f;
-        }
-      }
-      __syncwarp();                                  // every lane holds its pair in registers
-      if (lane == 0) mbar_arrive(&sEmpty[warp][st]);  // hand the stage back to the producer
-      tri_points<V, PTS, CONF, DIST, kSolverSecular>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], u, v, w2, src, X, du, dv, stt);
+      F2 ra[V], rb[V], du[V], dv[V];
+      row_residuals<V, F2>(a, b, fs.y0, fs.y1, fs.y2, ra, rb);
+      score_views<V, DIST, SAMEK, F2>(prm.cam, fs.y0, fs.y1, fs.y2, ra, rb, ut, vt, du, dv);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         if (LEAN || prm.err != nullptr) {
-          const float e0 = sqrt_fast(fmaf(du[0][k], du[0][k], dv[0][k] * dv[0][k]));
-          const float e1 = sqrt_fast(fmaf(du[1][k], du[1][k], dv[1][k] * dv[1][k]));
-          __stcs(reinterpret_cast<float2*>(prm.err + (int64_t)k * prm.c_sV + i0), make_float2(e0, e1));
+          const F2 e = sqrt_fast(vfma(du[k], du[k], vmul(dv[k], dv[k])));
+          SKA_ST(reinterpret_cast<float2*>(prm.err + (int64_t)k * prm.c_sV + i0), make_float2(e.x, e.y));
         }
         if (!LEAN && prm.proj != nullptr) {
-          __stcs(reinterpret_cast<float4*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)i0),
-                 make_float4(u[0][k] + du[0][k], v[0][k] + dv[0][k], u[1][k] + du[1][k], v[1][k] + dv[1][k]));
+          const F2 pu = vadd(ut[k], du[k]), pv = vadd(vt[k], dv[k]);
+          SKA_ST(reinterpret_cast<float4*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)i0), make_float4(pu.x, pv.x, pu.y, pv.y));
         }
       }
-    }
-    if (++st == kStages) {
-      st = 0;
-      par ^= 1u;
-    }
-    // ---- X through shared memory: 192 floats per warp leave as 48 128-bit stores
-    if constexpr (!(STREAM && V % 2 == 0 && V >= 4 && DIST <= 1 && !kStreamThreePass)) {
-      if (!LEAN && prm.status != nullptr) *reinterpret_cast<uchar2*>(prm.status + i0) = make_uchar2(stt[0], stt[1]);
+      if (!LEAN && prm.status != nullptr) *reinterpret_cast<uchar2*>(prm.status + i0) = make_uchar2(0, 0);
+      const F2 X0 = vadd(fs.y0, cx), X1 = vadd(fs.y1, cy), X2 = vadd(fs.y2, cz);
+      *reinterpret_cast<float2*>(sx + lane * 6) = make_float2(X0.x, X1.x);
+      *reinterpret_cast<float2*>(sx + lane * 6 + 2) = make_float2(X2.x, X0.y);
+      *reinterpret_cast<float2*>(sx + lane * 6 + 4) = make_float2(X1.y, X2.y);
+      // ---- X through shared memory: 192 floats per warp leave as 48 128-bit stores
+      __syncwarp();
+      float* gx = prm.X + (int64_t)wt * (kWarpPts * 3);
+      if (LEAN || prm.x_vec) {
+        SKA_ST(reinterpret_cast<float4*>(gx) + lane, reinterpret_cast<const float4*>(sx)[lane]);
+        if (lane < 16) SKA_ST(reinterpret_cast<float4*>(gx) + 32 + lane, reinterpret_cast<const float4*>(sx)[32 + lane]);
+      } else {
 #pragma unroll
-      for (int p = 0; p < PTS; ++p)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) sx[(lane * PTS + p) * 3 + k] = X[p][k];
+        for (int r = 0; r < 6; ++r) gx[lane + 32 * r] = sx[lane + 32 * r];
+      }
+      __syncwarp();  // sx is rewritten next iteration
     }
+    // ---- cold loop (rare): the tiles the vote rejected, with the general per-point code
     __syncwarp();
-    float* gx = prm.X + (int64_t)wt * (kWarpPts * 3);
-    if (LEAN || prm.x_vec) {
-      __stcs(reinterpret_cast<float4*>(gx) + lane, reinterpret_cast<const float4*>(sx)[lane]);
-      if (lane < 16) __stcs(reinterpret_cast<float4*>(gx) + 32 + lane, reinterpret_cast<const float4*>(sx)[32 + lane]);
-    } else {
+#pragma unroll 1
+    for (uint32_t ci = 0; ci < n_cold; ++ci) {
+      const uint32_t wt = cold[ci];
+      tri_pair_cold<V, CONF, DIST, SAMEK>(prm, wt * kWarpPts + 2u * lane, sx + lane * 6);
+      __syncwarp();
+      float* gx = prm.X + (int64_t)wt * (kWarpPts * 3);
+      if (prm.x_vec) {
+        __stcs(reinterpret_cast<float4*>(gx) + lane, reinterpret_cast<const float4*>(sx)[lane]);
+        if (lane < 16) __stcs(reinterpret_cast<float4*>(gx) + 32 + lane, reinterpret_cast<const float4*>(sx)[32 + lane]);
+      } else {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) gx[lane + 32 * r] = sx[lane + 32 * r];
+        for (int r = 0; r < 6; ++r) gx[lane + 32 * r] = sx[lane + 32 * r];
+      }
+      __syncwarp();
     }
-    __syncwarp();  // sx is rewritten next iteration
+    if (g >= n_groups) break;
   }
 }
 
-#ifndef SKA_WS_STREAM_WARPS
-#define SKA_WS_STREAM_WARPS 11
-#endif
-#ifndef SKA_WS_STREAM_MINB
-#define SKA_WS_STREAM_MINB 1
-#endif
-
-template <int V, bool CONF, int DIST, bool STREAM, bool LEAN>
-static cudaError_t launch_ws_impl(TriParams<V>& prm, cudaStream_t stream) {
-  constexpr int NW = STREAM ? SKA_WS_STREAM_WARPS : SKA_WS_WARPS, MINB = STREAM ? SKA_WS_STREAM_MINB : SKA_WS_MINB, BLOCK = 32 * (NW + 1);
-  auto kern = tri_kernel_ws<V, CONF, DIST, NW, MINB, STREAM, LEAN>;
-  constexpr size_t smem = WsSmem<V, NW, CONF, STREAM>::bytes;
-  static_assert(smem <= 227 * 1024, "tri_kernel_ws staging does not fit the SM's shared memory");
-  int dev = 0, sms = 0, per_sm = 0;
+template <int V, bool CONF, int DIST, bool SAMEK, bool LEAN>
+static cudaError_t launch_cta_impl(TriParams<V>& prm, cudaStream_t stream) {
+  constexpr int NW = SKA_CTA_WARPS, STAGES = SKA_CTA_STAGES, BLOCK = 32 * (NW + 1);
+  auto kern = tri_kernel_cta<V, CONF, DIST, NW, STAGES, SAMEK, LEAN>;
+  constexpr size_t smem = CtaSmem<V, NW, CONF, STAGES>::bytes;
+  static_assert(smem <= 227 * 1024, "tri_kernel_cta staging does not fit the SM's shared memory");
+  int dev = 0, sms = 0;
   cudaError_t ce = cudaGetDevice(&dev);
   if (ce != cudaSuccess) return ce;
   ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (ce != cudaSuccess) return ce;
   ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // idempotent
   if (ce != cudaSuccess) return ce;
-  ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem);
-  if (ce != cudaSuccess) return ce;
-  if (per_sm < 1) per_sm = 1;
-  const int64_t n_wt = prm.n_tiles;
-  const int64_t need = (n_wt + NW - 1) / NW;
-  int64_t grid = (int64_t)sms * per_sm;
-  if (grid > need) grid = need;
+  const int64_t n_groups = (prm.n_tiles + NW - 1) / NW;
+  int64_t grid = sms;  // one persistent CTA per SM
+  if (grid > n_groups) grid = n_groups;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(prm);
   return cudaGetLastError();
 }
 
-template <int V, bool CONF, int DIST, bool STREAM>
-static cudaError_t launch_ws(TriParams<V>& prm, cudaStream_t stream) {
-  const bool lean = !STREAM && prm.err != nullptr && prm.proj == nullptr && prm.status == nullptr && prm.x_vec;
-  return lean ? launch_ws_impl<V, CONF, DIST, STREAM, true>(prm, stream) : launch_ws_impl<V, CONF, DIST, STREAM, false>(prm, stream);
+// every view shares view 0's intrinsics and distortion bit for bit (the common rig: one camera model)
+template <int V>
+static bool same_intrinsics(const TriParams<V>& prm) {
+  const CamDev& r = prm.cam[0];
+  for (int k = 1; k < V; ++k) {
+    const CamDev& c = prm.cam[k];
+    bool same = c.fx == r.fx && c.fy == r.fy && c.skew == r.skew && c.ifx == r.ifx && c.ify == r.ify && c.ncx == r.ncx &&
+                c.ncy == r.ncy && c.p1 == r.p1 && c.p2 == r.p2 && c.tp1 == r.tp1 && c.tp2 == r.tp2;
+    for (int i = 0; i < 3; ++i) same = same && c.dk[i] == r.dk[i] && c.kd[i] == r.kd[i];
+    for (int i = 0; i < 4; ++i) same = same && c.s[i] == r.s[i];
+    if (!same) return false;
+  }
+  return true;
+}
+
+template <int V, bool CONF, int DIST>
+static cudaError_t launch_cta(TriParams<V>& prm, cudaStream_t stream) {
+  const bool lean = prm.err != nullptr && prm.proj == nullptr && prm.status == nullptr && prm.x_vec;
+  if constexpr (DIST == 1) {
+    if (same_intrinsics<V>(prm))
+      return lean ? launch_cta_impl<V, CONF, DIST, true, true>(prm, stream) : launch_cta_impl<V, CONF, DIST, true, false>(prm, stream);
+  }
+  return lean ? launch_cta_impl<V, CONF, DIST, false, true>(prm, stream) : launch_cta_impl<V, CONF, DIST, false, false>(prm, stream);
 }
 
 #ifndef SKA_MINB_SMALL
 #define SKA_MINB_SMALL 2  // V <= 4: resident CTAs per SM the register allocator must allow
 #endif
 #ifndef SKA_MINB_LARGE
-#define SKA_MINB_LARGE 1  // V >= 5
+#define SKA_MINB_LARGE 2  // V >= 5: 2 x 256 threads x 128 registers with the rows recomputed (SKA_VP_RECOMP); 1 x 256 x 206 with the rows kept
 #endif
 template <int V, int PTS, bool CONF, int DIST, uint32_t SOLVER = kSolverSecular, int MINB = (V <= 4 ? SKA_MINB_SMALL : SKA_MINB_LARGE)>
 static cudaError_t launch(TriParams<V>& prm, cudaStream_t stream) {
   // the hot path gets a lean-output instantiation (X and err only: measured 0.84 -> 0.70 ms on the 8-view shape - the
   // per-view pointer tests cost a BSSY/BSYNC pair and a scheduling barrier each); everything else the general one
-  constexpr bool kHasLean = (SOLVER == kSolverSecular) && (DIST <= 1);
+  constexpr bool kHasLean = (V >= 5) && (SOLVER == kSolverSecular) && (DIST <= 1);  // V <= 4: this kernel only sees tails and odd layouts
   const bool lean = kHasLean && prm.err != nullptr && prm.proj == nullptr && prm.status == nullptr;
   void (*kern)(TriParams<V>) = tri_kernel<V, PTS, CONF, DIST, SOLVER, MINB, false>;
   if constexpr (kHasLean) {
@@ -999,37 +814,19 @@ static int dispatch(const TriArgs& a) {
   prm.x_vec = al(a.X, 16) ? 1u : 0u;
   const bool conf = (a.conf != nullptr);
   // pair path: flat point index, even point count, vector-aligned streams
-#ifdef SKA_FORCE_PTS1
-  const bool pair_ok = false;
-#else
   const bool pair_ok = !fm && (prm.N % 2 == 0) && al(a.kpts, 16) && al(a.conf, 8) && al(a.err, 8) && al(a.proj, 16);
-#endif
-  // V <= 4: warp-specialised kernel, point pairs packed, rows in registers (tri_points).
-  // V >= 5 (and everything the pair path cannot take): tri_kernel, one point per thread; for even V its per-view work
-  //   is packed over view pairs (tri_point_vp).
-  // Measured and kept off (profiles/r01_tri_kernel_variants.txt): the warp-specialised kernel with staged confidences
-  //   for V = 6, 8 (SKA_WS_LARGE: view-pair arithmetic, 1.01 vs 0.84 ms at V = 8) and the streaming three-pass form
-  //   (SKA_STREAM_THREE_PASS / SKA_WS_STREAM_ALL: slower at V = 8, equal at V = 2).
-#if defined(SKA_WS_STREAM_ALL)
-  constexpr bool kStream = true;
-  constexpr bool kWs = true;
-#elif defined(SKA_WS_LARGE)
-  constexpr bool kStream = (V >= 6) && (V % 2 == 0);  // measurement variant: staged observations + view-pair arithmetic
-  constexpr bool kWs = (V <= 4) || kStream;
-#else
-  constexpr bool kStream = false;
-  constexpr bool kWs = (V <= 4);
-#endif
-  const bool ws_ok = kWs && pair_ok && (!kStream || !conf || (al(a.conf, 16) && prm.N % 4 == 0));
+  // V <= 4: tri_kernel_cta (bulk-staged whole 64-point tiles, point pairs packed, rows in registers) + tri_kernel for
+  //         the < 64-point tail and everything the pair path cannot take.
+  // V >= 5: tri_kernel, one point per thread; for even V its per-view work is packed over view pairs (tri_point_vp).
+  // Forms that were built, measured slower and removed: a producer LANE per consumer warp (22 single-lane copies per
+  // group), the bulk-staged kernel for V = 6, 8, a streaming three-pass form (profiles/r01_tri_kernel_variants.txt).
+  // the bulk copies need 16-byte aligned view bases: the confidence plane of view k starts at k * N floats
+  const bool cta_ok = (V <= 4) && pair_ok && (!conf || (al(a.conf, 16) && prm.N % 4 == 0));
   cudaError_t ce;
   cudaStream_t s = (cudaStream_t)a.stream;
 #define SKA_GO(PTS)                                                                      \
   (conf ? (dist ? launch<V, PTS, true, 1>(prm, s) : launch<V, PTS, true, 0>(prm, s))     \
         : (dist ? launch<V, PTS, false, 1>(prm, s) : launch<V, PTS, false, 0>(prm, s)))
-#define SKA_GO_WS(Q)                                                                                           \
-  (conf ? (dist ? launch_ws<V, true, 1, kStream>(Q, s) : launch_ws<V, true, 0, kStream>(Q, s))                 \
-        : (dist ? launch_ws<V, false, 1, kStream>(Q, s) : launch_ws<V, false, 0, kStream>(Q, s)))
-  constexpr int kTailPts = (V <= 4) ? 2 : 1;  // tri_kernel handles the < 64-point tail
   if (solver == kSolverJacobi64) {
     // exact / measurement solvers: one generic instantiation (weights and full distortion always on)
     ce = launch<V, 1, true, 2, kSolverJacobi64, 1>(prm, s);
@@ -1037,33 +834,33 @@ static int dispatch(const TriArgs& a) {
     ce = launch<V, 1, true, 2, kSolverJacobi32, 1>(prm, s);
   } else if (dist >= 2) {
     ce = launch<V, 1, true, 2, kSolverSecular, 1>(prm, s);  // thin prism / skew: rare, one generic instantiation
-#ifndef SKA_NO_BULK
-  } else if (ws_ok) {
-    // whole 64-point tiles -> warp-specialised bulk-staged kernel; the < 64-point tail -> tri_kernel
-    const int64_t n_full = prm.N / kWarpPts, done = n_full * kWarpPts;
-    ce = cudaSuccess;
-    if (n_full > 0) {
-      TriParams<V> q = prm;
-      q.n_tiles = n_full;
-      ce = SKA_GO_WS(q);
-    }
-    if (ce == cudaSuccess && done < prm.N) {
-      prm.N -= done;  // strides keep describing the whole clip
-      prm.kpts += 2 * done;
-      if (prm.conf != nullptr) prm.conf += done;
-      prm.X += 3 * done;
-      if (prm.err != nullptr) prm.err += done;
-      if (prm.proj != nullptr) prm.proj += 2 * done;
-      if (prm.status != nullptr) prm.status += done;
-      ce = SKA_GO(kTailPts);
-    }
-#endif
   } else if constexpr (V <= 4) {
-    ce = pair_ok ? SKA_GO(2) : SKA_GO(1);
+    if (cta_ok) {
+      // whole 64-point tiles -> bulk-staged kernel; the < 64-point tail -> tri_kernel
+      const int64_t n_full = prm.N / kWarpPts, done = n_full * kWarpPts;
+      ce = cudaSuccess;
+      if (n_full > 0) {
+        TriParams<V> q = prm;
+        q.n_tiles = n_full;
+        ce = conf ? (dist ? launch_cta<V, true, 1>(q, s) : launch_cta<V, true, 0>(q, s))
+                  : (dist ? launch_cta<V, false, 1>(q, s) : launch_cta<V, false, 0>(q, s));
+      }
+      if (ce == cudaSuccess && done < prm.N) {
+        prm.N -= done;  // strides keep describing the whole clip
+        prm.kpts += 2 * done;
+        if (prm.conf != nullptr) prm.conf += done;
+        prm.X += 3 * done;
+        if (prm.err != nullptr) prm.err += done;
+        if (prm.proj != nullptr) prm.proj += 2 * done;
+        if (prm.status != nullptr) prm.status += done;
+        ce = SKA_GO(2);
+      }
+    } else {
+      ce = pair_ok ? SKA_GO(2) : SKA_GO(1);
+    }
   } else {
     ce = SKA_GO(1);
   }
-#undef SKA_GO_WS
 #undef SKA_GO
   if (ce != cudaSuccess) return set_error((int)ce, cudaGetErrorString(ce));
   return SKA_OK;

@@ -54,13 +54,18 @@ static int run(const SkaCamera* cams, const double* centre, const float* kpts, c
         src.c_sV = N;
         src.weight_sqrt = (flags & SKA_WEIGHT_SQRT) ? 1u : 0u;
         const float cx = (float)c[0], cy = (float)c[1], cz = (float)c[2];
+        const bool recomp = (flags >> 13) & 1;  // rows formed a second time for the final residuals
+#define VP(CONF, DIST)                                                                                          \
+  do {                                                                                                          \
+    if (recomp) tri_point_vp<V, CONF, DIST, true>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);   \
+    else tri_point_vp<V, CONF, DIST, false>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);        \
+  } while (0)
         if (conf) {
-          if (dist) tri_point_vp<V, true, 1>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);
-          else tri_point_vp<V, true, 0>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);
+          if (dist) VP(true, 1); else VP(true, 0);
         } else {
-          if (dist) tri_point_vp<V, false, 1>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);
-          else tri_point_vp<V, false, 0>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);
+          if (dist) VP(false, 1); else VP(false, 0);
         }
+#undef VP
         for (int k = 0; k < 3; ++k) X[3 * i + k] = Xp[k];
         if (err)
           for (int v = 0; v < V; ++v) err[v * N + i] = sqrtf(du[v] * du[v] + dv[v] * dv[v]);
@@ -70,53 +75,6 @@ static int run(const SkaCamera* cams, const double* centre, const float* kpts, c
     } else {
       return SKA_EUNSUPPORTED;
     }
-  }
-  if ((flags >> 11) & 1) {
-    // test hook: the streaming three-pass form (tri_points_stream, packed pairs) the kernel uses for V >= 5
-    struct HostObs {
-      const float* kpts; const float* conf; int64_t N, i0; bool sqrtw;
-      void operator()(int k, F2& u, F2& v, F2& w2) const {
-        u = mk2(kpts[(k * N + i0) * 2], kpts[(k * N + i0 + 1) * 2]);
-        v = mk2(kpts[(k * N + i0) * 2 + 1], kpts[(k * N + i0 + 1) * 2 + 1]);
-        const float c0 = conf ? conf[k * N + i0] : 1.0f, c1 = conf ? conf[k * N + i0 + 1] : 1.0f;
-        w2 = sqrtw ? mk2(c0, c1) : mk2(c0 * c0, c1 * c1);
-      }
-    };
-    struct HostEmit {
-      float* err; int64_t N, i0;
-      void operator()(int k, F2, F2, F2 du, F2 dv) const {
-        if (err) {
-          err[k * N + i0] = sqrtf(du.x * du.x + dv.x * dv.x);
-          err[k * N + i0 + 1] = sqrtf(du.y * du.y + dv.y * dv.y);
-        }
-      }
-    };
-    for (int64_t i = 0; i + 1 < N + (N & 1); i += 2) {
-      const int64_t i0 = (i + 1 < N) ? i : N - 2;
-      HostObs obs{kpts, conf, N, i0, (flags & SKA_WEIGHT_SQRT) != 0};
-      HostEmit emit{err, N, i0};
-      PointSource src;
-      src.kpts = kpts + 2 * i0;
-      src.conf = conf ? conf + i0 : nullptr;
-      src.k_sV = 2 * N;
-      src.c_sV = N;
-      src.weight_sqrt = (flags & SKA_WEIGHT_SQRT) ? 1u : 0u;
-      const float cx = (float)c[0], cy = (float)c[1], cz = (float)c[2];
-      float Xp[2][3];
-      uint8_t st[2];
-      if (conf) {
-        if (dist) tri_points_stream<V, true, 1, F2>(cam, P64, cx, cy, cz, obs, src, Xp, st, emit);
-        else tri_points_stream<V, true, 0, F2>(cam, P64, cx, cy, cz, obs, src, Xp, st, emit);
-      } else {
-        if (dist) tri_points_stream<V, false, 1, F2>(cam, P64, cx, cy, cz, obs, src, Xp, st, emit);
-        else tri_points_stream<V, false, 0, F2>(cam, P64, cx, cy, cz, obs, src, Xp, st, emit);
-      }
-      for (int p = 0; p < 2; ++p) {
-        for (int k = 0; k < 3; ++k) X[3 * (i0 + p) + k] = Xp[p][k];
-        if (status) status[i0 + p] = st[p];
-      }
-    }
-    return 0;
   }
   if ((flags >> 10) & 1) {
     // test hook: the kernel's PTS = 2 path (two points as one packed F2 computation), pairs (i, i+1)

@@ -171,31 +171,11 @@ def test_hostemu_packed_pair_path_is_bit_identical_to_scalar(rig, T, J, use_conf
     np.testing.assert_array_equal(X3, X1[:33] if c is None else X3)
 
 
-@pytest.mark.parametrize("rig,T,J,use_conf,dist", CASES)
-def test_hostemu_streaming_three_pass_form_matches_oracle(rig, T, J, use_conf, dist):
-    """tri_points_stream (rows recomputed in three passes, packed pairs - the V >= 5 kernel path): same
-    tolerances as the register form, and the same 3D points as the register form to fp32 rounding."""
-    clip = synth.make_clip(rig, T, J, seed=0)
-    conf = clip.conf_vm if use_conf else None
-    V = len(clip.R)
-    Xo, eo = _oracle(clip, conf, dist)
-    cams = _cabi.make_cameras(clip.K, clip.R, clip.t, dist)
-    k = clip.x_vm.reshape(V, -1, 2)
-    c = None if conf is None else conf.reshape(V, -1)
-    X, err, st = hostemu.triangulate(cams, V, k, c, flags=1 << 11)
-    rel = np.linalg.norm(X - Xo, axis=1) / np.linalg.norm(Xo, axis=1)
-    assert rel.max() < X_REL_HELD < X_REL_TOL
-    assert np.abs(err - eo).max() < POINT_TOL
-    assert abs(np.sqrt((err.astype(np.float64) ** 2).mean()) - np.sqrt((eo ** 2).mean())) < RMSE_TOL
-    X1, e1, s1 = hostemu.triangulate(cams, V, k, c, flags=0)
-    np.testing.assert_array_equal(X, X1)       # same solve, bit for bit
-    np.testing.assert_array_equal(st, s1)
-    assert np.abs(err - e1).max() < 1e-4        # residuals evaluated directly at the final point vs updated (both within POINT_TOL of the oracle)
-
-
 @pytest.mark.parametrize("rig,T,J,use_conf,dist", [c for c in CASES if c[0] in ("4", "8")] + [("8", 16, 17, False, None), ("4", 32, 17, False, synth.DIST_CALIB)])
-def test_hostemu_view_pair_form_matches_oracle(rig, T, J, use_conf, dist):
-    """tri_point_vp (per-view work packed over pairs of views - the even V >= 4 kernel path)."""
+@pytest.mark.parametrize("recomp", [0, 1])
+def test_hostemu_view_pair_form_matches_oracle(rig, T, J, use_conf, dist, recomp):
+    """tri_point_vp (per-view work packed over pairs of views - the even V >= 4 kernel path), with the rows kept
+    in registers or formed a second time for the final residuals (identical arithmetic)."""
     clip = synth.make_clip(rig, T, J, seed=0)
     conf = clip.conf_vm if use_conf else None
     V = len(clip.R)
@@ -203,7 +183,7 @@ def test_hostemu_view_pair_form_matches_oracle(rig, T, J, use_conf, dist):
     cams = _cabi.make_cameras(clip.K, clip.R, clip.t, dist)
     k = clip.x_vm.reshape(V, -1, 2)
     c = None if conf is None else conf.reshape(V, -1)
-    X, err, st = hostemu.triangulate(cams, V, k, c, flags=1 << 12)
+    X, err, st = hostemu.triangulate(cams, V, k, c, flags=(1 << 12) | (recomp << 13))
     rel = np.linalg.norm(X - Xo, axis=1) / np.linalg.norm(Xo, axis=1)
     assert rel.max() < X_REL_HELD < X_REL_TOL
     assert np.abs(err - eo).max() < POINT_TOL

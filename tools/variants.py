@@ -1,40 +1,71 @@
-"""Build experimental variants of libska.so (different launch bounds / points per thread) so one
-gpurun call can time them side by side:  python tools/variants.py build ; python tools/variants.py run"""
-import json
+"""Build experimental variants of libska.so so ONE gpurun call can time them side by side.  Only the translation
+units named in TUS are recompiled with the variant's flags; every other object comes from the product build.
+
+    python tools/variants.py build [names...]     (here, no GPU)
+    python tools/variants.py run [names...]       (on the GPU box; BENCH = script + args, default tools/tri_bench.py c2 v8)
+"""
 import os
+import shlex
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
+TUS = ["ska_tri_v2.cu", "ska_tri_v8.cu"]
 VARIANTS = {
-    "sw9": ["-DSKA_WS_STREAM_WARPS=9"],     # V = 6, 8 view-pair ws kernel: 10 warps x <= 204 registers
-    "sw10": ["-DSKA_WS_STREAM_WARPS=10"],   # 11 warps x <= 186
-    "sw13": ["-DSKA_WS_STREAM_WARPS=13", "-DSKA_WS_STREAM_STAGES=2"],   # 14 warps x <= 146
-    "nowsl": ["-DSKA_NO_WS_LARGE"],         # V >= 5 in tri_kernel (view pairs, register prefetch)
+    "A": [],                                                                       # v2: 12 warps x 152 regs, 4 stages; v8: rows kept, 1 CTA x 256
+    "B": ["-DSKA_CTA_WARPS=15", "-DSKA_CTA_MAXREG=128", "-DSKA_VP_RECOMP=1", "-DSKA_MINB_LARGE=2"],
+    "C": ["-DSKA_CTA_WARPS=14", "-DSKA_CTA_MAXREG=136", "-DSKA_VP_RECOMP=1", "-DSKA_KBLOCK=128", "-DSKA_MINB_LARGE=3"],
+    "D": ["-DSKA_CTA_STAGES=6", "-DSKA_VP_RECOMP=1", "-DSKA_KBLOCK=128", "-DSKA_MINB_LARGE=4"],
+    "E": ["-DSKA_PLAIN_STORES", "-DSKA_VP_RECOMP=1", "-DSKA_MINB_LARGE=1"],
+    "F": ["-DSKA_CTA_STAGES=3", "-DSKA_CTA_WARPS=11", "-DSKA_CTA_MAXREG=168"],
 }
 LIBDIR = ROOT / "skiing_analysis_pytorch_b200" / "lib"
+
+
+def build_variant(name):
+    from skiing_analysis_pytorch_b200 import build as B
+
+    B.build()  # product objects up to date
+    vdir = B.CSRC / f"_obj_{name}"
+    vdir.mkdir(exist_ok=True)
+    objs = []
+    for src in B.sources():
+        if src.name in TUS:
+            obj = vdir / (src.stem + ".o")
+            cmd = [B._nvcc(), *B.ARCH_FLAGS, *B.NVCC_FLAGS, *VARIANTS[name], "-I", str(ROOT / "include"), "-c", str(src), "-o", str(obj)]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(r.stderr)
+            objs.append(obj)
+        else:
+            objs.append(B.OBJ / (src.stem + ".o"))
+    out = LIBDIR / f"libska_{name}.so"
+    r = subprocess.run([B._nvcc(), *B.ARCH_FLAGS, "-shared", "-o", str(out), *map(str, objs), "-cudart", "static"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr)
+    return out
 
 
 def main():
     cmd = sys.argv[1]
     names = sys.argv[2:] or list(VARIANTS)
     if cmd == "build":
-        from skiing_analysis_pytorch_b200 import build
+        from skiing_analysis_pytorch_b200 import build as B
 
-        for n in names:
-            print(n, build.build(out=LIBDIR / f"libska_{n}.so", extra_flags=VARIANTS[n]))
+        B.build()
+        with ThreadPoolExecutor(max_workers=4) as ex:
+            for n, p in zip(names, ex.map(build_variant, names)):
+                print(n, p)
     else:
-        extra = os.environ.get("BENCH_ARGS", "--steps 20 --warmup 3 --no-cpu-baseline").split()
+        bench = shlex.split(os.environ.get("BENCH", "tools/tri_bench.py c2 v8"))
         for n in names:
             env = dict(os.environ, SKA_LIB_PATH=str(LIBDIR / f"libska_{n}.so"))
-            r = subprocess.run([sys.executable, str(ROOT / "bench.py"), *extra], env=env, capture_output=True, text=True)
-            try:
-                j = json.loads(r.stdout.strip().splitlines()[-1])
-                print(f"{n:12s} ms/step {j['ms_per_step']:.4f}  frac {j['roofline']['frac']:.3f}")
-            except Exception:
-                print(n, "FAILED", r.stdout[-300:], r.stderr[-300:])
+            print(f"== {n}: {' '.join(VARIANTS[n])}", flush=True)
+            r = subprocess.run([sys.executable, *bench], env=env, capture_output=True, text=True, cwd=ROOT)
+            print(r.stdout.strip() if r.returncode == 0 else f"FAILED rc={r.returncode}\n{r.stdout[-500:]}\n{r.stderr[-800:]}", flush=True)
 
 
 if __name__ == "__main__":
