@@ -93,9 +93,11 @@ int ska_triangulate_reproject_f32(const SkaCamera* cams, int32_t V, const double
  * (triangulation/triangulate.py:76-82; vggt/multi_view_process.py:220-234 likewise).
  * d_Rt_frames  (T,V,12) fp64 device = [R row-major (9), t (3)] world->camera per frame and view;
  *              cams[v].K / dist are shared over the clip, cams[v].R / t are ignored.
- * d_workspace  >= ska_tri_frames_workspace_bytes(V, T), 16-byte aligned: the per-frame kernel-side
- *              cameras (a prep kernel builds them on the device with the same fp64 code the host
- *              uses for a static rig; conditioning origin chosen per frame).
+ * d_workspace  may be NULL (ws_bytes 0) when the fused kernel takes the call: view-major layout, V <= 4, >= 8 joints, no skew /
+ *              thin prism, d_kpts / d_X / d_proj (and d_conf, with T*J % 4 == 0) 16-byte aligned - it builds every frame's centred
+ *              cameras in shared memory (fp64, conditioning origin chosen per frame) and writes nothing per frame to global memory.
+ *              Any other call needs >= ska_tri_frames_workspace_bytes(V, T) bytes, 16-byte aligned (a prep kernel stores the
+ *              per-frame kernel-side cameras there) and returns SKA_EWORKSPACE without it.
  * Solver flags are ignored (fp32 secular path with fp64 fallback). */
 size_t ska_tri_frames_workspace_bytes(int32_t V, int64_t T);
 int ska_triangulate_reproject_frames_f32(const SkaCamera* cams, int32_t V, const double* d_Rt_frames,

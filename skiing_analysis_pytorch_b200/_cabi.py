@@ -30,6 +30,7 @@ BA_CTRL_COST, BA_CTRL_ACCEPTED = 7, 8
 BA_FORCE_WIDE = 1
 
 ERRORS = {-1: "SKA_EINVAL", -2: "SKA_EUNSUPPORTED", -3: "SKA_EALIGN", -4: "SKA_EWORKSPACE"}
+SKA_EWORKSPACE = -4
 
 
 class SkaCamera(C.Structure):

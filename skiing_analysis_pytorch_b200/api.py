@@ -133,13 +133,15 @@ def triangulate_reproject(
         return TriangulationResult(X=X, err=err, proj=proj, status=status)
     with torch.cuda.device(dev):
         if Rt_frames is not None:
-            ws_bytes = int(lib.ska_tri_frames_workspace_bytes(V, T))
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            rc = lib.ska_triangulate_reproject_frames_f32(
-                cams, V, _ptr(Rt_frames), _ptr(kpts), _ptr(conf), T, J, lay, flags, _ptr(X), _ptr(err), _ptr(proj),
-                _ptr(status), _ptr(ws), ws_bytes, _stream_ptr(dev),
-            )
-            ws.record_stream(torch.cuda.current_stream(dev))
+            # the fused kernel builds every frame's cameras in shared memory and needs no workspace; the general form
+            # (frame-major input, V > 4, skew / thin prism, tiny skeletons) answers SKA_EWORKSPACE and gets one
+            args = (cams, V, _ptr(Rt_frames), _ptr(kpts), _ptr(conf), T, J, lay, flags, _ptr(X), _ptr(err), _ptr(proj), _ptr(status))
+            rc = lib.ska_triangulate_reproject_frames_f32(*args, None, 0, _stream_ptr(dev))
+            if rc == _cabi.SKA_EWORKSPACE:
+                ws_bytes = int(lib.ska_tri_frames_workspace_bytes(V, T))
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                rc = lib.ska_triangulate_reproject_frames_f32(*args, _ptr(ws), ws_bytes, _stream_ptr(dev))
+                ws.record_stream(torch.cuda.current_stream(dev))
         else:
             rc = lib.ska_triangulate_reproject_f32(
                 cams, V, cptr, _ptr(kpts), _ptr(conf), T, J, lay, flags, _ptr(X), _ptr(err), _ptr(proj),

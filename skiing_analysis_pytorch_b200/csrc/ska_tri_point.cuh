@@ -171,13 +171,13 @@ struct LamEps {
 // cancellation costs ~1e-3 of lam - irrelevant for a correction that is itself < 3.2e-5 of |X| - and the
 // certificate uses the upper bound lam_c = (num + eps m33) / den, which keeps it rigorous.  (Evaluating the
 // quotient from the row residuals, as the general path does, costs 9 more FMAs per view.)
-template <int V, bool CONF, int LO, typename T>
-SKA_HD void fast_stage(const CamDev* __restrict__ cam, const float cx, const float cy, const float cz, const T* u, const T* v,
-                       const T* w2, T (*a)[4], T (*b)[4], Sym4T<T>& M, FastStage<T>& o) {
+// fast_stage_core: from the rows on.  CT = float (one centre for every point) or T (a centre per point: per-frame cameras).
+template <int V, bool CONF, typename T, typename CT>
+SKA_HD void fast_stage_core(const CT cx, const CT cy, const CT cz, const T* w2, const T (*a)[4], const T (*b)[4], Sym4T<T>& M,
+                            FastStage<T>& o) {
   sym4_zero(M);
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    dlt_rows_pts<LO>(cam[k], u[k], v[k], a[k], b[k]);
     if (CONF) {
       sym4_rank1(M, a[k], w2[k]);
       sym4_rank1(M, b[k], w2[k]);
@@ -218,6 +218,14 @@ SKA_HD void fast_stage(const CamDev* __restrict__ cam, const float cx, const flo
   o.ok = f0.pos;
 }
 
+template <int V, bool CONF, int LO, typename T>
+SKA_HD void fast_stage(const CamDev* __restrict__ cam, const float cx, const float cy, const float cz, const T* u, const T* v,
+                       const T* w2, T (*a)[4], T (*b)[4], Sym4T<T>& M, FastStage<T>& o) {
+#pragma unroll
+  for (int k = 0; k < V; ++k) dlt_rows_pts<LO>(cam[k], u[k], v[k], a[k], b[k]);
+  fast_stage_core<V, CONF, T, float>(cx, cy, cz, w2, a, b, M, o);
+}
+
 // row residuals (a . [Y;1], b . [Y;1]) of every view at the point Y
 template <int V, typename T>
 SKA_HD void row_residuals(const T (*a)[4], const T (*b)[4], T Y0, T Y1, T Y2, T* ra, T* rb) {
@@ -238,9 +246,7 @@ SKA_HD F2 pix_norm(F2 u, float s, float o) { return mk2(fmaf(u.x, s, o), fmaf(u.
 // c: the view's projection rows; ck: the camera whose intrinsics / distortion apply (the view's own, or view 0's
 // when the caller knows that all views share them - the constant loads then fold across views).
 template <int DIST, typename T>
-SKA_HD void score_view(const CamDev& c, const CamDev& ck, T Y0, T Y1, T Y2, T ra, T rb, T u, T v, T& eu, T& ev) {
-  // depth: the hi part alone is good to 6e-8 relative, which is all a divisor of a ~1 px quantity needs
-  const T z = vfma(c.Ph[8], Y0, vfma(c.Ph[9], Y1, vfma(c.Ph[10], Y2, c.Ph[11])));
+SKA_HD void score_core(const CamDev& c, const CamDev& ck, T z, T Y0, T Y1, T Y2, T ra, T rb, T u, T v, T& eu, T& ev) {
   const T iz = rcp_fast(z);
   eu = vmul(vneg(ra), iz);
   ev = vmul(vneg(rb), iz);
@@ -262,6 +268,12 @@ SKA_HD void score_view(const CamDev& c, const CamDev& ck, T Y0, T Y1, T Y2, T ra
     ev = vfma(dy, ck.fy, ev);
     if (DIST >= 2) eu = vfma(y, -ck.skew, eu);
   }
+}
+template <int DIST, typename T>
+SKA_HD void score_view(const CamDev& c, const CamDev& ck, T Y0, T Y1, T Y2, T ra, T rb, T u, T v, T& eu, T& ev) {
+  // depth: the hi part alone is good to 6e-8 relative, which is all a divisor of a ~1 px quantity needs
+  const T z = vfma(c.Ph[8], Y0, vfma(c.Ph[9], Y1, vfma(c.Ph[10], Y2, c.Ph[11])));
+  score_core<DIST, T>(c, ck, z, Y0, Y1, Y2, ra, rb, u, v, eu, ev);
 }
 
 template <int V, int DIST, bool SAMEK, typename T>
@@ -464,41 +476,82 @@ SKA_HD void tri_points(const CamDev* __restrict__ cam, const double (*P64)[12], 
 // Same arithmetic per view as tri_points<V, 1, ...> (each packed half is the scalar IEEE operation); sums over the
 // views are formed as (even views) + (odd views), so results agree with the scalar form to rounding, not bit for bit.
 // The rare general path and the fp64 fallback reuse the scalar per-view code on `cam`.
-// RECOMP: the rows are formed a second time for the final residuals instead of being kept in registers between the
-// normal-matrix pass and the scoring pass (12 more packed operations per view pair, 16 fewer live registers per view
-// pair: at 8 views the difference between 8 and 12+ resident warps per SM).
+// ROWS: where the DLT rows live between the normal-matrix pass and the final-residual pass
+//   kRowsRegs   in registers (16 per view pair: 206 registers at 8 views, 8 warps per SM)
+//   kRowsRecomp formed a second time (14 more packed operations + 15 constant loads per view pair)
+//   kRowsSmem   parked in the caller's shared-memory slab: one 8-byte chunk per (view pair, row entry) and thread,
+//               rowbuf[(8 i + m) * row_stride + thread] - conflict-free 64-bit accesses, no register shuffling
+// SAMEK: every view shares view 0's intrinsics / distortion: those constants are loaded once, not per view pair.
+enum : int { kRowsRegs = 0, kRowsRecomp = 1, kRowsSmem = 2 };
 #if defined(__CUDA_ARCH__)
 #define SKA_OPAQUE(x) asm volatile("" : "+f"(x))
 #else
 #define SKA_OPAQUE(x) (void)(x)
 #endif
-template <int V, bool CONF, int DIST, bool RECOMP = false, int LO = 1>
-SKA_HD void tri_point_vp(const CamPairDev* __restrict__ camp, const CamDev* __restrict__ cam, const double (*P64)[12],
-                         const float cx, const float cy, const float cz, const float* u, const float* v, const float* w2,
-                         const PointSource& src, float* X, float* du, float* dv, uint8_t& status) {
-  static_assert(V % 2 == 0 && DIST <= 1 && LO == 1, "view-pair form: even V, no skew / thin prism");
+// read a chunk back from the slab: volatile on the device, otherwise the compiler forwards the stored registers to
+// the loads and the rows stay live in registers after all
+SKA_HD F2 slab_load(const F2* p) {
+#if defined(__CUDA_ARCH__)
+  F2 r;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return r;
+#else
+  return *p;
+#endif
+}
+// DLT rows of one view pair: SCALAR per view (both coefficients of every FFMA come straight from the constant bank
+// and the result lands in its half of the pair for free; a packed row needs the pair (u_a, u_b) assembled from two
+// separate loads - the register allocator re-copies it in front of every use - plus 15 constant loads)
+template <int LO>
+SKA_HD void dlt_rows_pair(const CamDev& ca, const CamDev& cb, float ua, float va, float ub, float vb, F2 a[4], F2 b[4]) {
+  float a0[4], b0[4], a1[4], b1[4];
+  dlt_rows<LO>(ca, ua, va, a0, b0);
+  dlt_rows<LO>(cb, ub, vb, a1, b1);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    a[m] = mk2(a0[m], a1[m]);
+    b[m] = mk2(b0[m], b1[m]);
+  }
+}
+
+// rows of the view pairs kept in registers between the two halves (all pairs, or one transient pair)
+template <int V, int ROWS>
+struct VpRows {
+  static constexpr int H = V / 2;
+  static constexpr int HK = (ROWS == kRowsRegs) ? H : 1;
+  F2 a[HK][4], b[HK][4];
+};
+
+// First half: rows -> normal matrix -> LDL^T -> least-squares point -> first-order secular step -> certificate.
+// u2, v2, w22: the observations / squared weights packed by view pairs.
+template <int V, bool CONF, int ROWS>
+SKA_HD void vp_fast(const CamDev* __restrict__ cam, const float cx, const float cy, const float cz, const float* u, const float* v,
+                    const F2* w22, VpRows<V, ROWS>& rows, F2* rowbuf, int row_stride, Sym4& M, SecularState& s, bool& conv,
+                    bool& well) {
   constexpr int H = V / 2;
-  constexpr int HK = RECOMP ? 1 : H;  // rows kept: all pairs, or one transient pair
-  F2 a[HK][4], b[HK][4], u2[H], v2[H];
   Sym4T<F2> M2;
   sym4_zero(M2);
 #pragma unroll
   for (int i = 0; i < H; ++i) {
-    u2[i] = mk2(u[2 * i], u[2 * i + 1]);
-    v2[i] = mk2(v[2 * i], v[2 * i + 1]);
-    const F2 w22 = CONF ? mk2(w2[2 * i], w2[2 * i + 1]) : mk2(1.f, 1.f);
-    F2(&ai)[4] = a[RECOMP ? 0 : i];
-    F2(&bi)[4] = b[RECOMP ? 0 : i];
-    dlt_rows_vp(camp[i], u2[i], v2[i], ai, bi);
+    F2(&ai)[4] = rows.a[ROWS == kRowsRegs ? i : 0];
+    F2(&bi)[4] = rows.b[ROWS == kRowsRegs ? i : 0];
+    dlt_rows_pair<1>(cam[2 * i], cam[2 * i + 1], u[2 * i], v[2 * i], u[2 * i + 1], v[2 * i + 1], ai, bi);
+    if (ROWS == kRowsSmem) {
+      F2* r = rowbuf + (8 * i) * row_stride;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        r[m * row_stride] = ai[m];
+        r[(4 + m) * row_stride] = bi[m];
+      }
+    }
     if (CONF) {
-      sym4_rank1(M2, ai, w22);
-      sym4_rank1(M2, bi, w22);
+      sym4_rank1(M2, ai, w22[i]);
+      sym4_rank1(M2, bi, w22[i]);
     } else {
       sym4_rank1_unit(M2, ai);
       sym4_rank1_unit(M2, bi);
     }
   }
-  Sym4 M;
   M.m00 = M2.m00.x + M2.m00.y; M.m01 = M2.m01.x + M2.m01.y; M.m02 = M2.m02.x + M2.m02.y; M.m03 = M2.m03.x + M2.m03.y;
   M.m11 = M2.m11.x + M2.m11.y; M.m12 = M2.m12.x + M2.m12.y; M.m13 = M2.m13.x + M2.m13.y;
   M.m22 = M2.m22.x + M2.m22.y; M.m23 = M2.m23.x + M2.m23.y; M.m33 = M2.m33.x + M2.m33.y;
@@ -517,15 +570,86 @@ SKA_HD void tri_point_vp(const CamPairDev* __restrict__ camp, const CamDev* __re
   const float d0 = lam * z0, d1 = lam * z1, d2 = lam * z2;
   const float step2 = fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
   const float itr = ldl3_inv_trace(f0);
-  bool conv = f0.pos && (lam_c * itr < kFastLamTr) && (step2 <= kFastTol2 * den);
-  const bool well = (M.m00 + M.m11 + M.m22) * itr <= kCondMax;
-  SecularState s;
+  conv = f0.pos && (lam_c * itr < kFastLamTr) && (step2 <= kFastTol2 * den);
+  well = (M.m00 + M.m11 + M.m22) * itr <= kCondMax;
   s.y0 = y0 + d0;
   s.y1 = y1 + d1;
   s.y2 = y2 + d2;
   s.lam = lam;
   s.step2 = step2;
   s.ok = f0.pos;
+}
+
+// Second half: residuals of every view pair at the final point Y (rows from registers / recomputed / from the slab)
+// and the fused reprojection scoring; eu, ev: reprojected minus observed pixel, packed by view pairs.
+template <int V, int DIST, int ROWS, bool SAMEK>
+SKA_HD void vp_score(const CamPairDev* __restrict__ camp, const CamDev* __restrict__ cam, const float* Y, float* u, float* v,
+                     VpRows<V, ROWS>& rows, const F2* rowbuf, int row_stride, F2* eu2, F2* ev2) {
+  constexpr int H = V / 2;
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    const CamPairDev& c = camp[i];
+    const CamPairDev& ck = camp[SAMEK ? 0 : i];  // intrinsics / distortion
+    const CamDev& cka = cam[SAMEK ? 0 : 2 * i];
+    const CamDev& ckb = cam[SAMEK ? 0 : 2 * i + 1];
+    F2(&ai)[4] = rows.a[ROWS == kRowsRegs ? i : 0];
+    F2(&bi)[4] = rows.b[ROWS == kRowsRegs ? i : 0];
+    if (ROWS == kRowsRecomp) {
+      SKA_OPAQUE(u[2 * i]);  // a new value as far as the compiler knows: the rows are recomputed, not kept
+      SKA_OPAQUE(v[2 * i]);
+      SKA_OPAQUE(u[2 * i + 1]);
+      SKA_OPAQUE(v[2 * i + 1]);
+      dlt_rows_pair<1>(cam[2 * i], cam[2 * i + 1], u[2 * i], v[2 * i], u[2 * i + 1], v[2 * i + 1], ai, bi);
+    } else if (ROWS == kRowsSmem) {
+      const F2* r = rowbuf + (8 * i) * row_stride;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        ai[m] = slab_load(r + m * row_stride);
+        bi[m] = slab_load(r + (4 + m) * row_stride);
+      }
+    }
+    const F2 ra = vfma(ai[0], Y[0], vfma(ai[1], Y[1], vfma(ai[2], Y[2], ai[3])));
+    const F2 rb = vfma(bi[0], Y[0], vfma(bi[1], Y[1], vfma(bi[2], Y[2], bi[3])));
+    const F2 z = vfma(c.Ph[8], Y[0], vfma(c.Ph[9], Y[1], vfma(c.Ph[10], Y[2], c.Ph[11])));
+    const F2 iz = rcp_fast(z);
+    F2 eu = vmul(vneg(ra), iz), ev = vmul(vneg(rb), iz);
+    if (DIST) {
+      // normalised coordinate of the observed pixel: scalar per view (see dlt_rows_pair)
+      const F2 xn = mk2(fmaf(u[2 * i], cka.ifx, cka.ncx), fmaf(u[2 * i + 1], ckb.ifx, ckb.ncx));
+      const F2 yn = mk2(fmaf(v[2 * i], cka.ify, cka.ncy), fmaf(v[2 * i + 1], ckb.ify, ckb.ncy));
+      const F2 x = vfma(eu, ck.ifx, xn);
+      const F2 y = vfma(ev, ck.ify, yn);
+      F2 dx, dy;
+      distort_delta<false>(ck, x, y, dx, dy);
+      eu = vfma(dx, ck.fx, eu);
+      ev = vfma(dy, ck.fy, ev);
+    }
+    eu2[i] = eu;
+    ev2[i] = ev;
+  }
+}
+
+template <int V, bool CONF, int DIST, int ROWS = kRowsRegs, bool SAMEK = false, int LO = 1>
+SKA_HD void tri_point_vp(const CamPairDev* __restrict__ camp, const CamDev* __restrict__ cam, const double (*P64)[12],
+                         const float cx, const float cy, const float cz, const float* u, const float* v, const float* w2,
+                         const PointSource& src, float* X, float* du, float* dv, uint8_t& status, F2* rowbuf = nullptr,
+                         int row_stride = 0) {
+  static_assert(V % 2 == 0 && DIST <= 1 && LO == 1, "view-pair form: even V, no skew / thin prism");
+  constexpr int H = V / 2;
+  F2 w22[H];
+  float uu[V], vv[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    uu[k] = u[k];
+    vv[k] = v[k];
+  }
+#pragma unroll
+  for (int i = 0; i < H; ++i) w22[i] = CONF ? mk2(w2[2 * i], w2[2 * i + 1]) : mk2(1.f, 1.f);
+  VpRows<V, ROWS> rows;
+  Sym4 M;
+  SecularState s;
+  bool conv, well;
+  vp_fast<V, CONF, ROWS>(cam, cx, cy, cz, uu, vv, w22, rows, rowbuf, row_stride, M, s, conv, well);
   status = 0;
   if (!SKA_WARP_ALL(conv)) {
     // general path (rare): full secular iteration in scalar fp32 on the scalar cameras
@@ -566,35 +690,14 @@ SKA_HD void tri_point_vp(const CamPairDev* __restrict__ camp, const CamDev* __re
   X[1] = Y[1] + cy;
   X[2] = Y[2] + cz;
   if (!(fabsf(X[0]) <= 3.0e38f && fabsf(X[1]) <= 3.0e38f && fabsf(X[2]) <= 3.0e38f)) status = 2;
+  F2 eu2[H], ev2[H];
+  vp_score<V, DIST, ROWS, SAMEK>(camp, cam, Y, uu, vv, rows, rowbuf, row_stride, eu2, ev2);
 #pragma unroll
   for (int i = 0; i < H; ++i) {
-    const CamPairDev& c = camp[i];
-    F2(&ai)[4] = a[RECOMP ? 0 : i];
-    F2(&bi)[4] = b[RECOMP ? 0 : i];
-    if (RECOMP) {
-      SKA_OPAQUE(u2[i].x);  // a new value as far as the compiler knows: the rows are recomputed, not kept
-      SKA_OPAQUE(u2[i].y);
-      SKA_OPAQUE(v2[i].x);
-      SKA_OPAQUE(v2[i].y);
-      dlt_rows_vp(c, u2[i], v2[i], ai, bi);
-    }
-    const F2 ra = vfma(ai[0], Y[0], vfma(ai[1], Y[1], vfma(ai[2], Y[2], ai[3])));
-    const F2 rb = vfma(bi[0], Y[0], vfma(bi[1], Y[1], vfma(bi[2], Y[2], bi[3])));
-    const F2 z = vfma(c.Ph[8], Y[0], vfma(c.Ph[9], Y[1], vfma(c.Ph[10], Y[2], c.Ph[11])));
-    const F2 iz = rcp_fast(z);
-    F2 eu = vmul(vneg(ra), iz), ev = vmul(vneg(rb), iz);
-    if (DIST) {
-      const F2 x = vfma(eu, c.ifx, vfma(u2[i], c.ifx, c.ncx));
-      const F2 y = vfma(ev, c.ify, vfma(v2[i], c.ify, c.ncy));
-      F2 dx, dy;
-      distort_delta<false>(c, x, y, dx, dy);
-      eu = vfma(dx, c.fx, eu);
-      ev = vfma(dy, c.fy, ev);
-    }
-    du[2 * i] = eu.x;
-    du[2 * i + 1] = eu.y;
-    dv[2 * i] = ev.x;
-    dv[2 * i + 1] = ev.y;
+    du[2 * i] = eu2[i].x;
+    du[2 * i + 1] = eu2[i].y;
+    dv[2 * i] = ev2[i].x;
+    dv[2 * i + 1] = ev2[i].y;
   }
 }
 

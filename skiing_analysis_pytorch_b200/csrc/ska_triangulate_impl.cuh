@@ -43,8 +43,8 @@ struct TriParams {
   uint8_t* status;
 };
 
-#ifndef SKA_VP_RECOMP
-#define SKA_VP_RECOMP 1  // view-pair form: form the rows a second time for the final residuals (fewer live registers)
+#ifndef SKA_VP_ROWS
+#define SKA_VP_ROWS 2  // view-pair form: where the rows live between the two passes (kRowsRegs / kRowsRecomp / kRowsSmem)
 #endif
 #ifndef SKA_KBLOCK
 #define SKA_KBLOCK 256
@@ -112,9 +112,16 @@ __device__ __forceinline__ void load_tile(const TriParams<V>& prm, int64_t koff,
 // LEAN: the common output set (X and err, no proj / status) compiled without the per-view pointer tests.
 // (Alternating two prefetch buffers instead of copying `cur = nxt` was tried: the buffers went to local memory and
 //  the 8-view shape slowed from 0.84 to 1.05 ms.)
-template <int V, int PTS, bool CONF, int DIST, uint32_t SOLVER, int MINB, bool LEAN>
+template <int V, int PTS, uint32_t SOLVER, int DIST>
+struct TriKernelTraits {
+  static constexpr bool kVP = (PTS == 1) && (V >= 4) && (V % 2 == 0) && (DIST <= 1) && (SOLVER == kSolverSecular);
+  static constexpr size_t kSlabBytes = (kVP && SKA_VP_ROWS == kRowsSmem) ? (size_t)kBlock * (8 * (V / 2)) * sizeof(F2) : 0;
+};
+
+template <int V, int PTS, bool CONF, int DIST, uint32_t SOLVER, int MINB, bool LEAN, bool SAMEK>
 __global__ void __launch_bounds__(kBlock, MINB) tri_kernel(const __grid_constant__ TriParams<V> prm) {
   __shared__ __align__(16) float sX[kBlock / 32][32 * PTS * 3];
+  extern __shared__ __align__(16) unsigned char tri_slab[];  // view-pair form with kRowsSmem: the rows of every thread
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t N = (uint32_t)prm.N, n_tiles = (uint32_t)prm.n_tiles;
 
@@ -156,13 +163,13 @@ __global__ void __launch_bounds__(kBlock, MINB) tri_kernel(const __grid_constant
 
     float X[PTS][3], du[PTS][V], dv[PTS][V];
     uint8_t st[PTS];
-    constexpr bool kVP = (PTS == 1) && (V >= 4) && (V % 2 == 0) && (DIST <= 1) && (SOLVER == kSolverSecular);
+    constexpr bool kVP = TriKernelTraits<V, PTS, SOLVER, DIST>::kVP;
     if constexpr (kVP) {
       // many views: one point per thread, per-view work packed over pairs of views
-      tri_point_vp<V, CONF, DIST, (SKA_VP_RECOMP != 0)>(prm.camp, prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], cur.u[0], cur.v[0], w2[0], src, X[0],
-                                  du[0], dv[0], st[0]);
+      tri_point_vp<V, CONF, DIST, SKA_VP_ROWS, SAMEK>(prm.camp, prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], cur.u[0], cur.v[0], w2[0], src,
+                                                      X[0], du[0], dv[0], st[0], reinterpret_cast<F2*>(tri_slab) + threadIdx.x, kBlock);
     } else {
-      tri_points<V, PTS, CONF, DIST, SOLVER>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], cur.u, cur.v, w2, src, X, du, dv, st);
+      tri_points<V, PTS, CONF, DIST, SOLVER, 1, SAMEK>(prm.cam, prm.P64, prm.c[0], prm.c[1], prm.c[2], cur.u, cur.v, w2, src, X, du, dv, st);
     }
 
     // ---- per-view error / reprojection, coalesced
@@ -296,10 +303,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 constexpr int kWarpPts = 64;  // points per warp tile (2 per lane)
 constexpr int kColdCap = 32;  // per-warp list of tiles deferred to the cold loop
 
+// (A group of NW + 1 tiles whose extra tile rotates over the consumer warps that share the producer warp's scheduler - so
+// that every scheduler computes four tiles per group - was measured slower: 0.162 against 0.149 ms on config 2.)
+template <int NW>
+struct CtaGroup {
+  static constexpr int kTiles = NW;
+};
+
 template <int V, int NW, bool CONF, int STAGES>
 struct CtaSmem {  // dynamic shared-memory layout of tri_kernel_cta
-  static constexpr int kViewK = NW * kWarpPts * 2;           // floats of one view's keypoints in a stage
-  static constexpr int kViewC = CONF ? NW * kWarpPts : 0;    // ... confidences
+  static constexpr int GT = CtaGroup<NW>::kTiles;
+  static constexpr int kViewK = GT * kWarpPts * 2;           // floats of one view's keypoints in a stage
+  static constexpr int kViewC = CONF ? GT * kWarpPts : 0;    // ... confidences
   static constexpr int kKptFloats = V * kViewK;
   static constexpr int kStageFloats = kKptFloats + V * kViewC;
   static constexpr size_t oX = (size_t)STAGES * kStageFloats * sizeof(float);
@@ -362,10 +377,11 @@ __global__ void __maxnreg__(SKA_CTA_MAXREG) tri_kernel_cta(const __grid_constant
   uint32_t(*sCold)[kColdCap] = reinterpret_cast<uint32_t(*)[kColdCap]>(cta_smem + L::oCold);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n_wt = (uint32_t)prm.n_tiles;             // whole 64-point tiles
-  const uint32_t n_groups = (n_wt + NW - 1) / NW;
+  constexpr int GT = CtaGroup<NW>::kTiles;
+  const uint32_t n_groups = (n_wt + GT - 1) / GT;
   if (threadIdx.x < STAGES) {
     mbar_init(sFull + threadIdx.x, 1);
-    mbar_init(sEmpty + threadIdx.x, NW);
+    mbar_init(sEmpty + threadIdx.x, GT);  // one arrival per tile
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -377,9 +393,9 @@ __global__ void __maxnreg__(SKA_CTA_MAXREG) tri_kernel_cta(const __grid_constant
       int st = 0;
       uint32_t round = 0;  // how many times the ring wrapped
       for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        if (round > 0) mbar_wait(sEmpty + st, (round - 1) & 1u);  // every consumer warp released this stage
-        const uint32_t t0 = g * NW;
-        const uint32_t nt = (n_wt - t0 < (uint32_t)NW) ? (n_wt - t0) : (uint32_t)NW;
+        if (round > 0) mbar_wait(sEmpty + st, (round - 1) & 1u);  // every tile of the stage's previous group was taken
+        const uint32_t t0 = g * GT;
+        const uint32_t nt = (n_wt - t0 < (uint32_t)GT) ? (n_wt - t0) : (uint32_t)GT;
         float* stage = sK + (size_t)st * L::kStageFloats;
         mbar_expect_tx(sFull + st, (uint32_t)V * nt * (uint32_t)(kWarpPts * (CONF ? 12 : 8)));
 #pragma unroll
@@ -408,8 +424,9 @@ __global__ void __maxnreg__(SKA_CTA_MAXREG) tri_kernel_cta(const __grid_constant
   for (;;) {
     uint32_t n_cold = 0;
     // ---- hot loop: certified tiles only
-    for (; g < n_groups && n_cold < (uint32_t)kColdCap; g += gridDim.x) {
-      const uint32_t wt = g * NW + warp;
+    while (g < n_groups && n_cold < (uint32_t)kColdCap) {
+      const uint32_t slot = (uint32_t)warp;
+      const uint32_t wt = g * GT + slot;
       if (wt >= n_wt) {  // last, partial group: nothing follows for this CTA
         g = n_groups;
         break;
@@ -420,18 +437,19 @@ __global__ void __maxnreg__(SKA_CTA_MAXREG) tri_kernel_cta(const __grid_constant
       F2 ut[V], vt[V], w2[V];
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const float4 q = *reinterpret_cast<const float4*>(stage + k * L::kViewK + warp * (kWarpPts * 2) + 4 * lane);
+        const float4 q = *reinterpret_cast<const float4*>(stage + k * L::kViewK + slot * (kWarpPts * 2) + 4 * lane);
         ut[k] = mk2(q.x, q.z);
         vt[k] = mk2(q.y, q.w);
         if (CONF) {
-          const float2 cf = *reinterpret_cast<const float2*>(stage + L::kKptFloats + k * L::kViewC + warp * kWarpPts + 2 * lane);
+          const float2 cf = *reinterpret_cast<const float2*>(stage + L::kKptFloats + k * L::kViewC + slot * kWarpPts + 2 * lane);
           w2[k] = prm.weight_sqrt ? mk2(cf.x, cf.y) : mk2(cf.x * cf.x, cf.y * cf.y);
         } else {
           w2[k] = mk2(1.f, 1.f);
         }
       }
       __syncwarp();                               // every lane holds its pair in registers
-      if (lane == 0) mbar_arrive(sEmpty + st);    // hand the stage back to the producer
+      if (lane == 0) mbar_arrive(sEmpty + st);    // this tile's share of the stage goes back to the producer
+      g += gridDim.x;
       if (++st == STAGES) {
         st = 0;
         par ^= 1u;
@@ -512,11 +530,218 @@ static cudaError_t launch_cta_impl(TriParams<V>& prm, cudaStream_t stream) {
   if (ce != cudaSuccess) return ce;
   ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // idempotent
   if (ce != cudaSuccess) return ce;
-  const int64_t n_groups = (prm.n_tiles + NW - 1) / NW;
+  constexpr int GT = CtaGroup<NW>::kTiles;
+  const int64_t n_groups = (prm.n_tiles + GT - 1) / GT;
   int64_t grid = sms;  // one persistent CTA per SM
   if (grid > n_groups) grid = n_groups;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(prm);
   return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same CTA organisation for many views (even V >= 6): tri_kernel_cta_vp.  A warp tile is 32 points, ONE point per
+// lane, the per-view work packed over PAIRS OF VIEWS (vp_fast / vp_score of ska_tri_point.cuh).  The lane reads its
+// observations from the stage straight into view-pair registers (no global-load addressing, no prefetch registers,
+// no pair-assembling moves), parks the rows of the first pass in a shared-memory slab (kRowsSmem) or forms them a
+// second time (kRowsRecomp), and the rare tile goes to the deferred cold loop like in tri_kernel_cta.
+#ifndef SKA_CTA_VP_ROWS
+#define SKA_CTA_VP_ROWS 1  // measured at 8 views: rows formed twice 0.490 ms, rows parked in a shared-memory slab 0.530 ms
+#endif
+#ifndef SKA_CTA_VP_STAGES
+#define SKA_CTA_VP_STAGES 3
+#endif
+constexpr int kVpPts = 32;
+
+template <int V, int NW, bool CONF, int STAGES, int ROWS>
+struct CtaVpSmem {
+  static constexpr int kViewK = NW * kVpPts * 2;
+  static constexpr int kViewC = CONF ? NW * kVpPts : 0;
+  static constexpr int kKptFloats = V * kViewK;
+  static constexpr int kStageFloats = kKptFloats + V * kViewC;
+  static constexpr int kSlabChunks = (ROWS == kRowsSmem) ? 8 * (V / 2) : 0;  // 8-byte chunks per thread
+  static constexpr size_t oSlab = (size_t)STAGES * kStageFloats * sizeof(float);
+  static constexpr size_t oX = oSlab + (size_t)NW * 32 * kSlabChunks * sizeof(F2);
+  static constexpr size_t oFull = oX + (size_t)NW * kVpPts * 3 * sizeof(float);
+  static constexpr size_t oEmpty = oFull + (size_t)STAGES * sizeof(uint64_t);
+  static constexpr size_t oCold = oEmpty + (size_t)STAGES * sizeof(uint64_t);
+  static constexpr size_t bytes = oCold + (size_t)NW * kColdCap * sizeof(uint32_t);
+};
+
+template <int V, bool CONF, int DIST, int NW, int STAGES, int ROWS, bool SAMEK, bool LEAN>
+__global__ void __maxnreg__(SKA_CTA_MAXREG) tri_kernel_cta_vp(const __grid_constant__ TriParams<V> prm) {
+  using L = CtaVpSmem<V, NW, CONF, STAGES, ROWS>;
+  constexpr int H = V / 2;
+  extern __shared__ __align__(128) unsigned char cta_smem[];
+  float* sK = reinterpret_cast<float*>(cta_smem);
+  F2* sSlab = reinterpret_cast<F2*>(cta_smem + L::oSlab);
+  float(*sX)[kVpPts * 3] = reinterpret_cast<float(*)[kVpPts * 3]>(cta_smem + L::oX);
+  uint64_t* sFull = reinterpret_cast<uint64_t*>(cta_smem + L::oFull);
+  uint64_t* sEmpty = reinterpret_cast<uint64_t*>(cta_smem + L::oEmpty);
+  uint32_t(*sCold)[kColdCap] = reinterpret_cast<uint32_t(*)[kColdCap]>(cta_smem + L::oCold);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_wt = (uint32_t)prm.n_tiles;  // whole 32-point tiles
+  const uint32_t n_groups = (n_wt + NW - 1) / NW;
+  if (threadIdx.x < STAGES) {
+    mbar_init(sFull + threadIdx.x, 1);
+    mbar_init(sEmpty + threadIdx.x, NW);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  if (warp == NW) {
+    // ---------------------------------------------------------------- producer: one thread
+    if (lane == 0) {
+      int st = 0;
+      uint32_t round = 0;
+      for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        if (round > 0) mbar_wait(sEmpty + st, (round - 1) & 1u);
+        const uint32_t t0 = g * NW;
+        const uint32_t nt = (n_wt - t0 < (uint32_t)NW) ? (n_wt - t0) : (uint32_t)NW;
+        float* stage = sK + (size_t)st * L::kStageFloats;
+        mbar_expect_tx(sFull + st, (uint32_t)V * nt * (uint32_t)(kVpPts * (CONF ? 12 : 8)));
+#pragma unroll 1
+        for (int k = 0; k < V; ++k) {
+          bulk_g2s(stage + k * L::kViewK, prm.kpts + (int64_t)k * prm.k_sV + (int64_t)t0 * (kVpPts * 2), nt * (kVpPts * 8), sFull + st);
+          if (CONF)
+            bulk_g2s(stage + L::kKptFloats + k * L::kViewC, prm.conf + (int64_t)k * prm.c_sV + (int64_t)t0 * kVpPts, nt * (kVpPts * 4),
+                     sFull + st);
+        }
+        if (++st == STAGES) {
+          st = 0;
+          ++round;
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ consumer warps
+  int st = 0;
+  uint32_t par = 0;
+  float* sx = sX[warp];
+  uint32_t* cold = sCold[warp];
+  F2* rowbuf = sSlab + (size_t)warp * 32 * L::kSlabChunks + lane;  // chunk c of this lane: rowbuf[32 c]
+  const float cx = prm.c[0], cy = prm.c[1], cz = prm.c[2];
+  uint32_t g = blockIdx.x;
+  for (;;) {
+    uint32_t n_cold = 0;
+    // ---- hot loop: certified tiles only
+    for (; g < n_groups && n_cold < (uint32_t)kColdCap; g += gridDim.x) {
+      const uint32_t wt = g * NW + warp;
+      if (wt >= n_wt) {
+        g = n_groups;
+        break;
+      }
+      mbar_wait(sFull + st, par);
+      const float* stage = sK + (size_t)st * L::kStageFloats;
+      const uint32_t i0 = wt * kVpPts + lane;
+      float u[V], v[V];
+      F2 w22[H];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float2 q = *reinterpret_cast<const float2*>(stage + k * L::kViewK + warp * (kVpPts * 2) + 2 * lane);
+        u[k] = q.x;
+        v[k] = q.y;
+      }
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        if (CONF) {
+          const float* ca = stage + L::kKptFloats + (2 * i) * L::kViewC + warp * kVpPts + lane;
+          const float c0 = ca[0], c1 = ca[L::kViewC];
+          w22[i] = prm.weight_sqrt ? mk2(c0, c1) : mk2(c0 * c0, c1 * c1);
+        } else {
+          w22[i] = mk2(1.f, 1.f);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sEmpty + st);
+      if (++st == STAGES) {
+        st = 0;
+        par ^= 1u;
+      }
+      VpRows<V, ROWS> rows;
+      Sym4 M;
+      SecularState s;
+      bool conv, well;
+      vp_fast<V, CONF, ROWS>(prm.cam, cx, cy, cz, u, v, w22, rows, rowbuf, 32, M, s, conv, well);
+      if (!__all_sync(0xffffffffu, conv && well)) {  // conv is false for non-finite inputs as well
+        if (lane == 0) cold[n_cold] = wt;
+        ++n_cold;
+        continue;
+      }
+      const float Y[3] = {s.y0, s.y1, s.y2};
+      F2 eu2[H], ev2[H];
+      vp_score<V, DIST, ROWS, SAMEK>(prm.camp, prm.cam, Y, u, v, rows, rowbuf, 32, eu2, ev2);
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        if (LEAN || prm.err != nullptr) {
+          const F2 e = sqrt_fast(vfma(eu2[i], eu2[i], vmul(ev2[i], ev2[i])));
+          SKA_ST(prm.err + (int64_t)(2 * i) * prm.c_sV + i0, e.x);
+          SKA_ST(prm.err + (int64_t)(2 * i + 1) * prm.c_sV + i0, e.y);
+        }
+        if (!LEAN && prm.proj != nullptr) {
+          SKA_ST(reinterpret_cast<float2*>(prm.proj + (int64_t)(2 * i) * prm.k_sV + 2 * (int64_t)i0),
+                 make_float2(u[2 * i] + eu2[i].x, v[2 * i] + ev2[i].x));
+          SKA_ST(reinterpret_cast<float2*>(prm.proj + (int64_t)(2 * i + 1) * prm.k_sV + 2 * (int64_t)i0),
+                 make_float2(u[2 * i + 1] + eu2[i].y, v[2 * i + 1] + ev2[i].y));
+        }
+      }
+      if (!LEAN && prm.status != nullptr) prm.status[i0] = 0;
+      sx[lane * 3 + 0] = Y[0] + cx;
+      sx[lane * 3 + 1] = Y[1] + cy;
+      sx[lane * 3 + 2] = Y[2] + cz;
+      __syncwarp();
+      float* gx = prm.X + (int64_t)wt * (kVpPts * 3);
+      if (LEAN || prm.x_vec) {
+        if (lane < 24) SKA_ST(reinterpret_cast<float4*>(gx) + lane, reinterpret_cast<const float4*>(sx)[lane]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) gx[lane + 32 * r] = sx[lane + 32 * r];
+      }
+      __syncwarp();
+    }
+    // ---- cold loop (rare): the tiles the vote rejected, with the general per-point code
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t ci = 0; ci < n_cold; ++ci) {
+      const uint32_t wt = cold[ci];
+      const uint32_t i0 = wt * kVpPts + lane;
+      float u[V], v[V], w2[V], du[V], dv[V], Xp[3];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float2 q = *reinterpret_cast<const float2*>(prm.kpts + (int64_t)k * prm.k_sV + 2 * (int64_t)i0);
+        u[k] = q.x;
+        v[k] = q.y;
+        const float c = CONF ? prm.conf[(int64_t)k * prm.c_sV + i0] : 1.0f;
+        w2[k] = prm.weight_sqrt ? c : c * c;
+      }
+      PointSource src;
+      src.kpts = prm.kpts + 2 * (int64_t)i0;
+      src.conf = CONF ? prm.conf + i0 : nullptr;
+      src.k_sV = prm.k_sV;
+      src.c_sV = prm.c_sV;
+      src.weight_sqrt = prm.weight_sqrt;
+      uint8_t stt;
+      tri_point_vp<V, CONF, DIST, kRowsRecomp, SAMEK>(prm.camp, prm.cam, prm.P64, cx, cy, cz, u, v, w2, src, Xp, du, dv, stt);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        if (prm.err != nullptr) prm.err[(int64_t)k * prm.c_sV + i0] = sqrt_fast(fmaf(du[k], du[k], dv[k] * dv[k]));
+        if (prm.proj != nullptr)
+          *reinterpret_cast<float2*>(prm.proj + (int64_t)k * prm.k_sV + 2 * (int64_t)i0) = make_float2(u[k] + du[k], v[k] + dv[k]);
+      }
+      if (prm.status != nullptr) prm.status[i0] = stt;
+      sx[lane * 3 + 0] = Xp[0];
+      sx[lane * 3 + 1] = Xp[1];
+      sx[lane * 3 + 2] = Xp[2];
+      __syncwarp();
+      float* gx = prm.X + (int64_t)wt * (kVpPts * 3);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) gx[lane + 32 * r] = sx[lane + 32 * r];
+      __syncwarp();
+    }
+    if (g >= n_groups) break;
+  }
 }
 
 // every view shares view 0's intrinsics and distortion bit for bit (the common rig: one camera model)
@@ -544,6 +769,42 @@ static cudaError_t launch_cta(TriParams<V>& prm, cudaStream_t stream) {
   return lean ? launch_cta_impl<V, CONF, DIST, false, true>(prm, stream) : launch_cta_impl<V, CONF, DIST, false, false>(prm, stream);
 }
 
+template <int V, bool CONF, int DIST, bool SAMEK, bool LEAN>
+static cudaError_t launch_cta_vp_impl(TriParams<V>& prm, cudaStream_t stream) {
+  constexpr int NW = SKA_CTA_WARPS, STAGES = SKA_CTA_VP_STAGES, BLOCK = 32 * (NW + 1);
+  auto kern = tri_kernel_cta_vp<V, CONF, DIST, NW, STAGES, SKA_CTA_VP_ROWS, SAMEK, LEAN>;
+  constexpr size_t smem = CtaVpSmem<V, NW, CONF, STAGES, SKA_CTA_VP_ROWS>::bytes;
+  static_assert(smem <= 227 * 1024, "tri_kernel_cta_vp staging does not fit the SM's shared memory");
+  int dev = 0, sms = 0;
+  cudaError_t ce = cudaGetDevice(&dev);
+  if (ce != cudaSuccess) return ce;
+  ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (ce != cudaSuccess) return ce;
+  ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // idempotent
+  if (ce != cudaSuccess) return ce;
+  const int64_t n_groups = (prm.n_tiles + NW - 1) / NW;
+  int64_t grid = sms;
+  if (grid > n_groups) grid = n_groups;
+  kern<<<(unsigned)grid, BLOCK, smem, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+template <int V, bool CONF, int DIST>
+static cudaError_t launch_cta_vp(TriParams<V>& prm, cudaStream_t stream) {
+  const bool lean = prm.err != nullptr && prm.proj == nullptr && prm.status == nullptr && prm.x_vec;
+  if constexpr (DIST == 1) {
+    if (same_intrinsics<V>(prm))
+      return lean ? launch_cta_vp_impl<V, CONF, DIST, true, true>(prm, stream) : launch_cta_vp_impl<V, CONF, DIST, true, false>(prm, stream);
+  }
+  return lean ? launch_cta_vp_impl<V, CONF, DIST, false, true>(prm, stream) : launch_cta_vp_impl<V, CONF, DIST, false, false>(prm, stream);
+}
+
+}  // namespace ska
+
+#include "ska_tri_frames.cuh"
+
+namespace ska {
+
 #ifndef SKA_MINB_SMALL
 #define SKA_MINB_SMALL 2  // V <= 4: resident CTAs per SM the register allocator must allow
 #endif
@@ -555,10 +816,22 @@ static cudaError_t launch(TriParams<V>& prm, cudaStream_t stream) {
   // the hot path gets a lean-output instantiation (X and err only: measured 0.84 -> 0.70 ms on the 8-view shape - the
   // per-view pointer tests cost a BSSY/BSYNC pair and a scheduling barrier each); everything else the general one
   constexpr bool kHasLean = (V >= 5) && (SOLVER == kSolverSecular) && (DIST <= 1);  // V <= 4: this kernel only sees tails and odd layouts
+  constexpr bool kHasSameK = kHasLean && (DIST == 1) && (V % 2 == 0);                // view-pair form: shared intrinsics loaded once
   const bool lean = kHasLean && prm.err != nullptr && prm.proj == nullptr && prm.status == nullptr;
-  void (*kern)(TriParams<V>) = tri_kernel<V, PTS, CONF, DIST, SOLVER, MINB, false>;
+  void (*kern)(TriParams<V>) = tri_kernel<V, PTS, CONF, DIST, SOLVER, MINB, false, false>;
   if constexpr (kHasLean) {
-    if (lean) kern = tri_kernel<V, PTS, CONF, DIST, SOLVER, MINB, true>;
+    if (lean) kern = tri_kernel<V, PTS, CONF, DIST, SOLVER, MINB, true, false>;
+  }
+  if constexpr (kHasSameK) {
+    if (same_intrinsics<V>(prm)) {
+      kern = tri_kernel<V, PTS, CONF, DIST, SOLVER, MINB, false, true>;
+      if (lean) kern = tri_kernel<V, PTS, CONF, DIST, SOLVER, MINB, true, true>;
+    }
+  }
+  constexpr size_t slab = TriKernelTraits<V, PTS, SOLVER, DIST>::kSlabBytes;
+  if (slab > 48 * 1024 - sizeof(float) * kBlock * PTS * 3) {
+    const cudaError_t ca = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab);  // idempotent
+    if (ca != cudaSuccess) return ca;
   }
   const int64_t per_tile = (int64_t)kBlock * PTS;
   prm.n_tiles = (prm.N + per_tile - 1) / per_tile;
@@ -567,12 +840,12 @@ static cudaError_t launch(TriParams<V>& prm, cudaStream_t stream) {
   if (ce != cudaSuccess) return ce;
   ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (ce != cudaSuccess) return ce;
-  ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0);
+  ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, slab);
   if (ce != cudaSuccess) return ce;
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)sms * per_sm;  // one wave of resident CTAs, each walks tiles
   if (grid > prm.n_tiles) grid = prm.n_tiles;
-  kern<<<(unsigned)grid, kBlock, 0, stream>>>(prm);
+  kern<<<(unsigned)grid, kBlock, slab, stream>>>(prm);
   return cudaGetLastError();
 }
 
@@ -706,8 +979,82 @@ __global__ void __launch_bounds__(128) tri_frames_kernel(const TriFrameParams<V>
   if (prm.status != nullptr) prm.status[i] = st[0];
 }
 
+// fused path: view-major layout, V <= 4, no skew / thin prism, 16-byte aligned streams, skeletons of >= 8 joints
+template <int V>
+static int dispatch_frames_fused(const TriArgs& a, bool& taken) {
+  taken = false;
+  if constexpr (V <= 4) {
+    const bool fm = (a.layout == SKA_LAYOUT_FRAME_MAJOR);
+    const int64_t N = a.T * (int64_t)a.J;
+    auto al = [](const void* p, uintptr_t n) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % n) == 0; };
+    const bool conf = (a.conf != nullptr);
+    if (fm || N < 64 || !al(a.kpts, 16) || !al(a.X, 16) || !al(a.err, 8) || !al(a.proj, 16) || (N % 2 != 0) ||
+        (conf && (!al(a.conf, 16) || N % 4 != 0)) || !frames_table_fits<SKA_FR_WARPS>(a.J))
+      return SKA_OK;
+    TriFramesParams<V> prm;
+    int dist = 0;
+    const double origin[3] = {0.0, 0.0, 0.0};
+    for (int v = 0; v < V; ++v) {
+      double P[12];
+      int d = 0;
+      const char* why = "";
+      SkaCamera cam = a.cams[v];
+      for (int k = 0; k < 9; ++k) cam.R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+      cam.t[0] = cam.t[1] = cam.t[2] = 0.0;
+      const int rc = prep_camera(cam, origin, (a.flags & SKA_PINHOLE_REPROJ) != 0, prm.ck[v], P, d, &why);
+      if (rc != SKA_OK) return set_error(rc, why);
+      dist = d > dist ? d : dist;
+      const double k22 = a.cams[v].K[8];
+      prm.Kn[v][0] = a.cams[v].K[0] / k22;
+      prm.Kn[v][1] = a.cams[v].K[1] / k22;
+      prm.Kn[v][2] = a.cams[v].K[2] / k22;
+      prm.Kn[v][3] = a.cams[v].K[4] / k22;
+      prm.Kn[v][4] = a.cams[v].K[5] / k22;
+      prm.cams[v] = a.cams[v];
+    }
+    if (dist >= 2) return SKA_OK;
+    prm.Rt = a.Rt_frames;
+    prm.weight_sqrt = (a.flags & SKA_WEIGHT_SQRT) ? 1u : 0u;
+    prm.pinhole = (a.flags & SKA_PINHOLE_REPROJ) ? 1u : 0u;
+    prm.J = a.J;
+    prm.divJ = make_fastdiv((uint32_t)a.J);
+    prm.N = N;
+    prm.n_tiles = N / 64;
+    prm.k_sV = 2 * N;
+    prm.c_sV = N;
+    prm.kpts = a.kpts;
+    prm.conf = a.conf;
+    prm.X = a.X;
+    prm.err = a.err;
+    prm.proj = a.proj;
+    prm.status = a.status;
+    cudaStream_t s = (cudaStream_t)a.stream;
+    const bool lean = a.err != nullptr && a.proj == nullptr && a.status == nullptr;
+    cudaError_t ce;
+#define SKA_FR(CONF, DIST) (lean ? launch_frames_impl<V, CONF, DIST, true>(prm, s) : launch_frames_impl<V, CONF, DIST, false>(prm, s))
+    ce = conf ? (dist ? SKA_FR(true, 1) : SKA_FR(true, 0)) : (dist ? SKA_FR(false, 1) : SKA_FR(false, 0));
+#undef SKA_FR
+    if (ce == cudaSuccess && prm.n_tiles * 64 < N) {
+      const uint32_t first = (uint32_t)(prm.n_tiles * 64);
+      if (conf) tri_frames_tail_kernel<V, true><<<1, 64, 0, s>>>(prm, first);
+      else tri_frames_tail_kernel<V, false><<<1, 64, 0, s>>>(prm, first);
+      ce = cudaGetLastError();
+    }
+    if (ce != cudaSuccess) return set_error((int)ce, cudaGetErrorString(ce));
+    taken = true;
+  }
+  return SKA_OK;
+}
+
 template <int V>
 static int dispatch_frames(const TriArgs& a) {
+#ifndef SKA_NO_FRAMES_FUSED
+  {
+    bool taken = false;
+    const int rc = dispatch_frames_fused<V>(a, taken);
+    if (rc != SKA_OK || taken) return rc;
+  }
+#endif
   if (a.ws_bytes < (size_t)a.T * sizeof(FrameCams<V>) || a.workspace == nullptr)
     return set_error(SKA_EWORKSPACE, "workspace too small (see ska_tri_frames_workspace_bytes)");
   if (reinterpret_cast<uintptr_t>(a.workspace) % 16 != 0) return set_error(SKA_EALIGN, "workspace must be 16-byte aligned");
@@ -857,6 +1204,36 @@ static int dispatch(const TriArgs& a) {
       }
     } else {
       ce = pair_ok ? SKA_GO(2) : SKA_GO(1);
+    }
+  } else if constexpr (V % 2 == 0) {
+    // even V >= 6: whole 32-point tiles -> bulk-staged view-pair kernel; the tail and unaligned / frame-major input -> tri_kernel
+    const bool vp_ok = !fm && al(a.kpts, 16) && (prm.N % 2 == 0) && al(a.X, 16) && al(a.proj, 8) && (!conf || (al(a.conf, 16) && prm.N % 4 == 0));
+#ifdef SKA_NO_CTA_VP
+    const bool use_vp = false;
+#else
+    const bool use_vp = vp_ok;
+#endif
+    if (use_vp) {
+      const int64_t n_full = prm.N / kVpPts, done = n_full * kVpPts;
+      ce = cudaSuccess;
+      if (n_full > 0) {
+        TriParams<V> q = prm;
+        q.n_tiles = n_full;
+        ce = conf ? (dist ? launch_cta_vp<V, true, 1>(q, s) : launch_cta_vp<V, true, 0>(q, s))
+                  : (dist ? launch_cta_vp<V, false, 1>(q, s) : launch_cta_vp<V, false, 0>(q, s));
+      }
+      if (ce == cudaSuccess && done < prm.N) {
+        prm.N -= done;
+        prm.kpts += 2 * done;
+        if (prm.conf != nullptr) prm.conf += done;
+        prm.X += 3 * done;
+        if (prm.err != nullptr) prm.err += done;
+        if (prm.proj != nullptr) prm.proj += 2 * done;
+        if (prm.status != nullptr) prm.status += done;
+        ce = SKA_GO(1);
+      }
+    } else {
+      ce = SKA_GO(1);
     }
   } else {
     ce = SKA_GO(1);

@@ -54,11 +54,21 @@ static int run(const SkaCamera* cams, const double* centre, const float* kpts, c
         src.c_sV = N;
         src.weight_sqrt = (flags & SKA_WEIGHT_SQRT) ? 1u : 0u;
         const float cx = (float)c[0], cy = (float)c[1], cz = (float)c[2];
-        const bool recomp = (flags >> 13) & 1;  // rows formed a second time for the final residuals
-#define VP(CONF, DIST)                                                                                          \
-  do {                                                                                                          \
-    if (recomp) tri_point_vp<V, CONF, DIST, true>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);   \
-    else tri_point_vp<V, CONF, DIST, false>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st);        \
+        const int rows = (flags >> 13) & 3;  // where the rows live between the passes (kRowsRegs / Recomp / Smem)
+        const bool samek = (flags >> 15) & 1; // read every view's intrinsics from view 0 (caller knows they are equal)
+        F2 slab[4 * V];
+#define VP2(CONF, DIST, ROWS, SK) tri_point_vp<V, CONF, DIST, ROWS, SK>(camp, cam, P64, cx, cy, cz, u, vv, w2, src, Xp, du, dv, st, slab, 1)
+#define VP(CONF, DIST)                                          \
+  do {                                                          \
+    if (samek) {                                                \
+      if (rows == 1) VP2(CONF, DIST, kRowsRecomp, true);        \
+      else if (rows == 2) VP2(CONF, DIST, kRowsSmem, true);     \
+      else VP2(CONF, DIST, kRowsRegs, true);                    \
+    } else {                                                    \
+      if (rows == 1) VP2(CONF, DIST, kRowsRecomp, false);       \
+      else if (rows == 2) VP2(CONF, DIST, kRowsSmem, false);    \
+      else VP2(CONF, DIST, kRowsRegs, false);                   \
+    }                                                           \
   } while (0)
         if (conf) {
           if (dist) VP(true, 1); else VP(true, 0);
@@ -66,6 +76,7 @@ static int run(const SkaCamera* cams, const double* centre, const float* kpts, c
           if (dist) VP(false, 1); else VP(false, 0);
         }
 #undef VP
+#undef VP2
         for (int k = 0; k < 3; ++k) X[3 * i + k] = Xp[k];
         if (err)
           for (int v = 0; v < V; ++v) err[v * N + i] = sqrtf(du[v] * du[v] + dv[v] * dv[v]);

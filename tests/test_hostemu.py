@@ -172,10 +172,11 @@ def test_hostemu_packed_pair_path_is_bit_identical_to_scalar(rig, T, J, use_conf
 
 
 @pytest.mark.parametrize("rig,T,J,use_conf,dist", [c for c in CASES if c[0] in ("4", "8")] + [("8", 16, 17, False, None), ("4", 32, 17, False, synth.DIST_CALIB)])
-@pytest.mark.parametrize("recomp", [0, 1])
-def test_hostemu_view_pair_form_matches_oracle(rig, T, J, use_conf, dist, recomp):
+@pytest.mark.parametrize("rows", [0, 1, 2, 6])
+def test_hostemu_view_pair_form_matches_oracle(rig, T, J, use_conf, dist, rows):
     """tri_point_vp (per-view work packed over pairs of views - the even V >= 4 kernel path), with the rows kept
-    in registers or formed a second time for the final residuals (identical arithmetic)."""
+    in registers (0), formed a second time for the final residuals (1) or parked in a slab (2; 6 = slab + every view
+    reading view 0's intrinsics, which are equal on these rigs): identical arithmetic."""
     clip = synth.make_clip(rig, T, J, seed=0)
     conf = clip.conf_vm if use_conf else None
     V = len(clip.R)
@@ -183,7 +184,7 @@ def test_hostemu_view_pair_form_matches_oracle(rig, T, J, use_conf, dist, recomp
     cams = _cabi.make_cameras(clip.K, clip.R, clip.t, dist)
     k = clip.x_vm.reshape(V, -1, 2)
     c = None if conf is None else conf.reshape(V, -1)
-    X, err, st = hostemu.triangulate(cams, V, k, c, flags=(1 << 12) | (recomp << 13))
+    X, err, st = hostemu.triangulate(cams, V, k, c, flags=(1 << 12) | (rows << 13))
     rel = np.linalg.norm(X - Xo, axis=1) / np.linalg.norm(Xo, axis=1)
     assert rel.max() < X_REL_HELD < X_REL_TOL
     assert np.abs(err - eo).max() < POINT_TOL

@@ -15,12 +15,10 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 TUS = ["ska_tri_v2.cu", "ska_tri_v8.cu"]
 VARIANTS = {
-    "A": [],                                                                       # v2: 12 warps x 152 regs, 4 stages; v8: rows kept, 1 CTA x 256
-    "B": ["-DSKA_CTA_WARPS=15", "-DSKA_CTA_MAXREG=128", "-DSKA_VP_RECOMP=1", "-DSKA_MINB_LARGE=2"],
-    "C": ["-DSKA_CTA_WARPS=14", "-DSKA_CTA_MAXREG=136", "-DSKA_VP_RECOMP=1", "-DSKA_KBLOCK=128", "-DSKA_MINB_LARGE=3"],
-    "D": ["-DSKA_CTA_STAGES=6", "-DSKA_VP_RECOMP=1", "-DSKA_KBLOCK=128", "-DSKA_MINB_LARGE=4"],
-    "E": ["-DSKA_PLAIN_STORES", "-DSKA_VP_RECOMP=1", "-DSKA_MINB_LARGE=1"],
-    "F": ["-DSKA_CTA_STAGES=3", "-DSKA_CTA_WARPS=11", "-DSKA_CTA_MAXREG=168"],
+    "A": [],                                                      # v8: staged view-pair kernel, rows in the slab, 2 stages
+    "B": ["-DSKA_CTA_VP_ROWS=1", "-DSKA_CTA_VP_STAGES=3"],        # rows recomputed
+    "C": ["-DSKA_NO_CTA_VP"],                                     # v8 in the generic tri_kernel (slab rows)
+    "D": ["-DSKA_CTA_EXTRA_TILE"],                                # v2: extra-tile rotation
 }
 LIBDIR = ROOT / "skiing_analysis_pytorch_b200" / "lib"
 
