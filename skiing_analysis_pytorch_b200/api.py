@@ -37,6 +37,7 @@ class TriangulationResult:
     err: Optional[torch.Tensor]  # (V,T,J) or (T,V,J) f32 pixel error per view
     proj: Optional[torch.Tensor]  # same layout as kpts
     status: Optional[torch.Tensor]  # (T,J) uint8: 0 fast path, 1 Jacobi fallback, 2 non-finite
+    stats: Optional[torch.Tensor] = None  # (T,V,4) f32 rmse / mean / median / max per (frame, view) - host pipeline only
 
 
 def triangulate_reproject(
@@ -102,8 +103,14 @@ def triangulate_reproject(
         flags |= _cabi.PINHOLE_REPROJ
     dev = kpts.device
     Rt_frames = None
-    if (torch.is_tensor(R) and R.dim() == 4) or (not torch.is_tensor(R) and np.ndim(R) == 4):
+    if torch.is_tensor(R) and R.dim() == 3 and tuple(R.shape) == (T, V, 12) and t is None:
+        # per-frame extrinsics already packed as include/ska.h wants them: (T,V,12) fp64 CUDA [R row-major | t]
+        if R.dtype != torch.float64 or not R.is_cuda:
+            raise ValueError("packed per-frame extrinsics must be a float64 CUDA tensor (T,V,12)")
+        Rt_frames = R.contiguous()
+    elif (torch.is_tensor(R) and R.dim() == 4) or (not torch.is_tensor(R) and np.ndim(R) == 4):
         Rt_frames = _pack_frame_extrinsics(R, t, T, V, dev)
+    if Rt_frames is not None:
         cams = _cabi.make_cameras(K, np.broadcast_to(np.eye(3), (V, 3, 3)), np.zeros((V, 3)), dist)
     else:
         R = np.asarray(R.detach().cpu() if torch.is_tensor(R) else R, np.float64)
@@ -149,6 +156,14 @@ def triangulate_reproject(
             )
     _lib.check(rc)
     return TriangulationResult(X=X, err=err, proj=proj, status=status)
+
+
+def pack_frame_extrinsics(R, t, device) -> torch.Tensor:
+    """(T,V,3,3) + (T,V,3) -> the packed (T,V,12) fp64 CUDA tensor triangulate_reproject accepts as `R` (with t=None):
+    pack once per clip instead of on every call."""
+    R = torch.as_tensor(np.asarray(R, np.float64)) if not torch.is_tensor(R) else R
+    T, V = int(R.shape[0]), int(R.shape[1])
+    return _pack_frame_extrinsics(R, t, T, V, torch.device(device))
 
 
 def _pack_frame_extrinsics(R, t, T: int, V: int, dev) -> torch.Tensor:
@@ -235,6 +250,11 @@ def frame_stats(err: torch.Tensor, *, layout: str = "VTJ2") -> torch.Tensor:
 _HOST_PIPE_CACHE: dict = {}
 
 
+def clear_host_pipeline_cache() -> None:
+    """Drop the device staging buffers and streams triangulate_reproject_host keeps between calls."""
+    _HOST_PIPE_CACHE.clear()
+
+
 def triangulate_reproject_host(
     kpts: torch.Tensor,
     K,
@@ -253,6 +273,10 @@ def triangulate_reproject_host(
     (V,T,J,2) float32 HOST tensors in, HOST tensors out.  The clip is cut into frame chunks that
     flow H2D -> fused kernel -> D2H on `n_streams` CUDA streams so the two PCIe directions and the
     kernel overlap.  Pinned inputs/outputs make the copies asynchronous; pageable ones still work.
+    want: any of "X", "err", "proj", "status", "stats".  "stats" = the nan-aware per-(frame, view) rmse / mean / median /
+    max of the pixel errors, (T,V,4) - what process_triangulate consumes (triangulation/triangulate.py:111-114 reads
+    mean_err_L / mean_err_R only): asking for ("X", "stats") instead of ("X", "err") moves 16 V bytes per frame over
+    PCIe instead of 4 V J.  R / t may be a static rig or per-frame (T,V,3,3) / (T,V,3) host arrays.
     Returns after the last chunk has landed on the host."""
     if kpts.is_cuda:
         raise ValueError("triangulate_reproject_host takes host tensors; use triangulate_reproject for CUDA tensors")
@@ -262,17 +286,36 @@ def triangulate_reproject_host(
         raise ValueError("the host pipeline takes view-major (V,T,J,2) clips")
     kw.pop("layout", None)
     want = tuple(kw.pop("want", ("X", "err")))
+    bad = set(want) - {"X", "err", "proj", "status", "stats"}
+    if bad:
+        raise ValueError(f"unknown output(s) {sorted(bad)}")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     V, T, J, _ = kpts.shape
+    per_frame = (R.dim() if torch.is_tensor(R) else np.ndim(R)) == 4
+    if per_frame:
+        R = torch.as_tensor(np.asarray(R, np.float64)) if not torch.is_tensor(R) else R.to(torch.float64)
+        t = (torch.as_tensor(np.asarray(t, np.float64)) if not torch.is_tensor(t) else t.to(torch.float64)).reshape(T, V, 3)
+        if tuple(R.shape) != (T, V, 3, 3):
+            raise ValueError(f"per-frame R must be ({T},{V},3,3), got {tuple(R.shape)}")
+        hRt = torch.cat([R.reshape(T, V, 9).cpu(), t.cpu()], dim=-1).contiguous()
+        if not hRt.is_pinned():
+            hRt = hRt.pin_memory()
     out = out or {}
+
+    def host(name, shape, dtype=torch.float32):
+        if name not in want:
+            return None
+        buf = out.get(name)
+        return buf if buf is not None else torch.empty(shape, dtype=dtype).pin_memory()
+
     hX = out.get("X")
     if hX is None:
         hX = torch.empty((T, J, 3), dtype=torch.float32).pin_memory()
-    hE = out.get("err") if "err" in want else None
-    if "err" in want and hE is None:
-        hE = torch.empty((V, T, J), dtype=torch.float32).pin_memory()
+    hE, hP = host("err", (V, T, J)), host("proj", (V, T, J, 2))
+    hS, hSt = host("stats", (T, V, 4)), host("status", (T, J), torch.uint8)
     Tc = max(1, min(chunk_frames, T))
-    key = (dev.index, V, Tc, J, conf is not None, n_streams)
+    need_err = hE is not None or hS is not None
+    key = (dev.index, V, Tc, J, conf is not None, n_streams, hP is not None, hSt is not None, per_frame)
     slots = _HOST_PIPE_CACHE.get(key)
     if slots is None:
         slots = []
@@ -284,10 +327,14 @@ def triangulate_reproject_host(
                     "c": torch.empty((V, Tc, J), dtype=torch.float32, device=dev) if conf is not None else None,
                     "X": torch.empty((Tc, J, 3), dtype=torch.float32, device=dev),
                     "err": torch.empty((V, Tc, J), dtype=torch.float32, device=dev),
+                    "proj": torch.empty((V, Tc, J, 2), dtype=torch.float32, device=dev) if hP is not None else None,
+                    "status": torch.empty((Tc, J), dtype=torch.uint8, device=dev) if hSt is not None else None,
+                    "Rt": torch.empty((Tc, V, 12), dtype=torch.float64, device=dev) if per_frame else None,
                 }
             )
         _HOST_PIPE_CACHE.clear()
         _HOST_PIPE_CACHE[key] = slots
+    dwant = ("X",) + (("err",) if need_err else ()) + (("proj",) if hP is not None else ()) + (("status",) if hSt is not None else ())
     cur = torch.cuda.current_stream(dev)
     start = torch.cuda.Event()
     start.record(cur)
@@ -299,22 +346,37 @@ def triangulate_reproject_host(
         i += 1
         with torch.cuda.stream(s["stream"]):
             s["stream"].wait_event(start)
-            dk = s["k"] if n == Tc else s["k"].flatten()[: V * n * J * 2].view(V, n, J, 2)
-            dc = None
-            if conf is not None:
-                dc = s["c"] if n == Tc else s["c"].flatten()[: V * n * J].view(V, n, J)
+            part = lambda buf, *shape: buf if n == Tc else buf.flatten()[: int(np.prod(shape))].view(*shape)
+            dk = part(s["k"], V, n, J, 2)
+            dc = part(s["c"], V, n, J) if conf is not None else None
             dX = s["X"][:n]
-            dE = s["err"] if n == Tc else s["err"].flatten()[: V * n * J].view(V, n, J)
+            dE = part(s["err"], V, n, J)
+            outs = {"X": dX, "err": dE}
+            if hP is not None:
+                outs["proj"] = part(s["proj"], V, n, J, 2)
+            if hSt is not None:
+                outs["status"] = s["status"][:n]
             for v in range(V):
                 dk[v].copy_(kpts[v, a:b], non_blocking=True)
                 if dc is not None:
                     dc[v].copy_(conf[v, a:b], non_blocking=True)
-            triangulate_reproject(dk, K, R, t, conf=dc, dist=dist, want=want, out={"X": dX, "err": dE}, **kw)
+            if per_frame:
+                dRt = s["Rt"][:n]
+                dRt.copy_(hRt[a:b], non_blocking=True)
+                triangulate_reproject(dk, K, dRt, None, conf=dc, dist=dist, want=dwant, out=outs, **kw)
+            else:
+                triangulate_reproject(dk, K, R, t, conf=dc, dist=dist, want=dwant, out=outs, **kw)
             hX[a:b].copy_(dX, non_blocking=True)
-            if hE is not None:
-                for v in range(V):
+            if hS is not None:
+                hS[a:b].copy_(frame_stats(dE), non_blocking=True)
+            for v in range(V):
+                if hE is not None:
                     hE[v, a:b].copy_(dE[v], non_blocking=True)
+                if hP is not None:
+                    hP[v, a:b].copy_(outs["proj"][v], non_blocking=True)
+            if hSt is not None:
+                hSt[a:b].copy_(outs["status"], non_blocking=True)
     for s in slots:
         cur.wait_stream(s["stream"])
     cur.synchronize()
-    return TriangulationResult(X=hX, err=hE, proj=None, status=None)
+    return TriangulationResult(X=hX, err=hE, proj=hP, status=hSt, stats=hS)

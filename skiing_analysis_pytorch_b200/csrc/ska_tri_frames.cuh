@@ -70,86 +70,99 @@ struct TriFramesParams {
 };
 
 // The frame's conditioning origin: the point closest (least squares) to all optical axes, regularised towards the
-// mean camera centre - default_centre of ska_prep.h on the raw [R|t] rows.
+// mean camera centre - default_centre of ska_prep.h.  fp32 is enough: ANY point near the subject conditions the solve,
+// and the fp32 value chosen here enters the fp64 translation column below exactly.
 template <int V>
-__device__ __forceinline__ void frame_centre(const double* __restrict__ Rt, double c[3]) {
-  double A00 = 0, A01 = 0, A02 = 0, A11 = 0, A12 = 0, A22 = 0, b0 = 0, b1 = 0, b2 = 0, m0 = 0, m1 = 0, m2 = 0;
+__device__ __forceinline__ void frame_centre(const double* Rt /*V x 12, registers*/, float c[3]) {
+  float A00 = 0, A01 = 0, A02 = 0, A11 = 0, A12 = 0, A22 = 0, b0 = 0, b1 = 0, b2 = 0, m0 = 0, m1 = 0, m2 = 0;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    const double* R = Rt + 12 * v;
-    const double* t = R + 9;
-    const double C0 = -(R[0] * t[0] + R[3] * t[1] + R[6] * t[2]);
-    const double C1 = -(R[1] * t[0] + R[4] * t[1] + R[7] * t[2]);
-    const double C2 = -(R[2] * t[0] + R[5] * t[1] + R[8] * t[2]);
-    const double d0 = R[6], d1 = R[7], d2 = R[8];
-    m0 += C0 / V;
-    m1 += C1 / V;
-    m2 += C2 / V;
-    const double p00 = 1.0 - d0 * d0, p01 = -d0 * d1, p02 = -d0 * d2, p11 = 1.0 - d1 * d1, p12 = -d1 * d2, p22 = 1.0 - d2 * d2;
+    const double* Rd = Rt + 12 * v;
+    float R[9], t[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = (float)Rd[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t[k] = (float)Rd[9 + k];
+    const float C0 = -(R[0] * t[0] + R[3] * t[1] + R[6] * t[2]);
+    const float C1 = -(R[1] * t[0] + R[4] * t[1] + R[7] * t[2]);
+    const float C2 = -(R[2] * t[0] + R[5] * t[1] + R[8] * t[2]);
+    const float d0 = R[6], d1 = R[7], d2 = R[8];
+    m0 += C0 * (1.0f / V);
+    m1 += C1 * (1.0f / V);
+    m2 += C2 * (1.0f / V);
+    const float p00 = 1.0f - d0 * d0, p01 = -d0 * d1, p02 = -d0 * d2, p11 = 1.0f - d1 * d1, p12 = -d1 * d2, p22 = 1.0f - d2 * d2;
     A00 += p00; A01 += p01; A02 += p02; A11 += p11; A12 += p12; A22 += p22;
     b0 += p00 * C0 + p01 * C1 + p02 * C2;
     b1 += p01 * C0 + p11 * C1 + p12 * C2;
     b2 += p02 * C0 + p12 * C1 + p22 * C2;
   }
-  const double mu = 1e-6 * V;
+  const float mu = 1e-4f * V;  // (parallel axes leave A singular along them: pull those directions to the mean camera centre)
   A00 += mu; A11 += mu; A22 += mu;
   b0 += mu * m0; b1 += mu * m1; b2 += mu * m2;
   // symmetric 3x3 solve by cofactors (A is positive definite thanks to mu)
-  const double c00 = A11 * A22 - A12 * A12, c01 = A02 * A12 - A01 * A22, c02 = A01 * A12 - A02 * A11;
-  const double c11 = A00 * A22 - A02 * A02, c12 = A01 * A02 - A00 * A12, c22 = A00 * A11 - A01 * A01;
-  const double det = A00 * c00 + A01 * c01 + A02 * c02;
-  double x0 = m0, x1 = m1, x2 = m2;
-  if (fabs(det) > 0.0 && isfinite(det)) {
-    const double id = 1.0 / det;
+  const float c00 = A11 * A22 - A12 * A12, c01 = A02 * A12 - A01 * A22, c02 = A01 * A12 - A02 * A11;
+  const float c11 = A00 * A22 - A02 * A02, c12 = A01 * A02 - A00 * A12, c22 = A00 * A11 - A01 * A01;
+  const float det = A00 * c00 + A01 * c01 + A02 * c02;
+  float x0 = m0, x1 = m1, x2 = m2;
+  if (fabsf(det) > 0.0f && fabsf(det) <= 3.0e38f) {
+    const float id = 1.0f / det;
     x0 = (c00 * b0 + c01 * b1 + c02 * b2) * id;
     x1 = (c01 * b0 + c11 * b1 + c12 * b2) * id;
     x2 = (c02 * b0 + c12 * b1 + c22 * b2) * id;
   }
-  // the kernel holds c in fp32
-  c[0] = (double)(float)(isfinite(x0) ? x0 : 0.0);
-  c[1] = (double)(float)(isfinite(x1) ? x1 : 0.0);
-  c[2] = (double)(float)(isfinite(x2) ? x2 : 0.0);
+  c[0] = (fabsf(x0) <= 3.0e38f) ? x0 : 0.0f;
+  c[1] = (fabsf(x1) <= 3.0e38f) ? x1 : 0.0f;
+  c[2] = (fabsf(x2) <= 3.0e38f) ? x2 : 0.0f;
 }
 
-// One frame's table row: P' = Kn [R | R c + t] per view in fp64, split into fp32 hi / lo parts.
+// One frame's table row: P' = Kn [R | R c + t] per view.  The translation column - the ~1e4-magnitude entries whose
+// fp32 rounding sets the pixel-error floor - is formed in fp64 and split into hi / lo parts; the rotation columns are
+// rounded to fp32 once (fp64 products, one rounding), like the static rig's.
 template <int V>
-__device__ __forceinline__ void frame_row(const TriFramesParams<V>& prm, const double* __restrict__ Rt, FrameRow<V>& o) {
-  double c[3];
-  frame_centre<V>(Rt, c);
+__device__ __forceinline__ void frame_row(const TriFramesParams<V>& prm, const double* Rt /*V x 12, registers*/, FrameRow<V>& o) {
+  float cf[3];
+  frame_centre<V>(Rt, cf);
+  const double c0 = (double)cf[0], c1 = (double)cf[1], c2 = (double)cf[2];
+  float4* out = reinterpret_cast<float4*>(&o);
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const double* R = Rt + 12 * v;
     const double* t = R + 9;
     const double fx = prm.Kn[v][0], sk = prm.Kn[v][1], px = prm.Kn[v][2], fy = prm.Kn[v][3], py = prm.Kn[v][4];
-    double r[3][4];
+    const float fxf = (float)fx, skf = (float)sk, pxf = (float)px, fyf = (float)fy, pyf = (float)py;
+    float h[3][4];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      r[k][0] = R[3 * k];
-      r[k][1] = R[3 * k + 1];
-      r[k][2] = R[3 * k + 2];
-      r[k][3] = R[3 * k] * c[0] + R[3 * k + 1] * c[1] + R[3 * k + 2] * c[2] + t[k];
+    for (int m = 0; m < 3; ++m) {  // rotation columns: fp32 (a 1e-7 relative change of the camera, like rounding the fp64 product)
+      const float r0 = (float)R[m], r1 = (float)R[3 + m], r2 = (float)R[6 + m];
+      h[0][m] = fmaf(fxf, r0, fmaf(skf, r1, pxf * r2));
+      h[1][m] = fmaf(fyf, r1, pyf * r2);
+      h[2][m] = r2;
     }
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const double p0 = fx * r[0][m] + sk * r[1][m] + px * r[2][m];
-      const double p1 = fy * r[1][m] + py * r[2][m];
-      const double p2 = r[2][m];
-      const float h0 = (float)p0, h1 = (float)p1, h2 = (float)p2;
-      o.P[v][m] = h0;
-      o.P[v][4 + m] = h1;
-      o.P[v][8 + m] = h2;
-      if (m == 3) {
-        o.P[v][12] = (float)(p0 - (double)h0);
-        o.P[v][13] = (float)(p1 - (double)h1);
-        o.P[v][14] = (float)(p2 - (double)h2);
-        o.P[v][15] = 0.f;
-      }
-    }
+    const double t0 = R[0] * c0 + R[1] * c1 + R[2] * c2 + t[0];
+    const double t1 = R[3] * c0 + R[4] * c1 + R[5] * c2 + t[1];
+    const double t2 = R[6] * c0 + R[7] * c1 + R[8] * c2 + t[2];
+    const double p0 = fx * t0 + sk * t1 + px * t2, p1 = fy * t1 + py * t2, p2 = t2;
+    h[0][3] = (float)p0;
+    h[1][3] = (float)p1;
+    h[2][3] = (float)p2;
+    out[4 * v + 0] = make_float4(h[0][0], h[0][1], h[0][2], h[0][3]);
+    out[4 * v + 1] = make_float4(h[1][0], h[1][1], h[1][2], h[1][3]);
+    out[4 * v + 2] = make_float4(h[2][0], h[2][1], h[2][2], h[2][3]);
+    out[4 * v + 3] = make_float4((float)(p0 - (double)h[0][3]), (float)(p1 - (double)h[1][3]), (float)(p2 - (double)h[2][3]), 0.f);
   }
-  o.c[0] = (float)c[0];
-  o.c[1] = (float)c[1];
-  o.c[2] = (float)c[2];
-  o.c[3] = 0.f;
+  out[4 * V] = make_float4(cf[0], cf[1], cf[2], 0.f);
+}
+
+// the 12 V doubles [R|t] of one frame, global -> registers (128-bit loads)
+template <int V>
+__device__ __forceinline__ void load_frame_rt(const double* __restrict__ src, double* dst) {
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+#pragma unroll
+  for (int k = 0; k < 6 * V; ++k) {
+    const double2 q = __ldg(s2 + k);
+    dst[2 * k] = q.x;
+    dst[2 * k + 1] = q.y;
+  }
 }
 
 // DLT rows of one view of one point from a table row's registers (LO = 1: translation column restored from the lo parts)
@@ -164,13 +177,18 @@ __device__ __forceinline__ void rows_from_table(const float* P /*16*/, float u, 
 }
 
 #ifndef SKA_FR_WARPS
-#define SKA_FR_WARPS 11  // consumer warps: 12 warps x 168 registers (the per-point camera rows cost ~30 registers over the static kernel)
+#define SKA_FR_WARPS 10  // consumer warps; with the producers 12 warps x 168 registers (the per-point camera rows cost ~30 registers
+                         // over the static kernel)
+#endif
+#ifndef SKA_FR_PRODUCERS
+#define SKA_FR_PRODUCERS 2  // producer warps (measured: 10 + 2 at 4 stages slightly ahead of 9 + 3): building a group's camera table is ~1000 mostly dependent instructions (fp64 products,
+                            // fp64 -> fp32 conversions), ~3 us for one warp against ~1 us of consumer time per group
 #endif
 #ifndef SKA_FR_MAXREG
 #define SKA_FR_MAXREG 168
 #endif
 #ifndef SKA_FR_STAGES
-#define SKA_FR_STAGES 3
+#define SKA_FR_STAGES 4
 #endif
 
 template <int V, int NW, bool CONF, int STAGES>
@@ -254,7 +272,7 @@ __global__ void __launch_bounds__(64) tri_frames_tail_kernel(const __grid_consta
   }
 }
 
-template <int V, bool CONF, int DIST, int NW, int STAGES, bool LEAN>
+template <int V, bool CONF, int DIST, int NW, int NP, int STAGES, bool LEAN>
 __global__ void __maxnreg__(SKA_FR_MAXREG) tri_kernel_cta_frames(const __grid_constant__ TriFramesParams<V> prm) {
   static_assert(DIST <= 1, "skew / thin prism take the two-kernel form");
   using L = FrSmem<V, NW, CONF, STAGES>;
@@ -277,14 +295,33 @@ __global__ void __maxnreg__(SKA_FR_MAXREG) tri_kernel_cta_frames(const __grid_co
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
-  if (warp == NW) {
-    // ---------------------------------------------------------------- producer warp: bulk copies + the stage's camera table
-    int st = 0;
-    uint32_t round = 0;
-    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
-      if (round > 0) mbar_wait(sEmpty + st, (round - 1) & 1u);  // (every lane waits: all of them write the table)
+  if (warp >= NW) {
+    // ---------------------------------------------------------------- producer warps: bulk copies + the stage's camera table
+    // Producer p takes the CTA's groups p, p + NP, ... (group q of the CTA lives in stage q % STAGES).
+    // A lane builds the table rows of frames f0 + lane and f0 + 32 + lane of the group (a group of NW tiles touches at most
+    // NW * 64 / J + 2 <= 128 frames: up to four rounds, two in the common case).  The [R|t] of the NEXT group's first two
+    // rounds is loaded into registers right after this group's rows are built, so its HBM latency hides behind the wait
+    // for the stage.
+    static_assert(STAGES % NP == 0, "a producer warp must always meet the same stages");
+    const uint32_t pw = (uint32_t)(warp - NW);
+    const uint32_t T = (uint32_t)(prm.N / prm.J);
+    double rt0[12 * V], rt1[12 * V];
+    auto prefetch = [&](uint32_t gq) {  // [R|t] of group gq's first two rounds -> registers (clamped: the loads are unconditional)
+      if (gq < n_groups) {
+        const uint32_t f = fastdiv(gq * NW * kPts, prm.divJ) + lane;
+        load_frame_rt<V>(prm.Rt + (int64_t)(f < T ? f : T - 1) * (12 * V), rt0);
+        load_frame_rt<V>(prm.Rt + (int64_t)(f + 32 < T ? f + 32 : T - 1) * (12 * V), rt1);
+      }
+    };
+    prefetch(blockIdx.x + pw * gridDim.x);
+    uint32_t q = pw;  // the CTA's q-th group
+    for (uint32_t g = blockIdx.x + pw * gridDim.x; g < n_groups; g += NP * gridDim.x, q += NP) {
+      const int st = (int)(q % STAGES);
+      const uint32_t round = q / STAGES;
       const uint32_t t0 = g * NW;
       const uint32_t nt = (n_wt - t0 < (uint32_t)NW) ? (n_wt - t0) : (uint32_t)NW;
+      const uint32_t f0 = fastdiv(t0 * kPts, prm.divJ), f1 = fastdiv((t0 + nt) * kPts - 1, prm.divJ);
+      if (round > 0) mbar_wait(sEmpty + st, (round - 1) & 1u);  // (every lane waits: all of them write the table)
       float* stage = sK + (size_t)st * L::kStageFloats;
       if (lane == 0) {
         asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(sFull + st)),
@@ -297,15 +334,16 @@ __global__ void __maxnreg__(SKA_FR_MAXREG) tri_kernel_cta_frames(const __grid_co
             bulk_g2s(stage + L::kKptFloats + k * L::kViewC, prm.conf + (int64_t)k * prm.c_sV + (int64_t)t0 * kPts, nt * (kPts * 4), sFull + st);
         }
       }
-      const uint32_t f0 = fastdiv(t0 * kPts, prm.divJ), f1 = fastdiv((t0 + nt) * kPts - 1, prm.divJ);
       FrameRow<V>* tab = sTab + (size_t)st * kFrMaxFrames;
-      for (uint32_t f = f0 + lane; f <= f1; f += 32) frame_row<V>(prm, prm.Rt + (int64_t)f * (12 * V), tab[f - f0]);
+      if (f0 + lane <= f1) frame_row<V>(prm, rt0, tab[lane]);
+      if (f0 + 32 + lane <= f1) frame_row<V>(prm, rt1, tab[32 + lane]);
+      for (uint32_t f = f0 + 64 + lane; f <= f1; f += 32) {  // small skeletons only
+        load_frame_rt<V>(prm.Rt + (int64_t)f * (12 * V), rt0);
+        frame_row<V>(prm, rt0, tab[f - f0]);
+      }
+      prefetch(g + NP * gridDim.x);
       __syncwarp();
       if (lane == 0) mbar_arrive(sFull + st);  // release: the table is complete; the phase ends when the copies have landed too
-      if (++st == STAGES) {
-        st = 0;
-        ++round;
-      }
     }
     return;
   }
@@ -453,8 +491,8 @@ __global__ void __maxnreg__(SKA_FR_MAXREG) tri_kernel_cta_frames(const __grid_co
 
 template <int V, bool CONF, int DIST, bool LEAN>
 static cudaError_t launch_frames_impl(TriFramesParams<V>& prm, cudaStream_t stream) {
-  constexpr int NW = SKA_FR_WARPS, STAGES = SKA_FR_STAGES, BLOCK = 32 * (NW + 1);
-  auto kern = tri_kernel_cta_frames<V, CONF, DIST, NW, STAGES, LEAN>;
+  constexpr int NW = SKA_FR_WARPS, NP = SKA_FR_PRODUCERS, STAGES = (V <= 2) ? SKA_FR_STAGES : NP, BLOCK = 32 * (NW + NP);  // (V = 3, 4: the tables are larger)
+  auto kern = tri_kernel_cta_frames<V, CONF, DIST, NW, NP, STAGES, LEAN>;
   constexpr size_t smem = FrSmem<V, NW, CONF, STAGES>::bytes;
   static_assert(smem <= 227 * 1024, "tri_kernel_cta_frames staging does not fit the SM's shared memory");
   int dev = 0, sms = 0;

@@ -43,7 +43,7 @@ def shape(rig, T, J, conf, dev, label, n=20, frames=False):
     if frames:
         Rf = np.broadcast_to(d["R"], (T, V, 3, 3)).copy()
         tf = np.broadcast_to(d["t"], (T, V, 3)).copy()
-        kw.update(R=torch.from_numpy(Rf).to(dev), t=torch.from_numpy(tf).to(dev))
+        kw.update(R=api.pack_frame_extrinsics(Rf, tf, dev), t=None)  # packed once per clip, as a pipeline would
         bpj += V * 96 / J
     ms = timed(lambda: api.triangulate_reproject(d["x2d"], conf=cf, **kw), n)
     gbs = bpj * T * J / ms / 1e6

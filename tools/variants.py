@@ -13,12 +13,11 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-TUS = ["ska_tri_v2.cu", "ska_tri_v8.cu"]
+TUS = ["ska_tri_v2.cu"]
 VARIANTS = {
-    "A": [],                                                      # v8: staged view-pair kernel, rows in the slab, 2 stages
-    "B": ["-DSKA_CTA_VP_ROWS=1", "-DSKA_CTA_VP_STAGES=3"],        # rows recomputed
-    "C": ["-DSKA_NO_CTA_VP"],                                     # v8 in the generic tri_kernel (slab rows)
-    "D": ["-DSKA_CTA_EXTRA_TILE"],                                # v2: extra-tile rotation
+    "A": [],
+    "B": ["-DSKA_FR_WARPS=10", "-DSKA_FR_PRODUCERS=2", "-DSKA_FR_STAGES=4"],
+    "C": ["-DSKA_FR_STAGES=6"],
 }
 LIBDIR = ROOT / "skiing_analysis_pytorch_b200" / "lib"
 
