@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-ba", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=20000)
     ap.add_argument("--ba-iters", type=int, default=20)
+    ap.add_argument("--no-ba-graph", action="store_true", help="enqueue the LM trials one by one instead of replaying a captured CUDA graph")
+    ap.add_argument("--record-ba-parity", action="store_true", help="1 GPU: write the BA cost trajectories to gpurun_out/ba_parity_n1.json (commit as profiles/ba_parity_n1.json)")
     ap.add_argument("--no-extra", action="store_true", help="skip the 8-view north-star shape (extra object `tri_8view`)")
     ap.add_argument("--e2e-chunk", type=int, default=65536, help="frames per H2D -> kernel -> D2H chunk of the host pipeline")
     ap.add_argument("--e2e-streams", type=int, default=3)
@@ -142,7 +144,8 @@ def run_reference(a):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": workload_config(a, 2),
+        "config": dict(workload_config(a, 2), reference_sample_frames_per_step=per_step,
+                       note="the CPU arm times a bounded sample of the workload per step (a rate: joints/s does not depend on the clip length)"),
         "cpu_baseline": {
             "value": value,
             "unit": UNIT,
@@ -327,9 +330,16 @@ def run_ba(a, dev, world, rank, barrier, dist):
 
     out = {}
     peak, _ = hbm_peak()
+    ref_path = ROOT / "profiles" / "ba_parity_n1.json"
+    try:
+        parity_ref = json.loads(ref_path.read_text())
+    except Exception:
+        parity_ref = {}
     for name, (rig, T_total, J) in BA_CONFIGS.items():
         T = T_total // world
-        d = synth.make_clip_device(rig, T, J, dev, seed=100 + rank)
+        # the clip is a function of the GLOBAL frame index: N ranks hold exactly the frames one GPU would (synth.make_clip_device
+        # shardable=True), so the trajectory at N GPUs can be checked against the recorded single-GPU one
+        d = synth.make_clip_device(rig, T, J, dev, seed=100, shardable=True, frame_offset=rank * T)
         R0, t0 = synth.perturb_cameras(d["R"], d["t"], seed=1)
         C = len(R0)
         kv = d["x2d"].permute(1, 0, 2, 3).contiguous()
@@ -345,7 +355,7 @@ def run_ba(a, dev, world, rank, barrier, dist):
                                              prior_theta=synth.theta_from_K(d["K"]), max_iters=iters + 8)
         else:
             s = ba.BundleAdjuster(d["x2d"], d["conf"], d["K"], R0, t0, X0, max_iters=iters + 8)
-        graph = world == 1
+        graph = not a.no_ba_graph  # one trial (launches + NCCL all-reduces) captured and replayed at every N
         s.run(4, graph=graph)  # warm-up trials (also captures the graph)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -362,6 +372,21 @@ def run_ba(a, dev, world, rank, barrier, dist):
         note = ("latency / issue-bound (22 us of HBM time per trial)" if C == 2 else "CUDA-core (fp32 FMA pipe) bound: ~5k FMA per point")
         if calib:
             note = "issue-bound: the 24 x 24 reduced system + two 17 x 17 camera blocks cost ~4k warp instructions per 32 points"
+        # ---- parity against the recorded single-GPU trajectory of the same clip (profiles/ba_parity_n1.json, written by
+        #      `bench.py --record-ba-parity` on one GPU): cost per trial and the accept / reject decisions while decisive
+        costs = [h["cost"] for h in hist] + [s.cost]
+        acc = [bool(h["accepted"]) for h in hist]
+        parity = {"reference": "unrecorded", "ok": None}
+        ref = parity_ref.get(name)
+        if ref is not None:
+            n = min(len(ref["costs"]), len(costs))
+            rel = max(abs(x - y) / abs(y) for x, y in zip(costs[:n], ref["costs"][:n]))
+            decisive = [abs(h["cost"] - h["trial_cost"]) > 1e-3 * h["cost"] for h in hist]
+            same = all(x == y for x, y, dz in zip(acc, ref["accepted"], decisive) if dz)
+            parity = {"reference": f"profiles/ba_parity_n1.json ({ref.get('recorded', '?')})", "trials_compared": n, "max_rel_cost_dev": rel,
+                      "decisions_equal_while_decisive": same, "tolerance": 1e-5, "ok": bool(rel <= 1e-5 and same)}
+        if a.record_ba_parity and world == 1:
+            parity_ref[name] = {"costs": costs, "accepted": acc, "recorded": f"{T_total} frames x {J} joints x {C} cameras, seed 100, {len(hist)} trials"}
         out[name] = {
             "metric": "ba_lm_iterations_per_sec",
             "value": 1e3 / ms,
@@ -376,17 +401,23 @@ def run_ba(a, dev, world, rank, barrier, dist):
             "parameters": ("points + extrinsics (camera 0 = gauge) + fx fy cx cy k1 k2 p1 p2 k3 of every camera, Gaussian prior on the intrinsics"
                            if calib else "points + extrinsics (camera 0 = gauge)"),
             "launches_per_iter": 6,
+            "collectives_per_iter": 0 if world == 1 else 2,
             "cuda_graph": graph,
             "cost_first": hist[0]["cost"],
             "cost_last": s.cost,
             "accepted": int(sum(h["accepted"] for h in hist)),
             "trials": len(hist),
+            "parity": parity,
             "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "bytes_per_iter_per_gpu": alg,
                          "note": note + ", not HBM-bound: DESIGN.md section 6"},
         }
         del s, d, X0
         torch.cuda.empty_cache()
+    if a.record_ba_parity and world == 1 and rank == 0:
+        out_dir = ROOT / "gpurun_out"
+        out_dir.mkdir(exist_ok=True)
+        (out_dir / "ba_parity_n1.json").write_text(json.dumps(parity_ref, indent=1))
     return out
 
 
@@ -423,9 +454,9 @@ def run_tri_8view(a, dev, world, barrier, dist, T=1_000_000, J=17, key="tri_kern
     del outs
     return {"workload": label, "ms_per_step": ms,
             "value": world * T * J / (ms * 1e-3), "unit": UNIT, "steps": steps,
-            "roofline": {"bound": "hbm", "kernel": "ska::tri_kernel<8,...> (one point per thread, per-view work packed over view pairs)", "achieved": ach, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "ska::tri_kernel_cta_vp<8,...> (bulk-async staged, one point per lane, per-view work packed over view pairs)", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "bytes_per_joint": bpj, "traffic": recorded_traffic(key),
-                         "note": "fp32-pipe bound: ~800 FMA-pipe cycles per 32 points = the HBM roofline time"}}
+                         "note": "fp32-pipe bound: ~670 FMA-pipe cycles per 32 points against ~420 cycles of HBM time"}}
 
 
 def run_fusion(a, dev, world, barrier, dist):
@@ -594,27 +625,37 @@ def run_ours(a, out_fd=1):
         barrier()
         kernel_ms = ev0.elapsed_time(ev1)
 
-        # ---- end to end through the host-buffer API: pinned H2D + kernel + D2H, every step
+        # ---- end to end through the host-buffer API: pinned H2D + kernel + D2H, every step.  The result a caller of
+        #      process_triangulate consumes is the 3D joints and the per-frame reprojection statistics (triangulate.py:111-118
+        #      reads mean_err_L / mean_err_R and returns the joints): want=("X", "stats").  The per-joint error arrays - the
+        #      contents of reproject_and_visualize's dict - cost another 4 V J bytes per frame over PCIe: timed as well
+        #      (`e2e_per_joint_errors`).
         h_X = torch.empty((T, J, 3), dtype=torch.float32).pin_memory()
         h_err = torch.empty((V, T, J), dtype=torch.float32).pin_memory()
-        host_out = {"X": h_X, "err": h_err}
+        h_stats = torch.empty((T, V, 4), dtype=torch.float32).pin_memory()
         e2e_steps = max(3, min(a.steps, 10))
         kw_host = dict(kw, chunk_frames=a.e2e_chunk, n_streams=a.e2e_streams)
-        for _ in range(2):
-            api.triangulate_reproject_host(h_k, conf=h_c, out=host_out, **kw_host)
-        barrier()
-        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev2.record()
-        for _ in range(e2e_steps):
-            api.triangulate_reproject_host(h_k, conf=h_c, out=host_out, **kw_host)
-        ev3.record()
-        barrier()
-        e2e_ms = ev2.elapsed_time(ev3)
 
-    t_k = torch.tensor([kernel_ms, e2e_ms], dtype=torch.float64, device=dev)
+        def e2e_timed(want, host_out):
+            kwh = dict(kw_host, want=want)
+            for _ in range(2):
+                api.triangulate_reproject_host(h_k, conf=h_c, out=host_out, **kwh)
+            barrier()
+            ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev2.record()
+            for _ in range(e2e_steps):
+                api.triangulate_reproject_host(h_k, conf=h_c, out=host_out, **kwh)
+            ev3.record()
+            barrier()
+            return ev2.elapsed_time(ev3)
+
+        e2e_ms = e2e_timed(("X", "stats"), {"X": h_X, "stats": h_stats})
+        e2e_full_ms = e2e_timed(("X", "err"), {"X": h_X, "err": h_err})
+
+    t_k = torch.tensor([kernel_ms, e2e_ms, e2e_full_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_k, op=dist.ReduceOp.MAX)
-    kernel_ms, e2e_ms = (float(x) for x in t_k.cpu())
+    kernel_ms, e2e_ms, e2e_full_ms = (float(x) for x in t_k.cpu())
 
     pts = T * J
     value = n_gpus * pts * a.steps / (kernel_ms * 1e-3)
@@ -623,7 +664,8 @@ def run_ours(a, out_fd=1):
     peak, peak_src = hbm_peak()
     achieved = bytes_per_pt * pts / (kernel_ms * 1e-3 / a.steps) / 1e9
     h2d = h_k.numel() * 4 + (h_c.numel() * 4 if a.conf else 0)
-    d2h = h_X.numel() * 4 + h_err.numel() * 4
+    d2h = h_X.numel() * 4 + h_stats.numel() * 4
+    d2h_full = h_X.numel() * 4 + h_err.numel() * 4
 
     line = {
         "metric": METRIC,
@@ -647,11 +689,22 @@ def run_ours(a, out_fd=1):
             "d2h_bytes_per_step": d2h,
             "steps": e2e_steps,
             "ms_per_step": e2e_ms / e2e_steps,
+            "result": "X (T,J,3) + per-(frame, view) rmse / mean / median / max of the pixel errors (T,V,4): what process_triangulate consumes",
+            "note": "PCIe-bound: pinned copies measure ~55 GB/s per direction alone, ~47 + 47 GB/s both at once on this host (tools/pcie_bw.py)",
+        },
+        "e2e_per_joint_errors": {
+            "value": n_gpus * pts * e2e_steps / (e2e_full_ms * 1e-3),
+            "unit": UNIT,
+            "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h_full,
+            "steps": e2e_steps,
+            "ms_per_step": e2e_full_ms / e2e_steps,
+            "result": "X (T,J,3) + the per-joint pixel error of every view (V,T,J)",
         },
         "gpu_launches": a.steps,
         "roofline": {
             "bound": "hbm",
-            "kernel": "ska::tri_kernel_ws (warp-specialised bulk-async staging, packed FFMA2 pairs)",
+            "kernel": "ska::tri_kernel_cta (15 consumer warps + producer thread, one bulk-async copy per view and group of 15 tiles, packed FFMA2 pairs)",
             "achieved": achieved,
             "peak": peak,
             "peak_source": peak_src,
@@ -659,6 +712,7 @@ def run_ours(a, out_fd=1):
             "frac": achieved / peak,
             "bytes_per_joint": bytes_per_pt,
             "traffic": recorded_traffic("tri_kernel_config2"),
+            "traffic_source": "profiles/traffic.json: dram bytes of one launch from the committed ncu --set full capture of this kernel (not re-measured in this run)",
         },
     }
 
@@ -674,8 +728,8 @@ def run_ours(a, out_fd=1):
             "sample": f"first {frames} frames x {J} joints of the same clip, single-process per-frame "
             "cv2.triangulatePoints + cv2.projectPoints loop (oracle/reference_path.py), as the reference runs it",
         }
-    del d_k, d_c, outs, h_k, h_c, h_X, h_err, host_out
-    api._HOST_PIPE_CACHE.clear()
+    del d_k, d_c, outs, h_k, h_c, h_X, h_err, h_stats
+    api.clear_host_pipeline_cache()
     torch.cuda.empty_cache()
     if not a.no_extra:
         line["tri_8view"] = run_tri_8view(a, dev, world, barrier, dist)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SKA_ABI_VERSION 4
+#define SKA_ABI_VERSION 5
 
 #define SKA_OK 0
 #define SKA_EINVAL -1       /* null pointer / bad size / bad enum */
@@ -227,9 +227,10 @@ typedef struct SkaBaProblem {
                            free camera), cost, clamped count - all sums with raw conf weights */
   double* d_red2;       /* [SKA_BA_RED2_DOUBLES] */
   double* d_delta;      /* [C*6] camera step of the current trial */
-  double* d_hist;       /* nullable [max_iters][SKA_BA_HIST_DOUBLES] */
+  double* d_hist;       /* nullable [hist_rows][SKA_BA_HIST_DOUBLES] */
   void* d_workspace;    /* >= ska_ba_workspace_bytes(C), 16-byte aligned */
   size_t ws_bytes;
+  int64_t hist_rows;    /* rows of d_hist: trials beyond them still run, their history row is dropped */
 } SkaBaProblem;
 
 int32_t ska_ba_red_doubles(int32_t C);

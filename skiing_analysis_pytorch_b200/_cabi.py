@@ -5,7 +5,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_VIEWS = 8
 MAX_BA_VIEWS = 8
 MAX_BONES = 16
@@ -60,6 +60,7 @@ class SkaBaProblem(C.Structure):
         ("d_hist", C.c_void_p),
         ("d_workspace", C.c_void_p),
         ("ws_bytes", C.c_size_t),
+        ("hist_rows", C.c_int64),
     ]
 
 

@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(256) ba_solve_kernel(int C, uint64_t free_mask
 // One warp: lane 0 decides, all lanes commit the trial cameras (a serial copy by one thread is a
 // chain of dependent global round trips - microseconds in a 100-microsecond trial).
 __global__ void __launch_bounds__(32) ba_control_kernel(int C, const double* __restrict__ red, const double* __restrict__ red2,
-                                                        double* cams, double* ctrl, double* hist) {
+                                                        double* cams, double* ctrl, double* hist, int64_t hist_rows) {
   if (blockIdx.x != 0) return;
   const RedLayout L(C);
   int accepted_i = 0;
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(32) ba_control_kernel(int C, const double* __r
     const double rho = pred > 0.0 ? (F - Ft) / pred : 0.0;
     const bool accepted = ok && isfinite(Ft) && (Ft < F);
     const int it = (int)ctrl[kCtrlIter];
-    if (hist != nullptr) {
+    if (hist != nullptr && it < hist_rows) {
       double* h = hist + (int64_t)it * kHistRow;
       h[0] = (double)it;
       h[1] = F;
@@ -556,8 +556,8 @@ int ba_solve(int C, uint64_t free_mask, const double* red, double* cams, double*
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }
 
-int ba_control(int C, const double* red, const double* red2, double* cams, double* ctrl, double* hist, void* stream) {
-  ba_control_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(C, red, red2, cams, ctrl, hist);
+int ba_control(int C, const double* red, const double* red2, double* cams, double* ctrl, double* hist, int64_t hist_rows, void* stream) {
+  ba_control_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(C, red, red2, cams, ctrl, hist, hist_rows);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }

@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(256) ba_calib_solve_kernel(int C, uint64_t fre
 
 // LM controller (oracle/lm_calib.py run_lm): as ba_control_kernel with the prior inside the cost.
 __global__ void __launch_bounds__(32) ba_calib_control_kernel(int C, const double* __restrict__ red, const double* __restrict__ red2,
-                                                              double* cams, double* ctrl, double* hist) {
+                                                              double* cams, double* ctrl, double* hist, int64_t hist_rows) {
   if (blockIdx.x != 0) return;
   const CalibLayout L(C);
   int accepted_i = 0;
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(32) ba_calib_control_kernel(int C, const doubl
     const double rho = pred > 0.0 ? (F - Ft) / pred : 0.0;
     const bool accepted = ok && isfinite(Ft) && (Ft < F);
     const int it = (int)ctrl[kCtrlIter];
-    if (hist != nullptr) {
+    if (hist != nullptr && it < hist_rows) {
       double* h = hist + (int64_t)it * kHistRow;
       h[0] = (double)it;
       h[1] = F;
@@ -647,9 +647,9 @@ int ba_calib_solve(int C, uint64_t free_mask, const double* red, const double* p
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }
 
-int ba_calib_control(int C, const double* red, const double* red2, double* cams, double* ctrl, double* hist, void* stream) {
+int ba_calib_control(int C, const double* red, const double* red2, double* cams, double* ctrl, double* hist, int64_t hist_rows, void* stream) {
   if (C != 2) return unsupported_c();
-  ba_calib_control_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(C, red, red2, cams, ctrl, hist);
+  ba_calib_control_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(C, red, red2, cams, ctrl, hist, hist_rows);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }

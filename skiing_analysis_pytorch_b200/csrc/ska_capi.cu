@@ -279,7 +279,7 @@ int ska_ba_backsub_f32(const SkaBaProblem* p, void* stream) {
 int ska_ba_control_f64(const SkaBaProblem* p, void* stream) {
   const int rc = check_problem(p, false);
   if (rc != SKA_OK) return rc;
-  return ba_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, stream);
+  return ba_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, p->hist_rows, stream);
 }
 
 int32_t ska_ba_calib_red_doubles(int32_t C) { return C == 2 ? ba_calib_red_size(C) : 0; }
@@ -310,7 +310,7 @@ int ska_ba_calib_backsub_f32(const SkaBaProblem* p, void* stream) {
 int ska_ba_calib_control_f64(const SkaBaProblem* p, void* stream) {
   const int rc = check_problem(p, false);
   if (rc != SKA_OK) return rc;
-  return ba_calib_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, stream);
+  return ba_calib_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, p->hist_rows, stream);
 }
 
 size_t ska_fuse_workspace_bytes(int64_t T) { return fuse_workspace_bytes(T); }

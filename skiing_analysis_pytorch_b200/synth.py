@@ -176,11 +176,14 @@ def theta_to_K_dist(th):
 
 
 def make_clip_device(rig_name: str, T: int, J: int, device, seed: int = 0, noise_px: float = 1.0, layout: str = "TCJ2",
-                     chunk_frames: int = 65536):
+                     chunk_frames: int = 65536, frame_offset: int = 0, shardable: bool = False):
     """Same statistical model as make_clip but generated on the GPU with torch (synthetic-data
     plumbing for the full-size benchmark shapes: 1M frames x 70 joints x 8 views is 560M observations,
     minutes of numpy on the host).  Returns dict(x2d, conf, X, R, t, K) with x2d (T,C,J,2) / conf (T,C,J)
-    for layout "TCJ2" or (C,T,J,2) / (C,T,J) for "CTJ2"; R, t, K are host fp64 arrays."""
+    for layout "TCJ2" or (C,T,J,2) / (C,T,J) for "CTJ2"; R, t, K are host fp64 arrays.
+    shardable=True: every block of 500 frames draws from its own generator seeded by (seed, block index), so frames
+    [frame_offset, frame_offset + T) are the SAME numbers whichever rank generates them - a clip split over N GPUs is the
+    clip one GPU would hold (frame_offset and T multiples of 500)."""
     import torch
 
     R, t = rig(rig_name)
@@ -196,9 +199,17 @@ def make_clip_device(rig_name: str, T: int, J: int, device, seed: int = 0, noise
     x2d = torch.empty((T, V, J, 2) if fm else (V, T, J, 2), dtype=torch.float32, device=device)
     conf = torch.empty((T, V, J) if fm else (V, T, J), dtype=torch.float32, device=device)
     X = torch.empty((T, J, 3), **f64)
+    if shardable:
+        chunk_frames = 500
+        if frame_offset % chunk_frames or T % chunk_frames:
+            raise ValueError("shardable clips are generated in blocks of 500 frames")
+    elif frame_offset:
+        raise ValueError("frame_offset needs shardable=True")
     for a in range(0, T, chunk_frames):
         b = min(T, a + chunk_frames)
-        tt_ = torch.arange(a, b, **f64)
+        if shardable:
+            g = torch.Generator(device=device).manual_seed(seed * 1_000_003 + (frame_offset + a) // chunk_frames + 1)
+        tt_ = torch.arange(frame_offset + a, frame_offset + b, **f64)
         root = torch.stack([1.5 * torch.sin(2 * np.pi * tt_ / 300), 0.3 * torch.sin(2 * np.pi * tt_ / 90),
                             10.0 + 1.0 * torch.cos(2 * np.pi * tt_ / 240)], -1)
         Xc = root[:, None, :] + template[None] + torch.randn(b - a, J, 3, generator=g, **f64) * 0.02

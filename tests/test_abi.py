@@ -15,6 +15,15 @@ def _header_symbols():
     return sorted(set(re.findall(r"\b(ska_[a-z0-9_]+)\s*\(", txt)))
 
 
+def _cabi_version():
+    """SKA_ABI_VERSION of include/ska.h (the ctypes side carries its own copy and refuses a mismatching library)."""
+    from skiing_analysis_pytorch_b200 import _cabi
+
+    hdr = int(re.search(r"#define SKA_ABI_VERSION (\d+)", (ROOT / "include" / "ska.h").read_text()).group(1))
+    assert hdr == _cabi.ABI_VERSION
+    return hdr
+
+
 def test_library_builds_loads_and_exports_header_symbols():
     from skiing_analysis_pytorch_b200 import _lib, build
 
@@ -25,7 +34,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/ska.h but not exported by libska.so"
     assert sorted(_lib.exported_symbols()) == syms, "ctypes signature table and header disagree"
-    assert lib.ska_abi_version() == 4
+    assert lib.ska_abi_version() == _cabi_version()
     assert lib.ska_build_arch() == b"sm_100a"
 
 
@@ -67,7 +76,9 @@ def test_argument_errors_without_gpu():
         _cabi.make_cameras(synth.K_CALIB, R, t, [0.1] * 6)
     # per-frame extrinsics: workspace contract
     assert lib.ska_tri_frames_workspace_bytes(2, 10) > 0 and lib.ska_tri_frames_workspace_bytes(9, 10) == 0
-    fargs = [cams, 2, fake, fake, None, 4, 17, 0, 0, fake, None, None, None, fake, 16, None]
+    # (frame-major input takes the general two-kernel form, which needs the workspace; the fused kernel of the view-major
+    #  layout needs none)
+    fargs = [cams, 2, fake, fake, None, 4, 17, 1, 0, fake, None, None, None, fake, 16, None]
     assert lib.ska_triangulate_reproject_frames_f32(*fargs) == -4  # workspace too small
     fargs[2] = None
     assert lib.ska_triangulate_reproject_frames_f32(*fargs) == -1
