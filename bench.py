@@ -575,7 +575,7 @@ def run_ours(a, out_fd=1):
     import torch
     import torch.distributed as dist
 
-    from skiing_analysis_pytorch_b200 import api, synth
+    from skiing_analysis_pytorch_b200 import api, hostlink, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -584,6 +584,7 @@ def run_ours(a, out_fd=1):
         raise SystemExit("bench.py --impl ours needs a CUDA device: there is no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = hostlink.bind_to_device_numa(dev)  # before any pinned allocation: this rank's host buffers belong next to its GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -651,11 +652,16 @@ def run_ours(a, out_fd=1):
 
         e2e_ms = e2e_timed(("X", "stats"), {"X": h_X, "stats": h_stats})
         e2e_full_ms = e2e_timed(("X", "err"), {"X": h_X, "err": h_err})
+        # what the host side gives with all ranks copying at once: the ceiling of the end-to-end number at this N
+        link = hostlink.measure_link(dev, barrier=barrier)
 
     t_k = torch.tensor([kernel_ms, e2e_ms, e2e_full_ms], dtype=torch.float64, device=dev)
+    t_l = torch.tensor([link["h2d_alone"], link["d2h_alone"], link["both_each"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_k, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_l, op=dist.ReduceOp.MIN)  # the slowest rank's rates
     kernel_ms, e2e_ms, e2e_full_ms = (float(x) for x in t_k.cpu())
+    link_min = [float(x) for x in t_l.cpu()]
 
     pts = T * J
     value = n_gpus * pts * a.steps / (kernel_ms * 1e-3)
@@ -690,7 +696,14 @@ def run_ours(a, out_fd=1):
             "steps": e2e_steps,
             "ms_per_step": e2e_ms / e2e_steps,
             "result": "X (T,J,3) + per-(frame, view) rmse / mean / median / max of the pixel errors (T,V,4): what process_triangulate consumes",
-            "note": "PCIe-bound: pinned copies measure ~55 GB/s per direction alone, ~47 + 47 GB/s both at once on this host (tools/pcie_bw.py)",
+            "host_link": {
+                "per_rank_h2d_alone": link_min[0], "per_rank_d2h_alone": link_min[1], "per_rank_both_each_direction": link_min[2],
+                "aggregate_both": 2 * link_min[2] * n_gpus, "unit": "GB/s", "ranks_copying_at_once": n_gpus,
+                "note": "pinned 256 MB copies timed in this run with every rank copying at the same time (slowest rank): the "
+                        "end-to-end step moves max(h2d, d2h) bytes at the both-at-once rate, so it tracks this, not the kernel",
+            },
+            "link_bound_ms_per_step": max(h2d, d2h) / (link_min[2] * 1e9) * 1e3,
+            "numa": numa,
         },
         "e2e_per_joint_errors": {
             "value": n_gpus * pts * e2e_steps / (e2e_full_ms * 1e-3),

@@ -210,6 +210,9 @@ int ska_baseline_reg_f64(const double* d_R, const double* d_t, int64_t T, int32_
 #define SKA_BA_CTRL_ACCEPTED 8  /* out: last decision */
 
 #define SKA_BA_FORCE_WIDE 1u    /* flags: run the shared-memory SYRK linearisation even for C == 2 (testing) */
+#define SKA_BA_TENSOR_CORE 2u   /* flags: 5..8 cameras: Schur accumulation on the tensor cores (tcgen05 kind::tf32, three-product split).
+                                   Same reduced system to fp32 accuracy; measured SLOWER than the CUDA-core form on B200
+                                   (26.3 vs 23.1 ms per 1M x 70 x 8 linearisation, profiles/README.md), hence opt-in */
 
 typedef struct SkaBaProblem {
   int32_t C;            /* cameras, 2..SKA_MAX_VIEWS */

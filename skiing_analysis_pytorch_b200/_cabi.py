@@ -28,6 +28,7 @@ BA_RED2_DOUBLES = 4
 BA_CTRL_LAMBDA, BA_CTRL_NU, BA_CTRL_SUMCONF, BA_CTRL_CUR, BA_CTRL_ITER = 0, 1, 2, 3, 4
 BA_CTRL_COST, BA_CTRL_ACCEPTED = 7, 8
 BA_FORCE_WIDE = 1
+BA_TENSOR_CORE = 2
 
 ERRORS = {-1: "SKA_EINVAL", -2: "SKA_EUNSUPPORTED", -3: "SKA_EALIGN", -4: "SKA_EWORKSPACE"}
 SKA_EWORKSPACE = -4

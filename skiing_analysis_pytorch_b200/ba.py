@@ -126,7 +126,7 @@ class BundleAdjuster(LMSequencer):
     """
 
     def __init__(self, x2d, conf, K, R0, t0, X0, *, layout: str = "TCJ2", mode: str = "full", lam0: float = 1e-3,
-                 max_iters: int = 64, group=None, force_wide: bool = False, local_only: bool = False):
+                 max_iters: int = 64, group=None, force_wide: bool = False, local_only: bool = False, tensor_core: bool = False):
         self.local_only = bool(local_only)
         if not (x2d.is_cuda and conf.is_cuda and X0.is_cuda):
             raise RuntimeError("x2d, conf and X0 must be CUDA tensors: this package has no CPU path")
@@ -189,7 +189,7 @@ class BundleAdjuster(LMSequencer):
             ws = int(self.lib.ska_ba_workspace_bytes(Cn))
         self.ws = torch.empty(ws, dtype=torch.uint8, device=dev)
         self.prob = _cabi.SkaBaProblem(
-            C=Cn, J=J, T=T, layout=self.layout, flags=(_cabi.BA_FORCE_WIDE if force_wide else 0),
+            C=Cn, J=J, T=T, layout=self.layout, flags=(_cabi.BA_FORCE_WIDE if force_wide else 0) | (_cabi.BA_TENSOR_CORE if tensor_core else 0),
             d_x2d=self.x2d.data_ptr(), d_conf=self.conf.data_ptr(), d_Xpp=self.Xpp.data_ptr(),
             d_cams=self.cams.data_ptr(), d_ctrl=self.ctrl.data_ptr(), d_red=self.red.data_ptr(),
             d_red2=self.red2.data_ptr(), d_delta=self.delta.data_ptr(), d_hist=self.hist.data_ptr(),

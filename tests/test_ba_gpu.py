@@ -128,6 +128,31 @@ def test_wide_path_equals_register_path(cuda):
         assert abs(ha["trial_cost"] - hb["trial_cost"]) <= 1e-5 * ha["trial_cost"]
 
 
+@pytest.mark.parametrize("rig,T,J", [("5", 61, 9), ("6", 40, 17), ("7", 33, 17), ("8", 300, 70)])
+def test_tensor_core_schur_equals_cuda_core_form(cuda, rig, T, J):
+    """SKA_BA_TENSOR_CORE: Sw accumulated by tcgen05.mma (tf32 hi/lo split, three products) against the shared-memory SYRK -
+    the whole reduced system entry by entry, then the trajectory (ragged tiles: T J is not a multiple of the 48-point tile)."""
+    clip, R0, t0, X0 = lm.make_problem(rig, T, J)
+    x, c, X = _dev(clip, X0, cuda)
+    wide = ba.BundleAdjuster(x, c, clip.K, R0, t0, X)
+    tc = ba.BundleAdjuster(x, c, clip.K, R0, t0, X, tensor_core=True)
+    wide.linearize()
+    tc.linearize()
+    torch.cuda.synchronize()
+    rw, rt = wide.red.cpu().numpy(), tc.red.cpu().numpy()
+    L = _cabi.red_layout(len(R0))
+    for key, nxt in (("sw", "bw"), ("bw", "gc"), ("gc", "hcc"), ("hcc", "cost")):
+        a_, b_ = rw[L[key]: L[nxt]], rt[L[key]: L[nxt]]
+        np.testing.assert_allclose(b_, a_, rtol=0, atol=2e-5 * np.abs(a_).max(), err_msg=key)
+    assert abs(rt[L["cost"]] - rw[L["cost"]]) <= 1e-6 * rw[L["cost"]]
+    assert rt[L["clamp"]] == rw[L["clamp"]]
+    a = ba.ba_solve(x, c, clip.K, R0, t0, X, num_iters=6)
+    b = ba.ba_solve(x, c, clip.K, R0, t0, X, num_iters=6, tensor_core=True)
+    for ha, hb in zip(a.history, b.history):
+        assert abs(ha["trial_cost"] - hb["trial_cost"]) <= 1e-5 * ha["trial_cost"]
+        assert ha["accepted"] == hb["accepted"]
+
+
 def test_graph_replay_equals_eager(cuda):
     clip, R0, t0, X0 = lm.make_problem("2b", 300, 17)
     x, c, X = _dev(clip, X0, cuda)

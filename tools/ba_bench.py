@@ -50,7 +50,7 @@ def main():
         s = ba.CalibratingBundleAdjuster(d["x2d"], d["conf"], K_init, R0, t0, X0, dist=dist_init, prior_rho=synth.CALIB_PRIOR_RHO,
                                          prior_theta=synth.theta_from_K(d["K"]), max_iters=iters + 8)
     else:
-        s = ba.BundleAdjuster(d["x2d"], d["conf"], d["K"], R0, t0, X0, max_iters=iters + 8)
+        s = ba.BundleAdjuster(d["x2d"], d["conf"], d["K"], R0, t0, X0, max_iters=iters + 8, force_wide="--wide" in sys.argv, tensor_core="--tc" in sys.argv)
     s.run(3, graph=graph)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]

@@ -30,7 +30,7 @@ def main():
         a, b = ba.frame_shard(T, world, rank)
         s = ba.BundleAdjuster(d["x2d"][a:b].contiguous(), d["conf"][a:b].contiguous(), d["K"], R0, t0, X0[a:b].contiguous(),
                               max_iters=12, group=dist.group.WORLD)
-        s.run(10)
+        s.run(10, graph=True)  # the captured trial contains the two NCCL all-reduces
         h = s.history
         if rank == 0:
             ref = ba.BundleAdjuster(d["x2d"], d["conf"], d["K"], R0, t0, X0, max_iters=12, local_only=True)
@@ -53,7 +53,7 @@ def main():
     a, b = ba.frame_shard(20_000, world, rank)
     s = ba.CalibratingBundleAdjuster(d["x2d"][a:b].contiguous(), d["conf"][a:b].contiguous(), K_init, R0, t0, X0[a:b].contiguous(),
                                      group=dist.group.WORLD, **kw)
-    s.run(10)
+    s.run(10, graph=True)
     h = s.history
     if rank == 0:
         ref = ba.CalibratingBundleAdjuster(d["x2d"], d["conf"], K_init, R0, t0, X0, local_only=True, **kw)
