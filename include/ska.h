@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SKA_ABI_VERSION 5
+#define SKA_ABI_VERSION 6
 
 #define SKA_OK 0
 #define SKA_EINVAL -1       /* null pointer / bad size / bad enum */
@@ -280,6 +280,87 @@ int ska_ba_calib_linearize_f32(const SkaBaProblem* p, void* stream);
 int ska_ba_calib_solve_f64(const SkaBaProblem* p, uint64_t free_mask, const double* d_prior, void* stream);
 int ska_ba_calib_backsub_f32(const SkaBaProblem* p, void* stream);
 int ska_ba_calib_control_f64(const SkaBaProblem* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Regularised bundle adjustment: Levenberg-Marquardt over the reference's FULL configured objective
+ *     w_r reprojection_loss + w_s camera_smooth_loss + w_b baseline_reg_loss + w_l bone_length_loss + w_t pose_temporal_loss
+ *     (bundle_adjustment/loss.py:90-94, :103-106, :109-114, :134-150, :153-155; weights configs/vggt.yaml:46-50)
+ * with PER-FRAME cameras as the call site passes them (vggt/multi_view_process.py:546-564) - the second-order form of the
+ * optimiser the reference calls but never defines (run_local_ba).  Specification: oracle/lm_reg.py.  All fp64.
+ * The damped normal equations (J^T J + lambda diag(J^T J)) delta = -J^T r are solved matrix-free by conjugate gradients,
+ * preconditioned with each frame's exact reprojection system (Schur complement onto the frame's cameras).
+ *
+ * Frames are rows; every per-frame array carries ONE HALO ROW on each side (row 0 = the frame before this rank's first,
+ * row T_local + 1 = the frame after its last), which the CALLER fills from the neighbouring ranks when the clip is sharded
+ * by frame range (has_prev / has_next say whether those frames exist).  free_mask: bits 0..5 = [d_omega(3), d_t(3)] of
+ * EVERY camera of every frame are optimised ("pose_only" 0, "pose_cam_t" 0x38, "full" 0x3f; multi_view_process.py:338).
+ *   d_x2d (T_local,C,J,2) f32, d_conf (T_local,C,J) f32, d_K (C,9) f64
+ *   d_X    [2][T_local+2][J][3]   current / trial points (d_sc[SKA_BA_REG_SC_CUR] says which half is current)
+ *   d_cams [2][T_local+2][C][12]  R (9, row-major), t (3)
+ *   d_vec  [SKA_BA_REG_NVEC][T_local+2][3J+6C]: g, D, x (the step), r, z, p, y   - rows [J x xyz | C x (d_omega, d_t)]
+ *   d_pinv [T_local][J][6]; d_lfac [T_local][3C(6C+1)] (nullable when free_mask == 0)
+ *   d_sc   [SKA_BA_REG_SC_DOUBLES]: the caller sets CUR = 0, LAMBDA (1e-3), NU = 2, ITER = 0, TOL2 (squared relative CG
+ *          tolerance, 1e-16), COEF[5] = c_r c_l c_t c_s c_b (oracle/lm_reg.py coefficients()) and T_GLOBAL
+ *   d_sums [2][SKA_BA_REG_SUMS]: raw sums of the current / the trial point (the multi-GPU all-reduce payloads)
+ *   d_hist nullable [hist_rows][SKA_BA_REG_HIST_DOUBLES]: iter, cost, trial_cost, lambda, rho, accepted, n_clamped, pred,
+ *          cg_iters, reproj, smooth, baseline, bone_length, pose_temporal (terms of `cost`), final CG residual, pad
+ * One LM trial:
+ *   [set-up only: ska_ba_reg_cost_f64(p, 0) -> all-reduce d_sums[0] -> ska_ba_reg_finish_cost_f64(p, 0)]
+ *   ska_ba_reg_linearize_f64
+ *   ska_ba_reg_cg_f64(BEGIN) -> [all-reduce d_sc[DOT]] -> cg(INIT) -> cg(DIR)
+ *   repeat: [halo exchange of p] cg(MATVEC) -> [all-reduce DOT] -> cg(ALPHA) -> cg(UPDATE) -> [all-reduce DOT] -> cg(BETA) -> cg(DIR)
+ *           (a fixed number of times: once converged every kernel returns at once - no host round trip)
+ *   ska_ba_reg_apply_f64 -> [halo exchange of the trial X / cameras] -> ska_ba_reg_cost_f64(p, 1) -> [all-reduce d_sums[1]]
+ *   -> ska_ba_reg_finish_cost_f64(p, 1) -> ska_ba_reg_control_f64 */
+#define SKA_BA_REG_NVEC 7
+#define SKA_BA_REG_SUMS 40
+#define SKA_BA_REG_SC_DOUBLES 64
+#define SKA_BA_REG_HIST_DOUBLES 16
+#define SKA_BA_REG_SC_CUR 0
+#define SKA_BA_REG_SC_LAMBDA 1
+#define SKA_BA_REG_SC_NU 2
+#define SKA_BA_REG_SC_ITER 3
+#define SKA_BA_REG_SC_COST 4
+#define SKA_BA_REG_SC_ACCEPTED 7
+#define SKA_BA_REG_SC_TOL2 15
+#define SKA_BA_REG_SC_COEF 16
+#define SKA_BA_REG_SC_T_GLOBAL 21
+#define SKA_BA_REG_SC_DOT 47
+#define SKA_BA_REG_CG_BEGIN 0
+#define SKA_BA_REG_CG_INIT 1
+#define SKA_BA_REG_CG_MATVEC 2
+#define SKA_BA_REG_CG_ALPHA 3
+#define SKA_BA_REG_CG_UPDATE 4
+#define SKA_BA_REG_CG_BETA 5
+#define SKA_BA_REG_CG_DIR 6
+typedef struct SkaBaRegProblem {
+  int32_t C, J, n_bones;
+  uint32_t free_mask;
+  int64_t T_local;
+  int32_t has_prev, has_next;
+  int32_t bone_i[SKA_MAX_BONES], bone_j[SKA_MAX_BONES];
+  const float* d_x2d;
+  const float* d_conf;
+  const double* d_K;
+  double* d_X;
+  double* d_cams;
+  double* d_vec;
+  double* d_pinv;
+  double* d_lfac;
+  double* d_sc;
+  double* d_sums;
+  double* d_hist;
+  int64_t hist_rows;
+  void* d_workspace;
+  size_t ws_bytes;
+} SkaBaRegProblem;
+size_t ska_ba_reg_workspace_bytes(int64_t T_local);
+int ska_ba_reg_cost_f64(const SkaBaRegProblem* p, int32_t which, void* stream);
+int ska_ba_reg_finish_cost_f64(const SkaBaRegProblem* p, int32_t which, void* stream);
+int ska_ba_reg_linearize_f64(const SkaBaRegProblem* p, void* stream);
+int ska_ba_reg_cg_f64(const SkaBaRegProblem* p, int32_t op, void* stream);
+int ska_ba_reg_apply_f64(const SkaBaRegProblem* p, void* stream);
+int ska_ba_reg_control_f64(const SkaBaRegProblem* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Post-triangulation triage and temporal smoothing (the step right after the path).

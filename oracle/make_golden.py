@@ -422,8 +422,39 @@ def g11():
     print("g11 written: frames ok", int(out["plain_ok"].sum()), "of", T, "mean gain", out["plain_mean_gain"])
 
 
+def g12():
+    """Regularised LM (oracle/lm_reg.py, row N1 second-order form): the cost history of the exact-solve oracle, and the
+    reference's OWN bundle_adjustment/loss.py evaluated at the oracle's first and final iterates - what pins `cost`."""
+    import torch
+
+    from oracle import first_order as FO
+    from oracle import lm_reg
+
+    L = ref_import.load("bundle_adjustment.loss")
+    out = {}
+    tt = lambda a: torch.from_numpy(np.asarray(a, float))
+    for name, (rig, T, J, mode) in lm_reg.G12_CASES.items():
+        clip, R, t, X0 = lm_reg.make_problem(rig, T, J, cam_jitter=0.01)
+        x2d, conf = clip.x_fm.astype(float), clip.conf_fm.astype(float)
+        Ro, to, Xo, hist = lm_reg.run_lm(X0, R, t, clip.K, x2d, conf, num_iters=8, mode=mode)
+        out[f"{name}_cost"] = np.array([h["cost"] for h in hist])
+        out[f"{name}_trial_cost"] = np.array([h["trial_cost"] for h in hist])
+        out[f"{name}_accepted"] = np.array([h["accepted"] for h in hist])
+        coef = lm_reg.coefficients(T, J, R.shape[1], conf.sum(), None)
+        out[f"{name}_final_cost"] = sum(lm_reg.cost_terms(Xo, Ro, to, clip.K, x2d, conf, coef)[0].values())
+        ref0, _ = FO.total_loss(L, tt(X0), tt(R), tt(t), tt(clip.K), tt(x2d), tt(conf), FO.DEFAULT_WEIGHTS)
+        ref1, _ = FO.total_loss(L, tt(Xo), tt(Ro), tt(to), tt(clip.K), tt(x2d), tt(conf), FO.DEFAULT_WEIGHTS)
+        out[f"{name}_ref_loss_first"], out[f"{name}_ref_loss_final"] = float(ref0), float(ref1)
+        out[f"{name}_X"] = Xo
+        assert abs(float(ref0) - hist[0]["cost"]) <= 1e-12 * hist[0]["cost"], (name, float(ref0), hist[0]["cost"])
+    np.savez_compressed(OUT / "g12_lm_reg.npz", **out)
+    print("g12 written:", {n: (out[f"{n}_cost"][0], out[f"{n}_final_cost"], out[f"{n}_ref_loss_final"]) for n in lm_reg.G12_CASES})
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    if "--only-g12" in sys.argv:
+        return g12()
     if "--only-g11" in sys.argv:
         return g11()
     if "--only-g10" in sys.argv:

@@ -5,7 +5,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_VIEWS = 8
 MAX_BA_VIEWS = 8
 MAX_BONES = 16
@@ -62,6 +62,24 @@ class SkaBaProblem(C.Structure):
         ("d_workspace", C.c_void_p),
         ("ws_bytes", C.c_size_t),
         ("hist_rows", C.c_int64),
+    ]
+
+
+BA_REG_NVEC, BA_REG_SUMS, BA_REG_SC_DOUBLES, BA_REG_HIST_DOUBLES = 7, 40, 64, 16
+BA_REG_SC_CUR, BA_REG_SC_LAMBDA, BA_REG_SC_NU, BA_REG_SC_ITER, BA_REG_SC_COST, BA_REG_SC_ACCEPTED = 0, 1, 2, 3, 4, 7
+BA_REG_SC_TOL2, BA_REG_SC_COEF, BA_REG_SC_T_GLOBAL, BA_REG_SC_DOT = 15, 16, 21, 47
+BA_REG_CG_BEGIN, BA_REG_CG_INIT, BA_REG_CG_MATVEC, BA_REG_CG_ALPHA, BA_REG_CG_UPDATE, BA_REG_CG_BETA, BA_REG_CG_DIR = range(7)
+BA_REG_FREE = {"pose_only": 0, "pose_cam_t": 0x38, "full": 0x3F}
+
+
+class SkaBaRegProblem(C.Structure):
+    _fields_ = [
+        ("C", C.c_int32), ("J", C.c_int32), ("n_bones", C.c_int32), ("free_mask", C.c_uint32),
+        ("T_local", C.c_int64), ("has_prev", C.c_int32), ("has_next", C.c_int32),
+        ("bone_i", C.c_int32 * 16), ("bone_j", C.c_int32 * 16),
+        ("d_x2d", C.c_void_p), ("d_conf", C.c_void_p), ("d_K", C.c_void_p), ("d_X", C.c_void_p), ("d_cams", C.c_void_p),
+        ("d_vec", C.c_void_p), ("d_pinv", C.c_void_p), ("d_lfac", C.c_void_p), ("d_sc", C.c_void_p), ("d_sums", C.c_void_p),
+        ("d_hist", C.c_void_p), ("hist_rows", C.c_int64), ("d_workspace", C.c_void_p), ("ws_bytes", C.c_size_t),
     ]
 
 

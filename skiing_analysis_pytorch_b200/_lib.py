@@ -65,6 +65,13 @@ _SIGS = {
     "ska_ba_calib_solve_f64": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), C.c_uint64, _vp, _vp]),
     "ska_ba_calib_backsub_f32": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), _vp]),
     "ska_ba_calib_control_f64": (C.c_int, [C.POINTER(_cabi.SkaBaProblem), _vp]),
+    "ska_ba_reg_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "ska_ba_reg_cost_f64": (C.c_int, [C.POINTER(_cabi.SkaBaRegProblem), C.c_int32, _vp]),
+    "ska_ba_reg_finish_cost_f64": (C.c_int, [C.POINTER(_cabi.SkaBaRegProblem), C.c_int32, _vp]),
+    "ska_ba_reg_linearize_f64": (C.c_int, [C.POINTER(_cabi.SkaBaRegProblem), _vp]),
+    "ska_ba_reg_cg_f64": (C.c_int, [C.POINTER(_cabi.SkaBaRegProblem), C.c_int32, _vp]),
+    "ska_ba_reg_apply_f64": (C.c_int, [C.POINTER(_cabi.SkaBaRegProblem), _vp]),
+    "ska_ba_reg_control_f64": (C.c_int, [C.POINTER(_cabi.SkaBaRegProblem), _vp]),
     "ska_fuse_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "ska_fuse_frames_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.POINTER(_cabi.SkaFuseParams), _vp, _vp, _vp, _vp, _vp, _vp,
                                        C.c_size_t, _vp]),

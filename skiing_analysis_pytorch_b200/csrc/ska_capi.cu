@@ -282,6 +282,20 @@ int ska_ba_control_f64(const SkaBaProblem* p, void* stream) {
   return ba_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, p->hist_rows, stream);
 }
 
+size_t ska_ba_reg_workspace_bytes(int64_t T_local) { return T_local < 1 ? 0 : ba_reg_workspace_bytes(T_local); }
+#define SKA_REG_ENTRY(call)                                                        \
+  if (p == nullptr) return set_error(SKA_EINVAL, "problem pointer must not be NULL"); \
+  return call
+int ska_ba_reg_cost_f64(const SkaBaRegProblem* p, int32_t which, void* stream) { SKA_REG_ENTRY(ba_reg_cost(*p, which, (cudaStream_t)stream)); }
+int ska_ba_reg_finish_cost_f64(const SkaBaRegProblem* p, int32_t which, void* stream) {
+  SKA_REG_ENTRY(ba_reg_finish_cost(*p, which, (cudaStream_t)stream));
+}
+int ska_ba_reg_linearize_f64(const SkaBaRegProblem* p, void* stream) { SKA_REG_ENTRY(ba_reg_linearize(*p, (cudaStream_t)stream)); }
+int ska_ba_reg_cg_f64(const SkaBaRegProblem* p, int32_t op, void* stream) { SKA_REG_ENTRY(ba_reg_cg(*p, op, (cudaStream_t)stream)); }
+int ska_ba_reg_apply_f64(const SkaBaRegProblem* p, void* stream) { SKA_REG_ENTRY(ba_reg_apply(*p, (cudaStream_t)stream)); }
+int ska_ba_reg_control_f64(const SkaBaRegProblem* p, void* stream) { SKA_REG_ENTRY(ba_reg_control(*p, (cudaStream_t)stream)); }
+#undef SKA_REG_ENTRY
+
 int32_t ska_ba_calib_red_doubles(int32_t C) { return C == 2 ? ba_calib_red_size(C) : 0; }
 
 size_t ska_ba_calib_workspace_bytes(int32_t C) {

@@ -51,6 +51,14 @@ int ba_calib_solve(int C, uint64_t free_mask, const double* red, const double* p
                    void* stream);
 int ba_calib_control(int C, const double* red, const double* red2, double* cams, double* ctrl, double* hist, int64_t hist_rows, void* stream);
 
+// regularised LM over the full configured objective, per-frame cameras (ska_ba_reg.cu)
+size_t ba_reg_workspace_bytes(int64_t T_local);
+int ba_reg_cost(const SkaBaRegProblem& p, int which, cudaStream_t s);
+int ba_reg_finish_cost(const SkaBaRegProblem& p, int which, cudaStream_t s);
+int ba_reg_linearize(const SkaBaRegProblem& p, cudaStream_t s);
+int ba_reg_cg(const SkaBaRegProblem& p, int op, cudaStream_t s);
+int ba_reg_apply(const SkaBaRegProblem& p, cudaStream_t s);
+int ba_reg_control(const SkaBaRegProblem& p, cudaStream_t s);
 
 // standalone projection / losses (ska_project.cu, ska_losses.cu)
 int project_cv(const SkaCamera* cams, int V, const float* X, const float* kpts, int64_t T, int J, int layout, float* proj,

@@ -208,7 +208,7 @@ def test_run_local_ba_signature(cuda):
     R_opt, t_opt, X_opt, history = ba.run_local_ba(
         K_torch=torch.from_numpy(clip.K).float(), R_init_torch=R_init, t_init_torch=t_init,
         X3d_init_torch=torch.from_numpy(X0), x2d_torch=torch.from_numpy(clip.x_fm).float(),
-        conf2d_torch=torch.from_numpy(clip.conf_fm).float(), num_iters=10, lr=1e-3, device="cuda", mode="full", optimizer="lm")
+        conf2d_torch=torch.from_numpy(clip.conf_fm).float(), num_iters=10, lr=1e-3, device="cuda", mode="full", optimizer="lm_rig")
     assert R_opt.shape == (T, 2, 3, 3) and t_opt.shape == (T, 2, 3) and X_opt.shape == (T, 17, 3)
     assert X_opt.dtype == torch.float64 and len(history) == 10
     o = lm.run_lm(X0, R0, t0, clip.K, clip.x_fm, clip.conf_fm, num_iters=10)[3]
@@ -216,15 +216,15 @@ def test_run_local_ba_signature(cuda):
     args = (torch.from_numpy(clip.K), R_init, t_init, torch.from_numpy(X0), torch.from_numpy(clip.x_fm).float(),
             torch.from_numpy(clip.conf_fm).float())
     with pytest.raises(ValueError):
-        ba.run_local_ba(*args, mode="bogus", optimizer="lm")
+        ba.run_local_ba(*args, mode="bogus", optimizer="lm_rig")
     # pose_only: only the points are parameters - the caller's cameras come back bit for bit
-    Rp, tp, Xp, hp = ba.run_local_ba(*args, num_iters=4, mode="pose_only", optimizer="lm")
+    Rp, tp, Xp, hp = ba.run_local_ba(*args, num_iters=4, mode="pose_only", optimizer="lm_rig")
     assert torch.equal(Rp.cpu(), R_init) and torch.equal(tp.cpu(), t_init) and hp[-1]["cost"] <= hp[0]["cost"]
     # a rig that moves from frame to frame is not a static-rig problem: refuse instead of averaging it away
     R_mov = R_init.clone()
     R_mov[1:, 1] = torch.from_numpy(synth.so3_exp(np.array([0.0, 1e-3, 0.0])) @ R0[1])
     with pytest.raises(ValueError):
-        ba.run_local_ba(args[0], R_mov, *args[2:], num_iters=2, mode="full", optimizer="lm")
+        ba.run_local_ba(args[0], R_mov, *args[2:], num_iters=2, mode="full", optimizer="lm_rig")
     # the default is the reference's configured first-order objective over the per-frame cameras
     Ra, ta, Xa, ha = ba.run_local_ba(*args, num_iters=6, lr=1e-2, mode="pose_only")
     assert set(ha[0]) >= {"loss", "reproj", "bone_length", "pose_temporal"} and torch.equal(Ra.cpu(), R_init)
