@@ -67,8 +67,9 @@ class RegLMSequencer:
             return
         first, last, halo_prev, halo_next = self.edges(kind)
         mine = torch.stack([first, last]).contiguous()
-        everyone = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
-        torch.distributed.all_gather_into_tensor(everyone, mine, group=self.group)
+        flat = torch.empty(world * mine.numel(), dtype=mine.dtype, device=mine.device)
+        torch.distributed.all_gather_into_tensor(flat, mine.reshape(-1), group=self.group)
+        everyone = flat.view((world,) + tuple(mine.shape))
         if rank > 0:
             halo_prev.copy_(everyone[rank - 1, 1])
         if rank < world - 1:
@@ -252,8 +253,9 @@ class RegularisedBundleAdjuster(RegLMSequencer):
         for e, row in enumerate((1, self.Tl)):
             mine[:, e, :J3] = self.Xh[:, row].reshape(2, -1)
             mine[:, e, J3:] = self.Ch[:, row].reshape(2, -1)
-        everyone = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
-        torch.distributed.all_gather_into_tensor(everyone, mine, group=self.group)
+        flat = torch.empty(world * mine.numel(), dtype=mine.dtype, device=mine.device)
+        torch.distributed.all_gather_into_tensor(flat, mine.reshape(-1), group=self.group)
+        everyone = flat.view((world,) + tuple(mine.shape))
         if rank > 0:
             src = everyone[rank - 1, :, 1]
             self.Xh[:, 0] = src[:, :J3].view(2, self.J, 3)

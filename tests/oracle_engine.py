@@ -12,6 +12,7 @@ from oracle import geometry as G
 from oracle import lm
 from skiing_analysis_pytorch_b200 import _cabi
 from skiing_analysis_pytorch_b200.ba import LMSequencer
+from skiing_analysis_pytorch_b200.ba_reg import RegLMSequencer
 
 
 class OracleBundleAdjuster(LMSequencer):
@@ -190,3 +191,214 @@ class OracleCalibratingBundleAdjuster(LMSequencer):
         self.lam, self.nu = lm.nielsen_update(self.lam, self.nu, rho, accepted)
         if accepted:
             self.X, self.R, self.t, self.th = self.Xn, self.Rn, self.tn, self.thn
+
+
+class OracleRegularisedBundleAdjuster(RegLMSequencer):
+    """fp64 numpy engine of the regularised LM (oracle/lm_reg.py) behind the product's RegLMSequencer
+    (skiing_analysis_pytorch_b200/ba_reg.py), with the CUDA engine's payloads: the 40-double sums rows (include/ska.h
+    SKA_BA_REG_SUMS; same slots as csrc/ska_ba_reg.cu), the CG dot scalar, and one-frame halo rows of the CG direction and
+    of the state.  A rank multiplies only ITS rows of the damped normal matrix with [halo | own | halo] entries of p - a
+    wrong or missing halo exchange changes the trajectory.  (To obtain its rows the test engine assembles the global
+    system from an all-gather of the current state; that gather is test scaffolding, not part of the sequencer.)"""
+
+    SUM_REPROJ, SUM_CLAMP, SUM_TEMP, SUM_SMOOTH, SUM_B, SUM_B2, SUM_PRED, SUM_L, SUM_L2 = 0, 1, 2, 3, 4, 5, 6, 8, 24
+
+    def __init__(self, x2d, conf, K, R, t, X0, frame_range, global_obs, mode="pose_only", lam0=1e-3, max_iters=16, cg_iters=60,
+                 cg_tol=1e-10, group=None, weights=None):
+        import torch.distributed as dist
+
+        from oracle import lm_reg
+
+        self.lr = lm_reg
+        self.group, self.max_iters, self.cg_iters, self.mode = group, max_iters, cg_iters, mode
+        self.a, self.b = frame_range
+        self.gx2d, self.gconf = (np.asarray(v, float) for v in global_obs)
+        self.Tg = self.gx2d.shape[0]
+        Tl, C, J, _ = x2d.shape
+        self.Tl, self.C, self.J = Tl, C, J
+        self.x2d, self.conf, self.K = np.asarray(x2d, float), np.asarray(conf, float), np.asarray(K, float)
+        self.kf = {"pose_only": 0, "pose_cam_t": 3, "full": 6}[mode]
+        self.nfree = 3 * J + C * self.kf
+        self.state = torch.zeros((2, Tl + 2, 3 * J + 12 * C), dtype=torch.float64)
+        self.state[0, 1:-1, : 3 * J] = torch.from_numpy(np.asarray(X0, float).reshape(Tl, -1))
+        self.state[0, 1:-1, 3 * J:] = torch.from_numpy(np.concatenate([np.asarray(R, float).reshape(Tl, C, 9), np.asarray(t, float)], -1).reshape(Tl, -1))
+        self.state[1] = self.state[0]
+        self.cur = 0
+        self.p = torch.zeros((Tl + 2, self.nfree), dtype=torch.float64)
+        self.sums = torch.zeros((2, 40), dtype=torch.float64)
+        self.dot = torch.zeros(1, dtype=torch.float64)
+        self.coef = lm_reg.coefficients(self.Tg, J, C, float(self.gconf.sum()), weights)
+        self.bones = lm_reg.bones_for(J)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.lam, self.nu, self.tol2 = float(lam0), 2.0, cg_tol ** 2
+        self.history, self.iters_done, self._graph = [], 0, None
+        self.done = False
+        self.setup_cost()
+
+    # ---- state access
+    def _unpack(self, buf, halo=False):
+        s = self.state[buf].numpy()
+        s = s if halo else s[1:-1]
+        n = s.shape[0]
+        X = s[:, : 3 * self.J].reshape(n, self.J, 3)
+        cam = s[:, 3 * self.J:].reshape(n, self.C, 12)
+        return X, cam[..., :9].reshape(n, self.C, 3, 3), cam[..., 9:]
+
+    def edges(self, kind):
+        if kind == "p":
+            return self.p[1], self.p[self.Tl], self.p[0], self.p[self.Tl + 1]
+        s = self.state[self.cur if kind == "current" else 1 - self.cur]
+        return s[1], s[self.Tl], s[0], s[self.Tl + 1]
+
+    # ---- steps
+    def cost(self, which):
+        buf = self.cur if which == 0 else 1 - self.cur
+        X, R, t = self._unpack(buf, halo=True)
+        has_next = self.rank < self.world - 1
+        own = slice(1, self.Tl + 1)
+        _, uv, _, clamped = self.lr.project(X[own], R[own], t[own], self.K)
+        out = np.zeros(40)
+        out[self.SUM_REPROJ] = (self.conf * ((uv - self.x2d) ** 2).sum(-1)).sum()
+        out[self.SUM_CLAMP] = clamped.sum()
+        hi = self.Tl + 2 if has_next else self.Tl + 1  # pairs (t, t+1) owned by t
+        out[self.SUM_TEMP] = ((X[2:hi] - X[1:hi - 1]) ** 2).sum()
+        Cc = self.lr.centres(R, t)
+        out[self.SUM_SMOOTH] = ((Cc[2:hi] - Cc[1:hi - 1]) ** 2).sum()
+        for k, (i, j) in enumerate(self.bones):
+            L = np.linalg.norm(X[own][:, i] - X[own][:, j], axis=-1)
+            out[self.SUM_L + k], out[self.SUM_L2 + k] = L.sum(), (L ** 2).sum()
+        if self.C >= 2:
+            bl = np.linalg.norm(Cc[own][:, 0] - Cc[own][:, 1], axis=-1)
+            out[self.SUM_B], out[self.SUM_B2] = bl.sum(), (bl ** 2).sum()
+        if which == 1:
+            out[self.SUM_PRED] = self.pred_local
+        self.sums[which] = torch.from_numpy(out)
+
+    def _F(self, s):
+        c = self.coef
+        bone = sum(s[self.SUM_L2 + k] - s[self.SUM_L + k] ** 2 / self.Tg for k in range(len(self.bones)))
+        base = s[self.SUM_B2] - s[self.SUM_B] ** 2 / self.Tg if self.C >= 2 else 0.0
+        return (c["reproj"] * s[self.SUM_REPROJ] + c["smooth"] * s[self.SUM_SMOOTH] + c["baseline"] * base + c["bone_length"] * bone
+                + c["pose_temporal"] * s[self.SUM_TEMP])
+
+    def finish_cost(self, which):
+        s = self.sums[which].numpy()
+        if which == 0:
+            self.F, self.ncl = float(self._F(s)), int(s[self.SUM_CLAMP])
+        else:
+            self.Ft, self.pred = float(self._F(s)), float(s[self.SUM_PRED])
+
+    def _gather_global(self):
+        import torch.distributed as dist
+
+        mine = self.state[self.cur, 1:-1].numpy().copy()
+        if self.world == 1:
+            return mine
+        parts = [None] * self.world
+        dist.all_gather_object(parts, mine, group=self.group)
+        return np.concatenate(parts, 0)
+
+    def linearize(self):
+        lr, J, C, kf = self.lr, self.J, self.C, self.kf
+        g_state = self._gather_global()
+        X = g_state[:, : 3 * J].reshape(self.Tg, J, 3)
+        cam = g_state[:, 3 * J:].reshape(self.Tg, C, 12)
+        H, g, free, _ = lr.normal_system(X, cam[..., :9].reshape(self.Tg, C, 3, 3), cam[..., 9:], self.K, self.gx2d, self.gconf, self.coef, self.mode)
+        import scipy.sparse as sp
+
+        D = H.diagonal()
+        A = (H + self.lam * sp.diags(D)).tocsr()
+        nX = self.Tg * J * 3
+
+        def cols(f0, f1):  # free-column indices of frames [f0, f1), frame-row order [3J | C kf]
+            out = []
+            for f in range(f0, f1):
+                out.append(np.concatenate([np.arange(f * J * 3, (f + 1) * J * 3), nX + np.arange(f * C * kf, (f + 1) * C * kf)]))
+            return out
+
+        own = cols(self.a, self.b)
+        self.own_idx = np.concatenate(own)
+        lo, hi = max(self.a - 1, 0), min(self.b + 1, self.Tg)
+        self.ext_idx = np.concatenate(cols(lo, hi))
+        self.ext_rows = slice(1 - (self.a - lo), self.Tl + 1 + (hi - self.b))  # rows of [halo | own | halo] that exist
+        self.A_rows = A[self.own_idx][:, self.ext_idx]
+        self.Minv = [np.linalg.inv(A[ix][:, ix].toarray()) for ix in own]
+        self.g_own, self.D_own = g[self.own_idx], D[self.own_idx]
+
+    def _prec(self, r):
+        return np.concatenate([Mi @ r[k * self.nfree:(k + 1) * self.nfree] for k, Mi in enumerate(self.Minv)])
+
+    def cg(self, op):
+        from skiing_analysis_pytorch_b200 import _cabi as k
+
+        if op == k.BA_REG_CG_BEGIN:
+            self.x = np.zeros_like(self.g_own)
+            self.r = -self.g_own
+            self.p.zero_()
+            self.z = self._prec(self.r)
+            self.dot[0] = float(self.r @ self.z)
+            self.done, self.cg_used = False, 0
+        elif op == k.BA_REG_CG_INIT:
+            self.rz0 = self.rz = float(self.dot)
+            self.beta, self.alpha = 0.0, 0.0
+            self.done = not (self.rz0 > 0)
+        elif op == k.BA_REG_CG_DIR:
+            if self.done and self.cg_used > 0:
+                return
+            pn = self.z + self.beta * self.p[1:-1].numpy().reshape(-1)
+            self.p[1:-1] = torch.from_numpy(pn.reshape(self.Tl, self.nfree))
+        elif self.done:
+            return
+        elif op == k.BA_REG_CG_MATVEC:
+            p_ext = self.p.numpy()[self.ext_rows].reshape(-1)
+            self.y = self.A_rows @ p_ext
+            self.dot[0] = float(self.p[1:-1].numpy().reshape(-1) @ self.y)
+        elif op == k.BA_REG_CG_ALPHA:
+            pap = float(self.dot)
+            self.alpha = self.rz / pap
+        elif op == k.BA_REG_CG_UPDATE:
+            self.x = self.x + self.alpha * self.p[1:-1].numpy().reshape(-1)
+            self.r = self.r - self.alpha * self.y
+            self.z = self._prec(self.r)
+            self.dot[0] = float(self.r @ self.z)
+        elif op == k.BA_REG_CG_BETA:
+            v = float(self.dot)
+            self.beta, self.rz = v / self.rz, v
+            self.cg_used += 1
+            if not (v > self.tol2 * self.rz0):
+                self.done = True
+
+    def apply(self):
+        x = self.x.reshape(self.Tl, self.nfree)
+        self.pred_local = float(self.x @ (self.lam * self.D_own * self.x - self.g_own))
+        X, R, t = self._unpack(self.cur)
+        delta = np.zeros(self.Tl * self.J * 3 + self.Tl * self.C * 6)
+        delta[: self.Tl * self.J * 3] = x[:, : 3 * self.J].reshape(-1)
+        dc = np.zeros((self.Tl, self.C, 6))
+        if self.kf == 3:
+            dc[..., 3:] = x[:, 3 * self.J:].reshape(self.Tl, self.C, 3)
+        elif self.kf == 6:
+            dc[:] = x[:, 3 * self.J:].reshape(self.Tl, self.C, 6)
+        delta[self.Tl * self.J * 3:] = dc.reshape(-1)
+        Xn, Rn, tn = self.lr.apply_step(X.copy(), R.copy(), t.copy(), delta, self.mode)
+        s = self.state[1 - self.cur]
+        s[1:-1, : 3 * self.J] = torch.from_numpy(Xn.reshape(self.Tl, -1))
+        s[1:-1, 3 * self.J:] = torch.from_numpy(np.concatenate([Rn.reshape(self.Tl, self.C, 9), tn], -1).reshape(self.Tl, -1))
+
+    def control(self):
+        rho = (self.F - self.Ft) / self.pred if self.pred > 0 else 0.0
+        accepted = bool(np.isfinite(self.Ft) and self.Ft < self.F)
+        self.history.append(dict(iter=len(self.history), cost=self.F, trial_cost=self.Ft, lam=self.lam, rho=rho, accepted=accepted,
+                                 pred=self.pred, cg_iters=self.cg_used, n_clamped=self.ncl))
+        if accepted:
+            self.lam, self.nu = self.lam * max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3), 2.0
+            self.cur = 1 - self.cur
+            self.sums[0] = self.sums[1]
+            self.F, self.ncl = self.Ft, int(self.sums[1][self.SUM_CLAMP])
+        else:
+            self.lam, self.nu = self.lam * self.nu, 2.0 * self.nu
+
+    @property
+    def X(self):
+        return self._unpack(self.cur)[0]

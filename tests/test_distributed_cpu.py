@@ -148,3 +148,64 @@ def test_single_process_oracle_engine_equals_run_lm():
     np.testing.assert_allclose([h["trial_cost"] for h in ba.history], [h["trial_cost"] for h in hist], rtol=1e-10)
     assert [h["accepted"] for h in ba.history] == [h["accepted"] for h in hist]
     assert torch.is_tensor(ba.red) and ba.red.dtype == torch.float64
+
+
+def _reg_worker(rank, world, port, rig, T, J, mode, iters, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    from oracle import lm_reg
+    from skiing_analysis_pytorch_b200.ba import frame_shard
+    from tests.oracle_engine import OracleRegularisedBundleAdjuster
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        clip, R, t, X0 = lm_reg.make_problem(rig, T, J, cam_jitter=0.01)
+        a, b = frame_shard(T, world, rank)
+        s = OracleRegularisedBundleAdjuster(clip.x_fm[a:b], clip.conf_fm[a:b], clip.K, R[a:b], t[a:b], X0[a:b], (a, b), (clip.x_fm, clip.conf_fm),
+                                            mode=mode, max_iters=iters)
+        s.run(iters)
+        np.savez(Path(out_dir) / f"rank{rank}.npz", X=s.X, a=a, b=b,
+                 hist=np.array([[h["cost"], h["trial_cost"], h["lam"], float(h["accepted"]), h["cg_iters"]] for h in s.history]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,rig,T,J,mode", [(2, "2b", 21, 17, "pose_only"), (3, "2b", 14, 17, "full"), (2, "4", 9, 17, "pose_cam_t")])
+def test_sharded_regularised_lm_over_gloo_matches_single_process_oracle(tmp_path, world, rig, T, J, mode):
+    """Row e3: the regularised LM sharded by frame range - the product's RegLMSequencer moving the CG dot products, the
+    cost sums (bone / baseline means are global) and the one-frame halos of the CG direction and of the trial point over
+    gloo - reproduces the single-process exact-solve oracle (oracle/lm_reg.py)."""
+    from oracle import lm_reg
+
+    iters = 5
+    mp.spawn(_reg_worker, args=(world, _free_port(), rig, T, J, mode, iters, str(tmp_path)), nprocs=world, join=True)
+    clip, R, t, X0 = lm_reg.make_problem(rig, T, J, cam_jitter=0.01)
+    _, _, X, hist = lm_reg.run_lm(X0, R, t, clip.K, clip.x_fm.astype(float), clip.conf_fm.astype(float), num_iters=iters, mode=mode)
+    ref = np.array([[h["cost"], h["trial_cost"], h["lam"], float(h["accepted"])] for h in hist])
+    outs = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    for o in outs:
+        np.testing.assert_allclose(o["hist"][:, :2], ref[:, :2], rtol=1e-7)
+        decisive = np.abs(ref[:, 0] - ref[:, 1]) > 1e-9 * ref[:, 0]
+        n_ok = len(decisive) if decisive.all() else int(np.argmin(decisive))
+        assert n_ok >= 2  # pose_only converges quadratically: two decisive trials
+        np.testing.assert_array_equal(o["hist"][:n_ok, 3], ref[:n_ok, 3])
+        if n_ok == len(decisive):
+            np.testing.assert_allclose(o["X"], X[int(o["a"]): int(o["b"])], atol=1e-6)
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o["hist"], outs[0]["hist"])
+    assert sum(int(o["b"]) - int(o["a"]) for o in outs) == T
+
+
+def test_regularised_sequencer_needs_its_halo(tmp_path):
+    """World 1 through the same engine equals the oracle; the single-process engine adapter itself is faithful."""
+    from oracle import lm_reg
+    from tests.oracle_engine import OracleRegularisedBundleAdjuster
+
+    clip, R, t, X0 = lm_reg.make_problem("2b", 10, 17, cam_jitter=0.01)
+    s = OracleRegularisedBundleAdjuster(clip.x_fm, clip.conf_fm, clip.K, R, t, X0, (0, 10), (clip.x_fm, clip.conf_fm), mode="full", max_iters=4)
+    s.run(4)
+    _, _, _, hist = lm_reg.run_lm(X0, R, t, clip.K, clip.x_fm.astype(float), clip.conf_fm.astype(float), num_iters=4, mode="full")
+    np.testing.assert_allclose([h["trial_cost"] for h in s.history], [h["trial_cost"] for h in hist], rtol=1e-7)
+    assert [h["accepted"] for h in s.history] == [h["accepted"] for h in hist]
