@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 OBJ = CSRC / "_obj"
 LIB = PKG / "lib" / "libska.so"
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xfatbin=-compress-all"]
 
 
 def _nvcc() -> str:

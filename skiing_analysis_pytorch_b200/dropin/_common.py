@@ -6,6 +6,8 @@ from __future__ import annotations
 from pathlib import Path
 from typing import Optional, Sequence
 
+import warnings
+
 import numpy as np
 import torch
 
@@ -120,8 +122,8 @@ def visualize(img1, img2, proj, kptL, kptR, joint_names, circle_r, thickness, ou
 def reproject_pair(X3, K1, dist1, K2, dist2, R_rel, t_rel, kptL=None, kptR=None) -> dict:
     """cam1 = identity with (K1, dist1), cam2 = (R_rel, t_rel) with (K2, dist2); float32 in,
     float32 (J,2) out - the arithmetic of reproject_points on the GPU (ska_reproject_points_f32).
-    With the observed keypoints the per-joint errors (float64 like reproject.py:243-244, from float32
-    projections: quirk Q6) and the nan-aware rmse / mean / median / max (ska_frame_stats_f32) come back too."""
+    With the observed keypoints the per-joint errors and the nan-aware rmse / mean / median / max come back too, formed
+    like reproject.py:242-261 (float64, from the float32 projections: quirk Q6)."""
     from .. import api
 
     dev = device()
@@ -134,14 +136,20 @@ def reproject_pair(X3, K1, dist1, K2, dist2, R_rel, t_rel, kptL=None, kptR=None)
         proj, _ = api.reproject_points(X, K, R, t, dists, want=("proj",))
         p = proj.cpu().numpy()
         return {"proj_L": p[0, 0], "proj_R": p[1, 0]}
-    k = np.stack([np.asarray(kptL, np.float32).reshape(1, -1, 2), np.asarray(kptR, np.float32).reshape(1, -1, 2)])
-    proj, err = api.reproject_points(X, K, R, t, dists, kpts=torch.from_numpy(k).to(dev), want=("proj", "err"))
-    st = api.frame_stats(err).cpu().numpy().astype(np.float64)  # (1, 2, 4): rmse, mean, median, max
-    p, e = proj.cpu().numpy(), err.cpu().numpy().astype(np.float64)
-    out = {"proj_L": p[0, 0], "proj_R": p[1, 0], "err_L": e[0, 0], "err_R": e[1, 0]}
-    for v, side in enumerate("LR"):
-        out[f"rmse_{side}"] = float(st[0, v, 0])
-        out[f"mean_err_{side}"] = float(st[0, v, 1])
-        out[f"median_err_{side}"] = float(st[0, v, 2])
-        out[f"max_err_{side}"] = float(st[0, v, 3])
+    # The projections are the GPU's (float32, as cv2.projectPoints returns them for float32 input).  The per-joint errors and
+    # their nan-aware statistics are J numbers per view: formed here exactly as reproject.py:242-261 forms them - float64
+    # arithmetic on float32 projections minus the keypoints AT THEIR OWN PRECISION (np.asarray(kpt, float)) - so float64
+    # keypoints keep their last bits (quirk Q6).  Whole clips use api.reproject_points / api.frame_stats (float32 on the GPU).
+    proj, _ = api.reproject_points(X, K, R, t, dists, want=("proj",))
+    p = proj.cpu().numpy()
+    out = {"proj_L": p[0, 0], "proj_R": p[1, 0]}
+    with np.errstate(invalid="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)  # all-NaN frames: the reference's nanmean warns and returns nan too
+        for v, (side, kpt) in enumerate((("L", kptL), ("R", kptR))):
+            e = np.linalg.norm(p[v, 0] - np.asarray(kpt, float).reshape(-1, 2), axis=1)
+            out[f"err_{side}"] = e
+            out[f"rmse_{side}"] = float(np.sqrt(np.nanmean(e**2)))
+            out[f"mean_err_{side}"] = float(np.nanmean(e))
+            out[f"median_err_{side}"] = float(np.nanmedian(e))
+            out[f"max_err_{side}"] = float(np.nanmax(e))
     return out

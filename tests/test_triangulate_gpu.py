@@ -218,6 +218,37 @@ def test_full_size_properties_config2(cuda):
     assert ex.err.max().item() < 1e-3
 
 
+@pytest.mark.parametrize("T,J", [(1_000_000, 17), (500_000, 70)])
+def test_full_size_properties_8view(cuda, T, J):
+    """The north star's 8-view shape (1M frames x 17 joints x 8 views) and BASELINE config 4's per-GPU shard (500k frames x
+    70 joints x 8 views = 4M frames over 8 GPUs), confidence-weighted DLT + distortion scoring, through size-independent
+    properties: every contiguous frame shard gives bit-identical results (what makes the multi-GPU split exact), a seeded
+    sample matches the fp64 oracle, and the frame-major layout (the scalar kernel) agrees with the bulk-staged view-pair one."""
+    d = synth.make_clip_device("8", T, J, cuda, seed=3, layout="CTJ2")
+    R, t = d["R"], d["t"]
+    full = api.triangulate_reproject(d["x2d"], d["K"], R, t, conf=d["conf"], dist=synth.DIST_CALIB)
+    for a, b in ((0, 1000), (T // 3, 2 * T // 3 + 1), (T - 999, T), (T // 8 * 3, T // 8 * 4)):
+        part = api.triangulate_reproject(d["x2d"][:, a:b].contiguous(), d["K"], R, t, conf=d["conf"][:, a:b].contiguous(), dist=synth.DIST_CALIB)
+        assert torch.equal(part.X, full.X[a:b])
+        assert torch.equal(part.err, full.err[:, a:b])
+    n_fm = 50_000
+    fm = api.triangulate_reproject(d["x2d"][:, :n_fm].permute(1, 0, 2, 3).contiguous(), d["K"], R, t,
+                                   conf=d["conf"][:, :n_fm].permute(1, 0, 2).contiguous(), dist=synth.DIST_CALIB, layout="TVJ2")
+    assert (fm.X - full.X[:n_fm]).abs().max().item() < 2e-5  # two accumulation orders of the same fp32 sums
+    gen = torch.Generator(device=cuda).manual_seed(1)
+    idx = torch.randint(0, T * J, (20000,), device=cuda, generator=gen)
+    xs = d["x2d"].reshape(8, -1, 2)[:, idx].cpu().numpy()
+    ws = d["conf"].reshape(8, -1)[:, idx].cpu().numpy()
+    P = np.stack([G.make_P(d["K"][v], R[v], t[v]) for v in range(8)])
+    Xo = G.dlt_triangulate(P, xs, ws)
+    Xs = full.X.reshape(-1, 3)[idx].cpu().numpy()
+    assert (np.linalg.norm(Xs - Xo, axis=1) / np.linalg.norm(Xo, axis=1)).max() < X_REL_HELD
+    eo = np.stack([np.linalg.norm(G.project_cv(Xo, R[v], t[v], d["K"][v], synth.DIST_CALIB) - xs[v], axis=1) for v in range(8)])
+    es = full.err.reshape(8, -1)[:, idx].cpu().numpy()
+    assert np.abs(es - eo).max() < POINT_TOL
+    assert abs(_rmse(es) - _rmse(eo)) < RMSE_TOL
+
+
 def test_host_pipeline_matches_device_api(cuda):
     """triangulate_reproject_host (chunked H2D -> kernel -> D2H) returns what the device API returns, for every output
     it offers, on a static rig and with per-frame extrinsics; "stats" equals frame_stats of the errors."""
