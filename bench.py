@@ -55,8 +55,9 @@ def parse():
     ap.add_argument("--no-ba-graph", action="store_true", help="enqueue the LM trials one by one instead of replaying a captured CUDA graph")
     ap.add_argument("--record-ba-parity", action="store_true", help="1 GPU: write the BA cost trajectories to gpurun_out/ba_parity_n1.json (commit as profiles/ba_parity_n1.json)")
     ap.add_argument("--no-extra", action="store_true", help="skip the 8-view north-star shape (extra object `tri_8view`)")
-    ap.add_argument("--e2e-chunk", type=int, default=65536, help="frames per H2D -> kernel -> D2H chunk of the host pipeline")
+    ap.add_argument("--e2e-chunk", type=int, default=131072, help="frames per H2D -> kernel -> D2H chunk of the host pipeline")
     ap.add_argument("--e2e-streams", type=int, default=3)
+    ap.add_argument("--e2e-graph", action="store_true", help="replay the host pipeline's copies and kernels as one CUDA graph instead of enqueueing them call by call (same speed: the copies bound it)")
     return ap.parse_args()
 
 
@@ -709,7 +710,7 @@ def run_ours(a, out_fd=1):
         h_err = torch.empty((V, T, J), dtype=torch.float32).pin_memory()
         h_stats = torch.empty((T, V, 4), dtype=torch.float32).pin_memory()
         e2e_steps = max(3, min(a.steps, 10))
-        kw_host = dict(kw, chunk_frames=a.e2e_chunk, n_streams=a.e2e_streams)
+        kw_host = dict(kw, chunk_frames=a.e2e_chunk, n_streams=a.e2e_streams, graph=a.e2e_graph)
 
         def e2e_timed(want, host_out):
             kwh = dict(kw_host, want=want)
@@ -769,6 +770,7 @@ def run_ours(a, out_fd=1):
             "d2h_bytes_per_step": d2h,
             "steps": e2e_steps,
             "ms_per_step": e2e_ms / e2e_steps,
+            "pipeline": f"{a.e2e_chunk}-frame chunks on {a.e2e_streams} streams, " + ("replayed as one CUDA graph (copies + kernels)" if a.e2e_graph else "enqueued call by call"),
             "result": "X (T,J,3) + per-(frame, view) rmse / mean / median / max of the pixel errors (T,V,4): what process_triangulate consumes",
             "host_link": {
                 "per_rank_h2d_alone": link_min[0], "per_rank_d2h_alone": link_min[1], "per_rank_both_each_direction": link_min[2],

@@ -108,18 +108,33 @@ def exported_symbols():
 
 
 def load():
-    """Load libska.so once; build it first if the sources are newer (needs nvcc).  Raises if it
-    cannot be had - the product has no CPU path."""
+    """Load libska.so once; build it first if it is missing or older than its sources (build.needs_build; needs nvcc -
+    where nvcc is absent a stale prebuilt library is loaded with a warning).  Raises if it cannot be had - the product has
+    no CPU path."""
     global _LIB
     if _LIB is not None:
         return _LIB
     with _LOCK:
         if _LIB is not None:
             return _LIB
-        if not LIB_PATH.exists() or os.environ.get("SKA_REBUILD") == "1":
-            from . import build as _build
+        from . import build as _build
 
-            _build.build(force=os.environ.get("SKA_REBUILD") == "1")
+        default_lib = "SKA_LIB_PATH" not in os.environ
+        stale = False
+        if default_lib and LIB_PATH.exists():
+            try:
+                stale = _build.needs_build()  # a .cu / .cuh / ska.h newer than the library: never run old kernels silently
+            except OSError:
+                stale = False
+        if not LIB_PATH.exists() or os.environ.get("SKA_REBUILD") == "1" or stale:
+            try:
+                _build.build(force=os.environ.get("SKA_REBUILD") == "1")
+            except RuntimeError:
+                if not (stale and LIB_PATH.exists()):
+                    raise
+                import warnings  # no nvcc on this machine (a deployment box): the prebuilt library is what there is
+
+                warnings.warn(f"{LIB_PATH} is older than its sources and nvcc is not available to rebuild it")
         if not LIB_PATH.exists():
             raise RuntimeError(f"{LIB_PATH} is missing and could not be built; there is no CPU fallback")
         lib = C.CDLL(str(LIB_PATH))

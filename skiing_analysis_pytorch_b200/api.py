@@ -225,7 +225,7 @@ def reproject_points(
     return proj, err
 
 
-def frame_stats(err: torch.Tensor, *, layout: str = "VTJ2") -> torch.Tensor:
+def frame_stats(err: torch.Tensor, *, layout: str = "VTJ2", out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """nan-aware per-(frame, view) statistics of pixel errors: (T,V,4) f32 = [rmse, mean, median, max]
     (the scalars of reproject_and_visualize, triangulation/reproject.py:254-261)."""
     _require_cuda(err, "err")
@@ -240,19 +240,48 @@ def frame_stats(err: torch.Tensor, *, layout: str = "VTJ2") -> torch.Tensor:
         lay = _cabi.LAYOUT_FRAME_MAJOR
     else:
         raise ValueError(f"layout must be 'VTJ2' or 'TVJ2', got {layout!r}")
-    out = torch.empty((T, V, 4), dtype=torch.float32, device=err.device)
+    if out is None:
+        out = torch.empty((T, V, 4), dtype=torch.float32, device=err.device)
+    elif tuple(out.shape) != (T, V, 4) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != err.device:
+        raise ValueError(f"out must be a contiguous float32 ({T},{V},4) tensor on {err.device}")
     if T > 0:
         with torch.cuda.device(err.device):
             _lib.check(_lib.load().ska_frame_stats_f32(_ptr(err), T, J, V, lay, _ptr(out), _stream_ptr(err.device)))
     return out
 
 
+def chunk_schedule(T: int, chunk: int, ramp_from: int = 0):
+    """Frame ranges of the host pipeline: uniform chunks, or (ramp_from > 0) chunks that double from `ramp_from` up to
+    `chunk`, stay there, and halve again at the end, to shorten the pipeline's fill and drain.  Measured on B200 / PCIe 5
+    (tools/e2e_sweep.py, profiles/README.md): uniform 131072-frame chunks are the fastest (6.30 ms per 1M x 17 x 2 step);
+    every copy costs ~7 us of DMA set-up, so 16k-frame chunks lose 1.8 ms, and the ramp gains nothing - the default is 0."""
+    T, chunk = int(T), max(1, int(chunk))
+    up = []
+    c = int(ramp_from)
+    while 0 < c < chunk:
+        up.append(c)
+        c *= 2
+    if not up or T < 2 * sum(up) + chunk:
+        return [(a, min(a + chunk, T)) for a in range(0, T, chunk)]
+    sizes = list(up)
+    mid = T - 2 * sum(up)
+    sizes += [chunk] * (mid // chunk) + ([mid % chunk] if mid % chunk else [])
+    sizes += up[::-1]
+    out, a = [], 0
+    for n in sizes:
+        out.append((a, a + n))
+        a += n
+    return out
+
+
 _HOST_PIPE_CACHE: dict = {}
+_HOST_GRAPH_CACHE: dict = {}
 
 
 def clear_host_pipeline_cache() -> None:
     """Drop the device staging buffers and streams triangulate_reproject_host keeps between calls."""
     _HOST_PIPE_CACHE.clear()
+    _HOST_GRAPH_CACHE.clear()
 
 
 def triangulate_reproject_host(
@@ -264,19 +293,25 @@ def triangulate_reproject_host(
     dist=None,
     *,
     device=None,
-    chunk_frames: int = 65536,
+    chunk_frames: int = 131072,
     n_streams: int = 3,
     out: Optional[dict] = None,
+    graph: bool = False,
+    ramp_from: int = 0,
     **kw,
 ) -> TriangulationResult:
     """Host-buffer entry point (what a reference pipeline holding numpy clips calls): view-major
     (V,T,J,2) float32 HOST tensors in, HOST tensors out.  The clip is cut into frame chunks that
     flow H2D -> fused kernel -> D2H on `n_streams` CUDA streams so the two PCIe directions and the
-    kernel overlap.  Pinned inputs/outputs make the copies asynchronous; pageable ones still work.
+    kernel overlap (chunk_schedule).  Pinned inputs/outputs make the copies asynchronous; pageable ones still work.
     want: any of "X", "err", "proj", "status", "stats".  "stats" = the nan-aware per-(frame, view) rmse / mean / median /
     max of the pixel errors, (T,V,4) - what process_triangulate consumes (triangulation/triangulate.py:111-114 reads
     mean_err_L / mean_err_R only): asking for ("X", "stats") instead of ("X", "err") moves 16 V bytes per frame over
     PCIe instead of 4 V J.  R / t may be a static rig or per-frame (T,V,3,3) / (T,V,3) host arrays.
+    graph=True (pinned inputs AND caller-provided pinned `out` buffers): the whole chunked pipeline - every copy and kernel
+    on every stream - is captured once in a CUDA graph keyed on the buffer addresses, shapes and camera values, and
+    replayed on later calls with the same buffers: no host-side launch work per step (measured: the pipeline is bound by
+    the copies, not by the launches - replay and call-by-call run within 1 %, tools/e2e_sweep.py).
     Returns after the last chunk has landed on the host."""
     if kpts.is_cuda:
         raise ValueError("triangulate_reproject_host takes host tensors; use triangulate_reproject for CUDA tensors")
@@ -301,6 +336,20 @@ def triangulate_reproject_host(
         if not hRt.is_pinned():
             hRt = hRt.pin_memory()
     out = out or {}
+    gkey = None
+    if graph:
+        need = ("X",) + tuple(n for n in want if n != "X")
+        if per_frame or not kpts.is_pinned() or (conf is not None and not conf.is_pinned()) or any(out.get(n) is None or not out[n].is_pinned() for n in need):
+            raise ValueError("graph=True needs a static rig, pinned inputs and caller-provided pinned `out` buffers for every wanted output")
+        cam_bytes = b"".join(np.ascontiguousarray(np.asarray(a_, np.float64)).tobytes() for a_ in (K, R, t)) + (
+            b"" if dist is None else b"".join(np.ascontiguousarray(np.asarray(d_, np.float64)).tobytes() for d_ in (dist if isinstance(dist, (list, tuple)) else [dist])))
+        gkey = (dev.index, kpts.data_ptr(), tuple(kpts.shape), None if conf is None else conf.data_ptr(), tuple((n, out[n].data_ptr()) for n in need),
+                want, chunk_frames, n_streams, ramp_from, hash(cam_bytes), tuple(sorted((k_, repr(v_)) for k_, v_ in kw.items())))
+        hit = _HOST_GRAPH_CACHE.get(gkey)
+        if hit is not None:
+            hit[0].replay()
+            torch.cuda.current_stream(dev).synchronize()
+            return hit[1]
 
     def host(name, shape, dtype=torch.float32):
         if name not in want:
@@ -330,53 +379,66 @@ def triangulate_reproject_host(
                     "proj": torch.empty((V, Tc, J, 2), dtype=torch.float32, device=dev) if hP is not None else None,
                     "status": torch.empty((Tc, J), dtype=torch.uint8, device=dev) if hSt is not None else None,
                     "Rt": torch.empty((Tc, V, 12), dtype=torch.float64, device=dev) if per_frame else None,
+                    "stats": torch.empty((Tc, V, 4), dtype=torch.float32, device=dev),
                 }
             )
         _HOST_PIPE_CACHE.clear()
         _HOST_PIPE_CACHE[key] = slots
     dwant = ("X",) + (("err",) if need_err else ()) + (("proj",) if hP is not None else ()) + (("status",) if hSt is not None else ())
-    cur = torch.cuda.current_stream(dev)
-    start = torch.cuda.Event()
-    start.record(cur)
-    i = 0
-    for a in range(0, T, Tc):
-        b = min(a + Tc, T)
-        n = b - a
-        s = slots[i % n_streams]
-        i += 1
-        with torch.cuda.stream(s["stream"]):
-            s["stream"].wait_event(start)
-            part = lambda buf, *shape: buf if n == Tc else buf.flatten()[: int(np.prod(shape))].view(*shape)
-            dk = part(s["k"], V, n, J, 2)
-            dc = part(s["c"], V, n, J) if conf is not None else None
-            dX = s["X"][:n]
-            dE = part(s["err"], V, n, J)
-            outs = {"X": dX, "err": dE}
-            if hP is not None:
-                outs["proj"] = part(s["proj"], V, n, J, 2)
-            if hSt is not None:
-                outs["status"] = s["status"][:n]
-            for v in range(V):
-                dk[v].copy_(kpts[v, a:b], non_blocking=True)
-                if dc is not None:
-                    dc[v].copy_(conf[v, a:b], non_blocking=True)
-            if per_frame:
-                dRt = s["Rt"][:n]
-                dRt.copy_(hRt[a:b], non_blocking=True)
-                triangulate_reproject(dk, K, dRt, None, conf=dc, dist=dist, want=dwant, out=outs, **kw)
-            else:
-                triangulate_reproject(dk, K, R, t, conf=dc, dist=dist, want=dwant, out=outs, **kw)
-            hX[a:b].copy_(dX, non_blocking=True)
-            if hS is not None:
-                hS[a:b].copy_(frame_stats(dE), non_blocking=True)
-            for v in range(V):
-                if hE is not None:
-                    hE[v, a:b].copy_(dE[v], non_blocking=True)
+
+    def enqueue(cur):
+        start = torch.cuda.Event()
+        start.record(cur)
+        i = 0
+        for a, b in chunk_schedule(T, Tc, ramp_from):
+            n = b - a
+            s = slots[i % n_streams]
+            i += 1
+            with torch.cuda.stream(s["stream"]):
+                s["stream"].wait_event(start)
+                part = lambda buf, *shape: buf if n == Tc else buf.flatten()[: int(np.prod(shape))].view(*shape)
+                dk = part(s["k"], V, n, J, 2)
+                dc = part(s["c"], V, n, J) if conf is not None else None
+                dX = s["X"][:n]
+                dE = part(s["err"], V, n, J)
+                outs = {"X": dX, "err": dE}
                 if hP is not None:
-                    hP[v, a:b].copy_(outs["proj"][v], non_blocking=True)
-            if hSt is not None:
-                hSt[a:b].copy_(outs["status"], non_blocking=True)
-    for s in slots:
-        cur.wait_stream(s["stream"])
+                    outs["proj"] = part(s["proj"], V, n, J, 2)
+                if hSt is not None:
+                    outs["status"] = s["status"][:n]
+                for v in range(V):
+                    dk[v].copy_(kpts[v, a:b], non_blocking=True)
+                    if dc is not None:
+                        dc[v].copy_(conf[v, a:b], non_blocking=True)
+                if per_frame:
+                    dRt = s["Rt"][:n]
+                    dRt.copy_(hRt[a:b], non_blocking=True)
+                    triangulate_reproject(dk, K, dRt, None, conf=dc, dist=dist, want=dwant, out=outs, **kw)
+                else:
+                    triangulate_reproject(dk, K, R, t, conf=dc, dist=dist, want=dwant, out=outs, **kw)
+                hX[a:b].copy_(dX, non_blocking=True)
+                if hS is not None:
+                    hS[a:b].copy_(frame_stats(dE, out=s["stats"][:n]), non_blocking=True)
+                for v in range(V):
+                    if hE is not None:
+                        hE[v, a:b].copy_(dE[v], non_blocking=True)
+                    if hP is not None:
+                        hP[v, a:b].copy_(outs["proj"][v], non_blocking=True)
+                if hSt is not None:
+                    hSt[a:b].copy_(outs["status"], non_blocking=True)
+        for s in slots:
+            cur.wait_stream(s["stream"])
+
+    cur = torch.cuda.current_stream(dev)
+    result = TriangulationResult(X=hX, err=hE, proj=hP, status=hSt, stats=hS)
+    enqueue(cur)  # eager pass: the result of THIS call (and, for graph=True, the warm-up before capture)
     cur.synchronize()
-    return TriangulationResult(X=hX, err=hE, proj=hP, status=hSt, stats=hS)
+    if gkey is not None:
+        g = torch.cuda.CUDAGraph()
+        cs = torch.cuda.Stream(dev)
+        with torch.cuda.stream(cs):
+            with torch.cuda.graph(g, stream=cs, capture_error_mode="thread_local"):
+                enqueue(cs)
+        _HOST_GRAPH_CACHE.clear()  # one pipeline at a time: the graph pins the slot buffers
+        _HOST_GRAPH_CACHE[gkey] = (g, result, slots, kpts, conf, dict(out))
+    return result

@@ -539,8 +539,10 @@ int reprojection_loss(const S* X, int64_t T, int J, int C, const S* R, int64_t R
   }
   if (fR != nullptr || ft != nullptr || fK != nullptr) {
     const int64_t rows = T * C;
-    loss_cam_frames_kernel<S><<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(a, fR, ft, fK);
-    if ((ce = cudaGetLastError()) != cudaSuccess) return set_error((int)ce, cudaGetErrorString(ce));
+    if (rows > 0) {  // an empty clip has no per-frame camera gradients: a 0-block grid is a launch error
+      loss_cam_frames_kernel<S><<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(a, fR, ft, fK);
+      if ((ce = cudaGetLastError()) != cudaSuccess) return set_error((int)ce, cudaGetErrorString(ce));
+    }
   }
   return SKA_OK;
 }

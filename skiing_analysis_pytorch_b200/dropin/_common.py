@@ -23,6 +23,43 @@ def f32(a) -> np.ndarray:
     return np.asarray(a, dtype=np.float32)
 
 
+def rotation_as_projectpoints_sees_it(R) -> np.ndarray:
+    """The rotation cv2.projectPoints actually applies when the reference hands it R: reproject.py:69 converts the float32
+    matrix to a rotation VECTOR (cv2.Rodrigues: nearest rotation U V^T by SVD, then axis * angle, stored as float32) and
+    projectPoints turns that vector back into a matrix in double.  For an exactly orthonormal R this is R to ~1e-7; for
+    R2 @ R1.T formed in float32 or a network-predicted matrix it is the projection onto SO(3), not R itself."""
+    R32 = np.asarray(R, np.float32).reshape(3, 3).astype(np.float64)
+    U, _, Vt = np.linalg.svd(R32)
+    Ro = U @ Vt
+    r = np.array([Ro[2, 1] - Ro[1, 2], Ro[0, 2] - Ro[2, 0], Ro[1, 0] - Ro[0, 1]])
+    s = np.sqrt((r @ r) * 0.25)
+    c = np.clip((np.trace(Ro) - 1.0) * 0.5, -1.0, 1.0)
+    theta = np.arccos(c)
+    if s < 1e-5:
+        if c > 0:
+            rvec = np.zeros(3)
+        else:  # rotation by pi: axis from the diagonal, signs from the off-diagonal entries (OpenCV's branch)
+            t = (Ro[0, 0] + 1) * 0.5
+            rx = np.sqrt(max(t, 0.0))
+            t = (Ro[1, 1] + 1) * 0.5
+            ry = np.sqrt(max(t, 0.0)) * (-1.0 if Ro[0, 1] < 0 else 1.0)
+            t = (Ro[2, 2] + 1) * 0.5
+            rz = np.sqrt(max(t, 0.0)) * (-1.0 if Ro[0, 2] < 0 else 1.0)
+            if abs(rx) < abs(ry) and abs(rx) < abs(rz) and (Ro[1, 2] > 0) != (ry * rz > 0):
+                rz = -rz
+            v = np.array([rx, ry, rz])
+            rvec = v * (theta / max(np.linalg.norm(v), 1e-300))
+    else:
+        rvec = r * (theta / (2.0 * s))
+    rvec = rvec.astype(np.float32).astype(np.float64)
+    th = np.linalg.norm(rvec)
+    if th < 2.220446049250313e-16:
+        return np.eye(3)
+    k = rvec / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.cos(th) * np.eye(3) + (1 - np.cos(th)) * np.outer(k, k) + np.sin(th) * Kx
+
+
 def nan_stats(err: np.ndarray) -> dict:
     """rmse / mean / median / max exactly as reproject.py:254-261 (nan-aware, float64)."""
     return {
@@ -129,7 +166,7 @@ def reproject_pair(X3, K1, dist1, K2, dist2, R_rel, t_rel, kptL=None, kptR=None)
     dev = device()
     X = torch.from_numpy(np.ascontiguousarray(f32(X3).reshape(1, -1, 3))).to(dev)
     K = np.stack([f32(K1).reshape(3, 3), f32(K2).reshape(3, 3)]).astype(np.float64)
-    R = np.stack([np.eye(3), f32(R_rel).reshape(3, 3).astype(np.float64)])
+    R = np.stack([np.eye(3), rotation_as_projectpoints_sees_it(R_rel)])
     t = np.stack([np.zeros(3), f32(t_rel).reshape(3).astype(np.float64)])
     dists = [None if d is None else f32(d).reshape(-1).astype(np.float64) for d in (dist1, dist2)]
     if kptL is None:

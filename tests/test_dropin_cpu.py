@@ -121,3 +121,20 @@ def test_shims_fail_loudly_without_a_gpu():
     rep = dropin.shim("bundle_adjustment.reproject")
     with pytest.raises(ValueError, match="Unsupported R shape"):
         rep.reproject_points(np.zeros((17, 3)), np.eye(3), None, np.eye(3), None, np.zeros(9), np.zeros(3))
+
+
+def test_rotation_round_trip_is_what_cv2_applies():
+    """the reference hands cv2.projectPoints a rotation VECTOR made from the float32 matrix (reproject.py:69); the
+    shim's host-side restatement of that round trip (SVD projection onto SO(3), float32 vector, Rodrigues) equals cv2's."""
+    import cv2
+    import numpy as np
+
+    from skiing_analysis_pytorch_b200.dropin._common import rotation_as_projectpoints_sees_it as f
+
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        R = cv2.Rodrigues(rng.normal(size=3) * rng.choice([1e-4, 0.1, 1.0, 3.0]))[0]
+        R = (R + rng.normal(size=(3, 3)) * rng.choice([0, 1e-6, 1e-3, 0.05])).astype(np.float32)
+        rvec, _ = cv2.Rodrigues(R)
+        assert np.abs(f(R) - cv2.Rodrigues(rvec.astype(np.float64))[0]).max() < 1e-9
+    assert np.array_equal(f(np.eye(3)), np.eye(3))

@@ -218,6 +218,28 @@ def test_full_size_properties_config2(cuda):
     assert ex.err.max().item() < 1e-3
 
 
+def test_host_pipeline_graph_replay(cuda):
+    """graph=True: the captured pipeline (copies + kernels on every stream) returns what the call-by-call pipeline returns,
+    and a replay picks up new contents of the same pinned buffers."""
+    clip = synth.make_clip("2b", 5000, 17, seed=4)
+    hk = torch.from_numpy(clip.x_vm).pin_memory()
+    out = {"X": torch.empty((5000, 17, 3)).pin_memory(), "stats": torch.empty((5000, 2, 4)).pin_memory()}
+    kw = dict(K=clip.K, R=clip.R, t=clip.t, dist=synth.DIST_CALIB, want=("X", "stats"), chunk_frames=1024, n_streams=3)
+    eager = api.triangulate_reproject_host(hk, **kw)
+    a = api.triangulate_reproject_host(hk, out=out, graph=True, **kw)          # eager pass + capture
+    assert torch.equal(a.X, eager.X) and torch.equal(a.stats, eager.stats)
+    out["X"].zero_()
+    b = api.triangulate_reproject_host(hk, out=out, graph=True, **kw)          # replay
+    assert torch.equal(b.X, eager.X) and torch.equal(b.stats, eager.stats)
+    hk[:, :100] += 3.0                                                          # same buffers, new contents
+    c = api.triangulate_reproject_host(hk, out=out, graph=True, **kw)
+    fresh = api.triangulate_reproject_host(hk.clone().pin_memory(), **kw)
+    assert torch.equal(c.X, fresh.X) and torch.equal(c.stats, fresh.stats) and not torch.equal(c.X, eager.X)
+    with pytest.raises(ValueError):
+        api.triangulate_reproject_host(hk, graph=True, **kw)                    # no caller-provided pinned outputs
+    api.clear_host_pipeline_cache()
+
+
 @pytest.mark.parametrize("T,J", [(1_000_000, 17), (500_000, 70)])
 def test_full_size_properties_8view(cuda, T, J):
     """The north star's 8-view shape (1M frames x 17 joints x 8 views) and BASELINE config 4's per-GPU shard (500k frames x
