@@ -975,6 +975,208 @@ __global__ void reg_control_kernel(const RegArgs a, double* hist, int64_t hist_r
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ points only ("pose_only")
+// With the cameras fixed (the reference's configured default, configs/vggt.yaml:52) nothing is reduced over a frame: the
+// normal matrix is the 3x3 point blocks plus the bone / temporal couplings, and its block-Jacobi preconditioner is exact up
+// to those weak couplings (CG converges in 2 iterations).  ONE THREAD PER POINT then: every lane busy (a warp per frame
+// leaves 15 of 32 lanes idle at J = 17), no shuffles, no shared memory; the frame's cameras are read through L1.
+constexpr int kPtBlock = 256;
+constexpr int kPtMaxGrid = 148 * 8;
+
+__device__ __forceinline__ double block_sum_to(double v, double* sh) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < kPtBlock / 32; ++w) t += sh[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(kPtBlock) reg_pt_linearize_kernel(const RegArgs a) {
+  const double* sc = a.sc;
+  const int buf = (int)sc[SC_CUR];
+  const double lam = sc[SC_LAM], cr = sc[SC_CR], cl = sc[SC_CL], ct = sc[SC_CT];
+  const int64_t N = a.Tl * a.J;
+  for (int64_t i = blockIdx.x * (int64_t)kPtBlock + threadIdx.x; i < N; i += (int64_t)gridDim.x * kPtBlock) {
+    const int64_t f = i / a.J;
+    const int j = (int)(i - f * a.J);
+    const int64_t row = f + 1;
+    const double* Xf = frame_X(a, buf, row);
+    const double* Cm = frame_C(a, buf, row);
+    const bool prev = f > 0 || a.has_prev, next = f + 1 < a.Tl || a.has_next;
+    const double Xj[3] = {Xf[3 * j], Xf[3 * j + 1], Xf[3 * j + 2]};
+    double P[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < a.C; ++c) {
+      const double* cam = Cm + 12 * c;
+      const float2 uv = *reinterpret_cast<const float2*>(a.x2d + ((f * a.C + c) * a.J + j) * 2);
+      const double w = cr * (double)a.conf[(f * a.C + c) * a.J + j];
+      Obs o;
+      observe(cam, a.K + 9 * c, Xj, (double)uv.x, (double)uv.y, w, o);
+      double RtN[3][3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double col[3] = {cam[r], cam[3 + r], cam[6 + r]};
+        sym3vec(o.N, col, RtN[r]);
+      }
+      int e = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = r; k < 3; ++k, ++e) P[e] += RtN[r][0] * cam[k] + RtN[r][1] * cam[3 + k] + RtN[r][2] * cam[6 + k];
+      double gx[3];
+      matTvec3(cam, o.q, gx);
+      P[6] += gx[0], P[7] += gx[1], P[8] += gx[2];
+    }
+    for (int b = 0; b < a.nb; ++b) {
+      const int bi = a.bi[b], bj = a.bj[b];
+      if (bi != j && bj != j) continue;
+      const int o = bi == j ? bj : bi;
+      const double sgn = bi == j ? 1.0 : -1.0;
+      double u[3] = {sgn * (Xj[0] - Xf[3 * o]), sgn * (Xj[1] - Xf[3 * o + 1]), sgn * (Xj[2] - Xf[3 * o + 2])};
+      const double L = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+      const double iL = 1.0 / L;
+      u[0] *= iL, u[1] *= iL, u[2] *= iL;
+      const double res = cl * (L - sc[SC_REF + b]) * sgn;
+      P[0] += cl * u[0] * u[0], P[1] += cl * u[0] * u[1], P[2] += cl * u[0] * u[2];
+      P[3] += cl * u[1] * u[1], P[4] += cl * u[1] * u[2], P[5] += cl * u[2] * u[2];
+      P[6] += res * u[0], P[7] += res * u[1], P[8] += res * u[2];
+    }
+    const double nn = ct * ((prev ? 1.0 : 0.0) + (next ? 1.0 : 0.0));
+    P[0] += nn, P[3] += nn, P[5] += nn;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double gk = 0.0;
+      if (prev) gk += Xj[k] - Xf[3 * j + k - a.J * 3];
+      if (next) gk -= Xf[3 * j + k + a.J * 3] - Xj[k];
+      P[6 + k] += ct * gk;
+    }
+    const double d[3] = {P[0], P[3], P[5]};
+    const double Hd[6] = {P[0] + lam * d[0], P[1], P[2], P[3] + lam * d[1], P[4], P[5] + lam * d[2]};
+    double inv[6];
+    inv_sym3(Hd, inv);
+    double* gr = a.g + row * a.nf;
+    double* Dr = a.D + row * a.nf;
+    double* rr = a.r + row * a.nf;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gr[3 * j + k] = P[6 + k], rr[3 * j + k] = -P[6 + k], Dr[3 * j + k] = d[k];
+    double* pg = a.pinv + i * 6;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pg[k] = inv[k];
+    if (j == 0)
+      for (int k = 0; k < 6 * a.C; ++k) gr[3 * a.J + k] = 0.0, rr[3 * a.J + k] = 0.0, Dr[3 * a.J + k] = 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(kPtBlock) reg_pt_matvec_kernel(const RegArgs a) {
+  __shared__ double sh[kPtBlock / 32];
+  const double* sc = a.sc;
+  double dot = 0.0;
+  if (sc[SC_DONE] == 0.0) {
+    const int buf = (int)sc[SC_CUR];
+    const double lam = sc[SC_LAM], cr = sc[SC_CR], cl = sc[SC_CL], ct = sc[SC_CT];
+    const int64_t N = a.Tl * a.J;
+    for (int64_t i = blockIdx.x * (int64_t)kPtBlock + threadIdx.x; i < N; i += (int64_t)gridDim.x * kPtBlock) {
+      const int64_t f = i / a.J;
+      const int j = (int)(i - f * a.J);
+      const int64_t row = f + 1;
+      const double* Xf = frame_X(a, buf, row);
+      const double* Cm = frame_C(a, buf, row);
+      const double* pr = a.p + row * a.nf;
+      const bool prev = f > 0 || a.has_prev, next = f + 1 < a.Tl || a.has_next;
+      const double Xj[3] = {Xf[3 * j], Xf[3 * j + 1], Xf[3 * j + 2]};
+      const double pj[3] = {pr[3 * j], pr[3 * j + 1], pr[3 * j + 2]};
+      double y[3] = {0.0, 0.0, 0.0};
+      for (int c = 0; c < a.C; ++c) {
+        const double* cam = Cm + 12 * c;
+        const float2 uv = *reinterpret_cast<const float2*>(a.x2d + ((f * a.C + c) * a.J + j) * 2);
+        const double w = cr * (double)a.conf[(f * a.C + c) * a.J + j];
+        Obs o;
+        observe(cam, a.K + 9 * c, Xj, (double)uv.x, (double)uv.y, w, o);
+        double dxc[3], nq[3], back[3];
+        matvec3(cam, pj, dxc);
+        sym3vec(o.N, dxc, nq);
+        matTvec3(cam, nq, back);
+        y[0] += back[0], y[1] += back[1], y[2] += back[2];
+      }
+      for (int b = 0; b < a.nb; ++b) {
+        const int bi = a.bi[b], bj = a.bj[b];
+        if (bi != j && bj != j) continue;
+        double u[3] = {Xf[3 * bi] - Xf[3 * bj], Xf[3 * bi + 1] - Xf[3 * bj + 1], Xf[3 * bi + 2] - Xf[3 * bj + 2]};
+        const double iL = rsqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        u[0] *= iL, u[1] *= iL, u[2] *= iL;
+        const double s = cl * (u[0] * (pr[3 * bi] - pr[3 * bj]) + u[1] * (pr[3 * bi + 1] - pr[3 * bj + 1]) + u[2] * (pr[3 * bi + 2] - pr[3 * bj + 2]));
+        const double sg = bi == j ? s : -s;
+        y[0] += sg * u[0], y[1] += sg * u[1], y[2] += sg * u[2];
+      }
+      double* yr = a.y + row * a.nf;
+      const double* Dr = a.D + row * a.nf;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double tv = 0.0;
+        if (prev) tv += pj[k] - pr[3 * j + k - a.nf];
+        if (next) tv += pj[k] - pr[3 * j + k + a.nf];
+        const double yv = y[k] + ct * tv + lam * Dr[3 * j + k] * pj[k];
+        yr[3 * j + k] = yv;
+        dot += pj[k] * yv;
+      }
+      if (j == 0)
+        for (int k = 0; k < 6 * a.C; ++k) yr[3 * a.J + k] = 0.0;
+    }
+  }
+  const double t = block_sum_to(dot, sh);
+  if (threadIdx.x == 0) a.dpart[blockIdx.x] = t;
+}
+
+// x += alpha p, r -= alpha y, z = Dp^-1 r; partial dot r . z
+__global__ void __launch_bounds__(kPtBlock) reg_pt_precond_kernel(const RegArgs a, int first) {
+  __shared__ double sh[kPtBlock / 32];
+  const double* sc = a.sc;
+  double dot = 0.0;
+  if (first || sc[SC_DONE] == 0.0) {
+    const double alpha = first ? 0.0 : sc[SC_ALPHA];
+    const int64_t N = a.Tl * a.J;
+    for (int64_t i = blockIdx.x * (int64_t)kPtBlock + threadIdx.x; i < N; i += (int64_t)gridDim.x * kPtBlock) {
+      const int64_t f = i / a.J;
+      const int j = (int)(i - f * a.J);
+      const int64_t o = (f + 1) * a.nf + 3 * j;
+      double rv[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        rv[k] = a.r[o + k];
+        if (!first) {
+          a.x[o + k] += alpha * a.p[o + k];
+          rv[k] -= alpha * a.y[o + k];
+          a.r[o + k] = rv[k];
+        } else {
+          a.x[o + k] = 0.0;
+        }
+      }
+      const double* inv = a.pinv + i * 6;
+      const double iv[6] = {inv[0], inv[1], inv[2], inv[3], inv[4], inv[5]};
+      double zv[3];
+      sym3vec(iv, rv, zv);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        a.z[o + k] = zv[k];
+        dot += rv[k] * zv[k];
+      }
+      if (j == 0)
+        for (int k = 0; k < 6 * a.C; ++k) a.z[(f + 1) * a.nf + 3 * a.J + k] = 0.0, a.x[(f + 1) * a.nf + 3 * a.J + k] = 0.0;
+    }
+  }
+  const double t = block_sum_to(dot, sh);
+  if (threadIdx.x == 0) a.dpart[blockIdx.x] = t;
+}
+
+static int pt_grid(const RegArgs& a) {
+  int64_t g = (a.Tl * a.J + kPtBlock - 1) / kPtBlock;
+  if (g > kPtMaxGrid) g = kPtMaxGrid;
+  if (g > a.W) g = a.W;  // dpart holds W rows
+  return g < 1 ? 1 : (int)g;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static int grid_blocks(int64_t Tl) {
   int64_t b = (Tl + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -1054,6 +1256,10 @@ int ba_reg_linearize(const SkaBaRegProblem& p, cudaStream_t s) {
   RegArgs a;
   int rc = fill(p, a);
   if (rc != SKA_OK) return rc;
+  if (a.free6 == 0) {  // points only: one thread per point
+    reg_pt_linearize_kernel<<<pt_grid(a), kPtBlock, 0, s>>>(a);
+    return check_launch();
+  }
   const size_t per_warp = ((size_t)a.J * 12 + (size_t)a.C * 28 + a.nf + a.nS + (size_t)96 * a.n6) * sizeof(double);
   int wpb = kWarpsPerBlock;
   const size_t bytes = per_warp * wpb;
@@ -1070,6 +1276,18 @@ int ba_reg_cg(const SkaBaRegProblem& p, int op, cudaStream_t s) {
   switch (op) {
     case SKA_BA_REG_CG_BEGIN:
     case SKA_BA_REG_CG_UPDATE: {
+      if (a.free6 == 0) {
+        if (op == SKA_BA_REG_CG_BEGIN) {
+          const size_t n = (size_t)(a.Tl + 2) * a.nf * sizeof(double);
+          cudaError_t ce = cudaMemsetAsync(a.p, 0, n, s);
+          if (ce == cudaSuccess) ce = cudaMemsetAsync(a.y, 0, n, s);
+          if (ce != cudaSuccess) return set_error((int)ce, cudaGetErrorString(ce));
+        }
+        const int g = pt_grid(a);
+        reg_pt_precond_kernel<<<g, kPtBlock, 0, s>>>(a, op == SKA_BA_REG_CG_BEGIN ? 1 : 0);
+        if ((rc = check_launch()) != SKA_OK) return rc;
+        return launch_reduce(a.dpart, g, 1, a.sc + SC_DOT, s);
+      }
       const size_t bytes = ((size_t)a.nf + 6 * a.J + a.nS + a.n6) * sizeof(double) * kWarpsPerBlock;
       if ((rc = set_smem(reg_precond_kernel, bytes)) != SKA_OK) return rc;
       if (op == SKA_BA_REG_CG_BEGIN) {
@@ -1083,6 +1301,12 @@ int ba_reg_cg(const SkaBaRegProblem& p, int op, cudaStream_t s) {
       return launch_reduce(a.dpart, a.W, 1, a.sc + SC_DOT, s);
     }
     case SKA_BA_REG_CG_MATVEC: {
+      if (a.free6 == 0) {
+        const int g = pt_grid(a);
+        reg_pt_matvec_kernel<<<g, kPtBlock, 0, s>>>(a);
+        if ((rc = check_launch()) != SKA_OK) return rc;
+        return launch_reduce(a.dpart, g, 1, a.sc + SC_DOT, s);
+      }
       const size_t bytes = ((size_t)a.nf + 3 * a.J) * sizeof(double) * kWarpsPerBlock;
       if ((rc = set_smem(reg_matvec_kernel, bytes)) != SKA_OK) return rc;
       reg_matvec_kernel<<<blocks, 32 * kWarpsPerBlock, bytes, s>>>(a);
