@@ -403,6 +403,8 @@ def run_ba(a, dev, world, rank, barrier, dist):
                            if calib else "points + extrinsics (camera 0 = gauge)"),
             "launches_per_iter": 6,
             "collectives_per_iter": 0 if world == 1 else 2,
+            "exchange": "none (one GPU)" if world == 1 else ("single-CTA push / flag / sum kernel over NVLink peer memory (csrc/ska_peer.cu)"
+                                                            if s.peer is not None else "NCCL all-reduce (torch.distributed)"),
             "cuda_graph": graph,
             "cost_first": hist[0]["cost"],
             "cost_last": s.cost,
@@ -488,6 +490,8 @@ def run_ba_regularised(a, dev, world, rank, barrier, dist, parity_ref):
             "objective": "reprojection + bone_length + pose_temporal + camera_smooth + baseline_reg (configs/vggt.yaml:46-50), per-frame cameras",
             "solver": "matrix-free CG, per-frame Schur-complement preconditioner, relative residual 1e-8", "cg_iters_per_trial": cg,
             "cg_iters_captured": cg_iters, "collectives_per_cg_iter": 0 if world == 1 else 3, "cuda_graph": graph,
+            "exchange": "none (one GPU)" if world == 1 else ("single-CTA push / flag / sum kernels over NVLink peer memory (csrc/ska_peer.cu)"
+                                                            if s.peer is not None else "NCCL (torch.distributed)"),
             "cost_first": hist[0]["cost"], "cost_last": s.cost_value, "terms_last": {k: hist[-1][k] for k in ba_reg.HIST_KEYS[9:14]},
             "accepted": int(sum(acc)), "trials": len(hist), "parity": parity,
         }
@@ -856,6 +860,10 @@ def run_ours(a, out_fd=1):
     if rank == 0:
         os.write(out_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
+        from skiing_analysis_pytorch_b200 import peer
+
+        torch.cuda.synchronize(dev)
+        peer.close_all()
         dist.destroy_process_group()
     return 0
 

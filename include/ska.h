@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SKA_ABI_VERSION 6
+#define SKA_ABI_VERSION 7
 
 #define SKA_OK 0
 #define SKA_EINVAL -1       /* null pointer / bad size / bad enum */
@@ -361,6 +361,37 @@ int ska_ba_reg_linearize_f64(const SkaBaRegProblem* p, void* stream);
 int ska_ba_reg_cg_f64(const SkaBaRegProblem* p, int32_t op, void* stream);
 int ska_ba_reg_apply_f64(const SkaBaRegProblem* p, void* stream);
 int ska_ba_reg_control_f64(const SkaBaRegProblem* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The exchange step of the sharded solvers over NVLink peer memory (SURVEY row e: the NCCL all-reduce of the packed
+ * reduced system / the trial scalars / the CG dot products, and the all-gather of the one-frame halos, replaced by one
+ * single-CTA kernel per exchange).  Every rank pushes its payload into every peer's receive area with plain stores,
+ * publishes a release flag per peer, polls its own flags and sums (all-reduce, fixed rank order: bit-identical on every
+ * rank) or copies (all-gather) the world's payloads.  One process per GPU on one node; fp64 payloads of at most
+ * `slot_doubles`.  Set-up (host, once): ska_peer_alloc a region of ska_peer_region_bytes(world, slot_doubles)
+ * (cudaMalloc: IPC-exportable; zero-filled), ska_peer_export its 64-byte handle, exchange the handles (e.g.
+ * torch.distributed.all_gather_object), ska_peer_import the peers' regions, fill SkaPeerComm:
+ *   recv[r]  = region_r                                     [2][world][slot_doubles] doubles
+ *   flags[r] = (uint64_t*)(region_r + 2 world slot_doubles) [world]
+ *   d_state  = local [2] uint64 (zero): exchange counter, and the number of the first exchange that timed out (0 = none:
+ *              a peer that never arrives makes the kernel give up after 2^poll_limit_log2 polls instead of hanging the GPU)
+ * Every rank must issue the same sequence of exchanges.  Enqueues on `stream`; capturable in a CUDA graph. */
+#define SKA_MAX_PEERS 8
+typedef struct SkaPeerComm {
+  int32_t world, rank, slot_doubles;
+  int32_t poll_limit_log2; /* 0 = default (24) */
+  double* recv[SKA_MAX_PEERS];
+  uint64_t* flags[SKA_MAX_PEERS];
+  uint64_t* d_state;
+} SkaPeerComm;
+size_t ska_peer_region_bytes(int32_t world, int32_t slot_doubles);
+int ska_peer_alloc(size_t bytes, void** d_ptr);
+int ska_peer_free(void* d_ptr);
+int ska_peer_export(void* d_ptr, unsigned char* handle64);
+int ska_peer_import(const unsigned char* handle64, void** d_ptr);
+int ska_peer_close(void* d_ptr);
+int ska_peer_allreduce_f64(const SkaPeerComm* comm, double* d_buf, int32_t n, void* stream);
+int ska_peer_allgather_f64(const SkaPeerComm* comm, const double* d_in, int32_t n, double* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Post-triangulation triage and temporal smoothing (the step right after the path).

@@ -5,7 +5,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_VIEWS = 8
 MAX_BA_VIEWS = 8
 MAX_BONES = 16
@@ -81,6 +81,14 @@ class SkaBaRegProblem(C.Structure):
         ("d_vec", C.c_void_p), ("d_pinv", C.c_void_p), ("d_lfac", C.c_void_p), ("d_sc", C.c_void_p), ("d_sums", C.c_void_p),
         ("d_hist", C.c_void_p), ("hist_rows", C.c_int64), ("d_workspace", C.c_void_p), ("ws_bytes", C.c_size_t),
     ]
+
+
+MAX_PEERS = 8
+
+
+class SkaPeerComm(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("slot_doubles", C.c_int32), ("poll_limit_log2", C.c_int32),
+                ("recv", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("d_state", C.c_void_p)]
 
 
 class SkaFuseParams(C.Structure):

@@ -72,6 +72,14 @@ _SIGS = {
     "ska_ba_reg_cg_f64": (C.c_int, [C.POINTER(_cabi.SkaBaRegProblem), C.c_int32, _vp]),
     "ska_ba_reg_apply_f64": (C.c_int, [C.POINTER(_cabi.SkaBaRegProblem), _vp]),
     "ska_ba_reg_control_f64": (C.c_int, [C.POINTER(_cabi.SkaBaRegProblem), _vp]),
+    "ska_peer_region_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "ska_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "ska_peer_free": (C.c_int, [_vp]),
+    "ska_peer_export": (C.c_int, [_vp, C.c_char_p]),
+    "ska_peer_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ska_peer_close": (C.c_int, [_vp]),
+    "ska_peer_allreduce_f64": (C.c_int, [C.POINTER(_cabi.SkaPeerComm), _vp, C.c_int32, _vp]),
+    "ska_peer_allgather_f64": (C.c_int, [C.POINTER(_cabi.SkaPeerComm), _vp, C.c_int32, _vp, _vp]),
     "ska_fuse_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "ska_fuse_frames_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.POINTER(_cabi.SkaFuseParams), _vp, _vp, _vp, _vp, _vp, _vp,
                                        C.c_size_t, _vp]),

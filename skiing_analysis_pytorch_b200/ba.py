@@ -68,9 +68,14 @@ class LMSequencer:
         return (not self.local_only and torch.distributed.is_available() and torch.distributed.is_initialized()
                 and torch.distributed.get_world_size(self.group) > 1)
 
+    peer = None  # peer.PeerExchange: the exchange over NVLink peer memory instead of NCCL (CUDA engines)
+
     def _allreduce(self, t: torch.Tensor):
         if self._distributed():
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+            if self.peer is not None and self.peer.fits(t):
+                self.peer.all_reduce(t)
+            else:
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
 
     def trial(self):
         """Enqueue one LM trial (accepted or rejected by the controller)."""
@@ -126,7 +131,8 @@ class BundleAdjuster(LMSequencer):
     """
 
     def __init__(self, x2d, conf, K, R0, t0, X0, *, layout: str = "TCJ2", mode: str = "full", lam0: float = 1e-3,
-                 max_iters: int = 64, group=None, force_wide: bool = False, local_only: bool = False, tensor_core: bool = False):
+                 max_iters: int = 64, group=None, force_wide: bool = False, local_only: bool = False, tensor_core: bool = False,
+                 peer_exchange: bool = True):
         self.local_only = bool(local_only)
         if not (x2d.is_cuda and conf.is_cuda and X0.is_cuda):
             raise RuntimeError("x2d, conf and X0 must be CUDA tensors: this package has no CPU path")
@@ -160,6 +166,10 @@ class BundleAdjuster(LMSequencer):
         self.N = T * J
         self.dev = x2d.device
         self.group = group
+        if peer_exchange and self._distributed():
+            from . import peer as _peer
+
+            self.peer = _peer.shared(group, self.dev)  # None where peer memory cannot be mapped: NCCL then
         self.mask = free_mask(Cn, mode)
         self.mode = mode
         self.max_iters = int(max_iters)

@@ -56,9 +56,24 @@ class RegLMSequencer:
             return 1, 0
         return d.get_world_size(self.group), d.get_rank(self.group)
 
+    peer = None  # peer.PeerExchange: exchanges over NVLink peer memory instead of NCCL (CUDA engine)
+
     def _allreduce(self, t):
         if self._world()[0] > 1:
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+            if self.peer is not None and self.peer.fits(t):
+                self.peer.all_reduce(t)
+            else:
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+
+    def _allgather(self, mine):
+        """(world,) + mine.shape <- every rank's `mine`."""
+        world = self._world()[0]
+        flat = torch.empty(world * mine.numel(), dtype=mine.dtype, device=mine.device)
+        if self.peer is not None and self.peer.fits(mine):
+            self.peer.all_gather(flat, mine.reshape(-1))
+        else:
+            torch.distributed.all_gather_into_tensor(flat, mine.reshape(-1), group=self.group)
+        return flat.view((world,) + tuple(mine.shape))
 
     def exchange_halo(self, kind: str):
         """One all-gather of every rank's first / last row; rank r takes rank r-1's last row and rank r+1's first."""
@@ -67,9 +82,7 @@ class RegLMSequencer:
             return
         first, last, halo_prev, halo_next = self.edges(kind)
         mine = torch.stack([first, last]).contiguous()
-        flat = torch.empty(world * mine.numel(), dtype=mine.dtype, device=mine.device)
-        torch.distributed.all_gather_into_tensor(flat, mine.reshape(-1), group=self.group)
-        everyone = flat.view((world,) + tuple(mine.shape))
+        everyone = self._allgather(mine)
         if rank > 0:
             halo_prev.copy_(everyone[rank - 1, 1])
         if rank < world - 1:
@@ -155,7 +168,8 @@ class RegularisedBundleAdjuster(RegLMSequencer):
     torch.distributed is initialised); local_only=True solves this rank's frames alone."""
 
     def __init__(self, x2d, conf, K, R, t, X0, *, mode: str = "pose_only", weights=None, lam0: float = 1e-3, max_iters: int = 64,
-                 cg_iters: int = 64, cg_tol: float = 1e-8, check_every: int = 0, group=None, local_only: bool = False):
+                 cg_iters: int = 64, cg_tol: float = 1e-8, check_every: int = 0, group=None, local_only: bool = False,
+                 peer_exchange: bool = True):
         if mode not in MODES:
             raise ValueError(f"unknown mode {mode!r}; expected one of {MODES}")
         if not (x2d.is_cuda and conf.is_cuda):
@@ -171,6 +185,10 @@ class RegularisedBundleAdjuster(RegLMSequencer):
             raise ValueError("1..8 cameras and at most 96 joints")
         dev = x2d.device
         self.dev, self.group, self.local_only = dev, group, bool(local_only)
+        if peer_exchange and self._world()[0] > 1:
+            from . import peer as _peer
+
+            self.peer = _peer.shared(group, dev)  # None where peer memory cannot be mapped: NCCL then
         self.mode, self.Tl, self.C, self.J = mode, Tl, Cn, J
         self.cg_iters, self.check_every, self.max_iters = int(cg_iters), int(check_every), int(max_iters)
         self.lib = _lib.load()
@@ -253,9 +271,7 @@ class RegularisedBundleAdjuster(RegLMSequencer):
         for e, row in enumerate((1, self.Tl)):
             mine[:, e, :J3] = self.Xh[:, row].reshape(2, -1)
             mine[:, e, J3:] = self.Ch[:, row].reshape(2, -1)
-        flat = torch.empty(world * mine.numel(), dtype=mine.dtype, device=mine.device)
-        torch.distributed.all_gather_into_tensor(flat, mine.reshape(-1), group=self.group)
-        everyone = flat.view((world,) + tuple(mine.shape))
+        everyone = self._allgather(mine)
         if rank > 0:
             src = everyone[rank - 1, :, 1]
             self.Xh[:, 0] = src[:, :J3].view(2, self.J, 3)

@@ -296,6 +296,30 @@ int ska_ba_reg_apply_f64(const SkaBaRegProblem* p, void* stream) { SKA_REG_ENTRY
 int ska_ba_reg_control_f64(const SkaBaRegProblem* p, void* stream) { SKA_REG_ENTRY(ba_reg_control(*p, (cudaStream_t)stream)); }
 #undef SKA_REG_ENTRY
 
+size_t ska_peer_region_bytes(int32_t world, int32_t slot_doubles) {
+  if (world < 1 || world > SKA_MAX_PEERS || slot_doubles < 1) return 0;
+  return (size_t)2 * world * slot_doubles * sizeof(double) + (size_t)world * sizeof(uint64_t);
+}
+int ska_peer_alloc(size_t bytes, void** d_ptr) { return peer_alloc(bytes, d_ptr); }
+int ska_peer_free(void* d_ptr) { return peer_free(d_ptr); }
+int ska_peer_export(void* d_ptr, unsigned char* handle64) {
+  if (d_ptr == nullptr || handle64 == nullptr) return set_error(SKA_EINVAL, "pointers must not be NULL");
+  return peer_export(d_ptr, handle64);
+}
+int ska_peer_import(const unsigned char* handle64, void** d_ptr) {
+  if (d_ptr == nullptr || handle64 == nullptr) return set_error(SKA_EINVAL, "pointers must not be NULL");
+  return peer_import(handle64, d_ptr);
+}
+int ska_peer_close(void* d_ptr) { return peer_close(d_ptr); }
+int ska_peer_allreduce_f64(const SkaPeerComm* comm, double* d_buf, int32_t n, void* stream) {
+  if (comm == nullptr) return set_error(SKA_EINVAL, "comm must not be NULL");
+  return peer_allreduce(*comm, d_buf, n, (cudaStream_t)stream);
+}
+int ska_peer_allgather_f64(const SkaPeerComm* comm, const double* d_in, int32_t n, double* d_out, void* stream) {
+  if (comm == nullptr) return set_error(SKA_EINVAL, "comm must not be NULL");
+  return peer_allgather(*comm, d_in, n, d_out, (cudaStream_t)stream);
+}
+
 int32_t ska_ba_calib_red_doubles(int32_t C) { return C == 2 ? ba_calib_red_size(C) : 0; }
 
 size_t ska_ba_calib_workspace_bytes(int32_t C) {

@@ -59,6 +59,14 @@ int ba_reg_linearize(const SkaBaRegProblem& p, cudaStream_t s);
 int ba_reg_cg(const SkaBaRegProblem& p, int op, cudaStream_t s);
 int ba_reg_apply(const SkaBaRegProblem& p, cudaStream_t s);
 int ba_reg_control(const SkaBaRegProblem& p, cudaStream_t s);
+// exchange over NVLink peer memory (ska_peer.cu)
+int peer_allreduce(const SkaPeerComm& c, double* buf, int n, cudaStream_t s);
+int peer_allgather(const SkaPeerComm& c, const double* in, int n, double* out, cudaStream_t s);
+int peer_alloc(size_t bytes, void** out);
+int peer_free(void* p);
+int peer_export(void* p, unsigned char* handle64);
+int peer_import(const unsigned char* handle64, void** out);
+int peer_close(void* p);
 
 // standalone projection / losses (ska_project.cu, ska_losses.cu)
 int project_cv(const SkaCamera* cams, int V, const float* X, const float* kpts, int64_t T, int J, int layout, float* proj,

@@ -1,0 +1,153 @@
+// ska_peer.cu - the exchange step of the sharded solvers over NVLink peer memory, sm_100a.
+//
+// The only data-path exchange of this library is small and latency-bound: per LM trial the packed reduced camera system
+// (158 .. 1 179 doubles) and 4 trial scalars (csrc/ska_ba.cu), per CG iteration of the regularised LM two dot products
+// and a one-frame halo (csrc/ska_ba_reg.cu).  An NCCL collective costs ~20-30 us for such a payload on 8 GPUs - as much
+// as all the kernels of a config-3 trial together.  Here every rank PUSHES its payload straight into every peer's
+// receive area (plain stores to peer-mapped memory: NVLink / NVSwitch), publishes an arrival flag per peer
+// (st.release.sys after the payload), polls its OWN local flags (ld.acquire.sys) and then sums / copies the world's
+// payloads from its local receive area in fixed rank order - so every rank gets bit-identical results and takes
+// identical accept / reject decisions.  One single-CTA kernel per exchange, no host involvement, capturable in the
+// trial's CUDA graph.
+//
+// Buffers: receive areas are double-buffered by the parity of the exchange counter.  Overwriting area (k+1)&1 of peer P
+// is safe as soon as P's flag for exchange k has been seen: P finished reading exchange k-1 (the same parity) before it
+// pushed exchange k.  Every rank runs the same sequence of exchanges, so the counters agree without being communicated.
+// A flag that never arrives (a dead peer) makes the kernel give up after 2^poll_limit_log2 polls (default 2^24, seconds) and raise an error word the host
+// reads after the solve - it never hangs the GPU.
+//
+// Memory comes from cudaMalloc (exportable with cudaIpcGetMemHandle; one process per GPU) - ska_peer_alloc / export /
+// import below; the host side (peer.py) exchanges the 64-byte handles through torch.distributed once at set-up.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ska_internal.h"
+
+namespace ska {
+namespace {
+
+constexpr int kPeerThreads = 256;
+constexpr int kPeerDefaultPollsLog2 = 24;
+
+struct PeerArgs {
+  int world, rank, slot, n;
+  uint32_t max_polls;
+  double* recv[SKA_MAX_PEERS];    // recv[r]: rank r's receive area [2][world][slot]
+  uint64_t* flags[SKA_MAX_PEERS]; // flags[r]: rank r's arrival flags [world]
+  uint64_t* state;                // local: [0] exchange counter, [1] error word
+  const double* in;
+  double* out;                    // all-reduce: [n] (may alias in); all-gather: [world][n]
+  int gather;
+};
+
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kPeerThreads) peer_exchange_kernel(const PeerArgs a) {
+  __shared__ int s_fail;
+  const uint64_t epoch = a.state[0] + 1;  // this exchange's number (1, 2, ...)
+  const int par = (int)(epoch & 1);
+  if (threadIdx.x == 0) s_fail = 0;
+  // ---- push my payload into slot `rank` of every rank's receive area (my own included: one code path, one summation order)
+  for (int r = 0; r < a.world; ++r) {
+    double* dst = a.recv[r] + ((size_t)par * a.world + a.rank) * a.slot;
+    for (int i = threadIdx.x; i < a.n; i += kPeerThreads) dst[i] = a.in[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < a.world) st_release_sys(a.flags[threadIdx.x] + a.rank, epoch);
+  // ---- wait for the world's payloads (local polling)
+  if (threadIdx.x < a.world) {
+    const uint64_t* f = a.flags[a.rank] + threadIdx.x;
+    uint32_t polls = 0;
+    while (ld_acquire_sys(f) < epoch) {
+      if (++polls > a.max_polls) {
+        s_fail = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const double* mine = a.recv[a.rank] + (size_t)par * a.world * a.slot;
+  if (a.gather) {
+    for (int i = threadIdx.x; i < a.world * a.n; i += kPeerThreads) a.out[i] = mine[(size_t)(i / a.n) * a.slot + (i % a.n)];
+  } else {
+    for (int i = threadIdx.x; i < a.n; i += kPeerThreads) {
+      double s = 0.0;
+      for (int r = 0; r < a.world; ++r) s += mine[(size_t)r * a.slot + i];
+      a.out[i] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.state[0] = epoch;
+    if (s_fail && a.state[1] == 0) a.state[1] = epoch;  // the first exchange that timed out
+  }
+}
+
+int launch_exchange(const SkaPeerComm& c, const double* in, int n, double* out, int gather, cudaStream_t s) {
+  if (c.world < 1 || c.world > SKA_MAX_PEERS || c.rank < 0 || c.rank >= c.world) return set_error(SKA_EINVAL, "bad world / rank");
+  if (n < 0 || n > c.slot_doubles) return set_error(SKA_EINVAL, "payload larger than the peer slot");
+  if (in == nullptr || out == nullptr || c.d_state == nullptr) return set_error(SKA_EINVAL, "null device pointer");
+  PeerArgs a;
+  a.world = c.world, a.rank = c.rank, a.slot = c.slot_doubles, a.n = n;
+  if (c.poll_limit_log2 < 0 || c.poll_limit_log2 > 31) return set_error(SKA_EINVAL, "poll_limit_log2 must be in 0..31");
+  a.max_polls = 1u << (c.poll_limit_log2 ? c.poll_limit_log2 : kPeerDefaultPollsLog2);
+  for (int r = 0; r < SKA_MAX_PEERS; ++r) {
+    a.recv[r] = r < c.world ? c.recv[r] : nullptr;
+    a.flags[r] = r < c.world ? c.flags[r] : nullptr;
+    if (r < c.world && (a.recv[r] == nullptr || a.flags[r] == nullptr)) return set_error(SKA_EINVAL, "null peer pointer");
+  }
+  a.state = c.d_state, a.in = in, a.out = out, a.gather = gather;
+  peer_exchange_kernel<<<1, kPeerThreads, 0, s>>>(a);
+  const cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
+}
+
+}  // namespace
+
+int peer_allreduce(const SkaPeerComm& c, double* buf, int n, cudaStream_t s) { return launch_exchange(c, buf, n, buf, 0, s); }
+int peer_allgather(const SkaPeerComm& c, const double* in, int n, double* out, cudaStream_t s) { return launch_exchange(c, in, n, out, 1, s); }
+
+int peer_alloc(size_t bytes, void** out) {
+  if (out == nullptr || bytes == 0) return set_error(SKA_EINVAL, "bytes > 0 and a result pointer are required");
+  void* p = nullptr;
+  cudaError_t ce = cudaMalloc(&p, bytes);
+  if (ce == cudaSuccess) ce = cudaMemset(p, 0, bytes);
+  if (ce != cudaSuccess) return set_error((int)ce, cudaGetErrorString(ce));
+  *out = p;
+  return SKA_OK;
+}
+int peer_free(void* p) {
+  const cudaError_t ce = cudaFree(p);
+  return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
+}
+int peer_export(void* p, unsigned char* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  const cudaError_t ce = cudaIpcGetMemHandle(&h, p);
+  if (ce != cudaSuccess) return set_error((int)ce, cudaGetErrorString(ce));
+  for (int i = 0; i < 64; ++i) handle64[i] = reinterpret_cast<unsigned char*>(&h)[i];
+  return SKA_OK;
+}
+int peer_import(const unsigned char* handle64, void** out) {
+  cudaIpcMemHandle_t h;
+  for (int i = 0; i < 64; ++i) reinterpret_cast<unsigned char*>(&h)[i] = handle64[i];
+  void* p = nullptr;
+  const cudaError_t ce = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (ce != cudaSuccess) return set_error((int)ce, cudaGetErrorString(ce));
+  *out = p;
+  return SKA_OK;
+}
+int peer_close(void* p) {
+  const cudaError_t ce = cudaIpcCloseMemHandle(p);
+  return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
+}
+
+}  // namespace ska

@@ -102,6 +102,34 @@ def test_argument_errors_without_gpu():
     assert lib.ska_savgol_f32(fake, 10, 51, 9, 2, fake, fake, 1 << 30, None) == -1              # aliasing
 
 
+def test_regularised_ba_argument_errors_without_gpu():
+    """ska_ba_reg_*: validation happens before any CUDA call."""
+    from skiing_analysis_pytorch_b200 import _cabi, _lib
+
+    lib = _lib.load()
+    fake = 256
+
+    def prob(**kw):
+        base = dict(C=2, J=17, n_bones=12, free_mask=0, T_local=10, has_prev=0, has_next=0, d_x2d=fake, d_conf=fake, d_K=fake, d_X=fake,
+                    d_cams=fake, d_vec=fake, d_pinv=fake, d_lfac=None, d_sc=fake, d_sums=fake, d_hist=None, hist_rows=0, d_workspace=fake,
+                    ws_bytes=1 << 30)
+        base.update(kw)
+        p = _cabi.SkaBaRegProblem(**base)
+        for b in range(12):
+            p.bone_i[b], p.bone_j[b] = b, b + 1
+        return p
+
+    assert lib.ska_ba_reg_workspace_bytes(0) == 0 and lib.ska_ba_reg_workspace_bytes(100) >= 100 * 42 * 8
+    assert lib.ska_ba_reg_linearize_f64(None, None) == -1
+    for bad in (dict(C=0), dict(C=9), dict(J=0), dict(J=97), dict(n_bones=17), dict(T_local=0), dict(d_x2d=None), dict(d_sc=None),
+                dict(free_mask=0x3F)):  # free cameras need the Schur factor buffer
+        assert lib.ska_ba_reg_linearize_f64(C.byref(prob(**bad)), None) == -1, bad
+    assert lib.ska_ba_reg_cost_f64(C.byref(prob(ws_bytes=16)), 0, None) == -4
+    p = prob()
+    p.bone_j[3] = 17
+    assert lib.ska_ba_reg_cost_f64(C.byref(p), 0, None) == -1 and b"bone" in lib.ska_last_error()
+
+
 def test_api_refuses_cpu_tensors():
     import torch
 

@@ -151,3 +151,42 @@ def test_run_local_ba_lm_signature_and_modes(cuda):
             assert torch.equal(Ro.cpu(), torch.from_numpy(R)) and torch.equal(to.cpu(), torch.from_numpy(t))
         if mode == "pose_cam_t":
             assert torch.equal(Ro.cpu(), torch.from_numpy(R)) and not torch.equal(to.cpu(), torch.from_numpy(t))
+
+
+@pytest.mark.parametrize("rig,T,J,mode", [("2b", 1, 17, "full"), ("2b", 2, 5, "pose_cam_t"), ("2b", 7, 96, "pose_only"), ("3", 5, 17, "full")])
+def test_edge_shapes(cuda, rig, T, J, mode):
+    """One frame (no temporal / smoothness pairs), a skeleton too small for any bone (J = 5), the largest skeleton (J = 96:
+    three joints per lane), three cameras: trajectories against the exact-solve oracle."""
+    clip, R, t, X0 = lm_reg.make_problem(rig, T, J, cam_jitter=0.01)
+    s = ba_reg.RegularisedBundleAdjuster(torch.from_numpy(clip.x_fm).to(cuda), torch.from_numpy(clip.conf_fm).to(cuda), clip.K, R, t, X0,
+                                         mode=mode, max_iters=8, cg_iters=120)
+    s.run(4)
+    _, _, _, ref = lm_reg.run_lm(X0, R, t, clip.K, clip.x_fm.astype(float), clip.conf_fm.astype(float), num_iters=4, mode=mode)
+    assert _check(s.history, ref, 4) >= 2
+
+
+def test_unobserved_points_and_input_checks(cuda):
+    """A joint nobody observes (all confidences 0) has no reprojection rows: its point block comes from the regularisers
+    alone and the solve stays finite and on the oracle's trajectory.  Bad arguments raise before anything is launched."""
+    clip, R, t, X0 = lm_reg.make_problem("2b", 12, 17, cam_jitter=0.01)
+    conf = clip.conf_fm.copy()
+    conf[:, :, 3] = 0.0
+    conf[5] = 0.0
+    s = ba_reg.RegularisedBundleAdjuster(torch.from_numpy(clip.x_fm).to(cuda), torch.from_numpy(conf).to(cuda), clip.K, R, t, X0, mode="pose_only",
+                                         max_iters=8, cg_iters=60)
+    s.run(4)
+    _, _, _, ref = lm_reg.run_lm(X0, R, t, clip.K, clip.x_fm.astype(float), conf.astype(float), num_iters=4, mode="pose_only")
+    assert _check(s.history, ref, 4) >= 2 and torch.isfinite(s.X).all()
+    x = torch.from_numpy(clip.x_fm).to(cuda)
+    c = torch.from_numpy(clip.conf_fm).to(cuda)
+    with pytest.raises(ValueError):
+        ba_reg.RegularisedBundleAdjuster(x, c, clip.K, R, t, X0, mode="bogus")
+    with pytest.raises(ValueError):
+        ba_reg.RegularisedBundleAdjuster(x, c[:, :1], clip.K, R, t, X0)
+    with pytest.raises(ValueError):
+        ba_reg.RegularisedBundleAdjuster(x, c, clip.K, R[:5], t[:5], X0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ba_reg.RegularisedBundleAdjuster(x.cpu(), c.cpu(), clip.K, R, t, X0)
+    s2 = ba_reg.RegularisedBundleAdjuster(x, c, clip.K, R, t, X0, max_iters=2)
+    with pytest.raises(ValueError, match="history"):
+        s2.run(3)
