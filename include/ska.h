@@ -383,6 +383,8 @@ typedef struct SkaPeerComm {
   double* recv[SKA_MAX_PEERS];
   uint64_t* flags[SKA_MAX_PEERS];
   uint64_t* d_state;
+  const double* d_skip; /* nullable: a device flag that is IDENTICAL on every rank (e.g. the CG convergence flag computed from
+                           all-reduced scalars); non-zero = every rank skips this exchange */
 } SkaPeerComm;
 size_t ska_peer_region_bytes(int32_t world, int32_t slot_doubles);
 int ska_peer_alloc(size_t bytes, void** d_ptr);

@@ -88,7 +88,7 @@ MAX_PEERS = 8
 
 class SkaPeerComm(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("slot_doubles", C.c_int32), ("poll_limit_log2", C.c_int32),
-                ("recv", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("d_state", C.c_void_p)]
+                ("recv", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("d_state", C.c_void_p), ("d_skip", C.c_void_p)]
 
 
 class SkaFuseParams(C.Structure):

@@ -58,19 +58,25 @@ class RegLMSequencer:
 
     peer = None  # peer.PeerExchange: exchanges over NVLink peer memory instead of NCCL (CUDA engine)
 
-    def _allreduce(self, t):
+    cg_done = None  # engines: one-element fp64 device tensor, non-zero once CG has converged (identical on every rank)
+
+    def _allreduce(self, t, in_cg: bool = False):
         if self._world()[0] > 1:
             if self.peer is not None and self.peer.fits(t):
-                self.peer.all_reduce(t)
+                self.peer.all_reduce(t, skip=self.cg_done if in_cg else None)
             else:
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
 
-    def _allgather(self, mine):
+    def _allgather(self, mine, in_cg: bool = False):
         """(world,) + mine.shape <- every rank's `mine`."""
         world = self._world()[0]
-        flat = torch.empty(world * mine.numel(), dtype=mine.dtype, device=mine.device)
+        bufs = self.__dict__.setdefault("_gather_bufs", {})
+        key = (world * mine.numel(), mine.dtype, mine.device)
+        flat = bufs.get(key)
+        if flat is None:  # persistent: a skipped exchange (CG converged) leaves the previous, valid contents in place
+            flat = bufs[key] = torch.zeros(key[0], dtype=mine.dtype, device=mine.device)
         if self.peer is not None and self.peer.fits(mine):
-            self.peer.all_gather(flat, mine.reshape(-1))
+            self.peer.all_gather(flat, mine.reshape(-1), skip=self.cg_done if in_cg else None)
         else:
             torch.distributed.all_gather_into_tensor(flat, mine.reshape(-1), group=self.group)
         return flat.view((world,) + tuple(mine.shape))
@@ -82,7 +88,7 @@ class RegLMSequencer:
             return
         first, last, halo_prev, halo_next = self.edges(kind)
         mine = torch.stack([first, last]).contiguous()
-        everyone = self._allgather(mine)
+        everyone = self._allgather(mine, in_cg=(kind == "p"))
         if rank > 0:
             halo_prev.copy_(everyone[rank - 1, 1])
         if rank < world - 1:
@@ -101,12 +107,14 @@ class RegLMSequencer:
         for it in range(self.cg_iters):
             if self.check_every and not self._capturing and it and it % self.check_every == 0 and self.converged():
                 break
+            # inside the loop the convergence flag is current (set by INIT / BETA from all-reduced scalars, identical on every
+            # rank): once it is up the kernels return at once and the peer exchanges are skipped on every rank alike
             self.exchange_halo("p")
             self.cg(k.BA_REG_CG_MATVEC)
-            self._allreduce(self.dot)
+            self._allreduce(self.dot, in_cg=True)
             self.cg(k.BA_REG_CG_ALPHA)
             self.cg(k.BA_REG_CG_UPDATE)
-            self._allreduce(self.dot)
+            self._allreduce(self.dot, in_cg=True)
             self.cg(k.BA_REG_CG_BETA)
             self.cg(k.BA_REG_CG_DIR)
         self.apply()
@@ -222,6 +230,7 @@ class RegularisedBundleAdjuster(RegLMSequencer):
         self.sc = torch.zeros(_cabi.BA_REG_SC_DOUBLES, **f64)
         self.sums = torch.zeros((2, _cabi.BA_REG_SUMS), **f64)
         self.dot = self.sc[_cabi.BA_REG_SC_DOT: _cabi.BA_REG_SC_DOT + 1]
+        self.cg_done = self.sc[13:14]
         self.hist = torch.zeros((self.max_iters, _cabi.BA_REG_HIST_DOUBLES), **f64)
         with torch.cuda.device(dev):
             ws = int(self.lib.ska_ba_reg_workspace_bytes(Tl))

@@ -29,7 +29,7 @@ namespace ska {
 namespace {
 
 constexpr int kWarpsPerBlock = 4;
-constexpr int kMaxGridBlocks = 148 * 4;
+constexpr int kMaxGridBlocks = 148 * 8;
 constexpr int NS = SKA_BA_REG_SUMS;  // 40
 constexpr double kZMin = 1e-6;
 
@@ -302,7 +302,7 @@ __device__ __forceinline__ int up6(int r, int c) { return r * 6 - r * (r - 1) / 
 // ------------------------------------------------------------------------------------------------ linearisation
 // per frame: gradient g = J^T r, D = diag(J^T J), r_cg = -g, the damped point blocks' inverses, and the Cholesky factor of
 // the frame's Schur complement S = Dc - sum_j W_j^T Dp_j^-1 W_j  (Dp, Dc: damped diagonal blocks of J^T J).
-__global__ void __launch_bounds__(32 * kWarpsPerBlock) reg_linearize_kernel(const RegArgs a) {
+__global__ void __launch_bounds__(32 * kWarpsPerBlock, 4) reg_linearize_kernel(const RegArgs a) {
   extern __shared__ double smem_d[];
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wid = blockIdx.x * kWarpsPerBlock + wl;
   const size_t per_warp = (size_t)a.J * 12 + (size_t)a.C * 28 + a.nf + a.nS + (size_t)96 * a.n6;
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) reg_linearize_kernel(cons
 
 // ------------------------------------------------------------------------------------------------ matrix-vector product
 // y = (J^T J + lam D) p for the frame's row; partial dot p . y
-__global__ void __launch_bounds__(32 * kWarpsPerBlock) reg_matvec_kernel(const RegArgs a) {
+__global__ void __launch_bounds__(32 * kWarpsPerBlock, 4) reg_matvec_kernel(const RegArgs a) {
   extern __shared__ double smem_d[];
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wid = blockIdx.x * kWarpsPerBlock + wl;
   const double* sc = a.sc;
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) reg_matvec_kernel(const R
 
 // ------------------------------------------------------------------------------------------------ CG update + preconditioner
 // x += alpha p, r -= alpha y, z = M^-1 r (the frame's system through its Schur complement); partial dot r . z
-__global__ void __launch_bounds__(32 * kWarpsPerBlock) reg_precond_kernel(const RegArgs a, int first) {
+__global__ void __launch_bounds__(32 * kWarpsPerBlock, 4) reg_precond_kernel(const RegArgs a, int first) {
   extern __shared__ double smem_d[];
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wid = blockIdx.x * kWarpsPerBlock + wl;
   const double* sc = a.sc;

@@ -35,6 +35,7 @@ struct PeerArgs {
   double* recv[SKA_MAX_PEERS];    // recv[r]: rank r's receive area [2][world][slot]
   uint64_t* flags[SKA_MAX_PEERS]; // flags[r]: rank r's arrival flags [world]
   uint64_t* state;                // local: [0] exchange counter, [1] error word
+  const double* skip;             // nullable: a device flag every rank holds identically; non-zero = this exchange is not needed
   const double* in;
   double* out;                    // all-reduce: [n] (may alias in); all-gather: [world][n]
   int gather;
@@ -51,6 +52,7 @@ __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
 
 __global__ void __launch_bounds__(kPeerThreads) peer_exchange_kernel(const PeerArgs a) {
   __shared__ int s_fail;
+  if (a.skip != nullptr && *a.skip != 0.0) return;  // e.g. the CG loop has converged: every rank skips, the counters stay in step
   const uint64_t epoch = a.state[0] + 1;  // this exchange's number (1, 2, ...)
   const int par = (int)(epoch & 1);
   if (threadIdx.x == 0) s_fail = 0;
@@ -105,6 +107,7 @@ int launch_exchange(const SkaPeerComm& c, const double* in, int n, double* out, 
     if (r < c.world && (a.recv[r] == nullptr || a.flags[r] == nullptr)) return set_error(SKA_EINVAL, "null peer pointer");
   }
   a.state = c.d_state, a.in = in, a.out = out, a.gather = gather;
+  a.skip = c.d_skip;
   peer_exchange_kernel<<<1, kPeerThreads, 0, s>>>(a);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));

@@ -64,7 +64,8 @@ class PeerExchange:
         flag_off = 2 * self.world * self.slot * 8
         self.comm = _cabi.SkaPeerComm(world=self.world, rank=self.rank, slot_doubles=self.slot, poll_limit_log2=0,
                                       recv=(C.c_void_p * 8)(*ptrs), flags=(C.c_void_p * 8)(*[p + flag_off for p in ptrs]),
-                                      d_state=self.state.data_ptr())
+                                      d_state=self.state.data_ptr(), d_skip=None)
+        self._skip_comms = {}
         d.barrier(group=group)  # every rank has mapped every region before the first push
 
     @classmethod
@@ -91,18 +92,29 @@ class PeerExchange:
     def fits(self, t: torch.Tensor) -> bool:
         return t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() <= self.slot
 
-    def all_reduce(self, t: torch.Tensor):
+    def _comm(self, skip):
+        """skip: None, or a one-element fp64 device tensor that is identical on every rank; non-zero = skip the exchange."""
+        if skip is None:
+            return self.comm
+        key = skip.data_ptr()
+        if key not in self._skip_comms:
+            c = _cabi.SkaPeerComm.from_buffer_copy(self.comm)
+            c.d_skip = key
+            self._skip_comms[key] = c
+        return self._skip_comms[key]
+
+    def all_reduce(self, t: torch.Tensor, skip=None):
         """In-place sum over the ranks (fixed rank order: bit-identical everywhere)."""
         with torch.cuda.device(self.dev):
-            _lib.check(self.lib.ska_peer_allreduce_f64(C.byref(self.comm), C.c_void_p(t.data_ptr()), t.numel(), self._stream()))
+            _lib.check(self.lib.ska_peer_allreduce_f64(C.byref(self._comm(skip)), C.c_void_p(t.data_ptr()), t.numel(), self._stream()))
 
-    def all_gather(self, out: torch.Tensor, inp: torch.Tensor):
+    def all_gather(self, out: torch.Tensor, inp: torch.Tensor, skip=None):
         """out (world, n) <- every rank's inp (n,)."""
         if out.numel() != self.world * inp.numel():
             raise ValueError("out must hold world x inp.numel() elements")
         with torch.cuda.device(self.dev):
-            _lib.check(self.lib.ska_peer_allgather_f64(C.byref(self.comm), C.c_void_p(inp.data_ptr()), inp.numel(), C.c_void_p(out.data_ptr()),
-                                                       self._stream()))
+            _lib.check(self.lib.ska_peer_allgather_f64(C.byref(self._comm(skip)), C.c_void_p(inp.data_ptr()), inp.numel(),
+                                                       C.c_void_p(out.data_ptr()), self._stream()))
 
     def check(self):
         """Synchronises; raises if an exchange gave up waiting for a peer."""

@@ -209,3 +209,14 @@ def test_regularised_sequencer_needs_its_halo(tmp_path):
     _, _, _, hist = lm_reg.run_lm(X0, R, t, clip.K, clip.x_fm.astype(float), clip.conf_fm.astype(float), num_iters=4, mode="full")
     np.testing.assert_allclose([h["trial_cost"] for h in s.history], [h["trial_cost"] for h in hist], rtol=1e-7)
     assert [h["accepted"] for h in s.history] == [h["accepted"] for h in hist]
+
+
+def test_peer_exchange_is_optional_plumbing():
+    """No process group (or a single rank): peer.shared returns None and the sequencers keep their collectives - the peer
+    kernels are an accelerator of the exchange step, not a requirement (tests/test_peer_gpu.py exercises them on a GPU)."""
+    from skiing_analysis_pytorch_b200 import peer
+    from skiing_analysis_pytorch_b200.ba import LMSequencer
+    from skiing_analysis_pytorch_b200.ba_reg import RegLMSequencer
+
+    assert peer.PeerExchange.create(None, "cuda:0") is None
+    assert LMSequencer.peer is None and RegLMSequencer.peer is None
