@@ -10,6 +10,7 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 300 python tools/tri_bench.py 2>&1 | tee gpurun_out/tri_bench_$TAG.log
 timeout 300 python tools/ba_reg_bench.py 2>&1 | tee gpurun_out/ba_reg_bench_$TAG.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:tri_|ba_|reg_|fuse_|rigid_|ema_kernel|project|loss_|stats|post_|sg_|adam|so3|flag_counts|bone|pose_temporal|camera_|baseline" -c 3000 --csv --log-file gpurun_out/launches_ska_$TAG.csv python bench.py --steps 3 --warmup 3 --ba-iters 6 --no-cpu-baseline > gpurun_out/ncu_launch_ska_$TAG.log 2>&1
+python tools/launch_summary.py gpurun_out/launches_ska_$TAG.csv > gpurun_out/${TAG}_launches_summary.txt 2>&1
 full() {  # name, kernel regex, skip, command...
   local name=$1 k=$2 skip=$3; shift 3
   timeout 300 ncu --set full --clock-control none --import-source on -k "regex:$k" -s $skip -c 1 -o gpurun_out/prof_${name}_$TAG -f "$@" > gpurun_out/ncu_${name}_$TAG.log 2>&1
