@@ -138,3 +138,16 @@ def test_rotation_round_trip_is_what_cv2_applies():
         rvec, _ = cv2.Rodrigues(R)
         assert np.abs(f(R) - cv2.Rodrigues(rvec.astype(np.float64))[0]).max() < 1e-9
     assert np.array_equal(f(np.eye(3)), np.eye(3))
+
+
+def test_host_pipeline_chunk_schedule_partitions_the_clip():
+    from skiing_analysis_pytorch_b200.api import chunk_schedule
+
+    for T, chunk, ramp in ((1_000_000, 131072, 0), (1_000_000, 131072, 8192), (1_000_000, 65536, 4096), (5000, 1024, 8192), (100, 65536, 0),
+                           (300_000, 131072, 8192), (1, 1, 0), (17, 5, 2)):
+        sch = chunk_schedule(T, chunk, ramp)
+        assert sch[0][0] == 0 and sch[-1][1] == T and all(a[1] == b[0] for a, b in zip(sch, sch[1:]))
+        assert all(0 < b - a <= chunk for a, b in sch)
+    up = [b - a for a, b in chunk_schedule(1_000_000, 131072, 8192)]
+    assert up[:4] == [8192, 16384, 32768, 65536] and up[-4:] == [65536, 32768, 16384, 8192]
+    assert chunk_schedule(0, 1024) == []
