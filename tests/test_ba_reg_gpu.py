@@ -190,3 +190,16 @@ def test_unobserved_points_and_input_checks(cuda):
     s2 = ba_reg.RegularisedBundleAdjuster(x, c, clip.K, R, t, X0, max_iters=2)
     with pytest.raises(ValueError, match="history"):
         s2.run(3)
+
+
+@pytest.mark.parametrize("name", ["c3_pose", "c3_full", "c5_pose"])
+def test_bitwise_repeatable(cuda, name):
+    """Every reduction is a fixed-order sum (per-warp partial rows, column reduction): two runs are bit-identical - which a
+    data race between the warp-cooperative steps of a frame would break."""
+    runs = []
+    for _ in range(2):
+        s, *_ = _problem(name, cuda)
+        s.run(4)
+        runs.append((s.history, s.X.clone(), s.t.clone()))
+    assert runs[0][0] == runs[1][0]
+    assert torch.equal(runs[0][1], runs[1][1]) and torch.equal(runs[0][2], runs[1][2])
