@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SKA_ABI_VERSION 7
+#define SKA_ABI_VERSION 8
 
 #define SKA_OK 0
 #define SKA_EINVAL -1       /* null pointer / bad size / bad enum */
@@ -214,6 +214,7 @@ int ska_baseline_reg_f64(const double* d_R, const double* d_t, int64_t T, int32_
                                    Same reduced system to fp32 accuracy; measured SLOWER than the CUDA-core form on B200
                                    (26.3 vs 23.1 ms per 1M x 70 x 8 linearisation, profiles/README.md), hence opt-in */
 
+struct SkaPeerComm;
 typedef struct SkaBaProblem {
   int32_t C;            /* cameras, 2..SKA_MAX_VIEWS */
   int32_t J;            /* joints per frame */
@@ -234,6 +235,10 @@ typedef struct SkaBaProblem {
   void* d_workspace;    /* >= ska_ba_workspace_bytes(C), 16-byte aligned */
   size_t ws_bytes;
   int64_t hist_rows;    /* rows of d_hist: trials beyond them still run, their history row is dropped */
+  const struct SkaPeerComm* peer; /* nullable HOST pointer (see "exchange step" below).  Non-NULL: ska_ba_solve_f64 /
+                           ska_ba_calib_solve_f64 all-reduce d_red over NVLink peer memory in their prologue and
+                           ska_ba_control_f64 / ska_ba_calib_control_f64 do the same for d_red2 - exchange and consumer are ONE
+                           kernel, and the caller runs no collective: linearize -> solve -> backsub -> control */
 } SkaBaProblem;
 
 int32_t ska_ba_red_doubles(int32_t C);

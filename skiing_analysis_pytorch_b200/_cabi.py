@@ -5,7 +5,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_VIEWS = 8
 MAX_BA_VIEWS = 8
 MAX_BONES = 16
@@ -62,6 +62,7 @@ class SkaBaProblem(C.Structure):
         ("d_workspace", C.c_void_p),
         ("ws_bytes", C.c_size_t),
         ("hist_rows", C.c_int64),
+        ("peer", C.c_void_p),
     ]
 
 

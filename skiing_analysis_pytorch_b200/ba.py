@@ -77,13 +77,17 @@ class LMSequencer:
             else:
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
 
+    fused_exchange = False  # CUDA engines with a peer exchange: solve / control all-reduce their payloads in their own prologue
+
     def trial(self):
         """Enqueue one LM trial (accepted or rejected by the controller)."""
         self.linearize()
-        self._allreduce(self.red)
+        if not self.fused_exchange:
+            self._allreduce(self.red)
         self.solve()
         self.backsub()
-        self._allreduce(self.red2)
+        if not self.fused_exchange:
+            self._allreduce(self.red2)
         self.control()
 
     def run(self, num_iters: int, graph: bool = False):
@@ -132,7 +136,7 @@ class BundleAdjuster(LMSequencer):
 
     def __init__(self, x2d, conf, K, R0, t0, X0, *, layout: str = "TCJ2", mode: str = "full", lam0: float = 1e-3,
                  max_iters: int = 64, group=None, force_wide: bool = False, local_only: bool = False, tensor_core: bool = False,
-                 peer_exchange: bool = True):
+                 peer_exchange: bool = True, fuse_exchange: bool = True):
         self.local_only = bool(local_only)
         if not (x2d.is_cuda and conf.is_cuda and X0.is_cuda):
             raise RuntimeError("x2d, conf and X0 must be CUDA tensors: this package has no CPU path")
@@ -204,7 +208,9 @@ class BundleAdjuster(LMSequencer):
             d_cams=self.cams.data_ptr(), d_ctrl=self.ctrl.data_ptr(), d_red=self.red.data_ptr(),
             d_red2=self.red2.data_ptr(), d_delta=self.delta.data_ptr(), d_hist=self.hist.data_ptr(),
             d_workspace=self.ws.data_ptr(), ws_bytes=ws, hist_rows=self.max_iters,
+            peer=(C.addressof(self.peer.comm) if fuse_exchange and self.peer is not None and self.peer.slot >= 1024 else None),
         )
+        self.fused_exchange = bool(self.prob.peer)
         self._graph = None
         self.iters_done = 0
         # global sum of confidences (loss.py:94 denominator), computed on the device

@@ -26,6 +26,7 @@
 
 #include "ska_ba.cuh"
 #include "ska_internal.h"
+#include "ska_peer.cuh"
 
 namespace ska {
 
@@ -303,13 +304,16 @@ __global__ void __launch_bounds__(kBaBlock) ba_sum_kernel(const float* __restric
 // reduced camera system: one CTA, fp64
 constexpr int kMaxN = 6 * (SKA_MAX_VIEWS - 1);
 
-__global__ void __launch_bounds__(256) ba_solve_kernel(int C, uint64_t free_mask, const double* __restrict__ red, double* cams,
-                                                      double* ctrl, double* delta) {
+// `peer.world > 1`: the all-reduce of the packed reduced system over NVLink peer memory is this kernel's prologue (push /
+// release flag / poll / rank-ordered sum, ska_peer.cuh) - exchange and solve are one launch.
+__global__ void __launch_bounds__(256) ba_solve_kernel(int C, uint64_t free_mask, double* red, double* cams, double* ctrl, double* delta,
+                                                      const PeerDev peer) {
   __shared__ double S[kMaxN][kMaxN + 1];
   __shared__ double b[kMaxN], hd[kMaxN], gc[kMaxN], d[kMaxN];
   __shared__ int s_ok;
   const RedLayout L(C);
   const int n = L.n, tid = threadIdx.x, nt = blockDim.x;
+  if (peer.world > 1) peer_exchange_block(peer, red, L.size, red, 0);
   const double lam = ctrl[kCtrlLambda];
   const double s = 1.0 / (ctrl[kCtrlSumConf] + 1e-6);
   if (tid == 0) s_ok = 1;
@@ -405,9 +409,10 @@ __global__ void __launch_bounds__(256) ba_solve_kernel(int C, uint64_t free_mask
 // LM controller: gain ratio, accept / reject, Nielsen update (oracle/lm.py run_lm / nielsen_update).
 // One warp: lane 0 decides, all lanes commit the trial cameras (a serial copy by one thread is a
 // chain of dependent global round trips - microseconds in a 100-microsecond trial).
-__global__ void __launch_bounds__(32) ba_control_kernel(int C, const double* __restrict__ red, const double* __restrict__ red2,
-                                                        double* cams, double* ctrl, double* hist, int64_t hist_rows) {
+__global__ void __launch_bounds__(32) ba_control_kernel(int C, const double* red, double* red2, double* cams, double* ctrl, double* hist,
+                                                        int64_t hist_rows, const PeerDev peer) {
   if (blockIdx.x != 0) return;
+  if (peer.world > 1) peer_exchange_block(peer, red2, SKA_BA_RED2_DOUBLES, red2, 0);  // the trial scalars' all-reduce, fused
   const RedLayout L(C);
   int accepted_i = 0;
   if (threadIdx.x == 0) {
@@ -550,14 +555,30 @@ int ba_backsub(const SkaBaProblem& in, cudaStream_t s) {
   }
 }
 
-int ba_solve(int C, uint64_t free_mask, const double* red, double* cams, double* ctrl, double* delta, void* stream) {
-  ba_solve_kernel<<<1, C <= 3 ? 64 : 256, 0, (cudaStream_t)stream>>>(C, free_mask, red, cams, ctrl, delta);
+static int peer_of(const SkaPeerComm* c, int payload, PeerDev& pd) {
+  pd.world = 0;
+  if (c == nullptr) return SKA_OK;
+  const int rc = peer_fill(*c, pd);
+  if (rc != SKA_OK) return rc;
+  if (payload > c->slot_doubles) return set_error(SKA_EINVAL, "reduced system larger than the peer slot");
+  return SKA_OK;
+}
+
+int ba_solve(int C, uint64_t free_mask, double* red, double* cams, double* ctrl, double* delta, const SkaPeerComm* peer, void* stream) {
+  PeerDev pd;
+  const int rc = peer_of(peer, ba_red_size(C), pd);
+  if (rc != SKA_OK) return rc;
+  ba_solve_kernel<<<1, C <= 3 ? 64 : 256, 0, (cudaStream_t)stream>>>(C, free_mask, red, cams, ctrl, delta, pd);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }
 
-int ba_control(int C, const double* red, const double* red2, double* cams, double* ctrl, double* hist, int64_t hist_rows, void* stream) {
-  ba_control_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(C, red, red2, cams, ctrl, hist, hist_rows);
+int ba_control(int C, const double* red, double* red2, double* cams, double* ctrl, double* hist, int64_t hist_rows, const SkaPeerComm* peer,
+               void* stream) {
+  PeerDev pd;
+  const int rc = peer_of(peer, SKA_BA_RED2_DOUBLES, pd);
+  if (rc != SKA_OK) return rc;
+  ba_control_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(C, red, red2, cams, ctrl, hist, hist_rows, pd);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }

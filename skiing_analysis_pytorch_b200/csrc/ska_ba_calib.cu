@@ -32,6 +32,7 @@
 #include "ska_ba.cuh"
 #include "ska_ba_calib.cuh"
 #include "ska_internal.h"
+#include "ska_peer.cuh"
 
 namespace ska {
 
@@ -380,13 +381,14 @@ __global__ void __launch_bounds__(kBaBlock, 2) ba_calib_backsub_kernel(const Cal
 // reduced camera system with the intrinsics prior: one CTA, fp64
 constexpr int kCalibMaxN = kCalibP * 2 - 6;  // C == 2
 
-__global__ void __launch_bounds__(256) ba_calib_solve_kernel(int C, uint64_t free_mask, const double* __restrict__ red,
-                                                            const double* __restrict__ prior, double* cams, double* ctrl, double* delta) {
+__global__ void __launch_bounds__(256) ba_calib_solve_kernel(int C, uint64_t free_mask, double* red, const double* __restrict__ prior,
+                                                            double* cams, double* ctrl, double* delta, const PeerDev peer) {
   __shared__ double S[kCalibMaxN][kCalibMaxN + 1];
   __shared__ double b[kCalibMaxN], hd[kCalibMaxN], g[kCalibMaxN], d[kCalibMaxN];
   __shared__ int s_ok;
   const CalibLayout L(C);
   const int n = L.n, tid = threadIdx.x, nt = blockDim.x;
+  if (peer.world > 1) peer_exchange_block(peer, red, L.size, red, 0);  // the reduced system's all-reduce, fused (ska_peer.cuh)
   const double lam = ctrl[kCtrlLambda];
   const double s = 1.0 / (ctrl[kCtrlSumConf] + 1e-6);
   if (tid == 0) s_ok = 1;
@@ -504,9 +506,10 @@ __global__ void __launch_bounds__(256) ba_calib_solve_kernel(int C, uint64_t fre
 }
 
 // LM controller (oracle/lm_calib.py run_lm): as ba_control_kernel with the prior inside the cost.
-__global__ void __launch_bounds__(32) ba_calib_control_kernel(int C, const double* __restrict__ red, const double* __restrict__ red2,
-                                                              double* cams, double* ctrl, double* hist, int64_t hist_rows) {
+__global__ void __launch_bounds__(32) ba_calib_control_kernel(int C, const double* red, double* red2, double* cams, double* ctrl,
+                                                              double* hist, int64_t hist_rows, const PeerDev peer) {
   if (blockIdx.x != 0) return;
+  if (peer.world > 1) peer_exchange_block(peer, red2, SKA_BA_RED2_DOUBLES, red2, 0);
   const CalibLayout L(C);
   int accepted_i = 0;
   if (threadIdx.x == 0) {
@@ -640,16 +643,33 @@ int ba_calib_backsub(const SkaBaProblem& in, cudaStream_t s) {
   return launch_reduce(a.partials, (int)grid, kCalibBackAcc, in.d_red2, s);
 }
 
-int ba_calib_solve(int C, uint64_t free_mask, const double* red, const double* prior, double* cams, double* ctrl, double* delta, void* stream) {
+static int calib_peer_of(const SkaPeerComm* c, int payload, PeerDev& pd) {
+  pd.world = 0;
+  if (c == nullptr) return SKA_OK;
+  const int rc = peer_fill(*c, pd);
+  if (rc != SKA_OK) return rc;
+  if (payload > c->slot_doubles) return set_error(SKA_EINVAL, "reduced system larger than the peer slot");
+  return SKA_OK;
+}
+
+int ba_calib_solve(int C, uint64_t free_mask, double* red, const double* prior, double* cams, double* ctrl, double* delta,
+                   const SkaPeerComm* peer, void* stream) {
   if (C != 2) return unsupported_c();
-  ba_calib_solve_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(C, free_mask, red, prior, cams, ctrl, delta);
+  PeerDev pd;
+  const int rc = calib_peer_of(peer, ba_calib_red_size(C), pd);
+  if (rc != SKA_OK) return rc;
+  ba_calib_solve_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(C, free_mask, red, prior, cams, ctrl, delta, pd);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }
 
-int ba_calib_control(int C, const double* red, const double* red2, double* cams, double* ctrl, double* hist, int64_t hist_rows, void* stream) {
+int ba_calib_control(int C, const double* red, double* red2, double* cams, double* ctrl, double* hist, int64_t hist_rows,
+                     const SkaPeerComm* peer, void* stream) {
   if (C != 2) return unsupported_c();
-  ba_calib_control_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(C, red, red2, cams, ctrl, hist, hist_rows);
+  PeerDev pd;
+  const int rc = calib_peer_of(peer, SKA_BA_RED2_DOUBLES, pd);
+  if (rc != SKA_OK) return rc;
+  ba_calib_control_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(C, red, red2, cams, ctrl, hist, hist_rows, pd);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }

@@ -267,7 +267,7 @@ int ska_ba_linearize_f32(const SkaBaProblem* p, void* stream) {
 int ska_ba_solve_f64(const SkaBaProblem* p, uint64_t free_mask, void* stream) {
   const int rc = check_problem(p, false);
   if (rc != SKA_OK) return rc;
-  return ba_solve(p->C, free_mask, p->d_red, p->d_cams, p->d_ctrl, p->d_delta, stream);
+  return ba_solve(p->C, free_mask, p->d_red, p->d_cams, p->d_ctrl, p->d_delta, p->peer, stream);
 }
 
 int ska_ba_backsub_f32(const SkaBaProblem* p, void* stream) {
@@ -279,7 +279,7 @@ int ska_ba_backsub_f32(const SkaBaProblem* p, void* stream) {
 int ska_ba_control_f64(const SkaBaProblem* p, void* stream) {
   const int rc = check_problem(p, false);
   if (rc != SKA_OK) return rc;
-  return ba_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, p->hist_rows, stream);
+  return ba_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, p->hist_rows, p->peer, stream);
 }
 
 size_t ska_ba_reg_workspace_bytes(int64_t T_local) { return T_local < 1 ? 0 : ba_reg_workspace_bytes(T_local); }
@@ -336,7 +336,7 @@ int ska_ba_calib_linearize_f32(const SkaBaProblem* p, void* stream) {
 int ska_ba_calib_solve_f64(const SkaBaProblem* p, uint64_t free_mask, const double* d_prior, void* stream) {
   const int rc = check_problem(p, false);
   if (rc != SKA_OK) return rc;
-  return ba_calib_solve(p->C, free_mask, p->d_red, d_prior, p->d_cams, p->d_ctrl, p->d_delta, stream);
+  return ba_calib_solve(p->C, free_mask, p->d_red, d_prior, p->d_cams, p->d_ctrl, p->d_delta, p->peer, stream);
 }
 
 int ska_ba_calib_backsub_f32(const SkaBaProblem* p, void* stream) {
@@ -348,7 +348,7 @@ int ska_ba_calib_backsub_f32(const SkaBaProblem* p, void* stream) {
 int ska_ba_calib_control_f64(const SkaBaProblem* p, void* stream) {
   const int rc = check_problem(p, false);
   if (rc != SKA_OK) return rc;
-  return ba_calib_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, p->hist_rows, stream);
+  return ba_calib_control(p->C, p->d_red, p->d_red2, p->d_cams, p->d_ctrl, p->d_hist, p->hist_rows, p->peer, stream);
 }
 
 size_t ska_fuse_workspace_bytes(int64_t T) { return fuse_workspace_bytes(T); }

@@ -40,16 +40,18 @@ int ba_sum(const float* x, int64_t n, double* out, void* workspace, size_t ws_by
 int ba_linearize(const SkaBaProblem& p, cudaStream_t s);
 int ba_linearize_wide(const SkaBaProblem& p, cudaStream_t s);
 int ba_backsub(const SkaBaProblem& p, cudaStream_t s);
-int ba_solve(int C, uint64_t free_mask, const double* red, double* cams, double* ctrl, double* delta, void* stream);
-int ba_control(int C, const double* red, const double* red2, double* cams, double* ctrl, double* hist, int64_t hist_rows, void* stream);
+int ba_solve(int C, uint64_t free_mask, double* red, double* cams, double* ctrl, double* delta, const SkaPeerComm* peer, void* stream);
+int ba_control(int C, const double* red, double* red2, double* cams, double* ctrl, double* hist, int64_t hist_rows, const SkaPeerComm* peer,
+               void* stream);
 int launch_reduce(const double* partials, int rows, int ncol, double* out, cudaStream_t s);
 // calibrating bundle adjustment: free intrinsics + distortion (ska_ba_calib.cu)
 int ba_calib_red_size(int C);
 int ba_calib_linearize(const SkaBaProblem& p, cudaStream_t s);
 int ba_calib_backsub(const SkaBaProblem& p, cudaStream_t s);
-int ba_calib_solve(int C, uint64_t free_mask, const double* red, const double* prior, double* cams, double* ctrl, double* delta,
-                   void* stream);
-int ba_calib_control(int C, const double* red, const double* red2, double* cams, double* ctrl, double* hist, int64_t hist_rows, void* stream);
+int ba_calib_solve(int C, uint64_t free_mask, double* red, const double* prior, double* cams, double* ctrl, double* delta,
+                   const SkaPeerComm* peer, void* stream);
+int ba_calib_control(int C, const double* red, double* red2, double* cams, double* ctrl, double* hist, int64_t hist_rows,
+                     const SkaPeerComm* peer, void* stream);
 
 // regularised LM over the full configured objective, per-frame cameras (ska_ba_reg.cu)
 size_t ba_reg_workspace_bytes(int64_t T_local);

@@ -22,93 +22,41 @@
 #include <stdint.h>
 
 #include "ska_internal.h"
+#include "ska_peer.cuh"
 
 namespace ska {
-namespace {
 
-constexpr int kPeerThreads = 256;
-constexpr int kPeerDefaultPollsLog2 = 24;
-
-struct PeerArgs {
-  int world, rank, slot, n;
-  uint32_t max_polls;
-  double* recv[SKA_MAX_PEERS];    // recv[r]: rank r's receive area [2][world][slot]
-  uint64_t* flags[SKA_MAX_PEERS]; // flags[r]: rank r's arrival flags [world]
-  uint64_t* state;                // local: [0] exchange counter, [1] error word
-  const double* skip;             // nullable: a device flag every rank holds identically; non-zero = this exchange is not needed
-  const double* in;
-  double* out;                    // all-reduce: [n] (may alias in); all-gather: [world][n]
-  int gather;
-};
-
-__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
-  uint64_t v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__global__ void __launch_bounds__(kPeerThreads) peer_exchange_kernel(const PeerArgs a) {
-  __shared__ int s_fail;
-  if (a.skip != nullptr && *a.skip != 0.0) return;  // e.g. the CG loop has converged: every rank skips, the counters stay in step
-  const uint64_t epoch = a.state[0] + 1;  // this exchange's number (1, 2, ...)
-  const int par = (int)(epoch & 1);
-  if (threadIdx.x == 0) s_fail = 0;
-  // ---- push my payload into slot `rank` of every rank's receive area (my own included: one code path, one summation order)
-  for (int r = 0; r < a.world; ++r) {
-    double* dst = a.recv[r] + ((size_t)par * a.world + a.rank) * a.slot;
-    for (int i = threadIdx.x; i < a.n; i += kPeerThreads) dst[i] = a.in[i];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < a.world) st_release_sys(a.flags[threadIdx.x] + a.rank, epoch);
-  // ---- wait for the world's payloads (local polling)
-  if (threadIdx.x < a.world) {
-    const uint64_t* f = a.flags[a.rank] + threadIdx.x;
-    uint32_t polls = 0;
-    while (ld_acquire_sys(f) < epoch) {
-      if (++polls > a.max_polls) {
-        s_fail = 1;
-        break;
-      }
-    }
-  }
-  __syncthreads();
-  const double* mine = a.recv[a.rank] + (size_t)par * a.world * a.slot;
-  if (a.gather) {
-    for (int i = threadIdx.x; i < a.world * a.n; i += kPeerThreads) a.out[i] = mine[(size_t)(i / a.n) * a.slot + (i % a.n)];
-  } else {
-    for (int i = threadIdx.x; i < a.n; i += kPeerThreads) {
-      double s = 0.0;
-      for (int r = 0; r < a.world; ++r) s += mine[(size_t)r * a.slot + i];
-      a.out[i] = s;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    a.state[0] = epoch;
-    if (s_fail && a.state[1] == 0) a.state[1] = epoch;  // the first exchange that timed out
-  }
-}
-
-int launch_exchange(const SkaPeerComm& c, const double* in, int n, double* out, int gather, cudaStream_t s) {
+int peer_fill(const SkaPeerComm& c, PeerDev& a) {
   if (c.world < 1 || c.world > SKA_MAX_PEERS || c.rank < 0 || c.rank >= c.world) return set_error(SKA_EINVAL, "bad world / rank");
-  if (n < 0 || n > c.slot_doubles) return set_error(SKA_EINVAL, "payload larger than the peer slot");
-  if (in == nullptr || out == nullptr || c.d_state == nullptr) return set_error(SKA_EINVAL, "null device pointer");
-  PeerArgs a;
-  a.world = c.world, a.rank = c.rank, a.slot = c.slot_doubles, a.n = n;
+  if (c.slot_doubles < 1 || c.d_state == nullptr) return set_error(SKA_EINVAL, "slot_doubles >= 1 and d_state are required");
   if (c.poll_limit_log2 < 0 || c.poll_limit_log2 > 31) return set_error(SKA_EINVAL, "poll_limit_log2 must be in 0..31");
-  a.max_polls = 1u << (c.poll_limit_log2 ? c.poll_limit_log2 : kPeerDefaultPollsLog2);
+  a.world = c.world, a.rank = c.rank, a.slot = c.slot_doubles;
+  a.max_polls = 1u << (c.poll_limit_log2 ? c.poll_limit_log2 : 24);
   for (int r = 0; r < SKA_MAX_PEERS; ++r) {
     a.recv[r] = r < c.world ? c.recv[r] : nullptr;
     a.flags[r] = r < c.world ? c.flags[r] : nullptr;
     if (r < c.world && (a.recv[r] == nullptr || a.flags[r] == nullptr)) return set_error(SKA_EINVAL, "null peer pointer");
   }
-  a.state = c.d_state, a.in = in, a.out = out, a.gather = gather;
+  a.state = c.d_state;
   a.skip = c.d_skip;
-  peer_exchange_kernel<<<1, kPeerThreads, 0, s>>>(a);
+  return SKA_OK;
+}
+
+namespace {
+
+constexpr int kPeerThreads = 256;
+
+__global__ void __launch_bounds__(kPeerThreads) peer_exchange_kernel(const PeerDev a, const double* in, int n, double* out, int gather) {
+  peer_exchange_block(a, in, n, out, gather);
+}
+
+int launch_exchange(const SkaPeerComm& c, const double* in, int n, double* out, int gather, cudaStream_t s) {
+  PeerDev a;
+  const int rc = peer_fill(c, a);
+  if (rc != SKA_OK) return rc;
+  if (n < 0 || n > c.slot_doubles) return set_error(SKA_EINVAL, "payload larger than the peer slot");
+  if (in == nullptr || out == nullptr) return set_error(SKA_EINVAL, "null device pointer");
+  peer_exchange_kernel<<<1, kPeerThreads, 0, s>>>(a, in, n, out, gather);
   const cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? SKA_OK : set_error((int)ce, cudaGetErrorString(ce));
 }

@@ -103,8 +103,8 @@ def main():
         R0, t0 = synth.perturb_cameras(d["R"], d["t"], seed=1)
         X0 = api.triangulate_reproject(d["x2d"].permute(1, 0, 2, 3).contiguous(), d["K"], R0, t0, want=("X",)).X
         res = {}
-        for use in (True, False):
-            s = ba.BundleAdjuster(d["x2d"], d["conf"], d["K"], R0, t0, X0, max_iters=iters + 8, peer_exchange=use)
+        for use in (True, "kernel", False):
+            s = ba.BundleAdjuster(d["x2d"], d["conf"], d["K"], R0, t0, X0, max_iters=iters + 8, peer_exchange=bool(use), fuse_exchange=use is True)
             s.run(4, graph=True)
             torch.cuda.synchronize()
             dist.barrier()
@@ -118,7 +118,8 @@ def main():
             res[use] = (float(t.item()), [h["cost"] for h in s.history], [h["accepted"] for h in s.history])
             del s
         dc = max(abs(x - y) / y for x, y in zip(res[True][1], res[False][1]))
-        say(f"  {name} ({T} x {J} over {world} GPUs): {res[True][0]:.4f} ms per trial with the peer exchange, {res[False][0]:.4f} with NCCL; "
+        say(f"  {name} ({T} x {J} over {world} GPUs): {res[True][0]:.4f} ms per trial with the peer exchange fused into solve / control, "
+            f"{res['kernel'][0]:.4f} with stand-alone exchange kernels, {res[False][0]:.4f} with NCCL; "
             f"cost trajectories agree to {dc:.1e}, decisions equal {res[True][2] == res[False][2]}")
         ok = ok and dc < 1e-9
         del d, X0
