@@ -358,6 +358,9 @@ typedef struct SkaBaRegProblem {
   int64_t hist_rows;
   void* d_workspace;
   size_t ws_bytes;
+  const struct SkaPeerComm* peer; /* nullable HOST pointer: non-NULL = ska_ba_reg_finish_cost_f64 all-reduces d_sums[which] and
+                                     ska_ba_reg_cg_f64(INIT / ALPHA / BETA) all-reduce d_sc[DOT] over NVLink peer memory in their own
+                                     prologue (the caller then runs no collective for them; the halo all-gathers stay the caller's) */
 } SkaBaRegProblem;
 size_t ska_ba_reg_workspace_bytes(int64_t T_local);
 int ska_ba_reg_cost_f64(const SkaBaRegProblem* p, int32_t which, void* stream);

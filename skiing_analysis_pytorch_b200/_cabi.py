@@ -80,7 +80,7 @@ class SkaBaRegProblem(C.Structure):
         ("bone_i", C.c_int32 * 16), ("bone_j", C.c_int32 * 16),
         ("d_x2d", C.c_void_p), ("d_conf", C.c_void_p), ("d_K", C.c_void_p), ("d_X", C.c_void_p), ("d_cams", C.c_void_p),
         ("d_vec", C.c_void_p), ("d_pinv", C.c_void_p), ("d_lfac", C.c_void_p), ("d_sc", C.c_void_p), ("d_sums", C.c_void_p),
-        ("d_hist", C.c_void_p), ("hist_rows", C.c_int64), ("d_workspace", C.c_void_p), ("ws_bytes", C.c_size_t),
+        ("d_hist", C.c_void_p), ("hist_rows", C.c_int64), ("d_workspace", C.c_void_p), ("ws_bytes", C.c_size_t), ("peer", C.c_void_p),
     ]
 
 

@@ -58,6 +58,7 @@ class RegLMSequencer:
 
     peer = None  # peer.PeerExchange: exchanges over NVLink peer memory instead of NCCL (CUDA engine)
 
+    fused_exchange = False  # CUDA engine with a peer exchange: finish_cost / the CG scalar kernels all-reduce in their own prologue
     cg_done = None  # engines: one-element fp64 device tensor, non-zero once CG has converged (identical on every rank)
 
     def _allreduce(self, t, in_cg: bool = False):
@@ -100,8 +101,10 @@ class RegLMSequencer:
     def trial(self):
         k = _cabi
         self.linearize()
+        fused = self.fused_exchange
         self.cg(k.BA_REG_CG_BEGIN)
-        self._allreduce(self.dot)
+        if not fused:
+            self._allreduce(self.dot)
         self.cg(k.BA_REG_CG_INIT)
         self.cg(k.BA_REG_CG_DIR)
         for it in range(self.cg_iters):
@@ -111,23 +114,27 @@ class RegLMSequencer:
             # rank): once it is up the kernels return at once and the peer exchanges are skipped on every rank alike
             self.exchange_halo("p")
             self.cg(k.BA_REG_CG_MATVEC)
-            self._allreduce(self.dot, in_cg=True)
+            if not fused:
+                self._allreduce(self.dot, in_cg=True)
             self.cg(k.BA_REG_CG_ALPHA)
             self.cg(k.BA_REG_CG_UPDATE)
-            self._allreduce(self.dot, in_cg=True)
+            if not fused:
+                self._allreduce(self.dot, in_cg=True)
             self.cg(k.BA_REG_CG_BETA)
             self.cg(k.BA_REG_CG_DIR)
         self.apply()
         self.exchange_halo("trial")
         self.cost(1)
-        self._allreduce(self.sums[1])
+        if not fused:
+            self._allreduce(self.sums[1])
         self.finish_cost(1)
         self.control()
 
     def setup_cost(self):
         self.exchange_halo("current")
         self.cost(0)
-        self._allreduce(self.sums[0])
+        if not self.fused_exchange:
+            self._allreduce(self.sums[0])
         self.finish_cost(0)
 
     def run(self, num_iters: int, graph: bool = False):
@@ -177,7 +184,7 @@ class RegularisedBundleAdjuster(RegLMSequencer):
 
     def __init__(self, x2d, conf, K, R, t, X0, *, mode: str = "pose_only", weights=None, lam0: float = 1e-3, max_iters: int = 64,
                  cg_iters: int = 64, cg_tol: float = 1e-8, check_every: int = 0, group=None, local_only: bool = False,
-                 peer_exchange: bool = True):
+                 peer_exchange: bool = True, fuse_exchange: bool = True):
         if mode not in MODES:
             raise ValueError(f"unknown mode {mode!r}; expected one of {MODES}")
         if not (x2d.is_cuda and conf.is_cuda):
@@ -255,7 +262,9 @@ class RegularisedBundleAdjuster(RegLMSequencer):
             bone_i=(C.c_int32 * 16)(*[b[0] for b in bones]), bone_j=(C.c_int32 * 16)(*[b[1] for b in bones]),
             d_x2d=P(self.x2d), d_conf=P(self.conf), d_K=P(self.K), d_X=P(self.Xh), d_cams=P(self.Ch), d_vec=P(self.vec),
             d_pinv=P(self.pinv), d_lfac=P(self.lfac), d_sc=P(self.sc), d_sums=P(self.sums), d_hist=P(self.hist),
-            hist_rows=self.max_iters, d_workspace=P(self.ws), ws_bytes=ws)
+            hist_rows=self.max_iters, d_workspace=P(self.ws), ws_bytes=ws,
+            peer=(C.addressof(self.peer.comm) if fuse_exchange and self.peer is not None else None))
+        self.fused_exchange = bool(self.prob.peer)
         self._edge_stage = {"x": torch.empty((2, 2, 3 * J + 12 * Cn), **f64)}
         self.iters_done = 0
         self._graph = None

@@ -24,6 +24,7 @@
 
 #include "ska_ba.cuh"
 #include "ska_internal.h"
+#include "ska_peer.cuh"
 
 namespace ska {
 namespace {
@@ -237,7 +238,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) reg_cost_kernel(const Reg
 }
 
 // after the all-reduce of the sums: the weighted terms, F, and (for the current point) the detached means
-__global__ void reg_finish_cost_kernel(const RegArgs a, int which) {
+__global__ void reg_finish_cost_kernel(const RegArgs a, int which, const PeerDev peer) {
+  if (peer.world > 1) peer_exchange_block(peer, a.sums + which * NS, NS, a.sums + which * NS, 0);  // the sums' all-reduce, fused
   if (threadIdx.x != 0) return;
   double* sc = a.sc;
   const double* s = a.sums + which * NS;
@@ -864,7 +866,8 @@ __global__ void reg_dir_kernel(const RegArgs a) {
 }
 
 // the scalar recurrences of CG, after the all-reduce of the dot in SC_DOT
-__global__ void reg_scalar_kernel(const RegArgs a, int stage) {
+__global__ void reg_scalar_kernel(const RegArgs a, int stage, const PeerDev peer) {
+  if (peer.world > 1) peer_exchange_block(peer, a.sc + SC_DOT, 1, a.sc + SC_DOT, 0);  // the dot product's all-reduce, fused
   if (threadIdx.x != 0) return;
   double* sc = a.sc;
   const double v = sc[SC_DOT];
@@ -1248,7 +1251,15 @@ int ba_reg_finish_cost(const SkaBaRegProblem& p, int which, cudaStream_t s) {
   RegArgs a;
   const int rc = fill(p, a);
   if (rc != SKA_OK) return rc;
-  reg_finish_cost_kernel<<<1, 32, 0, s>>>(a, which ? 1 : 0);
+  PeerDev pd;
+  pd.world = 0;
+  if (p.peer != nullptr) {
+    const int rp = peer_fill(*p.peer, pd);
+    if (rp != SKA_OK) return rp;
+    if (p.peer->slot_doubles < NS) return set_error(SKA_EINVAL, "peer slot smaller than the sums row");
+    pd.skip = nullptr;
+  }
+  reg_finish_cost_kernel<<<1, 32, 0, s>>>(a, which ? 1 : 0, pd);
   return check_launch();
 }
 
@@ -1322,9 +1333,17 @@ int ba_reg_cg(const SkaBaRegProblem& p, int op, cudaStream_t s) {
     }
     case SKA_BA_REG_CG_INIT:
     case SKA_BA_REG_CG_ALPHA:
-    case SKA_BA_REG_CG_BETA:
-      reg_scalar_kernel<<<1, 32, 0, s>>>(a, op);
+    case SKA_BA_REG_CG_BETA: {
+      PeerDev pd;
+      pd.world = 0;
+      if (p.peer != nullptr) {
+        if ((rc = peer_fill(*p.peer, pd)) != SKA_OK) return rc;
+        // inside the CG loop the convergence flag is current and identical on every rank: converged = every rank skips
+        pd.skip = op == SKA_BA_REG_CG_INIT ? nullptr : a.sc + SC_DONE;
+      }
+      reg_scalar_kernel<<<1, 32, 0, s>>>(a, op, pd);
       return check_launch();
+    }
     default:
       return set_error(SKA_EINVAL, "unknown CG operation");
   }
