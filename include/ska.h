@@ -373,14 +373,15 @@ int ska_ba_reg_control_f64(const SkaBaRegProblem* p, void* stream);
 /* ------------------------------------------------------------------------------------------------
  * The exchange step of the sharded solvers over NVLink peer memory (SURVEY row e: the NCCL all-reduce of the packed
  * reduced system / the trial scalars / the CG dot products, and the all-gather of the one-frame halos, replaced by one
- * single-CTA kernel per exchange).  Every rank pushes its payload into every peer's receive area with plain stores,
- * publishes a release flag per peer, polls its own flags and sums (all-reduce, fixed rank order: bit-identical on every
+ * single-CTA kernel per exchange).  Every rank pushes its payload into every peer's receive area with plain 8-byte stores
+ * (each word tagged with the exchange number), polls its own words and sums (all-reduce, fixed rank order: bit-identical on every
  * rank) or copies (all-gather) the world's payloads.  One process per GPU on one node; fp64 payloads of at most
  * `slot_doubles`.  Set-up (host, once): ska_peer_alloc a region of ska_peer_region_bytes(world, slot_doubles)
  * (cudaMalloc: IPC-exportable; zero-filled), ska_peer_export its 64-byte handle, exchange the handles (e.g.
  * torch.distributed.all_gather_object), ska_peer_import the peers' regions, fill SkaPeerComm:
- *   recv[r]  = region_r                                     [2][world][slot_doubles] doubles
- *   flags[r] = (uint64_t*)(region_r + 2 world slot_doubles) [world]
+ *   recv[r]  = region_r   [2][world][slot_doubles][2] 64-bit words: every double travels as {low half | exchange number} and
+ *              {high half | exchange number}, so a word is its own arrival flag (no fence, no separate flag round trip)
+ *   flags[r] = unused (reserved)
  *   d_state  = local [2] uint64 (zero): exchange counter, and the number of the first exchange that timed out (0 = none:
  *              a peer that never arrives makes the kernel give up after 2^poll_limit_log2 polls instead of hanging the GPU)
  * Every rank must issue the same sequence of exchanges.  Enqueues on `stream`; capturable in a CUDA graph. */

@@ -298,7 +298,7 @@ int ska_ba_reg_control_f64(const SkaBaRegProblem* p, void* stream) { SKA_REG_ENT
 
 size_t ska_peer_region_bytes(int32_t world, int32_t slot_doubles) {
   if (world < 1 || world > SKA_MAX_PEERS || slot_doubles < 1) return 0;
-  return (size_t)2 * world * slot_doubles * sizeof(double) + (size_t)world * sizeof(uint64_t);
+  return (size_t)2 * world * slot_doubles * 2 * sizeof(uint64_t);  // [parity][sender][slot] x two tagged 64-bit words per double
 }
 int ska_peer_alloc(size_t bytes, void** d_ptr) { return peer_alloc(bytes, d_ptr); }
 int ska_peer_free(void* d_ptr) { return peer_free(d_ptr); }

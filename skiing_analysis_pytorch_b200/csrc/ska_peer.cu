@@ -2,19 +2,18 @@
 //
 // The only data-path exchange of this library is small and latency-bound: per LM trial the packed reduced camera system
 // (158 .. 1 179 doubles) and 4 trial scalars (csrc/ska_ba.cu), per CG iteration of the regularised LM two dot products
-// and a one-frame halo (csrc/ska_ba_reg.cu).  An NCCL collective costs ~20-30 us for such a payload on 8 GPUs - as much
+// and a one-frame halo (csrc/ska_ba_reg.cu).  An NCCL collective costs ~20-35 us for such a payload on 8 GPUs - as much
 // as all the kernels of a config-3 trial together.  Here every rank PUSHES its payload straight into every peer's
-// receive area (plain stores to peer-mapped memory: NVLink / NVSwitch), publishes an arrival flag per peer
-// (st.release.sys after the payload), polls its OWN local flags (ld.acquire.sys) and then sums / copies the world's
-// payloads from its local receive area in fixed rank order - so every rank gets bit-identical results and takes
-// identical accept / reject decisions.  One single-CTA kernel per exchange, no host involvement, capturable in the
-// trial's CUDA graph.
+// receive area (plain 8-byte stores to peer-mapped memory: NVLink / NVSwitch), every 64-bit word carrying half a double
+// and the number of the exchange, so that a word is its own arrival flag (ska_peer.cuh); the receiver spins on its OWN
+// local words and sums / copies the world's payloads in fixed rank order - every rank gets bit-identical results and
+// takes identical accept / reject decisions.  One single CTA per exchange, no host involvement, capturable in the trial's
+// CUDA graph; the single-CTA consumer kernels (solve, control, CG scalars) run the exchange as their own prologue.
 //
-// Buffers: receive areas are double-buffered by the parity of the exchange counter.  Overwriting area (k+1)&1 of peer P
-// is safe as soon as P's flag for exchange k has been seen: P finished reading exchange k-1 (the same parity) before it
-// pushed exchange k.  Every rank runs the same sequence of exchanges, so the counters agree without being communicated.
-// A flag that never arrives (a dead peer) makes the kernel give up after 2^poll_limit_log2 polls (default 2^24, seconds) and raise an error word the host
-// reads after the solve - it never hangs the GPU.
+// Buffers: receive areas are double-buffered by the parity of the exchange counter.  Every rank runs the same sequence of
+// exchanges, so the counters agree without being communicated.  A word that never arrives (a dead peer) makes the kernel
+// give up after 2^poll_limit_log2 polls (default 2^24, seconds) and raise an error word the host reads after the solve - it
+// never hangs the GPU.
 //
 // Memory comes from cudaMalloc (exportable with cudaIpcGetMemHandle; one process per GPU) - ska_peer_alloc / export /
 // import below; the host side (peer.py) exchanges the 64-byte handles through torch.distributed once at set-up.
@@ -33,9 +32,8 @@ int peer_fill(const SkaPeerComm& c, PeerDev& a) {
   a.world = c.world, a.rank = c.rank, a.slot = c.slot_doubles;
   a.max_polls = 1u << (c.poll_limit_log2 ? c.poll_limit_log2 : 24);
   for (int r = 0; r < SKA_MAX_PEERS; ++r) {
-    a.recv[r] = r < c.world ? c.recv[r] : nullptr;
-    a.flags[r] = r < c.world ? c.flags[r] : nullptr;
-    if (r < c.world && (a.recv[r] == nullptr || a.flags[r] == nullptr)) return set_error(SKA_EINVAL, "null peer pointer");
+    a.recv[r] = r < c.world ? reinterpret_cast<uint64_t*>(c.recv[r]) : nullptr;
+    if (r < c.world && a.recv[r] == nullptr) return set_error(SKA_EINVAL, "null peer pointer");
   }
   a.state = c.d_state;
   a.skip = c.d_skip;

@@ -1,6 +1,6 @@
 // ska_peer.cuh - the peer-memory exchange as a device function, so that a single-CTA consumer kernel (the reduced-system
-// solve, the LM controller) performs its own all-reduce in its prologue: push / release flag / poll / rank-ordered sum
-// and the solve are ONE kernel (protocol and buffers: ska_peer.cu).
+// solve, the LM controller) performs its own all-reduce in its prologue: push / poll / rank-ordered sum and the solve are
+// ONE kernel (buffers: ska_peer.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,61 +12,77 @@ namespace ska {
 struct PeerDev {
   int world, rank, slot;
   uint32_t max_polls;
-  double* recv[SKA_MAX_PEERS];     // recv[r]: rank r's receive area [2][world][slot]
-  uint64_t* flags[SKA_MAX_PEERS];  // flags[r]: rank r's arrival flags [world]
+  uint64_t* recv[SKA_MAX_PEERS];   // recv[r]: rank r's receive area [2][world][slot][2] 64-bit words (see below)
   uint64_t* state;                 // local: [0] exchange counter, [1] first exchange that timed out
   const double* skip;              // nullable device flag, identical on every rank: non-zero = skip
 };
 
 int peer_fill(const SkaPeerComm& c, PeerDev& a);  // validates; world == 0 in `a` means "no exchange"
 
-__device__ __forceinline__ void peer_st_release_sys(uint64_t* p, uint64_t v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t peer_ld_acquire_sys(const uint64_t* p) {
+// Every double travels as TWO 64-bit words {low half | number of the exchange} and {high half | number of the exchange}: an
+// aligned 8-byte store is delivered whole, so the word IS its own arrival flag - the receiver spins on the words it is
+// about to sum until they carry this exchange's number.  No fence, no separate flag round trip (one NVLink flight
+// instead of payload -> __threadfence_system -> flag), at twice the (tiny) payload.
+__device__ __forceinline__ void peer_st_word(uint64_t* p, uint64_t v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ uint64_t peer_ld_word(const uint64_t* p) {
   uint64_t v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ double peer_wait_double(const uint64_t* w, uint32_t tag, uint32_t max_polls, int& fail) {
+  uint64_t lo, hi;
+  uint32_t polls = 0;
+  while ((uint32_t)((lo = peer_ld_word(w)) >> 32) != tag) {
+    if (++polls > max_polls) {
+      fail = 1;
+      break;
+    }
+  }
+  polls = 0;
+  while ((uint32_t)((hi = peer_ld_word(w + 1)) >> 32) != tag) {
+    if (++polls > max_polls) {
+      fail = 1;
+      break;
+    }
+  }
+  return __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+}
 
-// Called by EVERY thread of a single CTA (any block size >= world).  in / out may alias for the all-reduce.  Ends with a
-// CTA barrier: afterwards every thread sees `out`.
+// Called by EVERY thread of a single CTA.  in / out may alias for the all-reduce.  Ends with a CTA barrier: afterwards every
+// thread sees `out`.  Areas alternate with the parity of the exchange number: overwriting parity k+1 of a peer is safe once
+// its words of exchange k have been seen - it finished reading exchange k-1 (the same parity) before it pushed k.
 __device__ inline void peer_exchange_block(const PeerDev& a, const double* in, int n, double* out, int gather) {
   __shared__ int s_fail;
   if (a.skip != nullptr && *a.skip != 0.0) return;  // every rank holds the same flag: all skip, the counters stay in step
   const int tid = threadIdx.x, nt = blockDim.x;
   const uint64_t epoch = a.state[0] + 1;  // this exchange's number (1, 2, ...)
+  const uint32_t tag = (uint32_t)epoch;
   const int par = (int)(epoch & 1);
   if (tid == 0) s_fail = 0;
-  // push my payload into slot `rank` of every rank's receive area (my own included: one code path, one summation order)
-  for (int r = 0; r < a.world; ++r) {
-    double* dst = a.recv[r] + ((size_t)par * a.world + a.rank) * a.slot;
-    for (int i = tid; i < n; i += nt) dst[i] = in[i];
-  }
-  __threadfence_system();
   __syncthreads();
-  if (tid < a.world) peer_st_release_sys(a.flags[tid] + a.rank, epoch);
-  if (tid < a.world) {  // wait for the world's payloads: local polling
-    const uint64_t* f = a.flags[a.rank] + tid;
-    uint32_t polls = 0;
-    while (peer_ld_acquire_sys(f) < epoch) {
-      if (++polls > a.max_polls) {
-        s_fail = 1;
-        break;
-      }
+  // push my payload into slot `rank` of every rank's receive area (my own included: one code path, one summation order)
+  for (int i = tid; i < n; i += nt) {
+    const uint64_t bits = (uint64_t)__double_as_longlong(in[i]);
+    const uint64_t lo = (bits & 0xffffffffull) | ((uint64_t)tag << 32), hi = (bits >> 32) | ((uint64_t)tag << 32);
+    for (int r = 0; r < a.world; ++r) {
+      uint64_t* dst = a.recv[r] + (((size_t)par * a.world + a.rank) * a.slot + i) * 2;
+      peer_st_word(dst, lo);
+      peer_st_word(dst + 1, hi);
     }
   }
-  __syncthreads();
-  const double* mine = a.recv[a.rank] + (size_t)par * a.world * a.slot;
+  // collect: every word is waited for where it is used
+  int fail = 0;
+  const uint64_t* mine = a.recv[a.rank] + (size_t)par * a.world * a.slot * 2;
   if (gather) {
-    for (int i = tid; i < a.world * n; i += nt) out[i] = mine[(size_t)(i / n) * a.slot + (i % n)];
+    for (int i = tid; i < a.world * n; i += nt) out[i] = peer_wait_double(mine + ((size_t)(i / n) * a.slot + (i % n)) * 2, tag, a.max_polls, fail);
   } else {
     for (int i = tid; i < n; i += nt) {
       double s = 0.0;
-      for (int r = 0; r < a.world; ++r) s += mine[(size_t)r * a.slot + i];
+      for (int r = 0; r < a.world; ++r) s += peer_wait_double(mine + ((size_t)r * a.slot + i) * 2, tag, a.max_polls, fail);
       out[i] = s;
     }
   }
+  if (fail) s_fail = 1;
   __syncthreads();
   if (tid == 0) {
     a.state[0] = epoch;

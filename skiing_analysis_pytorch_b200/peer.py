@@ -61,9 +61,8 @@ class PeerExchange:
                     self._imported.append(p)
                     ptrs[r] = p.value
         self.state = torch.zeros(2, dtype=torch.int64, device=self.dev)
-        flag_off = 2 * self.world * self.slot * 8
         self.comm = _cabi.SkaPeerComm(world=self.world, rank=self.rank, slot_doubles=self.slot, poll_limit_log2=0,
-                                      recv=(C.c_void_p * 8)(*ptrs), flags=(C.c_void_p * 8)(*[p + flag_off for p in ptrs]),
+                                      recv=(C.c_void_p * 8)(*ptrs), flags=(C.c_void_p * 8)(),
                                       d_state=self.state.data_ptr(), d_skip=None)
         self._skip_comms = {}
         d.barrier(group=group)  # every rank has mapped every region before the first push

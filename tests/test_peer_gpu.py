@@ -17,9 +17,8 @@ def _comms(world, slot, dev, poll_limit_log2=0):
     regions = [torch.zeros(n // 8, dtype=torch.float64, device=dev) for _ in range(world)]
     states = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
     ptrs = [r.data_ptr() for r in regions]
-    off = 2 * world * slot * 8
     comms = [_cabi.SkaPeerComm(world=world, rank=r, slot_doubles=slot, poll_limit_log2=poll_limit_log2, recv=(C.c_void_p * 8)(*ptrs),
-                               flags=(C.c_void_p * 8)(*[p + off for p in ptrs]), d_state=states[r].data_ptr()) for r in range(world)]
+                               d_state=states[r].data_ptr()) for r in range(world)]
     return lib, comms, regions, states
 
 
@@ -68,4 +67,4 @@ def test_argument_checks(cuda):
     assert lib.ska_peer_allreduce_f64(None, C.c_void_p(x.data_ptr()), 4, None) == -1
     bad = _cabi.SkaPeerComm(world=9, rank=0, slot_doubles=16)
     assert lib.ska_peer_allreduce_f64(C.byref(bad), C.c_void_p(x.data_ptr()), 4, None) == -1
-    assert lib.ska_peer_region_bytes(0, 16) == 0 and lib.ska_peer_region_bytes(2, 16) == 2 * 2 * 16 * 8 + 16
+    assert lib.ska_peer_region_bytes(0, 16) == 0 and lib.ska_peer_region_bytes(2, 16) == 2 * 2 * 16 * 16
