@@ -29,23 +29,50 @@ __device__ __forceinline__ uint64_t peer_ld_word(const uint64_t* p) {
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ double peer_join(uint64_t lo, uint64_t hi) { return __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull))); }
+// one double: both words are loaded together (independent loads), re-read until both carry this exchange's number
 __device__ __forceinline__ double peer_wait_double(const uint64_t* w, uint32_t tag, uint32_t max_polls, int& fail) {
   uint64_t lo, hi;
   uint32_t polls = 0;
-  while ((uint32_t)((lo = peer_ld_word(w)) >> 32) != tag) {
+  for (;;) {
+    lo = peer_ld_word(w);
+    hi = peer_ld_word(w + 1);
+    if ((uint32_t)(lo >> 32) == tag && (uint32_t)(hi >> 32) == tag) break;
     if (++polls > max_polls) {
       fail = 1;
       break;
     }
   }
-  polls = 0;
-  while ((uint32_t)((hi = peer_ld_word(w + 1)) >> 32) != tag) {
+  return peer_join(lo, hi);
+}
+// element i of every rank: the 2 x world words are loaded in ONE batch of independent loads per attempt (polling them one
+// after the other costs a local-L2 round trip each: 16 dependent ones at 8 ranks), then summed in rank order
+__device__ __forceinline__ double peer_wait_sum(const uint64_t* mine, int world, int slot, int i, uint32_t tag, uint32_t max_polls, int& fail) {
+  uint64_t w[2 * SKA_MAX_PEERS];
+  uint32_t polls = 0;
+  for (;;) {
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < SKA_MAX_PEERS; ++r)
+      if (r < world) {
+        const uint64_t* q = mine + ((size_t)r * slot + i) * 2;
+        w[2 * r] = peer_ld_word(q);
+        w[2 * r + 1] = peer_ld_word(q + 1);
+      }
+#pragma unroll
+    for (int r = 0; r < SKA_MAX_PEERS; ++r)
+      if (r < world) ok = ok && (uint32_t)(w[2 * r] >> 32) == tag && (uint32_t)(w[2 * r + 1] >> 32) == tag;
+    if (ok) break;
     if (++polls > max_polls) {
       fail = 1;
       break;
     }
   }
-  return __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+  double s = 0.0;
+#pragma unroll
+  for (int r = 0; r < SKA_MAX_PEERS; ++r)
+    if (r < world) s += peer_join(w[2 * r], w[2 * r + 1]);
+  return s;
 }
 
 // Called by EVERY thread of a single CTA.  in / out may alias for the all-reduce.  Ends with a CTA barrier: afterwards every
@@ -76,11 +103,7 @@ __device__ inline void peer_exchange_block(const PeerDev& a, const double* in, i
   if (gather) {
     for (int i = tid; i < a.world * n; i += nt) out[i] = peer_wait_double(mine + ((size_t)(i / n) * a.slot + (i % n)) * 2, tag, a.max_polls, fail);
   } else {
-    for (int i = tid; i < n; i += nt) {
-      double s = 0.0;
-      for (int r = 0; r < a.world; ++r) s += peer_wait_double(mine + ((size_t)r * a.slot + i) * 2, tag, a.max_polls, fail);
-      out[i] = s;
-    }
+    for (int i = tid; i < n; i += nt) out[i] = peer_wait_sum(mine, a.world, a.slot, i, tag, a.max_polls, fail);
   }
   if (fail) s_fail = 1;
   __syncthreads();
