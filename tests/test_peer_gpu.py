@@ -68,3 +68,58 @@ def test_argument_checks(cuda):
     bad = _cabi.SkaPeerComm(world=9, rank=0, slot_doubles=16)
     assert lib.ska_peer_allreduce_f64(C.byref(bad), C.c_void_p(x.data_ptr()), 4, None) == -1
     assert lib.ska_peer_region_bytes(0, 16) == 0 and lib.ska_peer_region_bytes(2, 16) == 2 * 2 * 16 * 16
+
+
+def test_skip_flag_leaves_the_counters_in_step(cuda):
+    """d_skip: a device flag every rank holds identically (the CG convergence flag); non-zero = every rank skips the exchange."""
+    lib, comms, regions, states = _comms(2, 16, cuda)
+    skip = torch.ones(1, dtype=torch.float64, device=cuda)
+    x = torch.full((4,), 3.0, dtype=torch.float64, device=cuda)
+    c0 = _cabi.SkaPeerComm.from_buffer_copy(comms[0])
+    c0.d_skip = skip.data_ptr()
+    _lib.check(lib.ska_peer_allreduce_f64(C.byref(c0), C.c_void_p(x.data_ptr()), 4, None))  # alone: would time out if it did not skip
+    torch.cuda.synchronize()
+    assert states[0].tolist() == [0, 0] and torch.equal(x, torch.full((4,), 3.0, dtype=torch.float64, device=cuda))
+
+
+def test_two_co_resident_ranks_run_the_sharded_schur_lm(cuda):
+    """The frame-sharded Schur LM with the all-reduces FUSED into the solve / control kernels (SkaBaProblem.peer), on one GPU:
+    two solvers hold the two halves of a clip, their trials are enqueued on two streams, and each solve / control kernel
+    pushes its payload into the other's receive area and waits for the other's - exactly what two processes on two GPUs do
+    (tools/ba_multi_gpu_check.py, bench.py's `parity` objects).  Both must follow the unsharded solve."""
+    from oracle import lm
+    from skiing_analysis_pytorch_b200 import ba
+
+    clip, R0, t0, X0 = lm.make_problem("3", 64, 17)
+    x = torch.from_numpy(clip.x_fm).to(cuda)
+    c = torch.from_numpy(clip.conf_fm).to(cuda)
+    X = torch.from_numpy(X0.astype("float32")).to(cuda)
+    whole = ba.BundleAdjuster(x, c, clip.K, R0, t0, X, max_iters=8)
+    whole.run(6)
+    lib, comms, regions, states = _comms(2, 2048, cuda)
+    halves, streams = [], [torch.cuda.Stream(cuda) for _ in range(2)]
+    for r, (a, b) in enumerate(((0, 29), (29, 64))):
+        s = ba.BundleAdjuster(x[a:b].contiguous(), c[a:b].contiguous(), clip.K, R0, t0, X[a:b].contiguous(), max_iters=8)
+        s.ctrl[_cabi.BA_CTRL_SUMCONF] = whole.ctrl[_cabi.BA_CTRL_SUMCONF]  # the global sum of confidences (an all-reduce at set-up)
+        s.prob.peer = C.addressof(comms[r])
+        s.fused_exchange = True
+        halves.append(s)
+    torch.cuda.synchronize()
+    for _ in range(6):
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                halves[r].trial()
+                halves[r].iters_done += 1
+    torch.cuda.synchronize()
+    assert [st.tolist()[1] for st in states] == [0, 0]  # no exchange timed out
+    for s in halves:
+        n_ok = 0
+        for h, w in zip(s.history, whole.history):
+            assert abs(h["cost"] - w["cost"]) <= 1e-5 * w["cost"] and abs(h["trial_cost"] - w["trial_cost"]) <= 1e-5 * w["trial_cost"]
+            if abs(w["cost"] - w["trial_cost"]) < 1e-3 * w["cost"]:
+                break  # converged: the decision is rounding noise of two fp32 summation orders, the damping sequences part ways
+            assert h["accepted"] == w["accepted"]
+            n_ok += 1
+        assert n_ok >= 2
+    assert halves[0].history == halves[1].history  # bit-identical sums on both ranks: identical decisions and cameras
+    assert torch.equal(halves[0].cams, halves[1].cams)
