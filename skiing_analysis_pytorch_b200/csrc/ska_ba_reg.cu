@@ -306,7 +306,8 @@ __device__ __forceinline__ int up6(int r, int c) { return r * 6 - r * (r - 1) / 
 // the frame's Schur complement S = Dc - sum_j W_j^T Dp_j^-1 W_j  (Dp, Dc: damped diagonal blocks of J^T J).
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, 4) reg_linearize_kernel(const RegArgs a) {
   extern __shared__ double smem_d[];
-  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wid = blockIdx.x * kWarpsPerBlock + wl;
+  // launched with 4, 2 or 1 warps per block (the largest frames - 96 joints x 8 cameras - need 60 KB of shared memory per warp)
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, wid = blockIdx.x * (int)(blockDim.x >> 5) + wl;
   const size_t per_warp = (size_t)a.J * 12 + (size_t)a.C * 28 + a.nf + a.nS + (size_t)96 * a.n6;
   Smem sm(smem_d + wl * per_warp, a);
   const double* sc = a.sc;
@@ -1273,9 +1274,10 @@ int ba_reg_linearize(const SkaBaRegProblem& p, cudaStream_t s) {
   }
   const size_t per_warp = ((size_t)a.J * 12 + (size_t)a.C * 28 + a.nf + a.nS + (size_t)96 * a.n6) * sizeof(double);
   int wpb = kWarpsPerBlock;
+  while (wpb > 1 && per_warp * wpb > (size_t)227 * 1024) wpb /= 2;
   const size_t bytes = per_warp * wpb;
   if ((rc = set_smem(reg_linearize_kernel, bytes)) != SKA_OK) return rc;
-  reg_linearize_kernel<<<a.W / kWarpsPerBlock, 32 * kWarpsPerBlock, bytes, s>>>(a);
+  reg_linearize_kernel<<<a.W / wpb, 32 * wpb, bytes, s>>>(a);
   return check_launch();
 }
 

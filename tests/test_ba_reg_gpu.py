@@ -153,10 +153,12 @@ def test_run_local_ba_lm_signature_and_modes(cuda):
             assert torch.equal(Ro.cpu(), torch.from_numpy(R)) and not torch.equal(to.cpu(), torch.from_numpy(t))
 
 
-@pytest.mark.parametrize("rig,T,J,mode", [("2b", 1, 17, "full"), ("2b", 2, 5, "pose_cam_t"), ("2b", 7, 96, "pose_only"), ("3", 5, 17, "full")])
+@pytest.mark.parametrize("rig,T,J,mode", [("2b", 1, 17, "full"), ("2b", 2, 5, "pose_cam_t"), ("2b", 7, 96, "pose_only"), ("3", 5, 17, "full"),
+                                          ("8", 3, 96, "full")])
 def test_edge_shapes(cuda, rig, T, J, mode):
     """One frame (no temporal / smoothness pairs), a skeleton too small for any bone (J = 5), the largest skeleton (J = 96:
-    three joints per lane), three cameras: trajectories against the exact-solve oracle."""
+    three joints per lane), three cameras, and the largest frame the kernels take (96 joints x 8 free cameras: 60 KB of
+    shared memory per warp, two warps per block): trajectories against the exact-solve oracle."""
     clip, R, t, X0 = lm_reg.make_problem(rig, T, J, cam_jitter=0.01)
     s = ba_reg.RegularisedBundleAdjuster(torch.from_numpy(clip.x_fm).to(cuda), torch.from_numpy(clip.conf_fm).to(cuda), clip.K, R, t, X0,
                                          mode=mode, max_iters=8, cg_iters=120)
