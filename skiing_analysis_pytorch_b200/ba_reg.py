@@ -49,6 +49,7 @@ class RegLMSequencer:
     iters_done = 0
     _graph = None
     _capturing = False
+    _gather_bufs = None
 
     def _world(self):
         d = torch.distributed
@@ -71,7 +72,9 @@ class RegLMSequencer:
     def _allgather(self, mine, in_cg: bool = False):
         """(world,) + mine.shape <- every rank's `mine`."""
         world = self._world()[0]
-        bufs = self.__dict__.setdefault("_gather_bufs", {})
+        if self._gather_bufs is None:
+            self._gather_bufs = {}
+        bufs = self._gather_bufs
         key = (world * mine.numel(), mine.dtype, mine.device)
         flat = bufs.get(key)
         if flat is None:  # persistent: a skipped exchange (CG converged) leaves the previous, valid contents in place
