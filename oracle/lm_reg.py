@@ -26,7 +26,8 @@ functions through goldens G3/G4/G9, and golden G12 holds the reference's loss at
   control   as oracle/lm.py: accept iff F_trial < F; rho = (F - F_trial) / (delta^T (lam D delta - g)); Nielsen's lambda
             update, lam0 = 1e-3.  F_trial is the true objective at the trial point (its own bone / baseline means).
   pi        as loss.py:17-87: X_c = R X + t, z clamped at 1e-6 with zero derivative while the clamp is active.
-Multi-shard: `cost_terms` and `linearise` take frame ranges with a one-frame halo; every sum adds over shards (tests).
+Multi-shard: tests/oracle_engine.py (OracleRegularisedBundleAdjuster) runs this specification shard by shard - each rank
+multiplies only its rows of the normal matrix with [halo | own | halo] entries - behind the product's sequencer over gloo.
 """
 from __future__ import annotations
 
@@ -300,7 +301,7 @@ def run_lm(X0, R0, t0, K, x2d, conf, num_iters=10, mode="pose_only", weights=Non
         terms, ncl = cost_terms(X, R, t, K, x2d, conf, coef)
         F = sum(terms.values())
         H, g, free, r2 = normal_system(X, R, t, K, x2d, conf, coef, mode)
-        # |r|^2 differs from F only by the constant terms the mode cannot move?  No: every residual group is in r, so r2 == F
+        # every residual group is in r, so |r|^2 == F whatever the mode (tested)
         D = H.diagonal()
         if solver == "direct":
             d_free = spla.splu((H + lam * sp.diags(D)).tocsc()).solve(-g)
