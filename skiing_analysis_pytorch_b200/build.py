@@ -33,13 +33,35 @@ def sources():
     return sorted(CSRC.glob("*.cu"))
 
 
-def _deps_mtime() -> float:
-    files = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "ska.h"]
-    return max(f.stat().st_mtime for f in files)
+def _dep_files():
+    return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "ska.h"])
+
+
+def source_hash() -> str:
+    """sha256 over the sources and flags the library is built from.  The library carries it in a side file
+    (lib/libska.so.hash, written after a successful link): staleness is decided by CONTENT, not by mtimes - a snapshot
+    copied to another machine keeps its library whatever the copy did to the timestamps."""
+    import hashlib
+
+    h = hashlib.sha256()
+    h.update(" ".join(ARCH_FLAGS + NVCC_FLAGS).encode())
+    for f in _dep_files():
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()
+
+
+def _hash_file() -> Path:
+    return LIB.with_name(LIB.name + ".hash")
 
 
 def needs_build() -> bool:
-    return not LIB.exists() or LIB.stat().st_mtime < _deps_mtime()
+    if not LIB.exists():
+        return True
+    try:
+        return _hash_file().read_text().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False, extra_flags=(), out: Path | None = None) -> Path:
@@ -57,13 +79,33 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: Path 
     nvcc = _nvcc()
     OBJ.mkdir(parents=True, exist_ok=True)
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    hdr_m = max(
-        f.stat().st_mtime for f in list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "ska.h"]
-    )
+    import fcntl
+
+    with open(LIB.parent / ".build.lock", "w") as lock:  # one builder at a time (N ranks may import at once)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():  # somebody else built it while we waited
+            return LIB
+        return _build_locked(nvcc, force, verbose, extra_flags)
+
+
+def _build_locked(nvcc, force, verbose, extra_flags) -> Path:
+    import hashlib
+
+    hdr = hashlib.sha256(" ".join([*ARCH_FLAGS, *NVCC_FLAGS, *extra_flags]).encode())
+    for f in sorted(list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "ska.h"]):
+        hdr.update(f.name.encode())
+        hdr.update(f.read_bytes())
+    hdr_digest = hdr.hexdigest()
 
     def compile_one(src: Path) -> Path:
         obj = OBJ / (src.stem + ".o")
-        if not force and obj.exists() and obj.stat().st_mtime >= max(src.stat().st_mtime, hdr_m):
+        tag = obj.with_name(obj.name + ".hash")
+        want = hashlib.sha256((hdr_digest + src.name).encode() + src.read_bytes()).hexdigest()
+        try:  # an object is reused iff it was compiled from exactly these bytes with exactly these flags (content, not mtimes)
+            fresh = obj.exists() and tag.read_text().strip() == want
+        except OSError:
+            fresh = False
+        if not force and fresh:
             return obj
         cmd = [nvcc, *ARCH_FLAGS, *NVCC_FLAGS, *extra_flags, "-I", str(ROOT / "include"), "-c", str(src), "-o", str(obj)]
         if verbose:
@@ -73,6 +115,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: Path 
             sys.stderr.write(r.stderr)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src.name}:\n{r.stdout}\n{r.stderr}")
+        tag.write_text(want + "\n")
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
@@ -83,6 +126,8 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: Path 
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB)
+    if not extra_flags:
+        _hash_file().write_text(source_hash() + "\n")
     return LIB
 
 
