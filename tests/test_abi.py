@@ -138,3 +138,24 @@ def test_api_refuses_cpu_tensors():
     R, t = synth.rig("2b")
     with pytest.raises(RuntimeError, match="no CPU path"):
         api.triangulate_reproject(torch.zeros(2, 1, 17, 2), synth.K_CALIB, R, t)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/ska.h compiles as C11 (-Wall -Werror -pedantic) and a C program links against libska.so and calls it."""
+    import shutil
+    import subprocess
+
+    from skiing_analysis_pytorch_b200 import _lib, build
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    build.build()
+    exe = tmp_path / "link_check"
+    libdir = _lib.LIB_PATH.parent
+    cmd = [gcc, "-std=c11", "-Wall", "-Werror", "-pedantic", "-I", str(ROOT / "include"), str(ROOT / "tests" / "cabi" / "link_check.c"),
+           "-L", str(libdir), "-lska", f"-Wl,-rpath,{libdir}", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok abi"), (r.returncode, r.stdout, r.stderr)
