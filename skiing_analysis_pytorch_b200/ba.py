@@ -427,7 +427,7 @@ class _DeviceAdam:
 
 
 def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch, x2d_torch, conf2d_torch, num_iters=200, lr=1e-3,
-                             device="cuda", mode="pose_only", weights=None, graph=True, fused=True):
+                             device="cuda", mode="pose_only", weights=None, graph=True, fused=True, group=None):
     """First-order (Adam) minimisation of the reference's full configured objective (SURVEY row N1, first-order form;
     specification oracle/first_order.py):
         w_reproj reprojection_loss + w_smooth camera_smooth_loss + w_baseline baseline_reg_loss
@@ -441,6 +441,10 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
     directly and folds every weight / count into the multi-term Adam kernel (ska_adam_step_terms_*): ~35 launches per
     iteration and no element-wise torch arithmetic; fused=False goes through the autograd wrappers of losses.py (the
     same kernels plus ~100 small torch kernels of gradient scaling / accumulation) - kept as the cross-check.
+    group: a torch.distributed process group = the clip is sharded by contiguous frame ranges in rank order and the
+    arguments are THIS rank's frames.  The temporal / smoothness terms then read a one-frame halo of the
+    neighbouring shards (exchanged after every step), the bone / baseline means and every loss sum are all-reduced, the counts
+    are the clip's; every rank records the same history and returns its own frames.
     Returns (R_opt, t_opt, X_opt, history) with one history row per iteration:
     {iter, loss, reproj, smooth, baseline, bone_length, pose_temporal} (values before that iteration's step)."""
     from . import losses
@@ -462,6 +466,44 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
     lib = _lib.load()
     sfx = "f32" if dt == torch.float32 else "f64"
     num_iters = int(num_iters)
+    # ---- frame sharding: this rank's frames live in rows 1..Tl of buffers with one halo frame on each side
+    tdist = torch.distributed
+    world, rank = (tdist.get_world_size(group), tdist.get_rank(group)) if group is not None else (1, 0)
+    sharded = world > 1
+    Tl = X.shape[0]
+    T_glob = Tl
+    if sharded:
+        if not fused:
+            raise ValueError("the sharded first-order solve runs the fused form (fused=True)")
+        if Tl < 1:
+            raise ValueError("every rank needs at least one frame")
+        tot = torch.tensor([float(Tl)], dtype=torch.float64, device=dev)
+        tdist.all_reduce(tot, group=group)
+        T_glob = int(round(float(tot.item())))
+        Xe = torch.zeros((Tl + 2,) + tuple(X.shape[1:]), dtype=dt, device=dev)
+        Re = torch.eye(3, dtype=dt, device=dev).expand(Tl + 2, R.shape[1], 3, 3).contiguous()
+        te = torch.zeros((Tl + 2,) + tuple(t.shape[1:]), dtype=dt, device=dev)
+        Xe[1:-1], Re[1:-1], te[1:-1] = X, R, t
+        X, R, t = Xe[1:-1], Re[1:-1], te[1:-1]  # contiguous views: the kernels update the halo buffers' interior in place
+        has_prev, has_next = rank > 0, rank < world - 1
+        lo, hi = (0 if has_prev else 1), (Tl + 2 if has_next else Tl + 1)  # rows whose gradient needs both neighbours: [lo, hi)
+        n_edge = X.shape[1] * 3 + R.shape[1] * 12
+
+        def exchange_halo():
+            mine = torch.empty((2, n_edge), dtype=dt, device=dev)
+            for e, row_ in enumerate((1, Tl)):
+                mine[e] = torch.cat([Xe[row_].reshape(-1), Re[row_].reshape(-1), te[row_].reshape(-1)])
+            flat = torch.empty(world * mine.numel(), dtype=dt, device=dev)
+            tdist.all_gather_into_tensor(flat, mine.reshape(-1), group=group)
+            everyone = flat.view(world, 2, n_edge)
+            j3, c9 = X.shape[1] * 3, R.shape[1] * 9
+            for row_, src in ((0, everyone[rank - 1, 1] if has_prev else None), (Tl + 1, everyone[rank + 1, 0] if has_next else None)):
+                if src is not None:
+                    Xe[row_] = src[:j3].view_as(Xe[row_])
+                    Re[row_] = src[j3:j3 + c9].view_as(Re[row_])
+                    te[row_] = src[j3 + c9:].view_as(te[row_])
+
+        exchange_halo()
     opt = _DeviceAdam(lr, dev)
     n_rot = R.shape[0] * R.shape[1]
     gw = torch.empty((n_rot, 3), dtype=dt, device=dev)
@@ -474,8 +516,8 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
     Tn, Jn, Cn = X.shape[0], X.shape[1], R.shape[1]
     keep = [k for k, (i, j) in enumerate(losses.BONES) if i < Jn and j < Jn]
     nb = len(keep)
-    use = dict(reproj=bool(w["reproj"]), smooth=bool(w["smooth"]) and Tn > 1, baseline=bool(w["baseline"]) and Cn >= 2,
-               bone_length=bool(w["bone_length"]) and nb > 0, pose_temporal=bool(w["pose_temporal"]) and Tn > 1)
+    use = dict(reproj=bool(w["reproj"]), smooth=bool(w["smooth"]) and T_glob > 1, baseline=bool(w["baseline"]) and Cn >= 2,
+               bone_length=bool(w["bone_length"]) and nb > 0, pose_temporal=bool(w["pose_temporal"]) and T_glob > 1)
     cam_free, rot_free = mode != "pose_only", mode == "full"
     f64d = dict(dtype=torch.float64, device=dev)
     if fused:
@@ -488,14 +530,52 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
         gX_r, gX_b, gX_t = like(X, use["reproj"]), like(X, use["bone_length"]), like(X, use["pose_temporal"])
         gR_r, gR_s, gR_b = like(R, use["reproj"] and rot_free), like(R, use["smooth"] and cam_free), like(R, use["baseline"] and cam_free)
         gt_r, gt_s, gt_b = like(t, use["reproj"] and cam_free), like(t, use["smooth"] and cam_free), like(t, use["baseline"] and cam_free)
-        s_r, s_t, s_s, s_bl = torch.zeros(4, **f64d), torch.zeros(1, **f64d), torch.zeros(1, **f64d), torch.zeros(1, **f64d)
-        s_b0, s_b1, s_m = torch.zeros(_cabi.MAX_BONES, **f64d), torch.zeros(_cabi.MAX_BONES, **f64d), torch.zeros(1, **f64d)
+        # the loss sums in ONE buffer (one all-reduce per iteration when sharded), the two means in another (needed in between)
+        fin, mid = torch.zeros(7 + _cabi.MAX_BONES, **f64d), torch.zeros(_cabi.MAX_BONES + 1, **f64d)
+        s_r, s_t, s_s, s_bl, s_b1 = fin[0:4], fin[4:5], fin[5:6], fin[6:7], fin[7:]
+        s_b0, s_m = mid[:_cabi.MAX_BONES], mid[_cabi.MAX_BONES:]
+        if sharded:  # gradients of the coupled terms over [halo | own | halo]; the Adam step reads the interior
+            scratch1 = torch.zeros(1, **f64d)
+            gX_t_e = torch.zeros_like(Xe) if use["pose_temporal"] else None
+            gR_s_e = torch.zeros_like(Re) if use["smooth"] and cam_free else None
+            gt_s_e = torch.zeros_like(te) if use["smooth"] and cam_free else None
+            gX_t = gX_t_e[1:-1] if gX_t_e is not None else None
+            gR_s = gR_s_e[1:-1] if gR_s_e is not None else None
+            gt_s = gt_s_e[1:-1] if gt_s_e is not None else None
         gw3 = [torch.empty((n_rot, 3), dtype=dt, device=dev) for _ in range(3)] if rot_free else None
         P = lambda a: None if a is None else C.c_void_p(a.data_ptr())
         fn = lambda name: getattr(lib, f"{name}_{sfx}")
         strm = lambda: _stream_ptr(dev)
 
+        def eval_terms_sharded():
+            PO = lambda a, r0: None if a is None else C.c_void_p(a[r0:].data_ptr())
+            with torch.cuda.device(dev):
+                if use["reproj"]:
+                    _lib.check(fn("ska_reprojection_loss")(P(X), Tn, Jn, Cn, P(R), Cn * 9, P(t), Cn * 3, P(K), 0, P(x2d), P(conf), P(s_r), P(gX_r),
+                                                          P(gR_r), P(gt_r), None, P(ws), ws_bytes, strm()))
+                if use["pose_temporal"]:  # gradient over every row that has both neighbours here; value over the pairs (t, t+1) this rank owns
+                    _lib.check(fn("ska_pose_temporal")(PO(Xe, lo), hi - lo, Jn, P(scratch1), PO(gX_t_e, lo), P(ws), ws_bytes, strm()))
+                    _lib.check(fn("ska_pose_temporal")(PO(Xe, 1), hi - 1, Jn, P(s_t), None, P(ws), ws_bytes, strm()))
+                if use["smooth"]:
+                    _lib.check(fn("ska_camera_smooth")(PO(Re, lo), PO(te, lo), hi - lo, Cn, P(scratch1), PO(gR_s_e, lo), PO(gt_s_e, lo), P(ws), ws_bytes, strm()))
+                    _lib.check(fn("ska_camera_smooth")(PO(Re, 1), PO(te, 1), hi - 1, Cn, P(s_s), None, None, P(ws), ws_bytes, strm()))
+                if use["bone_length"]:
+                    _lib.check(fn("ska_bone_length")(P(X), Tn, Jn, bi, bj, nb, None, P(s_b0), None, P(ws), ws_bytes, strm()))
+                if use["baseline"]:
+                    _lib.check(fn("ska_baseline_reg")(P(R), P(t), Tn, Cn, None, P(s_m), None, None, P(ws), ws_bytes, strm()))
+            if use["bone_length"] or use["baseline"]:
+                tdist.all_reduce(mid, group=group)  # the clip's bone lengths / baselines
+                mid.div_(T_glob)
+            with torch.cuda.device(dev):
+                if use["bone_length"]:
+                    _lib.check(fn("ska_bone_length")(P(X), Tn, Jn, bi, bj, nb, P(s_b0), P(s_b1), P(gX_b), P(ws), ws_bytes, strm()))
+                if use["baseline"]:
+                    _lib.check(fn("ska_baseline_reg")(P(R), P(t), Tn, Cn, P(s_m), P(s_bl), P(gR_b), P(gt_b), P(ws), ws_bytes, strm()))
+            tdist.all_reduce(fin, group=group)
+
         def eval_terms():
+            if sharded:
+                return eval_terms_sharded()
             with torch.cuda.device(dev):
                 if use["reproj"]:
                     _lib.check(fn("ska_reprojection_loss")(P(X), Tn, Jn, Cn, P(R), Cn * 9, P(t), Cn * 3, P(K), 0, P(x2d), P(conf), P(s_r), P(gX_r),
@@ -516,10 +596,10 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
         eval_terms()  # set-up evaluation: the sum of confidences (constant over the solve) fixes the reprojection scale
         sum_conf = float(s_r[1].item()) if use["reproj"] else 1.0
         c_r = w["reproj"] / (sum_conf + 1e-6)
-        c_t = w["pose_temporal"] / max((Tn - 1) * Jn * 3, 1)
-        c_b = w["bone_length"] / max(Tn * nb, 1)
-        c_s = w["smooth"] / max((Tn - 1) * Cn * 3, 1)
-        c_bl = w["baseline"] / max(Tn, 1)
+        c_t = w["pose_temporal"] / max((T_glob - 1) * Jn * 3, 1)
+        c_b = w["bone_length"] / max(T_glob * nb, 1)
+        c_s = w["smooth"] / max((T_glob - 1) * Cn * 3, 1)
+        c_bl = w["baseline"] / max(T_glob, 1)
 
         def terms3(cands):
             live = [(g, sc) for g, sc in cands if g is not None]
@@ -560,6 +640,8 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
                 if cands:
                     with torch.cuda.device(dev):
                         _lib.check(fn("ska_so3_retract")(P(R), P(sw), n_rot, strm()))
+            if sharded:
+                exchange_halo()
 
     def iteration():
         if fused:
@@ -617,7 +699,7 @@ def run_local_ba_first_order(K_torch, R_init_torch, t_init_torch, X3d_init_torch
     h = hist[:num_iters].cpu().numpy()
     history = [dict(iter=i, loss=float(r[0]), **{n: float(r[1 + k]) for k, n in enumerate(FIRST_ORDER_TERMS)}) for i, r in enumerate(h)]
     od = R_init_torch.dtype
-    return R.to(od), t.to(t_init_torch.dtype), X.to(X3d_init_torch.dtype), history
+    return R.to(od).clone(), t.to(t_init_torch.dtype).clone(), X.to(X3d_init_torch.dtype).clone(), history
 
 
 def run_local_ba(K_torch, R_init_torch, t_init_torch, X3d_init_torch, x2d_torch, conf2d_torch, num_iters=200, lr=1e-3,
