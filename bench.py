@@ -267,36 +267,65 @@ def ba_cpu_iteration_rate(frames=1500, joints=17, rig="2b", iters=3):
     return iters / (time.perf_counter() - t0_)
 
 
-def run_first_order(a, dev, rank, n_gpus):
+def run_first_order(a, dev, rank, n_gpus, dist=None):
     """Row N1 (first-order form): Adam iterations/s on the reference's full configured objective (configs/vggt.yaml:43-52)
-    with per-frame cameras at config-3 size, one iteration replayed from a CUDA graph; beside it the same iteration
+    with per-frame cameras at config-3 size, one iteration replayed from a CUDA graph; N GPUs: the clip's frames sharded by
+    range (strong scaling; one-frame halos + all-reduced sums inside the graph).  Beside it, at N = 1, the same iteration
     (forward + backward of the five loss terms, all host threads) of the torch restatement on the CPU."""
     import torch
 
-    from skiing_analysis_pytorch_b200 import ba, synth
+    from skiing_analysis_pytorch_b200 import api, ba, synth
 
-    T, J = 100_000, 17
-    d = synth.make_clip_device("2b", T, J, dev, seed=100 + rank)
+    T_total, J = 100_000, 17
+    T = T_total // n_gpus
+    d = synth.make_clip_device("2b", T, J, dev, seed=100, shardable=True, frame_offset=rank * T)  # the same clip at every N
     R0, t0 = synth.perturb_cameras(d["R"], d["t"], seed=1)
     R = torch.tensor(R0, device=dev, dtype=torch.float32)[None].expand(T, 2, 3, 3).contiguous()
     t = torch.tensor(t0, device=dev, dtype=torch.float32)[None].expand(T, 2, 3).contiguous()
-    X0 = (d["X"] + 0.05 * torch.randn(T, J, 3, dtype=torch.float64, device=dev)).float()
+    X0 = api.triangulate_reproject(d["x2d"].permute(1, 0, 2, 3).contiguous(), d["K"], R0, t0, want=("X",)).X  # DLT under the perturbed rig
     args = (torch.tensor(d["K"], dtype=torch.float32), R, t, X0, d["x2d"], d["conf"])
-    ba.run_local_ba(*args, num_iters=8, lr=1e-2, mode="full", optimizer="adam")  # warm-up
+    kw = dict(lr=1e-2, device=dev, mode="full", group=dist.group.WORLD if n_gpus > 1 else None)
+    ba.run_local_ba_first_order(*args, num_iters=8, **kw)  # warm-up
     torch.cuda.synchronize()
+
     def wall(n):
         torch.cuda.synchronize()
+        if n_gpus > 1:
+            dist.barrier()
         t0_ = time.perf_counter()
-        out_ = ba.run_local_ba(*args, num_iters=n, lr=1e-2, mode="full", optimizer="adam")
+        out_ = ba.run_local_ba_first_order(*args, num_iters=n, **kw)
         torch.cuda.synchronize()
         return time.perf_counter() - t0_, out_[3]
 
     (t_short, _), (t_long, h) = wall(100), wall(500)   # set-up + graph capture cancel in the difference
     ms = 1e3 * (t_long - t_short) / 400
-    out = {"metric": "ba_first_order_iterations_per_sec", "value": 1e3 / ms, "unit": "iters/s", "ms_per_iter": ms, "frames": T, "joints": J,
+    if n_gpus > 1:
+        m = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        ms = float(m.item())
+    losses_rec = [h[k]["loss"] for k in (0, 99, 499)]
+    parity = {"reference": "unrecorded", "ok": None}
+    try:
+        ref = json.loads((ROOT / "profiles" / "ba_parity_n1.json").read_text()).get("first_order")
+    except Exception:
+        ref = None
+    if ref is not None:
+        rel = max(abs(x - y) / abs(y) for x, y in zip(losses_rec, ref["losses"]))
+        parity = {"reference": f"profiles/ba_parity_n1.json ({ref.get('recorded', '?')})", "max_rel_loss_dev": rel, "tolerance": 1e-4, "ok": bool(rel <= 1e-4)}
+    if a.record_ba_parity and n_gpus == 1:
+        f = ROOT / "gpurun_out" / "ba_parity_n1.json"
+        try:
+            rec = json.loads(f.read_text())
+        except Exception:
+            rec = {}
+        rec["first_order"] = {"losses": losses_rec, "recorded": f"loss at iterations 0 / 99 / 499, {T_total} frames x {J} joints x 2 per-frame cameras, float32, mode full"}
+        f.parent.mkdir(exist_ok=True)
+        f.write_text(json.dumps(rec, indent=1))
+    out = {"metric": "ba_first_order_iterations_per_sec", "value": 1e3 / ms, "unit": "iters/s", "ms_per_iter": ms, "scaling": "strong",
+           "frames_total": T * n_gpus, "frames_per_gpu": T, "joints": J,
            "cameras": 2, "mode": "full", "objective": "reproj + camera_smooth + baseline_reg + bone_length + pose_temporal (configs/vggt.yaml weights)",
            "timing": "(wall clock of 500 iterations - wall clock of 100) / 400: set-up and graph capture cancel; nothing synchronises inside",
-           "loss_first": h[0]["loss"], "loss_last": h[-1]["loss"]}
+           "collectives_per_iter": 0 if n_gpus == 1 else 3, "loss_first": h[0]["loss"], "loss_last": h[-1]["loss"], "parity": parity}
     if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
         from oracle import first_order as FO
         from oracle import torch_ref as TR
@@ -847,8 +876,7 @@ def run_ours(a, out_fd=1):
     if not a.no_ba:
         line["ba"] = run_ba(a, dev, world, rank, barrier, dist)
         line["gpu_launches_ba_per_iter"] = 6
-        if n_gpus == 1:
-            line["ba"]["first_order"] = run_first_order(a, dev, rank, n_gpus)
+        line["ba"]["first_order"] = run_first_order(a, dev, rank, n_gpus, dist)
         if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
             r = ba_cpu_iteration_rate()
             line["ba"]["cpu_baseline"] = {
