@@ -876,7 +876,10 @@ def run_ours(a, out_fd=1):
     if not a.no_ba:
         line["ba"] = run_ba(a, dev, world, rank, barrier, dist)
         line["gpu_launches_ba_per_iter"] = 6
-        line["ba"]["first_order"] = run_first_order(a, dev, rank, n_gpus, dist)
+        try:
+            line["ba"]["first_order"] = run_first_order(a, dev, rank, n_gpus, dist)
+        except Exception as e:  # an extra leg: never lose the line over it
+            line["ba"]["first_order"] = {"failed": repr(e)[:300]}
         if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
             r = ba_cpu_iteration_rate()
             line["ba"]["cpu_baseline"] = {
