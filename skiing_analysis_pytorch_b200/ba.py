@@ -240,6 +240,8 @@ class BundleAdjuster(LMSequencer):
     # ------------------------------------------------------------------ results (synchronise)
     @property
     def history(self):
+        if self.peer is not None:
+            self.peer.check()  # an exchange that gave up waiting for a peer invalidates the trajectory: raise, never return it
         h = self.hist[: self.iters_done].cpu().numpy()
         keys = ("iter", "cost", "trial_cost", "lam", "rho", "accepted", "n_clamped", "pred")
         out = []

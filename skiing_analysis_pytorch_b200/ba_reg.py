@@ -334,6 +334,8 @@ class RegularisedBundleAdjuster(RegLMSequencer):
     # ------------------------------------------------------------------ results (synchronise)
     @property
     def history(self):
+        if self.peer is not None:
+            self.peer.check()  # an exchange that gave up waiting for a peer invalidates the trajectory: raise, never return it
         out = []
         for row in self.hist[: self.iters_done].cpu().numpy():
             d = dict(zip(HIST_KEYS, (float(v) for v in row)))
