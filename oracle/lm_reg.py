@@ -123,8 +123,10 @@ def free_columns(T, J, C, mode):
     return m
 
 
-def jacobian(X, R, t, K, x2d, conf, coef):
-    """Residual vector r and sparse Jacobian J over ALL unknowns [X | cams] (columns masked later)."""
+def jacobian(X, R, t, K, x2d, conf, coef, refs=None):
+    """Residual vector r and sparse Jacobian J over ALL unknowns [X | cams] (columns masked later).
+    refs: None = the bone / baseline references are the means AT this point (what the LM uses: constants of the linearisation);
+    (ref_bone (B,), ref_base) = given constants (finite-difference checks hold them fixed while the point moves)."""
     T, J, _ = X.shape
     C = R.shape[1]
     nX = T * J * 3
@@ -169,7 +171,7 @@ def jacobian(X, R, t, K, x2d, conf, coef):
             for k in range(3):
                 add(rr, ix(tv, bi) + k, sq * u[:, k])
                 add(rr, ix(tv, bj) + k, -sq * u[:, k])
-            res.append(sq * (L - L.mean()))
+            res.append(sq * (L - (L.mean() if refs is None else refs[0][len(res) - 1])))
             nrow += T
     # ---- pose temporal
     if T > 1 and coef["pose_temporal"]:
@@ -206,7 +208,7 @@ def jacobian(X, R, t, K, x2d, conf, coef):
         for k in range(6):
             add(rr, ic(tv, 0) + k, sq * g0[:, k])
             add(rr, ic(tv, 1) + k, sq * g1[:, k])
-        res.append(sq * (b - b.mean()))
+        res.append(sq * (b - (b.mean() if refs is None else refs[1])))
         nrow += T
     Jm = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nrow, n)).tocsr()
     return np.concatenate(res), Jm
